@@ -1,0 +1,199 @@
+// Internal declarations shared by the translation units of libbotsort_b200.so.
+// Not part of the ABI (that is include/botsort_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/botsort_b200.h"
+
+struct bt_tracker;  // track_step.cu
+
+struct bt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int max_tracks = 0, max_dets = 0, feat_dim = 0;
+  uint32_t flags = 0;
+  int num_sms = 148;
+  std::string err;
+  int64_t launches = 0;
+  // bump arena for the stand-alone entry points (device) and a pinned mirror for small results
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
+  char* pinned = nullptr;
+  size_t pinned_cap = 0;
+  // LAP workspaces (lap.cu), sized for max_tracks x max_dets
+  struct bt_lap_ws* lap = nullptr;
+  // ReID similarity GEMM workspaces (reid_gemm.cu)
+  struct bt_gemm_ws* gemm = nullptr;
+  bt_tracker* trk = nullptr;
+};
+
+int32_t bt_fail(bt_ctx* ctx, int32_t code, const char* fmt, ...);
+extern thread_local std::string g_bt_create_error;
+
+#define BT_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return bt_fail(ctx, BT_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,               \
+                     cudaGetErrorString(e__));                                                     \
+  } while (0)
+
+#define BT_CHECK(cond, code, ...)                                                                  \
+  do {                                                                                             \
+    if (!(cond)) return bt_fail(ctx, code, __VA_ARGS__);                                           \
+  } while (0)
+
+#define BT_TRY(expr)                                                                               \
+  do {                                                                                             \
+    int32_t s__ = (expr);                                                                          \
+    if (s__ != BT_OK) return s__;                                                                  \
+  } while (0)
+
+#define BT_LAUNCHED(ctx)                                                                           \
+  do {                                                                                             \
+    (ctx)->launches++;                                                                             \
+    BT_CUDA(cudaGetLastError());                                                                   \
+  } while (0)
+
+// ---- arena ----------------------------------------------------------------------------------
+int32_t bt_arena_reset(bt_ctx* ctx);
+int32_t bt_arena_reserve(bt_ctx* ctx, size_t total);
+int32_t bt_arena_alloc(bt_ctx* ctx, size_t bytes, void** out);
+template <typename T>
+static inline int32_t bt_arena(bt_ctx* ctx, size_t count, T** out) {
+  void* p = nullptr;
+  int32_t s = bt_arena_alloc(ctx, count * sizeof(T), &p);
+  *out = reinterpret_cast<T*>(p);
+  return s;
+}
+// stage an input: loc==BT_DEVICE returns the pointer itself, BT_HOST copies into the arena
+int32_t bt_stage_in(bt_ctx* ctx, const void* src, size_t bytes, int32_t loc, const void** dev);
+// stage an output: loc==BT_DEVICE returns the pointer itself, BT_HOST an arena buffer
+int32_t bt_stage_out(bt_ctx* ctx, void* dst, size_t bytes, int32_t loc, void** dev);
+// finish an output: BT_HOST copies back (async) -- caller must bt_finish() afterwards
+int32_t bt_unstage_out(bt_ctx* ctx, void* dst, const void* dev, size_t bytes, int32_t loc);
+// BT_HOST: synchronise the stream so host buffers are valid; BT_DEVICE: nothing
+int32_t bt_finish(bt_ctx* ctx, int32_t loc);
+
+template <typename T>
+static inline int32_t bt_in(bt_ctx* ctx, const T* src, size_t count, int32_t loc, const T** dev) {
+  const void* p = nullptr;
+  int32_t s = bt_stage_in(ctx, src, count * sizeof(T), loc, &p);
+  *dev = reinterpret_cast<const T*>(p);
+  return s;
+}
+template <typename T>
+static inline int32_t bt_out(bt_ctx* ctx, T* dst, size_t count, int32_t loc, T** dev) {
+  void* p = nullptr;
+  int32_t s = bt_stage_out(ctx, dst, count * sizeof(T), loc, &p);
+  *dev = reinterpret_cast<T*>(p);
+  return s;
+}
+
+// ---- constants of the reference's Kalman filter (demo:163-164) -------------------------------
+#define BT_STD_POS (1.0 / 20)
+#define BT_STD_VEL (1.0 / 160)
+
+// ---- kernel launchers (device pointers only; enqueue on ctx->stream) --------------------------
+// kalman.cu
+int32_t btk_kalman_initiate(bt_ctx* ctx, const float* xywh, const int32_t* src_idx, double* mean,
+                            double* cov, double* tlbr, float* tlbr_f32, const int32_t* dst_idx, int32_t k);
+int32_t btk_kalman_predict(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
+                           const int32_t* state, const int32_t* idx, int32_t n, int32_t noise_f32);
+int32_t btk_kalman_update(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
+                          const double* meas, const int32_t* track_idx, const int32_t* meas_idx,
+                          const uint8_t* noise_f32, int32_t k);
+int32_t btk_kalman_project(bt_ctx* ctx, const double* mean, const double* cov, double* pmean,
+                           double* pcov, int32_t n);
+// iou.cu
+int32_t btk_iou_distance(bt_ctx* ctx, const double* a, int32_t n, const double* b, int32_t m,
+                         double* out);
+int32_t btk_fuse_score(bt_ctx* ctx, const double* d, const double* s, int32_t n, int32_t m, double* out);
+// emits (i, j) pairs with 1-IoU < limit between lists given by slot index; count via atomic
+int32_t btk_iou_pairs_below(bt_ctx* ctx, const double* tlbr, const int32_t* a_idx, int32_t n,
+                            const int32_t* b_idx, int32_t m, double limit, int32_t* pairs,
+                            int32_t* pair_count, int32_t pair_cap);
+
+// features.cu
+// det_prep: normalise rows, write fp32 normalised copy (optional) + fp16 copy; also boxes -> tlbr/xywh
+int32_t btk_feature_prep(bt_ctx* ctx, const float* feat, int32_t m, int32_t d, float* out_f32,
+                         __half* out_f16, int32_t normalise);
+int32_t btk_feature_ema(bt_ctx* ctx, float* smooth, float* curr, const float* feat,
+                        const int32_t* track_idx, const int32_t* feat_idx, const uint8_t* first,
+                        int32_t k, int32_t d, float alpha);
+// same, and also refreshes the fp16 bank row (GEMM A operand): bank16[track_idx[i]] = det16[feat_idx[i]]
+int32_t btk_feature_ema16(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
+                          const __half* det16, const int32_t* track_idx, const int32_t* feat_idx,
+                          const uint8_t* first, int32_t k, int32_t d, float alpha);
+
+// ---- association (reid_gemm.cu) ----------------------------------------------------------------
+// Row kinds / column kinds of the fused association kernel.
+enum { BT_ROW_NONE = 0, BT_ROW_POOL_TRACKED = 1, BT_ROW_POOL_OTHER = 2, BT_ROW_UNCONFIRMED = 3 };
+enum { BT_COL_NONE = 0, BT_COL_HIGH = 1, BT_COL_LOW = 2 };
+
+// Candidate lists ("ragged dense" adjacency): list s in {0,1,2} = association stage 1,2,3.
+// Row r owns entries [r*stride, r*stride + cnt[s*rows_cap + r]) of col/cost.
+struct bt_cand {
+  int32_t* cnt;    // [3][rows_cap]
+  int32_t* col;    // [3][rows_cap*stride]
+  double* cost;    // [3][rows_cap*stride]
+  int32_t rows_cap;
+  int32_t stride;  // = max_dets
+};
+
+struct bt_assoc_params {
+  // operands
+  const __half* a16;   // [n, d] track-side features (bank rows = slots)
+  const __half* b16;   // [m, d] detection features
+  const float* a32;    // fp32 variants for the SIMT kernel (may be null when tensor path is used)
+  const float* b32;
+  int32_t n, m, d;
+  // epilogue inputs (null => not used)
+  const double* row_tlbr;   // [n,4]
+  const float* row_tlbr_f32;// [n,4] conservative fp32 interval (lo down, hi up)
+  const uint8_t* row_kind;  // [n]
+  const double* col_tlbr;   // [m,4]
+  const uint8_t* col_kind;  // [m]
+  const float* face_sim;    // [n,m] or null
+  // thresholds
+  double match_thresh, second_thresh, unconf_thresh, proximity;
+  float appearance;
+  // outputs
+  bt_cand cand;             // candidate emission (cnt==null => off)
+  float* out_emb;           // [n,m] 1-max(0,sim)   (dense dump, null => off)
+  double* out_dists;        // [n,m] fused cost      (dense dump, null => off)
+  int32_t dense_stage;      // 1 or 3: which fusion rule the dense dump uses
+};
+int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& p, int32_t precision);
+int32_t bt_gemm_ws_create(bt_ctx* ctx);
+void bt_gemm_ws_destroy(bt_ctx* ctx);
+
+// ---- LAP (lap.cu) -------------------------------------------------------------------------------
+int32_t bt_lap_ws_create(bt_ctx* ctx);
+void bt_lap_ws_destroy(bt_ctx* ctx);
+// dense cost -> candidate list `list` of ctx->lap's own bt_cand
+int32_t btk_lap_compact_dense(bt_ctx* ctx, const double* cost, int32_t n, int32_t m, double thresh,
+                              const bt_cand& cand, int32_t list);
+// Solve list `list`: rows [0,n), cols [0,m).  row_block/col_block: optional int32 arrays, an edge
+// is valid only if row_block[r] < 0 and col_block[c] < 0 (results of an earlier stage).
+// x[n], y[m] outputs (device).
+int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n, int32_t m,
+                      double thresh, const int32_t* row_block, const int32_t* col_block, int32_t* x,
+                      int32_t* y);
+const bt_cand* bt_lap_own_cand(bt_ctx* ctx);
+
+// ---- detector side ------------------------------------------------------------------------------
+int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_config& cfg,
+                              double* out_boxes, int32_t max_out, int32_t* out_count);
+int32_t btk_reid_crop_gather(bt_ctx* ctx, const uint8_t* frame, int32_t h, int32_t w,
+                             const int32_t* boxes, int32_t n, int32_t out_h, int32_t out_w, float* out);
+
+// ---- tracker ------------------------------------------------------------------------------------
+int32_t bt_tracker_create(bt_ctx* ctx);
+void bt_tracker_destroy(bt_ctx* ctx);

@@ -1,0 +1,137 @@
+// ReID feature kernels: per-detection normalisation + fp16 staging for the tensor-core
+// similarity GEMM, and the batched feature EMA of STrack.update_body_features
+// (demo:492-502; demo = /root/reference/demo_bottrack_onnx_tflite.py).
+// One CTA per feature row (2048 floats = 8 KB: 256 threads x 2 float4), block reduction for
+// the L2 norm; HBM-bound: prep 4d in + (4d + 2d) out per detection, EMA 3*4*d B per match.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) s += red[i];
+  return s;
+}
+
+// Detection STrack construction normalises its feature row in place (demo:497-502 on the first
+// call): out = feat / ||feat||_2 (float32).  The fp16 copy is the B operand of the similarity GEMM.
+__global__ void __launch_bounds__(kThreads)
+feature_prep_kernel(const float* __restrict__ feat, int d, float* __restrict__ out_f32,
+                    __half* __restrict__ out_f16, int normalise) {
+  __shared__ float red[kThreads / 32];
+  const size_t row = blockIdx.x;
+  const float* src = feat + row * d;
+  float ss = 0.f;
+  if ((d & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < d; i += kThreads * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < d; i += kThreads) ss += src[i] * src[i];
+  }
+  float norm = 1.f;
+  if (normalise) norm = sqrtf(block_sum(ss, red));
+  if ((d & 3) == 0) {
+    for (int i = threadIdx.x * 4; i < d; i += kThreads * 4) {
+      float4 v = *reinterpret_cast<const float4*>(src + i);
+      if (normalise) { v.x /= norm; v.y /= norm; v.z /= norm; v.w /= norm; }
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * d + i) = v;
+      if (out_f16) {
+        __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(out_f16 + row * d + i) = pk;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < d; i += kThreads) {
+      float v = src[i];
+      if (normalise) v /= norm;
+      if (out_f32) out_f32[row * d + i] = v;
+      if (out_f16) out_f16[row * d + i] = __float2half_rn(v);
+    }
+  }
+}
+
+// mode (first[i]): 0 = EMA (demo:499-502), 1 = first call on a raw feature: smooth = feat/||feat||,
+// 2 = adopt an already-normalised detection feature (birth: smooth = curr = feat).
+// Optionally also refreshes the fp16 bank row used as the GEMM A operand.
+__global__ void __launch_bounds__(kThreads)
+feature_ema_kernel(float* __restrict__ smooth, float* __restrict__ curr, const float* __restrict__ feat,
+                   __half* __restrict__ bank16, const __half* __restrict__ det16,
+                   const int32_t* __restrict__ track_idx, const int32_t* __restrict__ feat_idx,
+                   const uint8_t* __restrict__ first, int d, float alpha) {
+  __shared__ float red[kThreads / 32];
+  const int i = blockIdx.x;
+  const size_t t = track_idx ? track_idx[i] : i;
+  const size_t f = feat_idx ? feat_idx[i] : i;
+  const int mode = first ? first[i] : 0;
+  if (bank16 && det16) {
+    if ((d & 3) == 0) {
+      const uint2* s = reinterpret_cast<const uint2*>(det16 + f * d);
+      uint2* o = reinterpret_cast<uint2*>(bank16 + t * d);
+      for (int j = threadIdx.x; j < d / 4; j += kThreads) o[j] = s[j];
+    } else {
+      for (int j = threadIdx.x; j < d; j += kThreads) bank16[t * d + j] = det16[f * d + j];
+    }
+  }
+  if (!smooth && !curr) return;
+  const float one_minus = (float)(1.0 - (double)alpha);
+  // pass 1: new smooth (unnormalised) kept in registers (d <= 8 * kThreads) else recomputed
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < d; j += kThreads) {
+    const float x = feat[f * d + j];
+    float s;
+    if (mode == 0) s = __fadd_rn(__fmul_rn(alpha, smooth[t * d + j]), __fmul_rn(one_minus, x));
+    else s = x;
+    ss += s * s;
+  }
+  float norm = 1.f;
+  if (mode != 2) norm = sqrtf(block_sum(ss, red));
+  for (int j = threadIdx.x; j < d; j += kThreads) {
+    const float x = feat[f * d + j];
+    float s;
+    if (mode == 0) s = __fadd_rn(__fmul_rn(alpha, smooth[t * d + j]), __fmul_rn(one_minus, x));
+    else s = x;
+    if (mode != 2) s = s / norm;
+    if (smooth) smooth[t * d + j] = s;
+    if (curr) curr[t * d + j] = (mode == 1) ? s : x;
+  }
+}
+
+}  // namespace
+
+int32_t btk_feature_prep(bt_ctx* ctx, const float* feat, int32_t m, int32_t d, float* out_f32,
+                         __half* out_f16, int32_t normalise) {
+  if (m <= 0) return BT_OK;
+  feature_prep_kernel<<<m, kThreads, 0, ctx->stream>>>(feat, d, out_f32, out_f16, normalise);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
+int32_t btk_feature_ema16(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
+                          const __half* det16, const int32_t* track_idx, const int32_t* feat_idx,
+                          const uint8_t* first, int32_t k, int32_t d, float alpha) {
+  if (k <= 0) return BT_OK;
+  feature_ema_kernel<<<k, kThreads, 0, ctx->stream>>>(smooth, curr, feat, bank16, det16, track_idx,
+                                                      feat_idx, first, d, alpha);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
+int32_t btk_feature_ema(bt_ctx* ctx, float* smooth, float* curr, const float* feat,
+                        const int32_t* track_idx, const int32_t* feat_idx, const uint8_t* first,
+                        int32_t k, int32_t d, float alpha) {
+  return btk_feature_ema16(ctx, smooth, curr, feat, nullptr, nullptr, track_idx, feat_idx, first, k, d, alpha);
+}

@@ -1,0 +1,516 @@
+// Fused association kernel: ReID similarity GEMM (tracks x detections x 2048-d) on the 5th-gen
+// tensor cores with the whole cost fusion of the reference in its epilogue.
+//
+// Reference arithmetic (demo = /root/reference/demo_bottrack_onnx_tflite.py):
+//   sim   = f_trk . f_det^T            in-graph cosine, README.md:185-195, consumed demo:1453-1460
+//   stage 1 (demo:1539-1554): emb = 1 - sim; emb[min(emb, face_emb) > 0.25] = 1;
+//                             dists = min(iou_dist, emb)            -> linear_assignment(0.8)
+//   stage 2 (demo:1568-1571): dists = iou_dist (Tracked rows x low-score dets) -> thresh 0.5
+//   stage 3 (demo:1593-1604): emb = 1 - max(0, sim); emb[emb > 0.25] = 1; emb[iou_d > 0.5] = 1;
+//                             dists = min(iou_dist, emb)            -> thresh 0.7
+//   iou_dist = 1 - bbox_iou (demo:1695-1713), float64.
+//
+// B200 design: A = per-slot fp16 feature bank [n, d] (K-major), B = per-frame fp16 detection
+// features [m, d] (K-major).  One persistent CTA per SM walks 128 x BN output tiles:
+//   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1   : tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM, 2 stages
+//   warps 2-5: epilogue -- tcgen05.ld the accumulator, apply the fusion rules above and emit
+//              only the *candidate edges* (cost < stage threshold) into per-row lists.
+// The N x M matrices never go to HBM on the tracker path (they are written only for the
+// stand-alone entry points / parity dumps): a 2000 x 2000 frame reads 2*8.2 MB of fp16
+// features and writes a few thousand edges.  Almost every pair is rejected by an fp32 test
+// (no box overlap possible AND appearance gate closed), the exact float64 IoU runs only for
+// the survivors.
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// epilogue element logic shared by the tensor-core and the CUDA-core kernels
+// ------------------------------------------------------------------------------------------------
+struct EpiParams {
+  const double* row_tlbr;
+  const float* row_tlbr_f32;
+  const uint8_t* row_kind;
+  const double* col_tlbr;
+  const uint8_t* col_kind;
+  const float* face_sim;
+  double match_thresh, second_thresh, unconf_thresh, proximity;
+  float appearance;
+  bt_cand cand;
+  float* out_emb;
+  double* out_dists;
+  int dense_stage;
+  int n, m;
+};
+
+__device__ __forceinline__ double iou_dist_f64(const double* __restrict__ a, const double* __restrict__ b) {
+  const double ixmin = fmax(a[0], b[0]), iymin = fmax(a[1], b[1]);
+  const double ixmax = fmin(a[2], b[2]), iymax = fmin(a[3], b[3]);
+  if (ixmax <= ixmin || iymax <= iymin) return 1.0;
+  const double inter = (ixmax - ixmin) * (iymax - iymin);
+  const double area1 = (a[2] - a[0]) * (a[3] - a[1]);
+  const double area2 = (b[2] - b[0]) * (b[3] - b[1]);
+  return 1.0 - inter / (area1 + area2 - inter);
+}
+
+__device__ __forceinline__ double fuse_stage1(double iou_d, float sim, float face, float appearance) {
+  float emb = 1.0f - sim;
+  const float face_emb = 1.0f - face;
+  if (fminf(emb, face_emb) > appearance) emb = 1.0f;
+  return fmin(iou_d, (double)emb);
+}
+
+__device__ __forceinline__ double fuse_stage3(double iou_d, float sim, float appearance, double proximity) {
+  float emb = 1.0f - fmaxf(0.0f, sim);
+  if (emb > appearance) emb = 1.0f;
+  if (iou_d > proximity) emb = 1.0f;
+  return fmin(iou_d, (double)emb);
+}
+
+__device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int col, double cost) {
+  const int k = atomicAdd(c.cnt + (size_t)list * c.rows_cap + row, 1);
+  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + k;
+  c.col[base] = col;
+  c.cost[base] = cost;
+}
+
+// exact path for one (row, col) pair that survived the cheap rejection test
+__device__ __noinline__ void assoc_exact(const EpiParams& p, int row, int col, float sim, int rkind,
+                                         int ckind) {
+  const double iou_d = iou_dist_f64(p.row_tlbr + (size_t)row * 4, p.col_tlbr + (size_t)col * 4);
+  const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
+  if (rkind == BT_ROW_UNCONFIRMED) {
+    if (ckind == BT_COL_HIGH) {
+      const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+      if (c3 < p.unconf_thresh) emit(p.cand, 2, row, col, c3);
+    }
+  } else {
+    if (ckind == BT_COL_HIGH) {
+      const double c1 = fuse_stage1(iou_d, sim, face, p.appearance);
+      if (c1 < p.match_thresh) emit(p.cand, 0, row, col, c1);
+    } else if (ckind == BT_COL_LOW && rkind == BT_ROW_POOL_TRACKED) {
+      if (iou_d < p.second_thresh) emit(p.cand, 1, row, col, iou_d);
+    }
+  }
+}
+
+__device__ __forceinline__ void assoc_dense(const EpiParams& p, int row, int col, float sim) {
+  if (p.out_emb) p.out_emb[(size_t)row * p.m + col] = 1.0f - fmaxf(0.0f, sim);
+  if (p.out_dists) {
+    const double iou_d = iou_dist_f64(p.row_tlbr + (size_t)row * 4, p.col_tlbr + (size_t)col * 4);
+    const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
+    p.out_dists[(size_t)row * p.m + col] = (p.dense_stage == 3)
+                                               ? fuse_stage3(iou_d, sim, p.appearance, p.proximity)
+                                               : fuse_stage1(iou_d, sim, face, p.appearance);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, 128-byte swizzle (as written by TMA SWIZZLE_128B):
+// rows of 64 fp16 = 128 B, 8-row groups 1024 B apart.  sm_100 descriptor: start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major, 1), SBO>>4 [32,46) = 1024>>4, version 1 at [46,48),
+// layout SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int BM = 128;
+constexpr int BK = 64;       // 64 fp16 = one 128 B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+
+template <int BN>
+struct TcSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kColF32Off = kStages * kStageBytes;            // float4[BN]  det box fp32
+  static constexpr int kColKindOff = kColF32Off + BN * 16;            // uint8[BN]
+  static constexpr int kBarOff = kColKindOff + BN;                    // barriers (8B aligned: BN%8==0)
+  static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
+  static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtrOff + 16;
+  static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024 B alignment
+};
+
+template <int BN, bool kDense>
+__global__ void __launch_bounds__(kTcThreads, 1)
+assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                EpiParams p, int d) {
+  using L = TcSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + kAccStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float4* s_col32 = reinterpret_cast<float4*>(smem + L::kColF32Off);
+  uint8_t* s_colkind = smem + L::kColKindOff;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.n + BM - 1) / BM, tiles_n = (p.m + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = d / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // whole warp: allocate all 512 TMEM columns (2 accumulator stages x BN<=256 fp32 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          tma_load_2d(sa, &tmap_a, kb * BK, m0, &full_bar[stage]);
+          tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, n0, &full_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (1<<4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
+            tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                            (uint32_t)((kb | k) != 0));
+          }
+          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes [32*(w%4), +32) =====
+    const int quarter = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int row = m0 + quarter * 32 + lane;
+      int rkind = BT_ROW_NONE;
+      float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!kDense) {
+        // stage this tile's detection boxes (fp32, exact: integer pixels) and kinds
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        for (int c = et; c < BN; c += 128) {
+          const int col = n0 + c;
+          float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+          uint8_t ck = BT_COL_NONE;
+          if (col < p.m) {
+            const double* s = p.col_tlbr + (size_t)col * 4;
+            cb = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+            ck = p.col_kind[col];
+          }
+          s_col32[c] = cb;
+          s_colkind[c] = ck;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row < p.n) {
+          rkind = p.row_kind[row];
+          rb = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), v);
+        tmem_ld_wait();
+        if (kDense) {
+          if (row < p.n) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int col = n0 + ch * 32 + c;
+              if (col < p.m) assoc_dense(p, row, col, __uint_as_float(v[c]));
+            }
+          }
+        } else if (rkind != BT_ROW_NONE) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int lc = ch * 32 + c;
+            const int ckind = s_colkind[lc];
+            const float sim = __uint_as_float(v[c]);
+            const float4 cb = s_col32[lc];
+            // conservative fp32 overlap test: false => exact IoU is 0 (row box interval is
+            // rounded outward, detection boxes are exact integers)
+            const bool ov = (fminf(rb.z, cb.z) > fmaxf(rb.x, cb.x)) && (fminf(rb.w, cb.w) > fmaxf(rb.y, cb.y));
+            const bool app = !((1.0f - sim) > p.appearance);
+            if (ckind != BT_COL_NONE && (ov || app || p.face_sim != nullptr))
+              assoc_exact(p, row, n0 + lc, sim, rkind, ckind);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core fp32 kernel (small problems, feature sizes that are not a multiple of 64, and the
+// on-device cross-check of the tensor path in the tests)
+// ------------------------------------------------------------------------------------------------
+constexpr int ST = 64, SK = 16;
+
+template <bool kDense>
+__global__ void __launch_bounds__(256)
+assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiParams p, int d) {
+  __shared__ float sa[SK][ST + 1];
+  __shared__ float sb[SK][ST + 1];
+  const int row0 = blockIdx.y * ST, col0 = blockIdx.x * ST;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += SK) {
+    for (int e = threadIdx.x; e < ST * SK; e += 256) {
+      const int r = e / SK, k = e % SK;
+      sa[k][r] = (row0 + r < p.n && k0 + k < d) ? a[(size_t)(row0 + r) * d + k0 + k] : 0.f;
+      sb[k][r] = (col0 + r < p.m && k0 + k < d) ? b[(size_t)(col0 + r) * d + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sa[k][ty * 4 + i]; bv[i] = sb[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row0 + ty * 4 + i;
+    if (row >= p.n) continue;
+    const int rkind = (!kDense) ? p.row_kind[row] : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + tx * 4 + j;
+      if (col >= p.m) continue;
+      if (kDense) {
+        assoc_dense(p, row, col, acc[i][j]);
+      } else {
+        const int ckind = p.col_kind[col];
+        if (rkind != BT_ROW_NONE && ckind != BT_COL_NONE) assoc_exact(p, row, col, acc[i][j], rkind, ckind);
+      }
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct bt_gemm_ws {
+  PFN_encodeTiled encode = nullptr;
+  bool attr_set = false;
+};
+
+int32_t bt_gemm_ws_create(bt_ctx* ctx) {
+  ctx->gemm = new bt_gemm_ws();
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  BT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  BT_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, BT_ERR_CUDA,
+           "cuTensorMapEncodeTiled not available from the driver");
+  ctx->gemm->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return BT_OK;
+}
+
+void bt_gemm_ws_destroy(bt_ctx* ctx) {
+  delete ctx->gemm;
+  ctx->gemm = nullptr;
+}
+
+static int32_t make_tmap(bt_ctx* ctx, CUtensorMap* tm, const __half* base, int rows, int d, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(__half)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = ctx->gemm->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), gdim,
+                                 gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BT_CHECK(r == CUDA_SUCCESS, BT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return BT_OK;
+}
+
+template <int BN, bool kDense>
+static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep) {
+  CUtensorMap ta, tb;
+  BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.n, ap.d, BM));
+  BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.m, ap.d, BN));
+  auto kern = assoc_tc_kernel<BN, kDense>;
+  BT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn));
+  const int tiles = ((ap.n + BM - 1) / BM) * ((ap.m + BN - 1) / BN);
+  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+  kern<<<grid, kTcThreads, TcSmem<BN>::kDyn, ctx->stream>>>(ta, tb, ep, ap.d);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
+int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
+  if (ap.n <= 0 || ap.m <= 0) return BT_OK;
+  EpiParams ep;
+  ep.row_tlbr = ap.row_tlbr; ep.row_tlbr_f32 = ap.row_tlbr_f32; ep.row_kind = ap.row_kind;
+  ep.col_tlbr = ap.col_tlbr; ep.col_kind = ap.col_kind; ep.face_sim = ap.face_sim;
+  ep.match_thresh = ap.match_thresh; ep.second_thresh = ap.second_thresh;
+  ep.unconf_thresh = ap.unconf_thresh; ep.proximity = ap.proximity; ep.appearance = ap.appearance;
+  ep.cand = ap.cand; ep.out_emb = ap.out_emb; ep.out_dists = ap.out_dists;
+  ep.dense_stage = ap.dense_stage; ep.n = ap.n; ep.m = ap.m;
+  const bool dense = (ap.out_emb != nullptr) || (ap.out_dists != nullptr);
+  if (precision == 0) {
+    BT_CHECK(ap.d % BK == 0 && ap.d >= BK, BT_ERR_INVALID,
+             "tensor-core similarity needs feat_dim %% 64 == 0 (got %d)", ap.d);
+    BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "fp16 operands missing");
+    if (dense) return launch_tc<256, true>(ctx, ap, ep);
+    return launch_tc<256, false>(ctx, ap, ep);
+  }
+  BT_CHECK(ap.a32 && ap.b32, BT_ERR_INVALID, "fp32 operands missing");
+  dim3 grid((ap.m + ST - 1) / ST, (ap.n + ST - 1) / ST);
+  if (dense) assoc_simt_kernel<true><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
+  else assoc_simt_kernel<false><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}

@@ -1,0 +1,732 @@
+// The stateful tracker: one BoTSORT.update (demo:1291-1639; demo =
+// /root/reference/demo_bottrack_onnx_tflite.py) per bt_update_arrays call, on a device-resident
+// track store.
+//
+// Device side (all arithmetic): per-slot Kalman state (fp64 AoS), cached tlbr, fp16/fp32 feature
+// banks; per frame: detection prep -> batched Kalman predict -> ONE fused association kernel over
+// (all live slots) x (all detections) that emits the candidate edges of the three association
+// stages at once -> three exact LAP solves chained on the device (stage 2 masked by stage 1's
+// unmatched rows, stage 3 by stage 1's unmatched columns) -> batched Kalman update / initiate /
+// feature EMA -> sparse duplicate test (tracked x lost, IoU distance < 0.15).
+//
+// Host side (this file, C++): only the list bookkeeping of demo:1414-1423 and demo:1558-1639
+// (who is tracked / lost / removed, ids, list order) on small index arrays, with two stream
+// synchronisations per frame.  SURVEY.md section 8(f) F1 lists moving this bookkeeping to the
+// device as the next step.
+#include "common.cuh"
+
+#include <algorithm>
+#include <string.h>
+
+namespace {
+
+struct SlotMeta {
+  int32_t state = BT_STATE_NEW;
+  int32_t activated = 0;
+  int32_t track_id = 0;
+  int32_t frame_id = 0;
+  int32_t start_frame = 0;
+  int32_t tracklet_len = 0;
+  float score = 0.f;
+  int32_t det_index = -1;
+  uint8_t in_removed = 0;  // id is in self.removed_stracks (demo:1636)
+  uint8_t f32_state = 0;   // mean/cov are still initiate()'s float32 values (NumPy >= 2 quirk)
+  uint8_t used = 0;
+  uint8_t mark = 0;        // scratch flag
+};
+
+// boxes int32 tlbr -> tlbr float64, xywh float64 (Kalman measurement, demo:599 + demo:664-670),
+// xywh float32 (initiate input, demo:561) and the score class of the detection
+// (demo:1501: high = score > 0.40; demo:1531: low = 0.1 <= score <= 0.40).
+__global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* __restrict__ scores, int m,
+                                float high, float low, double* __restrict__ tlbr, double* __restrict__ xywh,
+                                float* __restrict__ xywh32, uint8_t* __restrict__ kind) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const int4 b = *reinterpret_cast<const int4*>(boxes + (size_t)j * 4);
+  // STrack(tlbr_to_tlwh(int box)) -> float32 tlwh (demo:465); xywh = tl + wh/2 in float32 (exact)
+  const float x1 = (float)b.x, y1 = (float)b.y, w = (float)(b.z - b.x), h = (float)(b.w - b.y);
+  const float cx = x1 + w / 2, cy = y1 + h / 2;
+  double* t = tlbr + (size_t)j * 4;
+  // detection tlbr = tlwh (float32) with wh += tl (demo:643-648)
+  t[0] = x1; t[1] = y1; t[2] = (double)(w + x1); t[3] = (double)(h + y1);
+  double* z = xywh + (size_t)j * 4;
+  z[0] = cx; z[1] = cy; z[2] = w; z[3] = h;
+  *reinterpret_cast<float4*>(xywh32 + (size_t)j * 4) = make_float4(cx, cy, w, h);
+  const float s = scores[j];
+  kind[j] = (s > high) ? BT_COL_HIGH : ((s >= low) ? BT_COL_LOW : BT_COL_NONE);
+}
+
+__global__ void gather_rows_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx, int n,
+                                       int width, double* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * width) return;
+  const int r = (int)(i / width), c = (int)(i % width);
+  dst[i] = src[(size_t)idx[r] * width + c];
+}
+
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n,
+                                       int width, float* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * width) return;
+  const int r = (int)(i / width), c = (int)(i % width);
+  dst[i] = src[(size_t)idx[r] * width + c];
+}
+
+}  // namespace
+
+struct bt_tracker {
+  bt_config cfg;
+  int cap = 0, max_dets = 0, D = 0;
+  int max_time_lost = 0;
+  // ---- device track store (indexed by slot) ----
+  double *mean = nullptr, *cov = nullptr, *tlbr = nullptr;
+  float* tlbr_f32 = nullptr;
+  __half* feat16 = nullptr;
+  float *curr32 = nullptr, *smooth32 = nullptr;
+  uint8_t* row_kind = nullptr;
+  // ---- device per-frame buffers ----
+  int32_t* det_boxes = nullptr;
+  float* det_scores = nullptr;
+  float* det_feat_in = nullptr;   // staging of host features
+  float* det_feat32 = nullptr;    // normalised
+  __half* det_feat16 = nullptr;
+  double *det_tlbr = nullptr, *det_xywh = nullptr;
+  float* det_xywh32 = nullptr;
+  uint8_t* col_kind = nullptr;
+  int32_t *x[3] = {nullptr, nullptr, nullptr}, *y[3] = {nullptr, nullptr, nullptr};
+  int32_t *d_pool_idx = nullptr, *d_pool_state = nullptr;
+  int32_t *d_upd_track = nullptr, *d_upd_det = nullptr;
+  uint8_t *d_upd_f32 = nullptr, *d_ema_mode = nullptr;
+  int32_t *d_birth_slot = nullptr, *d_birth_det = nullptr;
+  int32_t *d_lista = nullptr, *d_listb = nullptr;
+  int32_t *d_pairs = nullptr, *d_pair_count = nullptr;
+  double* d_gather = nullptr;
+  int pair_cap = 0;
+  // ---- pinned host mirrors ----
+  char* pinned = nullptr;
+  uint8_t* h_row_kind = nullptr;
+  int32_t *h_pool_idx = nullptr, *h_pool_state = nullptr;
+  int32_t *h_x[3] = {nullptr, nullptr, nullptr}, *h_y[3] = {nullptr, nullptr, nullptr};
+  float* h_scores = nullptr;
+  int32_t *h_upd_track = nullptr, *h_upd_det = nullptr;
+  uint8_t *h_upd_f32 = nullptr, *h_ema_mode = nullptr;
+  int32_t *h_birth_slot = nullptr, *h_birth_det = nullptr;
+  int32_t *h_lista = nullptr, *h_listb = nullptr;
+  int32_t *h_pairs = nullptr, *h_pair_count = nullptr;
+  double* h_tlbr = nullptr;
+  // ---- host bookkeeping ----
+  std::vector<SlotMeta> meta;
+  std::vector<int> tracked, lost;
+  std::vector<int> free_slots;  // kept sorted descending: back() is the lowest free slot
+  int high_water = 0;
+  int id_count = 0;
+  int frame_id = 0;
+  int n_removed_total = 0;
+  std::vector<int32_t> matches[3];  // flattened (a, b) pairs in the reference's index spaces
+  std::vector<double> tlbr_cache;   // tlbr of `tracked` after the frame
+  bool tlbr_cache_valid = false;
+};
+
+namespace {
+
+template <typename T>
+int32_t dev_alloc(bt_ctx* ctx, T** p, size_t count) {
+  BT_CUDA(cudaMalloc(p, sizeof(T) * (count ? count : 1)));
+  return BT_OK;
+}
+
+template <typename T>
+T* carve(char*& cur, size_t count) {
+  T* p = reinterpret_cast<T*>(cur);
+  cur += (sizeof(T) * count + 255) & ~size_t(255);
+  return p;
+}
+
+int alloc_slot(bt_tracker* t) {
+  if (!t->free_slots.empty()) {
+    const int s = t->free_slots.back();
+    t->free_slots.pop_back();
+    return s;
+  }
+  if (t->high_water < t->cap) return t->high_water++;
+  return -1;
+}
+
+}  // namespace
+
+int32_t bt_tracker_create(bt_ctx* ctx) {
+  auto* t = new bt_tracker();
+  ctx->trk = t;
+  bt_default_config(&t->cfg);
+  t->cap = ctx->max_tracks;
+  t->max_dets = ctx->max_dets;
+  t->D = ctx->feat_dim;
+  const size_t cap = t->cap, md = t->max_dets, D = t->D;
+  const bool keep32 = !(ctx->flags & BT_FLAG_NO_F32_FEATURES);
+  BT_TRY(dev_alloc(ctx, &t->mean, cap * 8));
+  BT_TRY(dev_alloc(ctx, &t->cov, cap * 64));
+  BT_TRY(dev_alloc(ctx, &t->tlbr, cap * 4));
+  BT_TRY(dev_alloc(ctx, &t->tlbr_f32, cap * 4));
+  BT_TRY(dev_alloc(ctx, &t->feat16, cap * D));
+  BT_CUDA(cudaMemset(t->feat16, 0, sizeof(__half) * cap * D));
+  BT_CUDA(cudaMemset(t->tlbr, 0, sizeof(double) * cap * 4));
+  BT_CUDA(cudaMemset(t->tlbr_f32, 0, sizeof(float) * cap * 4));
+  if (keep32) {
+    BT_TRY(dev_alloc(ctx, &t->curr32, cap * D));
+    BT_TRY(dev_alloc(ctx, &t->smooth32, cap * D));
+    BT_CUDA(cudaMemset(t->curr32, 0, sizeof(float) * cap * D));
+    BT_CUDA(cudaMemset(t->smooth32, 0, sizeof(float) * cap * D));
+  }
+  BT_TRY(dev_alloc(ctx, &t->row_kind, cap));
+  BT_TRY(dev_alloc(ctx, &t->det_boxes, md * 4));
+  BT_TRY(dev_alloc(ctx, &t->det_scores, md));
+  BT_TRY(dev_alloc(ctx, &t->det_feat_in, md * D));
+  BT_TRY(dev_alloc(ctx, &t->det_feat32, md * D));
+  BT_TRY(dev_alloc(ctx, &t->det_feat16, md * D));
+  BT_TRY(dev_alloc(ctx, &t->det_tlbr, md * 4));
+  BT_TRY(dev_alloc(ctx, &t->det_xywh, md * 4));
+  BT_TRY(dev_alloc(ctx, &t->det_xywh32, md * 4));
+  BT_TRY(dev_alloc(ctx, &t->col_kind, md));
+  for (int s = 0; s < 3; ++s) {
+    BT_TRY(dev_alloc(ctx, &t->x[s], cap));
+    BT_TRY(dev_alloc(ctx, &t->y[s], md));
+  }
+  const size_t nupd = cap + md;
+  BT_TRY(dev_alloc(ctx, &t->d_pool_idx, cap));
+  BT_TRY(dev_alloc(ctx, &t->d_pool_state, cap));
+  BT_TRY(dev_alloc(ctx, &t->d_upd_track, nupd));
+  BT_TRY(dev_alloc(ctx, &t->d_upd_det, nupd));
+  BT_TRY(dev_alloc(ctx, &t->d_upd_f32, nupd));
+  BT_TRY(dev_alloc(ctx, &t->d_ema_mode, nupd));
+  BT_TRY(dev_alloc(ctx, &t->d_birth_slot, md));
+  BT_TRY(dev_alloc(ctx, &t->d_birth_det, md));
+  BT_TRY(dev_alloc(ctx, &t->d_lista, cap));
+  BT_TRY(dev_alloc(ctx, &t->d_listb, cap));
+  t->pair_cap = 1 << 20;
+  BT_TRY(dev_alloc(ctx, &t->d_pairs, (size_t)2 * t->pair_cap));
+  BT_TRY(dev_alloc(ctx, &t->d_pair_count, 1));
+  BT_TRY(dev_alloc(ctx, &t->d_gather, cap * 64));
+
+  size_t pinned_bytes = 0;
+  pinned_bytes += cap + 2 * cap * 4 + 3 * (cap + md) * 4 + md * 4 + 2 * nupd * 4 + 2 * nupd + 2 * md * 4 +
+                  2 * cap * 4 + (size_t)2 * t->pair_cap * 4 + 64 + cap * 4 * 8 + 64 * 256;
+  BT_CUDA(cudaMallocHost(&t->pinned, pinned_bytes));
+  char* cur = t->pinned;
+  t->h_row_kind = carve<uint8_t>(cur, cap);
+  t->h_pool_idx = carve<int32_t>(cur, cap);
+  t->h_pool_state = carve<int32_t>(cur, cap);
+  for (int s = 0; s < 3; ++s) {
+    t->h_x[s] = carve<int32_t>(cur, cap);
+    t->h_y[s] = carve<int32_t>(cur, md);
+  }
+  t->h_scores = carve<float>(cur, md);
+  t->h_upd_track = carve<int32_t>(cur, nupd);
+  t->h_upd_det = carve<int32_t>(cur, nupd);
+  t->h_upd_f32 = carve<uint8_t>(cur, nupd);
+  t->h_ema_mode = carve<uint8_t>(cur, nupd);
+  t->h_birth_slot = carve<int32_t>(cur, md);
+  t->h_birth_det = carve<int32_t>(cur, md);
+  t->h_lista = carve<int32_t>(cur, cap);
+  t->h_listb = carve<int32_t>(cur, cap);
+  t->h_pairs = carve<int32_t>(cur, (size_t)2 * t->pair_cap);
+  t->h_pair_count = carve<int32_t>(cur, 16);
+  t->h_tlbr = carve<double>(cur, cap * 4);
+  t->meta.assign(cap, SlotMeta());
+  t->max_time_lost = (int)(t->cfg.frame_rate / 30.0 * t->cfg.track_buffer);
+  return BT_OK;
+}
+
+void bt_tracker_destroy(bt_ctx* ctx) {
+  bt_tracker* t = ctx->trk;
+  if (!t) return;
+  void* ptrs[] = {t->mean, t->cov, t->tlbr, t->tlbr_f32, t->feat16, t->curr32, t->smooth32, t->row_kind,
+                  t->det_boxes, t->det_scores, t->det_feat_in, t->det_feat32, t->det_feat16, t->det_tlbr,
+                  t->det_xywh, t->det_xywh32, t->col_kind, t->x[0], t->x[1], t->x[2], t->y[0], t->y[1], t->y[2],
+                  t->d_pool_idx, t->d_pool_state, t->d_upd_track, t->d_upd_det, t->d_upd_f32, t->d_ema_mode,
+                  t->d_birth_slot, t->d_birth_det, t->d_lista, t->d_listb, t->d_pairs, t->d_pair_count,
+                  t->d_gather};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (t->pinned) cudaFreeHost(t->pinned);
+  delete t;
+  ctx->trk = nullptr;
+}
+
+extern "C" {
+
+int32_t bt_tracker_reset(bt_ctx* ctx, const bt_config* cfg) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  bt_tracker* t = ctx->trk;
+  BT_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cfg) t->cfg = *cfg;
+  else bt_default_config(&t->cfg);
+  t->max_time_lost = (int)(t->cfg.frame_rate / 30.0 * t->cfg.track_buffer);  // demo:1276-1277
+  t->meta.assign(t->cap, SlotMeta());
+  t->tracked.clear();
+  t->lost.clear();
+  t->free_slots.clear();
+  t->high_water = 0;
+  t->id_count = 0;  // BaseTrack.clear_count(), demo:1264 (per tracker here)
+  t->frame_id = 0;
+  t->n_removed_total = 0;
+  for (auto& m : t->matches) m.clear();
+  t->tlbr_cache_valid = false;
+  BT_CUDA(cudaMemsetAsync(t->feat16, 0, sizeof(__half) * (size_t)t->cap * t->D, ctx->stream));
+  return BT_OK;
+}
+
+int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores, const float* feats, int32_t m,
+                         int32_t loc, bt_frame_info* info) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  bt_tracker* t = ctx->trk;
+  const bt_config& cfg = t->cfg;
+  BT_CHECK(loc == BT_HOST || loc == BT_DEVICE, BT_ERR_INVALID, "bad loc");
+  BT_CHECK(m >= 0 && m <= t->max_dets, BT_ERR_CAPACITY, "%d detections exceed ctx max_dets %d", m, t->max_dets);
+  BT_CHECK(m == 0 || (boxes && scores), BT_ERR_INVALID, "NULL boxes/scores");
+  const bool reid = cfg.with_reid != 0;
+  BT_CHECK(!reid || m == 0 || feats, BT_ERR_INVALID, "with_reid is set but feats is NULL");
+  const int D = t->D;
+  const bool tensor_path = !(ctx->flags & BT_FLAG_SIMT_SIM) && (D % 64 == 0);
+  const bool keep32 = t->curr32 != nullptr;
+  cudaStream_t st = ctx->stream;
+  std::vector<SlotMeta>& meta = t->meta;
+
+  t->frame_id += 1;  // demo:1292
+  const int frame_id = t->frame_id;
+  t->tlbr_cache_valid = false;
+
+  // ---- inputs -> device ---------------------------------------------------------------------
+  const int32_t* d_boxes = boxes;
+  const float* d_scores = scores;
+  const float* d_feats = feats;
+  if (m > 0) {
+    if (loc == BT_HOST) {
+      BT_CUDA(cudaMemcpyAsync(t->det_boxes, boxes, sizeof(int32_t) * 4 * m, cudaMemcpyHostToDevice, st));
+      BT_CUDA(cudaMemcpyAsync(t->det_scores, scores, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+      d_boxes = t->det_boxes;
+      d_scores = t->det_scores;
+      if (reid) {
+        BT_CUDA(cudaMemcpyAsync(t->det_feat_in, feats, sizeof(float) * (size_t)m * D, cudaMemcpyHostToDevice, st));
+        d_feats = t->det_feat_in;
+      }
+      memcpy(t->h_scores, scores, sizeof(float) * m);
+    } else {
+      BT_CUDA(cudaMemcpyAsync(t->h_scores, scores, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+    }
+    det_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_boxes, d_scores, m, cfg.track_high_thresh,
+                                                     cfg.track_low_thresh, t->det_tlbr, t->det_xywh,
+                                                     t->det_xywh32, t->col_kind);
+    BT_LAUNCHED(ctx);
+    if (reid)
+      BT_TRY(btk_feature_prep(ctx, d_feats, m, D, keep32 || !tensor_path ? t->det_feat32 : nullptr,
+                              t->det_feat16, 1));
+  }
+
+  // ---- split lists (demo:1415-1423) -------------------------------------------------------------
+  std::vector<int> unconfirmed, pool;
+  for (int s : t->tracked) {
+    if (!meta[s].activated) unconfirmed.push_back(s);
+    else pool.push_back(s);
+  }
+  for (int s : t->lost) pool.push_back(s);  // joint_stracks: ids are unique per slot, no overlap
+  const int n_pool = (int)pool.size(), n_unc = (int)unconfirmed.size();
+  const int n_rows = t->high_water;
+
+  // ---- Kalman predict over the pool (demo:1426) ---------------------------------------------
+  bool all_f32 = n_pool > 0;
+  memset(t->h_row_kind, BT_ROW_NONE, n_rows);
+  for (int i = 0; i < n_pool; ++i) {
+    const int s = pool[i];
+    t->h_pool_idx[i] = s;
+    t->h_pool_state[i] = meta[s].state;
+    t->h_row_kind[s] = (meta[s].state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
+    all_f32 = all_f32 && meta[s].f32_state;
+  }
+  for (int s : unconfirmed) t->h_row_kind[s] = BT_ROW_UNCONFIRMED;
+  if (n_rows > 0)
+    BT_CUDA(cudaMemcpyAsync(t->row_kind, t->h_row_kind, n_rows, cudaMemcpyHostToDevice, st));
+  if (n_pool > 0) {
+    BT_CUDA(cudaMemcpyAsync(t->d_pool_idx, t->h_pool_idx, sizeof(int32_t) * n_pool, cudaMemcpyHostToDevice, st));
+    BT_CUDA(cudaMemcpyAsync(t->d_pool_state, t->h_pool_state, sizeof(int32_t) * n_pool, cudaMemcpyHostToDevice, st));
+    BT_TRY(btk_kalman_predict(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->d_pool_state, t->d_pool_idx,
+                              n_pool, all_f32 ? 1 : 0));
+    for (int s : pool) meta[s].f32_state = 0;
+  }
+
+  // ---- fused association over slots x detections + the three chained LAP solves -------------
+  const bt_cand& cand = *bt_lap_own_cand(ctx);
+  if (n_rows > 0) {
+    BT_CUDA(cudaMemsetAsync(cand.cnt, 0, sizeof(int32_t) * 3 * cand.rows_cap, st));
+    if (m > 0) {
+      bt_assoc_params p;
+      memset(&p, 0, sizeof(p));
+      p.a16 = t->feat16; p.b16 = t->det_feat16;
+      p.a32 = t->curr32; p.b32 = t->det_feat32;
+      p.n = n_rows; p.m = m; p.d = reid ? D : 0;
+      p.row_tlbr = t->tlbr; p.row_tlbr_f32 = t->tlbr_f32; p.row_kind = t->row_kind;
+      p.col_tlbr = t->det_tlbr; p.col_kind = t->col_kind; p.face_sim = nullptr;
+      p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
+      p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
+      p.appearance = cfg.appearance_thresh;
+      p.cand = cand;
+      BT_TRY(btk_assoc(ctx, p, (reid && tensor_path) ? 0 : 1));
+    }
+    BT_TRY(btk_lap_solve(ctx, cand, 0, n_rows, m, cfg.match_thresh, nullptr, nullptr, t->x[0], t->y[0]));
+    BT_TRY(btk_lap_solve(ctx, cand, 1, n_rows, m, cfg.second_thresh, t->x[0], nullptr, t->x[1], t->y[1]));
+    BT_TRY(btk_lap_solve(ctx, cand, 2, n_rows, m, cfg.unconfirmed_thresh, nullptr, t->y[0], t->x[2], t->y[2]));
+    for (int s = 0; s < 3; ++s)
+      BT_CUDA(cudaMemcpyAsync(t->h_x[s], t->x[s], sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, st));
+  }
+  BT_CUDA(cudaStreamSynchronize(st));  // sync 1: assignments (and scores) are on the host
+
+  // ---- detection lists (demo:1493-1532) -----------------------------------------------------
+  const float* sc = t->h_scores;
+  std::vector<int> hi_pos(m, -1), lo_pos(m, -1), hi_list, lo_list;
+  for (int j = 0; j < m; ++j) {
+    if (sc[j] > cfg.track_high_thresh) { hi_pos[j] = (int)hi_list.size(); hi_list.push_back(j); }
+    else if (sc[j] >= cfg.track_low_thresh) { lo_pos[j] = (int)lo_list.size(); lo_list.push_back(j); }
+  }
+  std::vector<uint8_t> det_taken(m, 0);
+
+  std::vector<int> activated, refind, lost_now, removed_now;
+  int n_upd = 0;
+  auto apply_match = [&](int slot, int det) {
+    SlotMeta& tm = meta[slot];
+    t->h_upd_track[n_upd] = slot;
+    t->h_upd_det[n_upd] = det;
+    t->h_upd_f32[n_upd] = tm.f32_state;
+    t->h_ema_mode[n_upd] = 0;
+    ++n_upd;
+    tm.f32_state = 0;
+    if (tm.state == BT_STATE_TRACKED) {  // STrack.update, demo:586-610
+      tm.tracklet_len += 1;
+      activated.push_back(slot);
+    } else {                             // STrack.re_activate, demo:570-584
+      tm.tracklet_len = 0;
+      refind.push_back(slot);
+    }
+    tm.frame_id = frame_id;
+    tm.state = BT_STATE_TRACKED;
+    tm.activated = 1;
+    tm.score = sc[det];
+    tm.det_index = det;
+    det_taken[det] = 1;
+  };
+
+  for (auto& mm : t->matches) mm.clear();
+  // first association (demo:1556-1566): matches in ascending pool order
+  std::vector<uint8_t> pool_matched(n_pool, 0);
+  for (int i = 0; i < n_pool; ++i) {
+    const int s = pool[i];
+    const int j = (n_rows > 0) ? t->h_x[0][s] : -1;
+    if (j >= 0) {
+      t->matches[0].push_back(i);
+      t->matches[0].push_back(hi_pos[j]);
+      pool_matched[i] = 1;
+    }
+  }
+  // the state test of stage 2 (demo:1569) reads the state BEFORE stage-1 updates touch the
+  // unmatched tracks, which they never do; build r_tracked first, then apply stage 1.
+  std::vector<int> r_tracked;
+  for (int i = 0; i < n_pool; ++i)
+    if (!pool_matched[i] && meta[pool[i]].state == BT_STATE_TRACKED) r_tracked.push_back(pool[i]);
+  for (int i = 0; i < n_pool; ++i)
+    if (pool_matched[i]) apply_match(pool[i], t->h_x[0][pool[i]]);
+  // second association (demo:1568-1586)
+  for (int i = 0; i < (int)r_tracked.size(); ++i) {
+    const int s = r_tracked[i];
+    const int j = t->h_x[1][s];
+    if (j >= 0) {
+      t->matches[1].push_back(i);
+      t->matches[1].push_back(lo_pos[j]);
+      apply_match(s, j);
+    }
+  }
+  for (int s : r_tracked) {
+    if (t->h_x[1][s] < 0 && meta[s].state != BT_STATE_LOST) {
+      meta[s].state = BT_STATE_LOST;  // mark_lost
+      lost_now.push_back(s);
+    }
+  }
+  // unconfirmed (demo:1588-1612): detections = unmatched high detections, in order
+  std::vector<int> u_det_pos(m, -1);
+  {
+    int k = 0;
+    for (int j : hi_list)
+      if (!det_taken[j]) u_det_pos[j] = k++;
+  }
+  for (int i = 0; i < n_unc; ++i) {
+    const int s = unconfirmed[i];
+    const int j = t->h_x[2][s];
+    if (j >= 0) {
+      t->matches[2].push_back(i);
+      t->matches[2].push_back(u_det_pos[j]);
+    }
+  }
+  for (int i = 0; i < n_unc; ++i) {
+    const int s = unconfirmed[i];
+    const int j = t->h_x[2][s];
+    if (j >= 0) apply_match(s, j);
+  }
+  for (int s : unconfirmed) {
+    if (t->h_x[2][s] < 0) {
+      meta[s].state = BT_STATE_REMOVED;  // mark_removed, demo:1609-1612
+      removed_now.push_back(s);
+    }
+  }
+  const int n_match_upd = n_upd;
+  // births (demo:1614-1621, STrack.activate demo:556-568)
+  int n_births = 0;
+  for (int j : hi_list) {
+    if (det_taken[j]) continue;
+    if (sc[j] < cfg.new_track_thresh) continue;
+    const int s = alloc_slot(t);
+    BT_CHECK(s >= 0, BT_ERR_CAPACITY, "track store full (%d slots)", t->cap);
+    SlotMeta& tm = meta[s];
+    tm = SlotMeta();
+    tm.used = 1;
+    tm.track_id = ++t->id_count;
+    tm.state = BT_STATE_TRACKED;
+    tm.activated = (frame_id == 1) ? 1 : 0;
+    tm.frame_id = frame_id;
+    tm.start_frame = frame_id;
+    tm.tracklet_len = 0;
+    tm.score = sc[j];
+    tm.det_index = j;
+    tm.f32_state = 1;
+    t->h_birth_slot[n_births] = s;
+    t->h_birth_det[n_births] = j;
+    ++n_births;
+    t->h_upd_track[n_upd] = s;
+    t->h_upd_det[n_upd] = j;
+    t->h_upd_f32[n_upd] = 0;
+    t->h_ema_mode[n_upd] = 2;
+    ++n_upd;
+    activated.push_back(s);
+  }
+  // expiry (demo:1623-1627)
+  for (int s : t->lost) {
+    if (frame_id - meta[s].frame_id > t->max_time_lost) {
+      meta[s].state = BT_STATE_REMOVED;
+      removed_now.push_back(s);
+    }
+  }
+
+  // ---- device: Kalman update / initiate / features ----------------------------------------------
+  if (n_upd > 0) {
+    BT_CUDA(cudaMemcpyAsync(t->d_upd_track, t->h_upd_track, sizeof(int32_t) * n_upd, cudaMemcpyHostToDevice, st));
+    BT_CUDA(cudaMemcpyAsync(t->d_upd_det, t->h_upd_det, sizeof(int32_t) * n_upd, cudaMemcpyHostToDevice, st));
+    BT_CUDA(cudaMemcpyAsync(t->d_upd_f32, t->h_upd_f32, n_upd, cudaMemcpyHostToDevice, st));
+    BT_CUDA(cudaMemcpyAsync(t->d_ema_mode, t->h_ema_mode, n_upd, cudaMemcpyHostToDevice, st));
+  }
+  if (n_match_upd > 0)
+    BT_TRY(btk_kalman_update(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->det_xywh, t->d_upd_track,
+                             t->d_upd_det, t->d_upd_f32, n_match_upd));
+  if (n_births > 0) {
+    BT_CUDA(cudaMemcpyAsync(t->d_birth_slot, t->h_birth_slot, sizeof(int32_t) * n_births, cudaMemcpyHostToDevice, st));
+    BT_CUDA(cudaMemcpyAsync(t->d_birth_det, t->h_birth_det, sizeof(int32_t) * n_births, cudaMemcpyHostToDevice, st));
+    BT_TRY(btk_kalman_initiate(ctx, t->det_xywh32, t->d_birth_det, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->d_birth_slot,
+                               n_births));
+  }
+  if (reid && n_upd > 0)
+    BT_TRY(btk_feature_ema16(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
+                             t->det_feat16, t->d_upd_track, t->d_upd_det, t->d_ema_mode, n_upd, D,
+                             cfg.ema_alpha));
+
+  // ---- merge lists (demo:1629-1636) -----------------------------------------------------------
+  std::vector<int> new_tracked;
+  for (int s : t->tracked)
+    if (meta[s].state == BT_STATE_TRACKED) { new_tracked.push_back(s); meta[s].mark = 1; }
+  for (int s : activated)
+    if (!meta[s].mark) { new_tracked.push_back(s); meta[s].mark = 1; }
+  for (int s : refind)
+    if (!meta[s].mark) { new_tracked.push_back(s); meta[s].mark = 1; }
+  std::vector<int> new_lost;
+  for (int s : t->lost)
+    if (!meta[s].mark) new_lost.push_back(s);       // sub_stracks(lost, tracked)
+  for (int s : lost_now) new_lost.push_back(s);     // extend(lost_stracks)
+  {
+    std::vector<int> tmp;
+    for (int s : new_lost)
+      if (!meta[s].in_removed) tmp.push_back(s);    // sub_stracks(lost, removed) BEFORE this frame's removals
+    new_lost.swap(tmp);
+  }
+  for (int s : new_tracked) meta[s].mark = 0;
+  for (int s : removed_now) meta[s].in_removed = 1; // removed_stracks.extend
+  t->n_removed_total += (int)removed_now.size();
+
+  // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) + result read-back --------------
+  const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
+  int n_pairs = 0;
+  if (nt > 0) {
+    memcpy(t->h_lista, new_tracked.data(), sizeof(int32_t) * nt);
+    BT_CUDA(cudaMemcpyAsync(t->d_lista, t->h_lista, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
+    if (nl > 0) {
+      memcpy(t->h_listb, new_lost.data(), sizeof(int32_t) * nl);
+      BT_CUDA(cudaMemcpyAsync(t->d_listb, t->h_listb, sizeof(int32_t) * nl, cudaMemcpyHostToDevice, st));
+      BT_CUDA(cudaMemsetAsync(t->d_pair_count, 0, sizeof(int32_t), st));
+      BT_TRY(btk_iou_pairs_below(ctx, t->tlbr, t->d_lista, nt, t->d_listb, nl, cfg.duplicate_iou_dist,
+                                 t->d_pairs, t->d_pair_count, t->pair_cap));
+      BT_CUDA(cudaMemcpyAsync(t->h_pair_count, t->d_pair_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    gather_rows_f64_kernel<<<(nt * 4 + 255) / 256, 256, 0, st>>>(t->tlbr, t->d_lista, nt, 4, t->d_gather);
+    BT_LAUNCHED(ctx);
+    BT_CUDA(cudaMemcpyAsync(t->h_tlbr, t->d_gather, sizeof(double) * 4 * nt, cudaMemcpyDeviceToHost, st));
+  }
+  BT_CUDA(cudaStreamSynchronize(st));  // sync 2: duplicate count + boxes of the returned list
+  if (nt > 0 && nl > 0) {
+    n_pairs = *t->h_pair_count;
+    BT_CHECK(n_pairs <= t->pair_cap, BT_ERR_CAPACITY, "%d duplicate pairs exceed capacity %d", n_pairs,
+             t->pair_cap);
+    if (n_pairs > 0) {
+      BT_CUDA(cudaMemcpyAsync(t->h_pairs, t->d_pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, st));
+      BT_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  std::vector<uint8_t> dupa(nt, 0), dupb(nl, 0);
+  for (int k = 0; k < n_pairs; ++k) {
+    const int p = t->h_pairs[2 * k], q = t->h_pairs[2 * k + 1];
+    const int timep = meta[new_tracked[p]].frame_id - meta[new_tracked[p]].start_frame;
+    const int timeq = meta[new_lost[q]].frame_id - meta[new_lost[q]].start_frame;
+    if (timep > timeq) dupb[q] = 1;
+    else dupa[p] = 1;
+  }
+  t->tracked.clear();
+  t->lost.clear();
+  t->tlbr_cache.clear();
+  for (int i = 0; i < nt; ++i)
+    if (!dupa[i]) {
+      t->tracked.push_back(new_tracked[i]);
+      for (int c = 0; c < 4; ++c) t->tlbr_cache.push_back(t->h_tlbr[4 * i + c]);
+    }
+  for (int i = 0; i < nl; ++i)
+    if (!dupb[i]) t->lost.push_back(new_lost[i]);
+  t->tlbr_cache_valid = true;
+
+  // ---- recycle slots that left both lists -----------------------------------------------------
+  for (int s : t->tracked) meta[s].mark = 1;
+  for (int s : t->lost) meta[s].mark = 1;
+  bool freed = false;
+  for (int s = 0; s < t->high_water; ++s) {
+    if (meta[s].used && !meta[s].mark) {
+      meta[s] = SlotMeta();
+      t->free_slots.push_back(s);
+      freed = true;
+    }
+    meta[s].mark = 0;
+  }
+  if (freed) std::sort(t->free_slots.begin(), t->free_slots.end(), std::greater<int>());
+
+  if (info) {
+    info->frame_id = frame_id;
+    info->n_tracked = (int)t->tracked.size();
+    info->n_lost = (int)t->lost.size();
+    info->n_removed_total = t->n_removed_total;
+    info->n_pool = n_pool;
+    info->n_high = (int)hi_list.size();
+    info->n_low = (int)lo_list.size();
+    info->n_unconfirmed = n_unc;
+    info->n_matches1 = (int)t->matches[0].size() / 2;
+    info->n_matches2 = (int)t->matches[1].size() / 2;
+    info->n_matches3 = (int)t->matches[2].size() / 2;
+    info->n_births = n_births;
+  }
+  return BT_OK;
+}
+
+int32_t bt_get_tracks(bt_ctx* ctx, int32_t which, int32_t cap, int32_t* n, int32_t* ids, int32_t* state,
+                      int32_t* activated, int32_t* frame_id, int32_t* start_frame, int32_t* tracklet_len,
+                      int32_t* det_index, float* score, double* tlbr, double* mean, double* cov) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  bt_tracker* t = ctx->trk;
+  BT_CHECK(which == 0 || which == 1, BT_ERR_INVALID, "which must be 0 (tracked) or 1 (lost)");
+  const std::vector<int>& lst = which == 0 ? t->tracked : t->lost;
+  const int cnt = (int)lst.size();
+  if (n) *n = cnt;
+  BT_CHECK(cnt <= cap || !(ids || state || activated || frame_id || start_frame || tracklet_len || det_index ||
+                           score || tlbr || mean || cov),
+           BT_ERR_CAPACITY, "list has %d tracks, buffers hold %d", cnt, cap);
+  for (int i = 0; i < cnt; ++i) {
+    const SlotMeta& tm = t->meta[lst[i]];
+    if (ids) ids[i] = tm.track_id;
+    if (state) state[i] = tm.state;
+    if (activated) activated[i] = tm.activated;
+    if (frame_id) frame_id[i] = tm.frame_id;
+    if (start_frame) start_frame[i] = tm.start_frame;
+    if (tracklet_len) tracklet_len[i] = tm.tracklet_len;
+    if (det_index) det_index[i] = tm.det_index;
+    if (score) score[i] = tm.score;
+  }
+  if (cnt == 0) return BT_OK;
+  if (tlbr && which == 0 && t->tlbr_cache_valid) {
+    memcpy(tlbr, t->tlbr_cache.data(), sizeof(double) * 4 * cnt);
+    tlbr = nullptr;
+  }
+  if (tlbr || mean || cov) {
+    cudaStream_t st = ctx->stream;
+    memcpy(t->h_lista, lst.data(), sizeof(int32_t) * cnt);
+    BT_CUDA(cudaMemcpyAsync(t->d_lista, t->h_lista, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
+    struct Job { const double* src; double* dst; int width; };
+    const Job jobs[3] = {{t->tlbr, tlbr, 4}, {t->mean, mean, 8}, {t->cov, cov, 64}};
+    for (const Job& j : jobs) {
+      if (!j.dst) continue;
+      gather_rows_f64_kernel<<<(unsigned)(((size_t)cnt * j.width + 255) / 256), 256, 0, st>>>(
+          j.src, t->d_lista, cnt, j.width, t->d_gather);
+      BT_LAUNCHED(ctx);
+      BT_CUDA(cudaMemcpyAsync(j.dst, t->d_gather, sizeof(double) * (size_t)cnt * j.width, cudaMemcpyDeviceToHost, st));
+      BT_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  return BT_OK;
+}
+
+int32_t bt_get_track_features(bt_ctx* ctx, int32_t which, int32_t cap, float* curr, float* smooth) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  bt_tracker* t = ctx->trk;
+  BT_CHECK(which == 0 || which == 1, BT_ERR_INVALID, "which must be 0 (tracked) or 1 (lost)");
+  BT_CHECK(t->curr32 != nullptr, BT_ERR_STATE, "ctx was created with BT_FLAG_NO_F32_FEATURES");
+  const std::vector<int>& lst = which == 0 ? t->tracked : t->lost;
+  const int cnt = (int)lst.size();
+  BT_CHECK(cnt <= cap, BT_ERR_CAPACITY, "list has %d tracks, buffers hold %d", cnt, cap);
+  if (cnt == 0) return BT_OK;
+  cudaStream_t st = ctx->stream;
+  memcpy(t->h_lista, lst.data(), sizeof(int32_t) * cnt);
+  BT_CUDA(cudaMemcpyAsync(t->d_lista, t->h_lista, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, st));
+  const float* srcs[2] = {t->curr32, t->smooth32};
+  float* dsts[2] = {curr, smooth};
+  for (int k = 0; k < 2; ++k) {
+    if (!dsts[k]) continue;
+    // reuse the normalised-detection staging buffer as gather scratch in chunks of max_dets rows
+    for (int off = 0; off < cnt; off += t->max_dets) {
+      const int rows = std::min(t->max_dets, cnt - off);
+      gather_rows_f32_kernel<<<(unsigned)(((size_t)rows * t->D + 255) / 256), 256, 0, st>>>(
+          srcs[k], t->d_lista + off, rows, t->D, t->det_feat_in);
+      BT_LAUNCHED(ctx);
+      BT_CUDA(cudaMemcpyAsync(dsts[k] + (size_t)off * t->D, t->det_feat_in, sizeof(float) * (size_t)rows * t->D,
+                              cudaMemcpyDeviceToHost, st));
+      BT_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+  return BT_OK;
+}
+
+int32_t bt_get_matches(bt_ctx* ctx, int32_t stage, int32_t cap, int32_t* n, int32_t* pairs) {
+  if (!ctx) return BT_ERR_INVALID;
+  bt_tracker* t = ctx->trk;
+  BT_CHECK(stage >= 1 && stage <= 3, BT_ERR_INVALID, "stage must be 1, 2 or 3");
+  const std::vector<int32_t>& mm = t->matches[stage - 1];
+  const int cnt = (int)mm.size() / 2;
+  if (n) *n = cnt;
+  if (pairs) {
+    BT_CHECK(cnt <= cap, BT_ERR_CAPACITY, "%d matches, buffer holds %d", cnt, cap);
+    if (cnt) memcpy(pairs, mm.data(), sizeof(int32_t) * 2 * cnt);
+  }
+  return BT_OK;
+}
+
+}  // extern "C"

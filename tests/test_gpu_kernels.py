@@ -1,0 +1,240 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+
+Tolerances (north_star): assignment indices / ids bit-exact; Kalman means/covariances and the
+distance matrices within 1e-4 (float64 kernels land around 1e-10; the tensor-core similarity
+uses fp16 operands with fp32 accumulation: ~3e-5 on unit-norm 2048-d features).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _rand_tracks(rng, n, scale=1.0):
+    """Plausible Kalman states: initiate from random boxes then a few oracle predict/update steps."""
+    xywh = np.stack([rng.uniform(50, 4000, n), rng.uniform(50, 3000, n), rng.uniform(30, 120, n) * scale,
+                     rng.uniform(60, 200, n) * scale], axis=1).astype(np.float32)
+    means, covs = [], []
+    for z in xywh:
+        m, c = O.kf_initiate(z)
+        m = m.astype(np.float64)
+        c = c.astype(np.float64)
+        for _ in range(3):
+            mm, cc = O.kf_multi_predict(m[None], c[None])
+            m, c = mm[0], cc[0]
+            zz = m[:4] + rng.normal(0, 1.5, 4)
+            m, c = O.kf_update(m, c, zz)
+        means.append(m)
+        covs.append(c)
+    return np.array(means), np.array(covs)
+
+
+def test_kalman_initiate(ctx):
+    rng = np.random.default_rng(1)
+    z = np.stack([rng.uniform(0, 4000, 257), rng.uniform(0, 3000, 257), rng.integers(20, 200, 257),
+                  rng.integers(40, 300, 257)], axis=1).astype(np.float32)
+    mean, cov = ctx.kalman_initiate(z)
+    for i in range(len(z)):
+        m, c = O.kf_initiate(z[i])
+        np.testing.assert_array_equal(mean[i], m.astype(np.float64))
+        np.testing.assert_array_equal(cov[i], np.asarray(c, dtype=np.float64))
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 513, 2000])
+def test_kalman_multi_predict(ctx, n):
+    rng = np.random.default_rng(n)
+    mean, cov = _rand_tracks(rng, n)
+    state = rng.choice([O.ST_TRACKED, O.ST_LOST, O.ST_REMOVED], size=n, p=[0.7, 0.2, 0.1]).astype(np.int32)
+    ref_in = mean.copy()
+    ref_in[state != O.ST_TRACKED, 6:] = 0
+    rm, rc = O.kf_multi_predict(ref_in, cov)
+    gm, gc = ctx.kalman_multi_predict(mean, cov, state)
+    assert np.max(np.abs(gm - rm)) <= 1e-9
+    assert np.max(np.abs(gc - rc)) <= 1e-9
+    # no state flags == plain KalmanFilter.multi_predict
+    rm, rc = O.kf_multi_predict(mean, cov)
+    gm, gc = ctx.kalman_multi_predict(mean, cov)
+    assert np.max(np.abs(gm - rm)) <= 1e-9 and np.max(np.abs(gc - rc)) <= 1e-9
+
+
+def test_kalman_multi_predict_float32_noise(ctx):
+    """Frame-2 case: every pooled mean is still initiate()'s float32 (NumPy >= 2 promotion)."""
+    rng = np.random.default_rng(5)
+    z = np.stack([rng.uniform(0, 4000, 300), rng.uniform(0, 3000, 300), rng.integers(20, 200, 300),
+                  rng.integers(40, 300, 300)], axis=1).astype(np.float32)
+    ms, cs = zip(*[O.kf_initiate(v) for v in z])
+    m32 = np.asarray(ms)
+    c32 = np.asarray(cs)
+    assert m32.dtype == np.float32
+    rm, rc = O.kf_multi_predict(m32, c32)
+    gm, gc = ctx.kalman_multi_predict(m32.astype(np.float64), c32.astype(np.float64), None, noise_f32=True)
+    np.testing.assert_array_equal(gm, rm)
+    assert np.max(np.abs(gc - rc)) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 2000])
+def test_kalman_update(ctx, n):
+    rng = np.random.default_rng(100 + n)
+    mean, cov = _rand_tracks(rng, n)
+    mm, cc = O.kf_multi_predict(mean, cov)
+    z = (mm[:, :4] + rng.normal(0, 2.0, (n, 4))).astype(np.float32).astype(np.float64)
+    gm, gc = ctx.kalman_update(mm, cc, z)
+    for i in range(n):
+        rm, rc = O.kf_update(mm[i], cc[i], z[i])
+        assert np.max(np.abs(gm[i] - rm)) <= TOL
+        assert np.max(np.abs(gc[i] - rc)) <= TOL
+        assert np.max(np.abs(gm[i] - rm)) <= 1e-8 and np.max(np.abs(gc[i] - rc)) <= 1e-8
+    # batched oracle, float32-noise rows (never-predicted unconfirmed tracks)
+    f32 = rng.uniform(size=n) < 0.3
+    rm, rc = O.kf_update_batch(mm, cc, z, f32)
+    gm, gc = ctx.kalman_update(mm, cc, z, noise_f32=f32)
+    assert np.max(np.abs(gm - rm)) <= 1e-8 and np.max(np.abs(gc - rc)) <= 1e-8
+
+
+def test_kalman_project(ctx):
+    rng = np.random.default_rng(3)
+    mean, cov = _rand_tracks(rng, 33)
+    pm, pc = ctx.kalman_project(mean, cov)
+    for i in range(33):
+        rm, rc = O.kf_project(mean[i], cov[i])
+        assert np.max(np.abs(pm[i] - rm)) <= 1e-10 and np.max(np.abs(pc[i] - rc)) <= 1e-10
+
+
+def _rand_boxes(rng, n, extent=1500.0, ints=False):
+    x1 = rng.uniform(0, extent, n)
+    y1 = rng.uniform(0, extent, n)
+    w = rng.uniform(20, 200, n)
+    h = rng.uniform(40, 300, n)
+    b = np.stack([x1, y1, x1 + w, y1 + h], axis=1)
+    return np.floor(b) if ints else b
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (3, 130), (64, 64), (257, 511), (2000, 2000)])
+def test_iou_distance(ctx, n, m):
+    rng = np.random.default_rng(n * 7 + m)
+    a = _rand_boxes(rng, n, extent=600 if n < 1000 else 3000)
+    b = _rand_boxes(rng, m, extent=600 if n < 1000 else 3000, ints=True)
+    # touching / degenerate boxes: strict `<=` rule (demo:1702)
+    if n > 2 and m > 2:
+        b[0] = [a[0, 2], a[0, 1], a[0, 2] + 10, a[0, 3]]      # shares an edge -> IoU 0
+        b[1] = a[1]                                            # identical -> IoU 1
+    got = ctx.iou_distance(a, b)
+    ref = O.iou_distance(a, b, "vectorized")
+    assert got.shape == (n, m)
+    assert np.max(np.abs(got - ref)) <= 1e-12
+    if n * m <= 64 * 64:
+        np.testing.assert_allclose(got, O.iou_distance(list(a), list(b), "faithful"), atol=1e-12)
+    assert np.all(got[ref == 1.0] == 1.0)
+
+
+def _unit_feats(rng, n, d):
+    f = rng.standard_normal((n, d)).astype(np.float32)
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    return f
+
+
+@pytest.mark.parametrize("n,m,d", [(5, 9, 64), (64, 64, 2048), (130, 300, 512), (2000, 2000, 2048)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_embedding_distance(ctx, n, m, d, precision):
+    rng = np.random.default_rng(n + m + d)
+    a = _unit_feats(rng, n, d)
+    b = _unit_feats(rng, m, d)
+    k = min(n, m)
+    b[:k] = a[:k] + 0.01 * rng.standard_normal((k, d)).astype(np.float32)   # correlated pairs
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    got = ctx.embedding_distance(a, b, precision=precision)
+    ref = O.embedding_distance(a, b)
+    err = float(np.max(np.abs(got - ref)))
+    assert got.shape == (n, m)
+    assert err <= (TOL if precision == 0 else 2e-5), err
+
+
+def test_embedding_distance_simt_odd_dim(ctx):
+    rng = np.random.default_rng(9)
+    a, b = _unit_feats(rng, 33, 37), _unit_feats(rng, 65, 37)
+    got = ctx.embedding_distance(a, b, precision=1)
+    assert np.max(np.abs(got - O.embedding_distance(a, b))) <= 1e-5
+    with pytest.raises(ValueError):
+        ctx.embedding_distance(a, b, precision=0)
+
+
+@pytest.mark.parametrize("stage", [1, 3])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_fused_cost(ctx, stage, precision):
+    rng = np.random.default_rng(11 + stage)
+    n, m, d = 300, 280, 2048
+    trk = _rand_boxes(rng, n, extent=800)
+    det = trk[rng.permutation(n)[:m]] + rng.uniform(-6, 6, (m, 4))
+    det = np.floor(det)
+    a = _unit_feats(rng, n, d)
+    perm = rng.permutation(n)[:m]
+    b = a[perm] + 0.005 * rng.standard_normal((m, d)).astype(np.float32)
+    b /= np.linalg.norm(b, axis=1, keepdims=True)
+    got = ctx.fused_cost(trk, det, a, b, stage=stage, precision=precision)
+    iou_d = O.iou_distance(trk, det)
+    if stage == 1:
+        ref = O.fuse_stage1(iou_d, np.matmul(a, b.T))
+    else:
+        ref = O.fuse_stage3(iou_d, O.embedding_distance(a, b))
+    assert np.max(np.abs(got - ref)) <= TOL
+    assert np.array_equal(got == 1.0, ref == 1.0)
+
+
+def test_fuse_score(ctx):
+    rng = np.random.default_rng(2)
+    d = rng.uniform(0, 1, (40, 70))
+    s = rng.uniform(0.1, 1, 70)
+    np.testing.assert_allclose(ctx.fuse_score(d, s), O.fuse_score(d, s), atol=1e-15)
+
+
+@pytest.mark.parametrize("n,m,density", [(1, 1, 1.0), (4, 7, 1.0), (64, 64, 0.2), (100, 40, 1.0), (40, 100, 0.5),
+                                          (512, 512, 0.02), (300, 300, 1.0), (2000, 2000, 0.002)])
+def test_linear_assignment_random(ctx, n, m, density):
+    rng = np.random.default_rng(n * 31 + m)
+    cost = rng.uniform(0.0, 1.0, (n, m))
+    cost[rng.uniform(size=(n, m)) > density] = 1.0          # forced entries (demo:1547/1552)
+    for thresh in (0.8, 0.5):
+        x, y = ctx.lapjv(cost, thresh)
+        rx, ry = O.lapjv_extended(cost, thresh, "jv")
+        np.testing.assert_array_equal(x, rx)
+        np.testing.assert_array_equal(y, ry)
+
+
+def test_linear_assignment_edge_cases(ctx):
+    # nothing below the threshold
+    x, y = ctx.lapjv(np.ones((5, 3)), 0.8)
+    assert np.all(x == -1) and np.all(y == -1)
+    # chain component: optimum differs from greedy
+    c = np.array([[0.10, 0.20, 1.0], [0.15, 1.0, 1.0], [1.0, 0.30, 0.70]])
+    x, y = ctx.lapjv(c, 0.8)
+    rx, ry = O.lapjv_extended(c, 0.8, "scipy")
+    np.testing.assert_array_equal(x, rx)
+    np.testing.assert_array_equal(y, ry)
+    # a pair whose joint cost is worse than leaving one unmatched
+    c = np.array([[0.75, 0.79], [0.05, 1.0]])
+    x, y = ctx.lapjv(c, 0.8)
+    rx, ry = O.lapjv_extended(c, 0.8, "scipy")
+    np.testing.assert_array_equal(x, rx)
+    # capacity error maps to ValueError
+    with pytest.raises(ValueError):
+        ctx.lapjv(np.ones((ctx.max_tracks + 200, 2)), 0.8)
+
+
+def test_feature_ema(ctx):
+    rng = np.random.default_rng(4)
+    k, d = 37, 2048
+    smooth = _unit_feats(rng, k, d)
+    curr = _unit_feats(rng, k, d)
+    feat = _unit_feats(rng, k, d)
+    s, c = ctx.feature_ema(smooth, curr, feat)
+    ref = 0.9 * smooth + (1 - 0.9) * feat
+    ref = (ref / np.linalg.norm(ref, axis=1, keepdims=True)).astype(np.float32)
+    assert np.max(np.abs(s - ref)) <= 1e-6
+    np.testing.assert_array_equal(c, feat)
+    first = np.ones(k, np.uint8)
+    s, c = ctx.feature_ema(smooth, curr, 3.0 * feat, first=first)
+    assert np.max(np.abs(s - feat)) <= 1e-6 and np.max(np.abs(c - feat)) <= 1e-6

@@ -1,0 +1,117 @@
+"""GPU parity of the whole frame step (bt_update_arrays through ctypes) against the CPU oracle
+restatement of BoTSORT.update on identical seeded synthetic streams.
+
+ids / states / list order / matches: exact.  Kalman means, covariances, boxes: 1e-4.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+from botsort_b200.synthetic import SceneConfig, SyntheticScene
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+INT_FIELDS = ("ids", "state", "activated", "frame_id", "start_frame", "tracklet_len", "det_index")
+
+
+def _compare_frame(ctx, oracle, frame_no):
+    snap = oracle.snapshot()
+    for which, name in ((0, "tracked"), (1, "lost")):
+        got = ctx.get_tracks(which, with_state=True)
+        ref = snap[name]
+        for f in INT_FIELDS:
+            np.testing.assert_array_equal(got[f], ref[f].astype(np.int32), err_msg=f"frame {frame_no} {name}.{f}")
+        np.testing.assert_allclose(got["score"], ref["score"], atol=1e-7, err_msg=f"frame {frame_no} {name}.score")
+        if len(ref["ids"]):
+            assert np.max(np.abs(got["tlbr"] - ref["tlbr"])) <= TOL, f"frame {frame_no} {name}.tlbr"
+            assert np.max(np.abs(got["mean"] - ref["mean"])) <= TOL, f"frame {frame_no} {name}.mean"
+            assert np.max(np.abs(got["cov"] - ref["cov"])) <= TOL, f"frame {frame_no} {name}.cov"
+    for stage in (1, 2, 3):
+        np.testing.assert_array_equal(ctx.get_matches(stage), oracle.last[f"matches{stage}"].astype(np.int32),
+                                      err_msg=f"frame {frame_no} matches{stage}")
+
+
+def _run(ctx, scene_cfg, frames, with_reid=True):
+    cfg = ctx.default_config()
+    cfg.with_reid = 1 if with_reid else 0
+    ctx.tracker_reset(cfg)
+    scene = SyntheticScene(scene_cfg)
+    oracle = O.OracleBoTSORT(mode="vectorized", lap_solver="jv", use_features=with_reid)
+    infos = []
+    for k in range(frames):
+        fr = scene.next_frame()
+        feats = fr["feats"] if with_reid else None
+        oracle.update_arrays(fr["boxes"], fr["scores"], feats)
+        infos.append(ctx.update_arrays(fr["boxes"], fr["scores"], feats))
+        _compare_frame(ctx, oracle, k + 1)
+    return infos
+
+
+def test_c1_64x64_reid(ctx):
+    """BASELINE config 1: 64 tracks x 64 dets, 2048-d features, births/lost/refind/unconfirmed paths."""
+    infos = _run(ctx, SceneConfig(n_ids=64, feat_dim=2048, seed=3, low_frac=0.15, drop_frac=0.1, mid_frac=0.05,
+                                  newcomer_every=3), frames=40)
+    assert sum(i["n_matches2"] for i in infos) > 0
+    assert sum(i["n_matches3"] for i in infos) > 0
+    assert any(i["n_lost"] > 0 for i in infos)
+
+
+def test_c1_crowded(ctx):
+    """Dense scene: boxes overlap their neighbours, the candidate graph has multi-row components."""
+    _run(ctx, SceneConfig(n_ids=96, feat_dim=2048, seed=5, pitch_x=30.0, pitch_y=50.0, low_frac=0.2,
+                          drop_frac=0.15, walk=5.0), frames=30)
+
+
+def test_c2_512_iou_only(ctx):
+    """BASELINE config 2: 512 x 512, IoU-only association (no ReID)."""
+    infos = _run(ctx, SceneConfig(n_ids=512, feat_dim=2048, seed=7, low_frac=0.1, drop_frac=0.05,
+                                  with_features=False, pitch_x=45.0, pitch_y=80.0), frames=12, with_reid=False)
+    assert infos[-1]["n_pool"] >= 480
+
+
+def test_c3_2000x2000(ctx):
+    """BASELINE config 3: 2000 x 2000 x 2048-d."""
+    infos = _run(ctx, SceneConfig(n_ids=2000, feat_dim=2048, seed=11, low_frac=0.05, drop_frac=0.02), frames=4)
+    assert infos[-1]["n_pool"] >= 1900
+
+
+def test_empty_and_ragged_frames(ctx):
+    ctx.tracker_reset()
+    oracle = O.OracleBoTSORT()
+    scene = SyntheticScene(SceneConfig(n_ids=20, feat_dim=2048, seed=1))
+    empty = (np.zeros((0, 4), np.int32), np.zeros(0, np.float32), np.zeros((0, 2048), np.float32))
+    seq = []
+    seq.append(empty)                                   # frame 1 without detections
+    f = scene.next_frame(); seq.append((f["boxes"], f["scores"], f["feats"]))
+    f = scene.next_frame(); seq.append((f["boxes"][:7], f["scores"][:7], f["feats"][:7]))
+    seq.append(empty)                                   # everything goes lost
+    f = scene.next_frame(); seq.append((f["boxes"], f["scores"], f["feats"]))
+    f = scene.next_frame(); seq.append((f["boxes"], np.full(len(f["boxes"]), 0.3, np.float32), f["feats"]))
+    for k, (b, s, ft) in enumerate(seq):
+        oracle.update_arrays(b, s, ft)
+        ctx.update_arrays(b, s, ft)
+        _compare_frame(ctx, oracle, k + 1)
+
+
+def test_track_features_state(ctx):
+    """A10 exposed state: curr / smooth feature banks follow STrack.update_body_features."""
+    ctx.tracker_reset()
+    oracle = O.OracleBoTSORT()
+    scene = SyntheticScene(SceneConfig(n_ids=32, feat_dim=2048, seed=9))
+    for _ in range(5):
+        f = scene.next_frame()
+        oracle.update_arrays(f["boxes"], f["scores"], f["feats"])
+        ctx.update_arrays(f["boxes"], f["scores"], f["feats"])
+    curr, smooth = ctx.get_track_features(0)
+    ref_curr = np.array([t.curr_feat for t in oracle.tracked])
+    ref_smooth = np.array([t.smooth_feat for t in oracle.tracked])
+    assert np.max(np.abs(curr - ref_curr)) <= 1e-6
+    assert np.max(np.abs(smooth - ref_smooth)) <= 1e-6
+
+
+def test_capacity_error(ctx):
+    ctx.tracker_reset()
+    with pytest.raises(ValueError):
+        ctx.update_arrays(np.zeros((ctx.max_dets + 1, 4), np.int32), np.zeros(ctx.max_dets + 1, np.float32),
+                          np.zeros((ctx.max_dets + 1, 2048), np.float32))
