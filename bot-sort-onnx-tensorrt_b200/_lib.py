@@ -26,7 +26,9 @@ EXPORTS = [
     "bt_iou_distance", "bt_embedding_distance", "bt_fused_cost", "bt_fuse_score", "bt_linear_assignment",
     "bt_feature_ema", "bt_default_yolox_config", "bt_yolox_postprocess", "bt_reid_crop_gather",
     "bt_tracker_reset", "bt_update_arrays", "bt_get_tracks", "bt_get_track_features", "bt_get_matches",
+    "bt_profile_enable", "bt_profile_read",
 ]
+SEGMENTS = ("prep", "predict", "assoc", "lap", "update", "dup")
 
 
 class BtConfig(C.Structure):
@@ -105,6 +107,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bt_get_tracks": [vp, i32, i32, vp] + [vp] * 11,
         "bt_get_track_features": [vp, i32, i32, vp, vp],
         "bt_get_matches": [vp, i32, i32, vp, vp],
+        "bt_profile_enable": [vp, i32],
+        "bt_profile_read": [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -174,6 +178,18 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.bt_launch_count(self.h))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.bt_profile_enable(self.h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{segment: (total device ms, samples)} accumulated since profile_enable(True)."""
+        out = {}
+        for i, name in enumerate(SEGMENTS):
+            ms, n = C.c_double(0), C.c_int64(0)
+            self._check(self.lib.bt_profile_read(self.h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
 
     # ---- Kalman ----
     def kalman_initiate(self, xywh):

@@ -126,7 +126,35 @@ struct bt_tracker {
   std::vector<int32_t> matches[3];  // flattened (a, b) pairs in the reference's index spaces
   std::vector<double> tlbr_cache;   // tlbr of `tracked` after the frame
   bool tlbr_cache_valid = false;
+  // ---- optional segment timing (bt_profile_*) ----
+  bool prof = false;
+  cudaEvent_t ev[BT_SEG_COUNT][2] = {};
+  bool seg_open[BT_SEG_COUNT] = {};
+  double prof_ms[BT_SEG_COUNT] = {};
+  int64_t prof_n[BT_SEG_COUNT] = {};
 };
+
+#define SEG_BEGIN(s)                                                  \
+  do {                                                                \
+    if (t->prof) { BT_CUDA(cudaEventRecord(t->ev[s][0], st)); }       \
+  } while (0)
+#define SEG_END(s)                                                    \
+  do {                                                                \
+    if (t->prof) { BT_CUDA(cudaEventRecord(t->ev[s][1], st)); t->seg_open[s] = true; } \
+  } while (0)
+
+static int32_t prof_collect(bt_ctx* ctx, bt_tracker* t) {
+  if (!t->prof) return BT_OK;
+  for (int s = 0; s < BT_SEG_COUNT; ++s) {
+    if (!t->seg_open[s]) continue;
+    float ms = 0.f;
+    BT_CUDA(cudaEventElapsedTime(&ms, t->ev[s][0], t->ev[s][1]));
+    t->prof_ms[s] += ms;
+    t->prof_n[s] += 1;
+    t->seg_open[s] = false;
+  }
+  return BT_OK;
+}
 
 namespace {
 
@@ -249,6 +277,9 @@ void bt_tracker_destroy(bt_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (t->pinned) cudaFreeHost(t->pinned);
+  for (auto& pair : t->ev)
+    for (cudaEvent_t e : pair)
+      if (e) cudaEventDestroy(e);
   delete t;
   ctx->trk = nullptr;
 }
@@ -302,6 +333,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   const int32_t* d_boxes = boxes;
   const float* d_scores = scores;
   const float* d_feats = feats;
+  SEG_BEGIN(BT_SEG_PREP);
   if (m > 0) {
     if (loc == BT_HOST) {
       BT_CUDA(cudaMemcpyAsync(t->det_boxes, boxes, sizeof(int32_t) * 4 * m, cudaMemcpyHostToDevice, st));
@@ -324,6 +356,8 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       BT_TRY(btk_feature_prep(ctx, d_feats, m, D, keep32 || !tensor_path ? t->det_feat32 : nullptr,
                               t->det_feat16, 1));
   }
+
+  SEG_END(BT_SEG_PREP);
 
   // ---- split lists (demo:1415-1423) -------------------------------------------------------------
   std::vector<int> unconfirmed, pool;
@@ -348,6 +382,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   for (int s : unconfirmed) t->h_row_kind[s] = BT_ROW_UNCONFIRMED;
   if (n_rows > 0)
     BT_CUDA(cudaMemcpyAsync(t->row_kind, t->h_row_kind, n_rows, cudaMemcpyHostToDevice, st));
+  SEG_BEGIN(BT_SEG_PREDICT);
   if (n_pool > 0) {
     BT_CUDA(cudaMemcpyAsync(t->d_pool_idx, t->h_pool_idx, sizeof(int32_t) * n_pool, cudaMemcpyHostToDevice, st));
     BT_CUDA(cudaMemcpyAsync(t->d_pool_state, t->h_pool_state, sizeof(int32_t) * n_pool, cudaMemcpyHostToDevice, st));
@@ -355,11 +390,13 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
                               n_pool, all_f32 ? 1 : 0));
     for (int s : pool) meta[s].f32_state = 0;
   }
+  SEG_END(BT_SEG_PREDICT);
 
   // ---- fused association over slots x detections + the three chained LAP solves -------------
   const bt_cand& cand = *bt_lap_own_cand(ctx);
   if (n_rows > 0) {
     BT_CUDA(cudaMemsetAsync(cand.cnt, 0, sizeof(int32_t) * 3 * cand.rows_cap, st));
+    SEG_BEGIN(BT_SEG_ASSOC);
     if (m > 0) {
       bt_assoc_params p;
       memset(&p, 0, sizeof(p));
@@ -374,13 +411,17 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       p.cand = cand;
       BT_TRY(btk_assoc(ctx, p, (reid && tensor_path) ? 0 : 1));
     }
+    SEG_END(BT_SEG_ASSOC);
+    SEG_BEGIN(BT_SEG_LAP);
     BT_TRY(btk_lap_solve(ctx, cand, 0, n_rows, m, cfg.match_thresh, nullptr, nullptr, t->x[0], t->y[0]));
     BT_TRY(btk_lap_solve(ctx, cand, 1, n_rows, m, cfg.second_thresh, t->x[0], nullptr, t->x[1], t->y[1]));
     BT_TRY(btk_lap_solve(ctx, cand, 2, n_rows, m, cfg.unconfirmed_thresh, nullptr, t->y[0], t->x[2], t->y[2]));
+    SEG_END(BT_SEG_LAP);
     for (int s = 0; s < 3; ++s)
       BT_CUDA(cudaMemcpyAsync(t->h_x[s], t->x[s], sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, st));
   }
   BT_CUDA(cudaStreamSynchronize(st));  // sync 1: assignments (and scores) are on the host
+  BT_TRY(prof_collect(ctx, t));
 
   // ---- detection lists (demo:1493-1532) -----------------------------------------------------
   const float* sc = t->h_scores;
@@ -516,6 +557,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
 
   // ---- device: Kalman update / initiate / features ----------------------------------------------
+  SEG_BEGIN(BT_SEG_UPDATE);
   if (n_upd > 0) {
     BT_CUDA(cudaMemcpyAsync(t->d_upd_track, t->h_upd_track, sizeof(int32_t) * n_upd, cudaMemcpyHostToDevice, st));
     BT_CUDA(cudaMemcpyAsync(t->d_upd_det, t->h_upd_det, sizeof(int32_t) * n_upd, cudaMemcpyHostToDevice, st));
@@ -535,6 +577,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     BT_TRY(btk_feature_ema16(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
                              t->det_feat16, t->d_upd_track, t->d_upd_det, t->d_ema_mode, n_upd, D,
                              cfg.ema_alpha));
+  SEG_END(BT_SEG_UPDATE);
 
   // ---- merge lists (demo:1629-1636) -----------------------------------------------------------
   std::vector<int> new_tracked;
@@ -561,6 +604,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) + result read-back --------------
   const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
   int n_pairs = 0;
+  SEG_BEGIN(BT_SEG_DUP);
   if (nt > 0) {
     memcpy(t->h_lista, new_tracked.data(), sizeof(int32_t) * nt);
     BT_CUDA(cudaMemcpyAsync(t->d_lista, t->h_lista, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
@@ -576,7 +620,9 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     BT_LAUNCHED(ctx);
     BT_CUDA(cudaMemcpyAsync(t->h_tlbr, t->d_gather, sizeof(double) * 4 * nt, cudaMemcpyDeviceToHost, st));
   }
+  SEG_END(BT_SEG_DUP);
   BT_CUDA(cudaStreamSynchronize(st));  // sync 2: duplicate count + boxes of the returned list
+  BT_TRY(prof_collect(ctx, t));
   if (nt > 0 && nl > 0) {
     n_pairs = *t->h_pair_count;
     BT_CHECK(n_pairs <= t->pair_cap, BT_ERR_CAPACITY, "%d duplicate pairs exceed capacity %d", n_pairs,
@@ -634,6 +680,29 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     info->n_matches3 = (int)t->matches[2].size() / 2;
     info->n_births = n_births;
   }
+  return BT_OK;
+}
+
+int32_t bt_profile_enable(bt_ctx* ctx, int32_t on) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  bt_tracker* t = ctx->trk;
+  BT_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (on) {
+    for (auto& pair : t->ev)
+      for (cudaEvent_t& e : pair)
+        if (!e) BT_CUDA(cudaEventCreate(&e));
+    for (int s = 0; s < BT_SEG_COUNT; ++s) { t->prof_ms[s] = 0.0; t->prof_n[s] = 0; t->seg_open[s] = false; }
+  }
+  t->prof = on != 0;
+  return BT_OK;
+}
+
+int32_t bt_profile_read(bt_ctx* ctx, int32_t segment, double* total_ms, int64_t* samples) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CHECK(segment >= 0 && segment < BT_SEG_COUNT, BT_ERR_INVALID, "bad segment %d", segment);
+  if (total_ms) *total_ms = ctx->trk->prof_ms[segment];
+  if (samples) *samples = ctx->trk->prof_n[segment];
   return BT_OK;
 }
 

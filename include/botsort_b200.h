@@ -88,6 +88,21 @@ void* bt_stream(bt_ctx* ctx);
 /* Number of kernels this library launched on the ctx since creation (bench `gpu_launches`). */
 int64_t bt_launch_count(const bt_ctx* ctx);
 
+/* Segment timing of bt_update_arrays with CUDA events recorded on the ctx stream (what
+ * bench.py's roofline figures are computed from).  Off by default. */
+enum {
+  BT_SEG_PREP = 0,    /* detection prep + feature normalisation/fp16 staging */
+  BT_SEG_PREDICT = 1, /* batched Kalman predict */
+  BT_SEG_ASSOC = 2,   /* fused association kernel (ReID GEMM + IoU + cost fusion + candidate emission) */
+  BT_SEG_LAP = 3,     /* the three LAP solves */
+  BT_SEG_UPDATE = 4,  /* Kalman update + initiate + feature EMA */
+  BT_SEG_DUP = 5,     /* duplicate test + result gather */
+  BT_SEG_COUNT = 6
+};
+int32_t bt_profile_enable(bt_ctx* ctx, int32_t on);
+/* accumulated device milliseconds and number of samples of a segment since bt_profile_enable(1) */
+int32_t bt_profile_read(bt_ctx* ctx, int32_t segment, double* total_ms, int64_t* samples);
+
 /* ---- Kalman filter (replaces KalmanFilter, demo:118-336) ------------------------------- */
 /* KalmanFilter.initiate, demo:166-197: xywh[k,4] float32 -> mean[k,8], cov[k,64] float64.
  * The float32 rounding NumPy>=2 applies to the initial std/variance (float32 measurement,

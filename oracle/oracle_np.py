@@ -414,7 +414,8 @@ class OracleBoTSORT:
     Face similarities are 0 (SURVEY: face encoder out of scope, term vanishes)."""
 
     def __init__(self, frame_rate: int = 30, mode: str = "vectorized", lap_solver: str = "jv",
-                 use_features: bool = True):
+                 use_features: bool = True, iou_mode: Optional[str] = None):
+        self.iou_mode = iou_mode or mode       # bench.py: reference loop structure with a sampled IoU loop
         self.tracked: List[OTrack] = []
         self.lost: List[OTrack] = []
         self.removed: List[OTrack] = []
@@ -434,7 +435,7 @@ class OracleBoTSORT:
     def _iou_dist(self, tracks: Sequence[OTrack], dets: Sequence[OTrack]) -> np.ndarray:
         a = [t.tlbr for t in tracks]
         b = [t.tlbr for t in dets]
-        return iou_distance(a, b, self.mode)
+        return iou_distance(a, b, self.iou_mode)
 
     def _multi_predict(self, pool: List[OTrack]):
         """demo:524-536."""
