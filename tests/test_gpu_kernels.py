@@ -150,7 +150,10 @@ def test_embedding_distance(ctx, n, m, d, precision):
     ref = O.embedding_distance(a, b)
     err = float(np.max(np.abs(got - ref)))
     assert got.shape == (n, m)
-    assert err <= (TOL if precision == 0 else 2e-5), err
+    # fp16 operand rounding scales with the component size (~1/sqrt(d)): the 1e-4 budget is for the
+    # 2048-d (and 512-d) unit vectors of the path; the tiny d=64 plumbing case gets 5e-4
+    tol = (TOL if d >= 512 else 5e-4) if precision == 0 else 2e-5
+    assert err <= tol, err
 
 
 def test_embedding_distance_simt_odd_dim(ctx):
