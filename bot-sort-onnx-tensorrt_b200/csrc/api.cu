@@ -398,7 +398,8 @@ int32_t bt_linear_assignment(bt_ctx* ctx, const double* cost, int32_t n, int32_t
   BT_TRY(bt_out(ctx, x, (size_t)n, loc, &d_x));
   BT_TRY(bt_out(ctx, y, (size_t)m, loc, &d_y));
   const bt_cand& cand = *bt_lap_own_cand(ctx);
-  if (n > 0) BT_CUDA(cudaMemsetAsync(cand.cnt, 0, sizeof(int32_t) * n, ctx->stream));
+  if (n > 0) BT_CUDA(cudaMemsetAsync(cand.cnt, 0, sizeof(int32_t) * (size_t)n * cand.nseg, ctx->stream));
+  BT_CUDA(cudaMemsetAsync(cand.total, 0, sizeof(int32_t) * 4, ctx->stream));
   BT_TRY(btk_lap_compact_dense(ctx, d_cost, n, m, thresh, cand, 0));
   BT_TRY(btk_lap_solve(ctx, cand, 0, n, m, thresh, nullptr, nullptr, d_x, d_y));
   BT_TRY(bt_unstage_out(ctx, x, d_x, sizeof(int32_t) * n, loc));

@@ -139,12 +139,23 @@ enum { BT_COL_NONE = 0, BT_COL_HIGH = 1, BT_COL_LOW = 2 };
 
 // Candidate lists ("ragged dense" adjacency): list s in {0,1,2} = association stage 1,2,3.
 // Row r owns entries [r*stride, r*stride + cnt[s*rows_cap + r]) of col/cost.
+// A row's region of `stride` entries is cut into `nseg` segments of BT_CAND_SEG columns: the
+// edges of row r found in columns [g*SEG, (g+1)*SEG) are written to
+// [r*stride + g*SEG, r*stride + g*SEG + cnt[list][r][g]).  The tensor-core epilogue owns one
+// (row, segment) pair per thread, so it appends with plain stores and a register counter -- no
+// atomics; the LAP set-up compacts the segments of a row to the front of its region.
+#define BT_CAND_SEG 128
 struct bt_cand {
-  int32_t* cnt;    // [3][rows_cap]
+  int32_t* cnt;    // [3][rows_cap][nseg]
+  int32_t* total;  // [4] per list: non-zero when any edge was emitted (lets the LAP skip empty stages)
+  unsigned long long* segmask;  // [3][rows_cap] bit g: segment g of the row is non-empty (nseg <= 64)
+  int32_t* deg;    // [3][rows_cap]  row degree after compaction (written by the LAP set-up)
   int32_t* col;    // [3][rows_cap*stride]
   double* cost;    // [3][rows_cap*stride]
   int32_t rows_cap;
-  int32_t stride;  // = max_dets
+  int32_t stride;  // = round_up(max_dets, BT_CAND_SEG)
+  int32_t nseg;    // = stride / BT_CAND_SEG
+  size_t clear_bytes;  // cnt, total and segmask live in one allocation: one memset of this many bytes at cnt
 };
 
 struct bt_assoc_params {
@@ -154,6 +165,8 @@ struct bt_assoc_params {
   const float* a32;    // fp32 variants for the SIMT kernel (may be null when tensor path is used)
   const float* b32;
   int32_t n, m, d;
+  int32_t a_rows_alloc, b_rows_alloc;  // rows the operand buffers really hold (0 = n / m): lets the TMA
+                                       // descriptors be cached across frames; rows >= n / m are masked
   // epilogue inputs (null => not used)
   const double* row_tlbr;   // [n,4]
   const float* row_tlbr_f32;// [n,4] conservative fp32 interval (lo down, hi up)
@@ -187,6 +200,9 @@ int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n,
                       double thresh, const int32_t* row_block, const int32_t* col_block, int32_t* x,
                       int32_t* y);
 const bt_cand* bt_lap_own_cand(bt_ctx* ctx);
+// the three chained association stages of a frame in ONE launch (lists 0,1,2)
+int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, int32_t n, int32_t m, const double thresh[3],
+                       int32_t* const x[3], int32_t* const y[3]);
 
 // ---- detector side ------------------------------------------------------------------------------
 int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_config& cfg,

@@ -9,30 +9,42 @@
 // a max-weight (not perfect) bipartite matching over the edges with c_ij < thresh.  Instead of
 // the dense 4000 x 4000 float64 matrix of the reference (128 MB at 2000 x 2000) this solver
 // works on the *candidate edge lists* the association epilogue emits:
-//   1. lap_setup_kernel  (one CTA): connected components of the candidate graph by min-label
-//      propagation with pointer jumping; component row lists / scratch slices by block scans.
-//   2. lap_solve_kernel  (one warp per component): exact shortest-augmenting-path assignment
-//      (Jonker-Volgenant / Crouse formulation, float64 duals) where every row owns a private
-//      zero-cost dummy column ("stay unmatched"); lanes parallelise the edge relaxations and the
-//      minimum scans.  Components of a tracking scene are tiny (1-5 rows), so thousands of
-//      warps run independently; a single giant component is still solved exactly, just slower.
+// ONE kernel launch (`lap_cluster_kernel`) solves up to three chained association stages.  It runs
+// as a single thread-block cluster (up to 8 CTAs x 1024 threads) so that the phases below can be
+// separated by hardware cluster barriers instead of kernel boundaries:
+//   P1  per row: compact the (row, column-segment) sub-lists, count valid edges, column in-degrees
+//   P2  isolated edges (row degree 1, column in-degree 1) are matched on the spot -- the bulk of a
+//       tracking scene; the remaining "complex" rows are collected
+//   P3  connected components of the complex part: min-label propagation + pointer jumping
+//   P4  component row lists / scratch slices by block scans (CTA 0)
+//   P5  one warp per component: exact shortest-augmenting-path assignment (Jonker-Volgenant /
+//       Crouse formulation, float64 duals) where every row owns a private zero-cost dummy column
+//       ("stay unmatched"); lanes parallelise the edge relaxations and the minimum scans.
+// Stage 2 is masked by stage 1's matched rows and stage 3 by stage 1's matched columns, so the
+// three solves of a frame chain inside the launch.  A single giant component (dense adversarial
+// cost matrix) is still solved exactly, just slower.
 // Ties between equal-cost optima are broken by lowest index, lap's own tie-breaking is not
 // reproducible without its sources: "bit-exact" is defined on inputs with a unique optimum.
 #include "common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 struct bt_lap_ws {
   bt_cand cand;            // ctx-wide candidate lists (3 lists)
   int32_t* label = nullptr;     // [rows]
   int32_t* collabel = nullptr;  // [cols]
-  int32_t* compidx = nullptr;   // [rows]  component index of a root row
+  int32_t* indeg = nullptr;     // [cols]  valid in-degree
+  int32_t* nvalid = nullptr;    // [rows]  valid out-degree
+  int32_t* onlycol = nullptr;   // [rows]  a valid column of the row (the only one when nvalid == 1)
+  int32_t* clist = nullptr;     // [rows]  complex rows
+  int32_t* compidx = nullptr;   // [rows]  component index of a root row (indexed by row)
+  int32_t* isroot = nullptr;    // [rows]  scan scratch (indexed by clist position)
   int32_t* rowcnt = nullptr;    // [rows+1] per component -> exclusive scan = row_start
   int32_t* colcnt = nullptr;    // [rows+1] per component -> exclusive scan = col_start
   int32_t* fill = nullptr;      // [rows]
   int32_t* sorted_rows = nullptr;  // [rows]
-  int32_t* comp_root = nullptr;    // [rows]
-  int32_t* ncomp = nullptr;        // [1]
+  int32_t* counters = nullptr;     // [8]: 0 ncomplex, 1 ncomp, 2/3 changed flags
   double* u = nullptr;             // [rows]
   double* v = nullptr;             // [cols]
   double* dist = nullptr;          // [cols]
@@ -48,19 +60,40 @@ struct bt_lap_ws {
 
 namespace {
 
-constexpr int kSetupThreads = 1024;
+constexpr int kLapThreads = 1024;
+constexpr int kLapMaxCtas = 8;
 constexpr int kInf = 0x7fffffff;
+
+struct LapStage {
+  int list;
+  double thresh;
+  const int32_t* row_block;  // edge valid only if row_block[r] < 0 (nullptr: all rows)
+  const int32_t* col_block;  // edge valid only if col_block[c] < 0
+  int32_t* x;
+  int32_t* y;
+};
+struct LapParams {
+  LapStage st[3];
+  int nstages;
+  int n, m;
+  int debug;   // BT_LAP_DEBUG=1: phase timestamps (ns) by device printf
+};
 
 __device__ __forceinline__ bool edge_ok(const int32_t* __restrict__ col_block, int c) {
   return col_block == nullptr || col_block[c] < 0;
 }
 
-// exclusive scan of data[0..n) in place, returns total; all threads of the (single) CTA call it
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// exclusive scan of data[0..n) in place by ONE CTA, returns total
 __device__ int block_exclusive_scan(int32_t* data, int n, int32_t* s_warp, int32_t* s_carry) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *s_carry = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += kSetupThreads) {
+  for (int base = 0; base < n; base += kLapThreads) {
     const int i = base + tid;
     const int val = (i < n) ? data[i] : 0;
     int incl = val;
@@ -78,115 +111,17 @@ __device__ int block_exclusive_scan(int32_t* data, int n, int32_t* s_warp, int32
         const int t = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += t;
       }
-      s_warp[lane] = w;  // inclusive over warps
+      s_warp[lane] = w;
     }
     __syncthreads();
     const int carry = *s_carry;
     const int warp_off = (warp == 0) ? 0 : s_warp[warp - 1];
     if (i < n) data[i] = carry + warp_off + incl - val;
     __syncthreads();
-    if (tid == kSetupThreads - 1) *s_carry = carry + s_warp[31];
+    if (tid == kLapThreads - 1) *s_carry = carry + s_warp[31];
     __syncthreads();
   }
   return *s_carry;
-}
-
-__global__ void __launch_bounds__(kSetupThreads)
-lap_setup_kernel(bt_cand cand, int list, int n, int m, const int32_t* __restrict__ row_block,
-                 const int32_t* __restrict__ col_block, bt_lap_ws ws, int32_t* __restrict__ x,
-                 int32_t* __restrict__ y) {
-  __shared__ int32_t s_warp[32];
-  __shared__ int32_t s_carry;
-  __shared__ int s_changed;
-  const int tid = threadIdx.x;
-  const int32_t* cnt = cand.cnt + (size_t)list * cand.rows_cap;
-  const int32_t* ecol = cand.col + (size_t)list * cand.rows_cap * cand.stride;
-
-  for (int c = tid; c < m; c += kSetupThreads) {
-    y[c] = -1;
-    ws.collabel[c] = kInf;
-    ws.v[c] = 0.0;
-    ws.seen[c] = 0;
-    ws.insc[c] = 0;
-  }
-  for (int r = tid; r <= n; r += kSetupThreads) {
-    ws.rowcnt[r] = 0;
-    ws.colcnt[r] = 0;
-  }
-  for (int r = tid; r < n; r += kSetupThreads) {
-    x[r] = -1;
-    ws.u[r] = 0.0;
-    ws.fill[r] = 0;
-    int lab = kInf;
-    if (row_block == nullptr || row_block[r] < 0) {
-      const int deg = cnt[r];
-      const int32_t* e = ecol + (size_t)r * cand.stride;
-      for (int k = 0; k < deg; ++k)
-        if (edge_ok(col_block, e[k])) { lab = r; break; }
-    }
-    ws.label[r] = lab;
-  }
-  __syncthreads();
-
-  // ---- connected components: min-label propagation over edges + pointer jumping ----
-  while (true) {
-    if (tid == 0) s_changed = 0;
-    __syncthreads();
-    bool changed = false;
-    for (int r = tid; r < n; r += kSetupThreads) {
-      int lr = ws.label[r];
-      if (lr == kInf) continue;
-      const int deg = cnt[r];
-      const int32_t* e = ecol + (size_t)r * cand.stride;
-      const int l0 = lr;
-      for (int k = 0; k < deg; ++k) {
-        const int c = e[k];
-        if (!edge_ok(col_block, c)) continue;
-        const int lc = ws.collabel[c];
-        if (lc < lr) lr = lc;
-        else if (lc > lr) { atomicMin(&ws.collabel[c], lr); changed = true; }
-      }
-      if (lr < l0) { atomicMin(&ws.label[r], lr); changed = true; }
-    }
-    __syncthreads();
-    for (int r = tid; r < n; r += kSetupThreads) {
-      const int l = ws.label[r];
-      if (l == kInf) continue;
-      const int ll = ws.label[l];
-      if (ll < l) { atomicMin(&ws.label[r], ll); changed = true; }
-    }
-    if (changed) s_changed = 1;
-    __syncthreads();
-    const int any = s_changed;
-    __syncthreads();
-    if (!any) break;
-  }
-
-  // ---- component bookkeeping ----
-  for (int r = tid; r < n; r += kSetupThreads) ws.compidx[r] = (ws.label[r] == r) ? 1 : 0;
-  __syncthreads();
-  const int ncomp = block_exclusive_scan(ws.compidx, n, s_warp, &s_carry);
-  for (int r = tid; r < n; r += kSetupThreads) {
-    const int l = ws.label[r];
-    if (l == kInf) continue;
-    if (l == r) ws.comp_root[ws.compidx[r]] = r;
-    atomicAdd(&ws.rowcnt[ws.compidx[l]], 1);
-  }
-  for (int c = tid; c < m; c += kSetupThreads) {
-    const int l = ws.collabel[c];
-    if (l != kInf) atomicAdd(&ws.colcnt[ws.compidx[l]], 1);
-  }
-  if (tid == 0) { *ws.ncomp = ncomp; }
-  __syncthreads();
-  block_exclusive_scan(ws.rowcnt, ncomp + 1, s_warp, &s_carry);
-  block_exclusive_scan(ws.colcnt, ncomp + 1, s_warp, &s_carry);
-  for (int r = tid; r < n; r += kSetupThreads) {
-    const int l = ws.label[r];
-    if (l == kInf) continue;
-    const int k = ws.compidx[l];
-    const int pos = ws.rowcnt[k] + atomicAdd(&ws.fill[k], 1);
-    ws.sorted_rows[pos] = r;
-  }
 }
 
 struct MinPair { double d; int c; int freecol; };
@@ -198,18 +133,26 @@ __device__ __forceinline__ bool better(const MinPair& a, const MinPair& b) {
   return a.c < b.c;
 }
 
-__global__ void __launch_bounds__(256)
-lap_solve_kernel(bt_cand cand, int list, double thresh, const int32_t* __restrict__ col_block,
-                 bt_lap_ws ws, int32_t* __restrict__ x, int32_t* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int ncomp = *ws.ncomp;
-  const int32_t* cnt = cand.cnt + (size_t)list * cand.rows_cap;
-  const int32_t* ecol = cand.col + (size_t)list * cand.rows_cap * cand.stride;
-  const double* ecost = cand.cost + (size_t)list * cand.rows_cap * cand.stride;
+// Arrays the component solver works on: global scratch (large problems) or shared memory of CTA 0
+// with local row / column ids (the usual case: a handful of complex rows).
+struct SolveArrays {
+  const int32_t* rowcnt; const int32_t* colcnt;   // component -> row-list start, scratch start
+  int32_t* sorted_rows; int32_t* touched; int32_t* treerows;
+  double* u; double* v; double* dist;
+  int32_t* pathrow; int32_t* seen; int32_t* insc;
+  const int32_t* rstart;   // CSR edge start per row, or nullptr: row * stride
+  size_t stride;
+};
+__device__ __forceinline__ size_t ebase(const SolveArrays& a, int row) {
+  return a.rstart ? (size_t)a.rstart[row] : (size_t)row * a.stride;
+}
 
-  for (int comp = warp_global; comp < ncomp; comp += nwarps) {
+// one warp solves one connected component exactly
+__device__ void solve_component(const SolveArrays& ws, int comp, double thresh,
+                                const int32_t* col_block, const int32_t* cnt,
+                                const int32_t* ecol, const double* ecost,
+                                int32_t* x, int32_t* y, int lane) {
+  {
     const int r0 = ws.rowcnt[comp], nr = ws.rowcnt[comp + 1] - r0;
     const int c0 = ws.colcnt[comp];
     int32_t* rows = ws.sorted_rows + r0;
@@ -222,9 +165,9 @@ lap_solve_kernel(bt_cand cand, int list, double thresh, const int32_t* __restric
       const int deg = cnt[r];
       MinPair best{DBL_MAX, kInf, 0};
       for (int k = lane; k < deg; k += 32) {
-        const int c = ecol[(size_t)r * cand.stride + k];
+        const int c = ecol[ebase(ws, r) + k];
         if (!edge_ok(col_block, c)) continue;
-        MinPair cur{ecost[(size_t)r * cand.stride + k], c, 0};
+        MinPair cur{ecost[ebase(ws, r) + k], c, 0};
         if (better(cur, best)) best = cur;
       }
 #pragma unroll
@@ -233,7 +176,7 @@ lap_solve_kernel(bt_cand cand, int list, double thresh, const int32_t* __restric
         if (better(oth, best)) best = oth;
       }
       if (lane == 0 && best.c != kInf) { x[r] = best.c; y[best.c] = r; }
-      continue;
+      return;
     }
 
     // deterministic processing order: ascending row index (rank sort of the scattered list)
@@ -277,9 +220,9 @@ lap_solve_kernel(bt_cand cand, int list, double thresh, const int32_t* __restric
           bool fresh = false;
           int c = -1;
           if (k < deg) {
-            c = ecol[(size_t)i * cand.stride + k];
+            c = ecol[ebase(ws, i) + k];
             if (edge_ok(col_block, c) && ws.insc[c] != sid) {
-              const double r = minVal + (ecost[(size_t)i * cand.stride + k] - thresh) - ui - ws.v[c];
+              const double r = minVal + (ecost[ebase(ws, i) + k] - thresh) - ui - ws.v[c];
               if (ws.seen[c] != sid) {
                 ws.seen[c] = sid;
                 ws.dist[c] = r;
@@ -364,6 +307,326 @@ lap_solve_kernel(bt_cand cand, int list, double thresh, const int32_t* __restric
   }
 }
 
+// ---- on-chip path for the usual case: a handful of complex rows -------------------------------
+// CTA 0 pulls the complex rows' valid edges into shared memory (CSR, local row ids; a column's
+// local id is the smallest local edge index that touches it), labels components, groups them and
+// lets its 32 warps solve them -- all with shared-memory latencies instead of L2 round trips.
+constexpr int kSmallRows = 512;
+constexpr int kSmallEdges = 2048;
+
+struct SmallSmem {
+  int32_t rg[kSmallRows], rdeg[kSmallRows], rstart[kSmallRows + 1], rlabel[kSmallRows], xl[kSmallRows];
+  int32_t sorted_rows[kSmallRows], treerows[kSmallRows], compidx[kSmallRows], isroot[kSmallRows];
+  int32_t rowcnt[kSmallRows + 1], colcnt[kSmallRows + 1], fill[kSmallRows + 1];
+  double u[kSmallRows];
+  int32_t lcl[kSmallEdges];
+  double ecst[kSmallEdges];
+  int32_t cglob[kSmallEdges], clabel[kSmallEdges], pathrow[kSmallEdges], seen[kSmallEdges], insc[kSmallEdges];
+  int32_t yl[kSmallEdges], touched[kSmallEdges];
+  double v[kSmallEdges], dist[kSmallEdges];
+  int changed;
+};
+
+__device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, const LapStage& S, int nC,
+                                    const int32_t* cnt, const int32_t* ecol, const double* ecost,
+                                    int32_t* x, int32_t* y, SmallSmem& sm, int32_t* s_warp, int32_t* s_carry) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // S1: valid degree per complex row -> CSR offsets
+  for (int i = tid; i < nC; i += kLapThreads) {
+    const int r = W.clist[i];
+    sm.rg[i] = r;
+    const int deg = cnt[r];
+    const int32_t* e = ecol + (size_t)r * cand.stride;
+    int v = 0;
+    for (int k = 0; k < deg; ++k) v += edge_ok(S.col_block, e[k]) ? 1 : 0;
+    sm.rdeg[i] = v;
+    sm.rstart[i] = v;
+    sm.rlabel[i] = i;
+    sm.xl[i] = -1;
+    sm.u[i] = 0.0;
+  }
+  if (tid == 0) sm.rstart[nC] = 0;
+  __syncthreads();
+  const int E = block_exclusive_scan(sm.rstart, nC + 1, s_warp, s_carry);
+  // S2: edges; column representative = smallest local edge index touching the column
+  for (int i = tid; i < nC; i += kLapThreads) {
+    const int r = sm.rg[i];
+    const int deg = cnt[r];
+    const int32_t* e = ecol + (size_t)r * cand.stride;
+    const double* w = ecost + (size_t)r * cand.stride;
+    int pos = sm.rstart[i];
+    for (int k = 0; k < deg; ++k) {
+      const int c = e[k];
+      if (!edge_ok(S.col_block, c)) continue;
+      sm.lcl[pos] = c;               // global column for now
+      sm.ecst[pos] = w[k];
+      atomicMin(&W.collabel[c], pos);
+      ++pos;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += kLapThreads) {
+    const int c = sm.lcl[e];
+    const int rep = __ldcg(&W.collabel[c]);
+    sm.lcl[e] = rep;
+    if (rep == e) sm.cglob[e] = c;
+    sm.clabel[e] = kInf;
+    sm.v[e] = 0.0;
+    sm.seen[e] = 0;
+    sm.insc[e] = 0;
+    sm.yl[e] = -1;
+  }
+  __syncthreads();
+  // S4: components by min-label propagation + pointer jumping (shared memory)
+  while (true) {
+    if (tid == 0) sm.changed = 0;
+    __syncthreads();
+    bool changed = false;
+    for (int i = tid; i < nC; i += kLapThreads) {
+      int lr = sm.rlabel[i];
+      const int l0 = lr;
+      for (int k = sm.rstart[i]; k < sm.rstart[i] + sm.rdeg[i]; ++k) {
+        const int c = sm.lcl[k];
+        const int lc = sm.clabel[c];
+        if (lc < lr) lr = lc;
+        else if (lc > lr) { atomicMin(&sm.clabel[c], lr); changed = true; }
+      }
+      if (lr < l0) { atomicMin(&sm.rlabel[i], lr); changed = true; }
+    }
+    __syncthreads();
+    for (int i = tid; i < nC; i += kLapThreads) {
+      const int l = sm.rlabel[i];
+      const int ll = sm.rlabel[l];
+      if (ll < l) { atomicMin(&sm.rlabel[i], ll); changed = true; }
+    }
+    if (changed) sm.changed = 1;
+    __syncthreads();
+    const int any = sm.changed;
+    __syncthreads();
+    if (!any) break;
+  }
+  // S5: grouping
+  for (int i = tid; i < nC; i += kLapThreads) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
+  for (int i = tid; i <= nC; i += kLapThreads) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
+  __syncthreads();
+  const int ncomp = block_exclusive_scan(sm.isroot, nC, s_warp, s_carry);
+  for (int i = tid; i < nC; i += kLapThreads)
+    if (sm.rlabel[i] == i) sm.compidx[i] = sm.isroot[i];
+  __syncthreads();
+  for (int i = tid; i < nC; i += kLapThreads) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
+  for (int e = tid; e < E; e += kLapThreads)
+    if (sm.lcl[e] == e) atomicAdd(&sm.colcnt[sm.compidx[sm.clabel[e]]], 1);
+  __syncthreads();
+  block_exclusive_scan(sm.rowcnt, ncomp + 1, s_warp, s_carry);
+  block_exclusive_scan(sm.colcnt, ncomp + 1, s_warp, s_carry);
+  for (int i = tid; i < nC; i += kLapThreads) {
+    const int k = sm.compidx[sm.rlabel[i]];
+    sm.sorted_rows[sm.rowcnt[k] + atomicAdd(&sm.fill[k], 1)] = i;
+  }
+  __syncthreads();
+  // S6: one warp per component, everything in shared memory
+  const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
+                      sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
+  for (int comp = warp; comp < ncomp; comp += kLapThreads / 32)
+    solve_component(A, comp, S.thresh, nullptr, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl, lane);
+  __syncthreads();
+  // S7: write back with global ids
+  for (int i = tid; i < nC; i += kLapThreads) {
+    const int c = sm.xl[i];
+    if (c >= 0) {
+      x[sm.rg[i]] = sm.cglob[c];
+      y[sm.cglob[c]] = sm.rg[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kLapThreads, 1)
+lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
+  __shared__ int32_t s_warp[32];
+  __shared__ int32_t s_carry;
+  extern __shared__ __align__(16) unsigned char lap_dyn_smem[];
+  SmallSmem& sm = *reinterpret_cast<SmallSmem*>(lap_dyn_smem);
+  uint32_t nctas, crank;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nctas));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gtid = (int)crank * kLapThreads + tid;
+  const int GT = (int)nctas * kLapThreads;
+  const int gwarp = gtid >> 5, nwarps = GT >> 5;
+  const int n = P.n, m = P.m;
+  unsigned long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define LAP_T(i) do { if (P.debug && gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[i])); } while (0)
+  LAP_T(0);
+
+  // ---- P0 (all stages at once): outputs and per-stage scratch ----
+  for (int stage = 0; stage < P.nstages; ++stage) {
+    const LapStage S = P.st[stage];
+    const size_t co = (size_t)stage * ws.cols, ro = (size_t)stage * ws.rows;
+    for (int c = gtid; c < m; c += GT) {
+      S.y[c] = -1;
+      ws.collabel[co + c] = kInf;
+      ws.indeg[co + c] = 0;
+      ws.v[co + c] = 0.0;
+      ws.seen[co + c] = 0;
+      ws.insc[co + c] = 0;
+    }
+    for (int r = gtid; r < n; r += GT) {
+      S.x[r] = -1;
+      ws.u[ro + r] = 0.0;
+    }
+  }
+  if (gtid < 24) ws.counters[gtid] = 0;
+  cluster_barrier();
+  LAP_T(1);
+
+  for (int stage = 0; stage < P.nstages; ++stage) {
+    const LapStage S = P.st[stage];
+    if (cand.total[S.list] == 0) continue;   // nothing was emitted for this stage (cluster-uniform)
+    bt_lap_ws W = ws;                          // this stage's slices of the scratch arrays
+    W.collabel += (size_t)stage * ws.cols; W.indeg += (size_t)stage * ws.cols; W.v += (size_t)stage * ws.cols;
+    W.seen += (size_t)stage * ws.cols; W.insc += (size_t)stage * ws.cols; W.u += (size_t)stage * ws.rows;
+    W.counters += stage * 8;
+    int32_t* cnt = cand.deg + (size_t)S.list * cand.rows_cap;
+    int32_t* ecol = cand.col + (size_t)S.list * cand.rows_cap * cand.stride;
+    double* ecost = cand.cost + (size_t)S.list * cand.rows_cap * cand.stride;
+    int32_t* x = S.x;
+    int32_t* y = S.y;
+
+    // ---- P1: compact the row's segments (in place, ascending copy), valid degree, column in-degree ----
+    int my_valid = 0, my_last = -1;   // the thread's first row stays in registers for P2
+    for (int r = gtid; r < n; r += GT) {
+      W.label[r] = kInf;
+      int total = 0, valid = 0, last = -1;
+      if (S.row_block == nullptr || S.row_block[r] < 0) {
+        const int32_t* segcnt = cand.cnt + ((size_t)S.list * cand.rows_cap + r) * cand.nseg;
+        int32_t* rc = ecol + (size_t)r * cand.stride;
+        double* rv = ecost + (size_t)r * cand.stride;
+        unsigned long long mask = cand.segmask[(size_t)S.list * cand.rows_cap + r];
+        while (mask) {                          // only the non-empty segments, in ascending order
+          const int g = __ffsll((long long)mask) - 1;
+          mask &= mask - 1;
+          const int k = segcnt[g];
+          const int src = g * BT_CAND_SEG;
+          for (int e = 0; e < k; ++e) {
+            const int c = rc[src + e];
+            if (src + e != total) { rc[total] = c; rv[total] = rv[src + e]; }
+            ++total;
+            if (edge_ok(S.col_block, c)) { ++valid; last = c; atomicAdd(&W.indeg[c], 1); }
+          }
+        }
+      }
+      cnt[r] = total;
+      if (r == gtid) { my_valid = valid; my_last = last; }
+      else { W.nvalid[r] = valid; W.onlycol[r] = last; }
+    }
+    cluster_barrier();
+    LAP_T(2);
+
+    // ---- P2: isolated edges are final; everything else is "complex" ----
+    for (int r = gtid; r < n; r += GT) {
+      const int valid = (r == gtid) ? my_valid : W.nvalid[r];
+      if (valid == 0) continue;
+      const int c = (r == gtid) ? my_last : W.onlycol[r];
+      if (valid == 1 && W.indeg[c] == 1) {
+        x[r] = c;
+        y[c] = r;
+      } else {
+        const int pos = atomicAdd(&W.counters[0], 1);
+        atomicAdd(&W.counters[4], valid);            // valid edges of the complex part
+        W.clist[pos] = r;
+        W.label[r] = r;
+      }
+    }
+    cluster_barrier();
+    const int nC = W.counters[0];
+    LAP_T(3);
+
+    const bool small = nC > 0 && nC <= kSmallRows && W.counters[4] <= kSmallEdges;
+    if (small) {
+      if (crank == 0) small_complex_solve(cand, W, S, nC, cnt, ecol, ecost, x, y, sm, s_warp, &s_carry);
+      LAP_T(4); tq[5] = tq[4];
+    } else if (nC > 0) {
+      // ---- P3: connected components of the complex part ----
+      for (int iter = 0;; ++iter) {
+        int32_t* flag = &W.counters[2 + (iter & 1)];
+        bool changed = false;
+        for (int i = gtid; i < nC; i += GT) {
+          const int r = W.clist[i];
+          int lr = W.label[r];
+          const int l0 = lr;
+          const int deg = cnt[r];
+          const int32_t* e = ecol + (size_t)r * cand.stride;
+          for (int k = 0; k < deg; ++k) {
+            const int c = e[k];
+            if (!edge_ok(S.col_block, c)) continue;
+            const int lc = W.collabel[c];
+            if (lc < lr) lr = lc;
+            else if (lc > lr) { atomicMin(&W.collabel[c], lr); changed = true; }
+          }
+          if (lr < l0) { atomicMin(&W.label[r], lr); changed = true; }
+        }
+        cluster_barrier();
+        for (int i = gtid; i < nC; i += GT) {
+          const int r = W.clist[i];
+          const int l = W.label[r];
+          const int ll = W.label[l];
+          if (ll < l) { atomicMin(&W.label[r], ll); changed = true; }
+        }
+        if (changed) *flag = 1;
+        if (gtid == 0) W.counters[2 + ((iter + 1) & 1)] = 0;   // the other flag, for the next round
+        cluster_barrier();
+        if (*flag == 0) break;
+      }
+
+      LAP_T(4);
+      // ---- P4: component bookkeeping (CTA 0) ----
+      if (crank == 0) {
+        for (int i = tid; i < nC; i += kLapThreads) {
+          const int r = W.clist[i];
+          W.isroot[i] = (W.label[r] == r) ? 1 : 0;
+        }
+        for (int i = tid; i <= nC; i += kLapThreads) { W.rowcnt[i] = 0; W.colcnt[i] = 0; W.fill[i] = 0; }
+        __syncthreads();
+        const int ncomp = block_exclusive_scan(W.isroot, nC, s_warp, &s_carry);
+        for (int i = tid; i < nC; i += kLapThreads) {
+          const int r = W.clist[i];
+          if (W.label[r] == r) W.compidx[r] = W.isroot[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < nC; i += kLapThreads) atomicAdd(&W.rowcnt[W.compidx[W.label[W.clist[i]]]], 1);
+        for (int c = tid; c < m; c += kLapThreads) {
+          const int l = W.collabel[c];
+          if (l != kInf) atomicAdd(&W.colcnt[W.compidx[l]], 1);
+        }
+        if (tid == 0) W.counters[1] = ncomp;
+        __syncthreads();
+        block_exclusive_scan(W.rowcnt, ncomp + 1, s_warp, &s_carry);
+        block_exclusive_scan(W.colcnt, ncomp + 1, s_warp, &s_carry);
+        for (int i = tid; i < nC; i += kLapThreads) {
+          const int r = W.clist[i];
+          const int k = W.compidx[W.label[r]];
+          W.sorted_rows[W.rowcnt[k] + atomicAdd(&W.fill[k], 1)] = r;
+        }
+      }
+      cluster_barrier();
+      LAP_T(5);
+
+      // ---- P5: one warp per component ----
+      const int ncomp = W.counters[1];
+      const SolveArrays GA{W.rowcnt, W.colcnt, W.sorted_rows, W.touched, W.treerows, W.u, W.v, W.dist,
+                           W.pathrow, W.seen, W.insc, nullptr, (size_t)cand.stride};
+      for (int comp = gwarp; comp < ncomp; comp += nwarps)
+        solve_component(GA, comp, S.thresh, S.col_block, cnt, ecol, ecost, x, y, lane);
+    }
+    if (stage + 1 < P.nstages) cluster_barrier();   // x / y of this stage gate the next one
+    LAP_T(6);
+    if (P.debug && gtid == 0)
+      printf("lap stage %d: n=%d m=%d complex=%d comps=%d | init %llu P1 %llu P2 %llu P3 %llu P4 %llu P5 %llu ns\n", stage, n, m,
+             nC, W.counters[1], tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4], tq[6] - tq[5]);
+    LAP_T(1);
+  }
+}
+
 // dense float64 cost -> candidate list (ordered by column): one warp per row
 __global__ void __launch_bounds__(256)
 lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double thresh, bt_cand cand,
@@ -373,20 +636,30 @@ lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double t
   if (row >= n) return;
   int32_t* ecol = cand.col + ((size_t)list * cand.rows_cap + row) * cand.stride;
   double* ecost = cand.cost + ((size_t)list * cand.rows_cap + row) * cand.stride;
+  int32_t* segcnt = cand.cnt + ((size_t)list * cand.rows_cap + row) * cand.nseg;
   int count = 0;
   for (int c0 = 0; c0 < m; c0 += 32) {
+    if (c0 > 0 && (c0 % BT_CAND_SEG) == 0) {     // next segment
+      if (lane == 0) segcnt[c0 / BT_CAND_SEG - 1] = count;
+      count = 0;
+    }
     const int c = c0 + lane;
     const double v = (c < m) ? cost[(size_t)row * m + c] : DBL_MAX;
     const bool keep = (c < m) && (v < thresh);
     const unsigned ball = __ballot_sync(0xffffffffu, keep);
     if (keep) {
-      const int pos = count + __popc(ball & ((1u << lane) - 1));
+      const int pos = (c0 / BT_CAND_SEG) * BT_CAND_SEG + count + __popc(ball & ((1u << lane) - 1));
       ecol[pos] = c;
       ecost[pos] = v;
     }
     count += __popc(ball);
   }
-  if (lane == 0) cand.cnt[(size_t)list * cand.rows_cap + row] = count;
+  if (lane == 0) segcnt[(m - 1) / BT_CAND_SEG] = count;
+  if (lane == 0) {
+    atomicAdd(&cand.total[list], 1);   // any non-zero value means "stage not empty"
+    const int nseg_used = (m - 1) / BT_CAND_SEG + 1;
+    cand.segmask[(size_t)list * cand.rows_cap + row] = (nseg_used >= 64) ? ~0ull : ((1ull << nseg_used) - 1);
+  }
 }
 
 }  // namespace
@@ -397,28 +670,40 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
   const int rows = ctx->max_tracks, cols = ctx->max_dets;
   ws->rows = rows;
   ws->cols = cols;
+  const int stride = (cols + BT_CAND_SEG - 1) / BT_CAND_SEG * BT_CAND_SEG;
   ws->cand.rows_cap = rows;
-  ws->cand.stride = cols;
-  BT_CUDA(cudaMalloc(&ws->cand.cnt, sizeof(int32_t) * 3 * rows));
-  BT_CUDA(cudaMalloc(&ws->cand.col, sizeof(int32_t) * 3 * (size_t)rows * cols));
-  BT_CUDA(cudaMalloc(&ws->cand.cost, sizeof(double) * 3 * (size_t)rows * cols));
-  BT_CUDA(cudaMemset(ws->cand.cnt, 0, sizeof(int32_t) * 3 * rows));
+  ws->cand.stride = stride;
+  ws->cand.nseg = stride / BT_CAND_SEG;
+  const size_t cnt_ints = (3 * (size_t)rows * ws->cand.nseg + 4 + 1) & ~size_t(1);   // keeps segmask 8 B aligned
+  ws->cand.clear_bytes = sizeof(int32_t) * cnt_ints + sizeof(unsigned long long) * 3 * rows;
+  BT_CUDA(cudaMalloc(&ws->cand.cnt, ws->cand.clear_bytes));
+  ws->cand.total = ws->cand.cnt + 3 * (size_t)rows * ws->cand.nseg;   // cleared by the same memset as cnt
+  ws->cand.segmask = reinterpret_cast<unsigned long long*>(ws->cand.cnt + cnt_ints);
+  BT_CUDA(cudaMalloc(&ws->cand.deg, sizeof(int32_t) * 3 * rows));
+  BT_CUDA(cudaMalloc(&ws->cand.col, sizeof(int32_t) * 3 * (size_t)rows * stride));
+  BT_CUDA(cudaMalloc(&ws->cand.cost, sizeof(double) * 3 * (size_t)rows * stride));
+  BT_CUDA(cudaMemset(ws->cand.cnt, 0, ws->cand.clear_bytes));
+  BT_CHECK(ws->cand.nseg <= 64, BT_ERR_CAPACITY, "max_dets %d exceeds %d", cols, 64 * BT_CAND_SEG);
 #define BT_LAP_ALLOC(field, type, count) BT_CUDA(cudaMalloc(&ws->field, sizeof(type) * (size_t)(count)))
   BT_LAP_ALLOC(label, int32_t, rows);
-  BT_LAP_ALLOC(collabel, int32_t, cols);
+  BT_LAP_ALLOC(collabel, int32_t, 3 * (size_t)cols);
+  BT_LAP_ALLOC(indeg, int32_t, 3 * (size_t)cols);
+  BT_LAP_ALLOC(nvalid, int32_t, rows);
+  BT_LAP_ALLOC(onlycol, int32_t, rows);
+  BT_LAP_ALLOC(clist, int32_t, rows);
   BT_LAP_ALLOC(compidx, int32_t, rows);
+  BT_LAP_ALLOC(isroot, int32_t, rows);
   BT_LAP_ALLOC(rowcnt, int32_t, rows + 1);
   BT_LAP_ALLOC(colcnt, int32_t, rows + 1);
-  BT_LAP_ALLOC(fill, int32_t, rows);
+  BT_LAP_ALLOC(fill, int32_t, rows + 1);
   BT_LAP_ALLOC(sorted_rows, int32_t, rows);
-  BT_LAP_ALLOC(comp_root, int32_t, rows);
-  BT_LAP_ALLOC(ncomp, int32_t, 1);
-  BT_LAP_ALLOC(u, double, rows);
-  BT_LAP_ALLOC(v, double, cols);
+  BT_LAP_ALLOC(counters, int32_t, 24);
+  BT_LAP_ALLOC(u, double, 3 * (size_t)rows);
+  BT_LAP_ALLOC(v, double, 3 * (size_t)cols);
   BT_LAP_ALLOC(dist, double, cols);
   BT_LAP_ALLOC(pathrow, int32_t, cols);
-  BT_LAP_ALLOC(seen, int32_t, cols);
-  BT_LAP_ALLOC(insc, int32_t, cols);
+  BT_LAP_ALLOC(seen, int32_t, 3 * (size_t)cols);
+  BT_LAP_ALLOC(insc, int32_t, 3 * (size_t)cols);
   BT_LAP_ALLOC(touched, int32_t, cols);
   BT_LAP_ALLOC(treerows, int32_t, rows);
   BT_LAP_ALLOC(x, int32_t, rows);
@@ -430,9 +715,10 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
 void bt_lap_ws_destroy(bt_ctx* ctx) {
   bt_lap_ws* ws = ctx->lap;
   if (!ws) return;
-  void* ptrs[] = {ws->cand.cnt, ws->cand.col, ws->cand.cost, ws->label, ws->collabel, ws->compidx,
-                  ws->rowcnt, ws->colcnt, ws->fill, ws->sorted_rows, ws->comp_root, ws->ncomp, ws->u,
-                  ws->v, ws->dist, ws->pathrow, ws->seen, ws->insc, ws->touched, ws->treerows, ws->x, ws->y};
+  void* ptrs[] = {ws->cand.cnt, ws->cand.deg, ws->cand.col, ws->cand.cost, ws->label, ws->collabel, ws->indeg,
+                  ws->nvalid, ws->onlycol, ws->clist, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
+                  ws->sorted_rows, ws->counters, ws->u, ws->v, ws->dist, ws->pathrow, ws->seen, ws->insc,
+                  ws->touched, ws->treerows, ws->x, ws->y};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ws;
@@ -449,20 +735,57 @@ int32_t btk_lap_compact_dense(bt_ctx* ctx, const double* cost, int32_t n, int32_
   return BT_OK;
 }
 
+static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const LapParams& P) {
+  BT_CHECK(P.n <= ctx->lap->rows && P.m <= ctx->lap->cols, BT_ERR_CAPACITY,
+           "linear assignment %d x %d exceeds ctx capacity %d x %d", P.n, P.m, ctx->lap->rows, ctx->lap->cols);
+  if (P.n <= 0 && P.m <= 0) return BT_OK;
+  const int work = P.n > P.m ? P.n : P.m;
+  int nctas = (work + 255) / 256;          // ~256 rows per CTA keeps every thread busy in the row phases
+  if (nctas < 1) nctas = 1;
+  if (nctas > kLapMaxCtas) nctas = kLapMaxCtas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nctas);
+  cfg.blockDim = dim3(kLapThreads);
+  cfg.dynamicSmemBytes = sizeof(SmallSmem);
+  cfg.stream = ctx->stream;
+  static bool attr_done = false;
+  if (!attr_done) {
+    BT_CUDA(cudaFuncSetAttribute(lap_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SmallSmem)));
+    attr_done = true;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BT_CUDA(cudaLaunchKernelEx(&cfg, lap_cluster_kernel, cand, *ctx->lap, P));
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
 int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n, int32_t m,
                       double thresh, const int32_t* row_block, const int32_t* col_block, int32_t* x,
                       int32_t* y) {
-  BT_CHECK(n <= ctx->lap->rows && m <= ctx->lap->cols, BT_ERR_CAPACITY,
-           "linear assignment %d x %d exceeds ctx capacity %d x %d", n, m, ctx->lap->rows, ctx->lap->cols);
-  if (n <= 0 && m <= 0) return BT_OK;
-  lap_setup_kernel<<<1, kSetupThreads, 0, ctx->stream>>>(cand, list, n, m, row_block, col_block, *ctx->lap, x, y);
-  BT_LAUNCHED(ctx);
-  if (n > 0 && m > 0) {
-    const int warps = n;
-    int blocks = (warps * 32 + 255) / 256;
-    if (blocks > 4 * ctx->num_sms) blocks = 4 * ctx->num_sms;
-    lap_solve_kernel<<<blocks, 256, 0, ctx->stream>>>(cand, list, thresh, col_block, *ctx->lap, x, y);
-    BT_LAUNCHED(ctx);
-  }
-  return BT_OK;
+  LapParams P = {};
+  P.nstages = 1;
+  P.n = n;
+  P.m = m;
+  P.st[0] = LapStage{list, thresh, row_block, col_block, x, y};
+  return launch_lap(ctx, cand, P);
+}
+
+int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, int32_t n, int32_t m, const double thresh[3],
+                       int32_t* const x[3], int32_t* const y[3]) {
+  LapParams P = {};
+  P.nstages = 3;
+  P.n = n;
+  P.m = m;
+  P.st[0] = LapStage{0, thresh[0], nullptr, nullptr, x[0], y[0]};
+  P.st[1] = LapStage{1, thresh[1], x[0], nullptr, x[1], y[1]};   // stage 2: rows unmatched in stage 1
+  P.st[2] = LapStage{2, thresh[2], nullptr, y[0], x[2], y[2]};   // stage 3: columns unmatched in stage 1
+  P.debug = getenv("BT_LAP_DEBUG") != nullptr;
+  return launch_lap(ctx, cand, P);
 }

@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -44,6 +45,7 @@ struct EpiParams {
   double* out_dists;
   int dense_stage;
   int n, m;
+  int debug;   // BT_ASSOC_DEBUG=1: per-CTA phase timestamps via device printf (profiling aid)
 };
 
 __device__ __forceinline__ double iou_dist_f64(const double* __restrict__ a, const double* __restrict__ b) {
@@ -70,9 +72,19 @@ __device__ __forceinline__ double fuse_stage3(double iou_d, float sim, float app
   return fmin(iou_d, (double)emb);
 }
 
+// atomic append into the (row, column-segment) sub-list (CUDA-core kernel: several threads share a row)
 __device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int col, double cost) {
-  const int k = atomicAdd(c.cnt + (size_t)list * c.rows_cap + row, 1);
-  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + k;
+  const int seg = col / BT_CAND_SEG;
+  const int k = atomicAdd(c.cnt + ((size_t)list * c.rows_cap + row) * c.nseg + seg, 1);
+  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * BT_CAND_SEG + k;
+  c.col[base] = col;
+  c.cost[base] = cost;
+  atomicAdd(&c.total[list], 1);
+  if (k == 0) atomicOr(&c.segmask[(size_t)list * c.rows_cap + row], 1ull << seg);
+}
+// plain append: the caller owns (row, segment) exclusively and keeps the count in a register
+__device__ __forceinline__ void emit_owned(const bt_cand& c, int list, int row, int seg, int k, int col, double cost) {
+  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * BT_CAND_SEG + k;
   c.col[base] = col;
   c.cost[base] = cost;
 }
@@ -144,6 +156,32 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in cta_mask and
+// signals the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tmap, int x, int y,
+                                               uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y),
+        "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -195,7 +233,9 @@ constexpr int BK = 64;       // 64 fp16 = one 128 B swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kEpiWarps = 8;     // two per SM sub-partition: warp w and w+4 share TMEM lane quarter w%4
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kTcThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN>
 struct TcSmem {
@@ -204,18 +244,30 @@ struct TcSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColF32Off = kStages * kStageBytes;            // float4[BN]  det box fp32
   static constexpr int kColKindOff = kColF32Off + BN * 16;            // uint8[BN]
-  static constexpr int kBarOff = kColKindOff + BN;                    // barriers (8B aligned: BN%8==0)
+  static constexpr int kColValidOff = kColKindOff + BN;               // uint32[BN/32] bit c: kind != NONE
+  static constexpr int kColF64Off = kColValidOff + 64;                // double[BN][4] det box float64 (exact path)
+  static constexpr int kBarOff = kColF64Off + BN * 32;                // barriers (8B aligned)
   static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
   static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024 B alignment
 };
 
-template <int BN, bool kDense>
+// Thread-block cluster of CM x CN CTAs (cluster rank = rm * CN + rn) covering CM x CN adjacent output
+// tiles.  The CN CTAs of a cluster row need the same A tile and the CM CTAs of a cluster column the
+// same B tile: every CTA loads a 1/CN slice of its A tile and a 1/CM slice of its B tile and TMA
+// multicasts them to its row / column mates, cutting the L2->SM operand traffic per CTA from
+// (BM + BN) to (BM/CN + BN/CM) rows per k-block (the v1 kernel was bound by exactly that traffic,
+// profiles/README.md).
+template <int BN, bool kDense, int CM, int CN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 EpiParams p, int d) {
   using L = TcSmem<BN>;
+  constexpr int CS = CM * CN;
+  constexpr int kASlice = BM / CN, kBSlice = BN / CM;  // rows each CTA loads itself
+  static_assert(kASlice % 8 == 0 && kBSlice % 8 == 0, "slices must keep the 8-row swizzle atoms whole");
+  static_assert(BN == 2 * BT_CAND_SEG, "one epilogue thread owns one (row, candidate segment) pair");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -225,11 +277,26 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   float4* s_col32 = reinterpret_cast<float4*>(smem + L::kColF32Off);
   uint8_t* s_colkind = smem + L::kColKindOff;
+  uint32_t* s_colvalid = reinterpret_cast<uint32_t*>(smem + L::kColValidOff);
+  double* s_col64 = reinterpret_cast<double*>(smem + L::kColF64Off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = clock64();
   const int tiles_m = (p.n + BM - 1) / BM, tiles_n = (p.m + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = d / BK;
+  // cluster geometry: cluster `cid` walks "cluster tiles" of CM x CN output tiles; tiles past the
+  // matrix edge are still executed by their CTA (TMA zero-fills, the epilogue masks) so that every
+  // CTA of a cluster runs the same number of pipeline steps.
+  const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
+  const int rm = crank / CN, rn = crank % CN;
+  const int cid = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+  const int ctiles_n = (tiles_n + CN - 1) / CN;
+  const int num_ctiles = ((tiles_m + CM - 1) / CM) * ctiles_n;
+  uint16_t row_mask = 0, col_mask = 0;   // my cluster-row mates (share A), my cluster-column mates (share B)
+#pragma unroll
+  for (int j = 0; j < CN; ++j) row_mask |= (uint16_t)(1u << (rm * CN + j));
+#pragma unroll
+  for (int i = 0; i < CM; ++i) col_mask |= (uint16_t)(1u << (i * CN + rn));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -237,8 +304,9 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+      // a slot is free again when every CTA that receives my slices has consumed it
+      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CM + CN - 1); }
+      for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -249,7 +317,8 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -258,14 +327,17 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
+        const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);   // the whole stage lands here (own + mates' slices)
           uint8_t* sa = smem + stage * L::kStageBytes;
-          tma_load_2d(sa, &tmap_a, kb * BK, m0, &full_bar[stage]);
-          tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, n0, &full_bar[stage]);
+          uint8_t* sb = sa + L::kABytes;
+          if (CN > 1) tma_load_2d_mc(sa + rn * kASlice * 128, &tmap_a, kb * BK, m0 + rn * kASlice, &full_bar[stage], row_mask);
+          else tma_load_2d(sa, &tmap_a, kb * BK, m0, &full_bar[stage]);
+          if (CM > 1) tma_load_2d_mc(sb + rm * kBSlice * 128, &tmap_b, kb * BK, n0 + rm * kBSlice, &full_bar[stage], col_mask);
+          else tma_load_2d(sb, &tmap_b, kb * BK, n0, &full_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -277,7 +349,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -293,7 +365,9 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                             (uint32_t)((kb | k) != 0));
           }
-          tcgen05_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (here and at every mate that multicasts into it) when these MMAs retire
+          if (CS > 1) tcgen05_commit_mc(&empty_bar[stage], (uint16_t)(row_mask | col_mask));
+          else tcgen05_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
@@ -301,42 +375,60 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
     }
   } else {
-    // ===== epilogue: 4 warps, warp w owns TMEM lanes [32*(w%4), +32) =====
+    // ===== epilogue: 8 warps; warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a
+    // lane quarter split the tile's columns in halves of BN/2 =====
     const int quarter = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
+    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
+      const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
       const int row = m0 + quarter * 32 + lane;
       int rkind = BT_ROW_NONE;
       float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      double rbox[4] = {0.0, 0.0, 0.0, 0.0};
       if (!kDense) {
         // stage this tile's detection boxes (fp32, exact: integer pixels) and kinds
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
-        for (int c = et; c < BN; c += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // previous tile's readers are done
+        for (int c = et; c < BN; c += kEpiThreads) {
           const int col = n0 + c;
           float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
           uint8_t ck = BT_COL_NONE;
+          double4 cd = make_double4(0.0, 0.0, 0.0, 0.0);
           if (col < p.m) {
-            const double* s = p.col_tlbr + (size_t)col * 4;
-            cb = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+            const double2* s = reinterpret_cast<const double2*>(p.col_tlbr + (size_t)col * 4);
+            const double2 lo = s[0], hi = s[1];
+            cd = make_double4(lo.x, lo.y, hi.x, hi.y);
+            cb = make_float4((float)lo.x, (float)lo.y, (float)hi.x, (float)hi.y);
             ck = p.col_kind[col];
           }
           s_col32[c] = cb;
           s_colkind[c] = ck;
+          reinterpret_cast<double2*>(s_col64 + c * 4)[0] = make_double2(cd.x, cd.y);
+          reinterpret_cast<double2*>(s_col64 + c * 4)[1] = make_double2(cd.z, cd.w);
+          const uint32_t vmask = __ballot_sync(0xffffffffu, ck != BT_COL_NONE);   // c>>5 is warp-uniform
+          if (lane == 0) s_colvalid[c >> 5] = vmask;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (row < p.n) {
           rkind = p.row_kind[row];
           rb = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
+          if (rkind != BT_ROW_NONE) {
+            const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (size_t)row * 4);
+            const double2 lo = s[0], hi = s[1];
+            rbox[0] = lo.x; rbox[1] = lo.y; rbox[2] = hi.x; rbox[3] = hi.y;
+          }
         }
       }
+      int cnt_a = 0, cnt_b = 0;   // edges this thread appended for its row in this column segment
+      const int seg = n0 / BT_CAND_SEG + half;
       mbar_wait(&tmem_full[acc], acc_phase);
+      const long long t_acc = clock64();
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half * (BN / 64); ch < (half + 1) * (BN / 64); ++ch) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), v);
         tmem_ld_wait();
@@ -349,30 +441,80 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           }
         } else if (rkind != BT_ROW_NONE) {
+          // Pass 1 (branch-free, all 32 shared loads independent): which of the 32 pairs can have
+          // a cost below 1?  Conservative fp32 overlap test (row box rounded outward, detection
+          // boxes exact integers: false => exact IoU is 0) OR appearance gate open.
+          const uint32_t colbase = smem_u32(s_col32) + (uint32_t)(ch * 32) * 16u;
+          uint32_t hot = 0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            const int lc = ch * 32 + c;
-            const int ckind = s_colkind[lc];
+            float4 cb;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(cb.x), "=f"(cb.y), "=f"(cb.z), "=f"(cb.w)
+                         : "r"(colbase + (uint32_t)c * 16u));
             const float sim = __uint_as_float(v[c]);
-            const float4 cb = s_col32[lc];
-            // conservative fp32 overlap test: false => exact IoU is 0 (row box interval is
-            // rounded outward, detection boxes are exact integers)
             const bool ov = (fminf(rb.z, cb.z) > fmaxf(rb.x, cb.x)) && (fminf(rb.w, cb.w) > fmaxf(rb.y, cb.y));
             const bool app = !((1.0f - sim) > p.appearance);
-            if (ckind != BT_COL_NONE && (ov || app || p.face_sim != nullptr))
-              assoc_exact(p, row, n0 + lc, sim, rkind, ckind);
+            hot |= (uint32_t)(ov || app) << c;
           }
+          if (p.face_sim != nullptr) hot = 0xffffffffu;
+          hot &= s_colvalid[ch];
+          // Pass 2 (rare): exact float64 IoU + fusion rule + candidate emission for the survivors.
+          // Lanes walk their own hot bits in lock-step (lane i handles its k-th survivor while lane j
+          // handles its own), so a warp pays max-over-lanes iterations, not the sum.
+          while (hot) {
+            const int c = __ffs(hot) - 1;
+            hot &= hot - 1;
+            float sim = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (c == k) sim = __uint_as_float(v[k]);
+            const int lc = ch * 32 + c;
+            const int col = n0 + lc;
+            const int ckind = s_colkind[lc];
+            const double iou_d = iou_dist_f64(rbox, s_col64 + lc * 4);
+            const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
+            if (rkind == BT_ROW_UNCONFIRMED) {
+              if (ckind == BT_COL_HIGH) {
+                const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+                if (c3 < p.unconf_thresh) emit_owned(p.cand, 2, row, seg, cnt_a++, col, c3);
+              }
+            } else if (ckind == BT_COL_HIGH) {
+              const double c1 = fuse_stage1(iou_d, sim, face, p.appearance);
+              if (c1 < p.match_thresh) emit_owned(p.cand, 0, row, seg, cnt_a++, col, c1);
+            } else if (ckind == BT_COL_LOW && rkind == BT_ROW_POOL_TRACKED) {
+              if (iou_d < p.second_thresh) emit_owned(p.cand, 1, row, seg, cnt_b++, col, iou_d);
+            }
+          }
+        }
+      }
+      if (!kDense && rkind != BT_ROW_NONE) {
+        const int la = (rkind == BT_ROW_UNCONFIRMED) ? 2 : 0;
+        if (cnt_a) {
+          p.cand.cnt[((size_t)la * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_a;
+          atomicAdd(&p.cand.total[la], cnt_a);
+          atomicOr(&p.cand.segmask[(size_t)la * p.cand.rows_cap + row], 1ull << seg);
+        }
+        if (cnt_b) {
+          p.cand.cnt[((size_t)1 * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_b;
+          atomicAdd(&p.cand.total[1], cnt_b);
+          atomicOr(&p.cand.segmask[(size_t)1 * p.cand.rows_cap + row], 1ull << seg);
         }
       }
       tcgen05_fence_before();
       __syncwarp();
+      if (p.debug && et == 0 && (blockIdx.x % 37) == 0)
+        printf("cta %d: accumulator ready at %lld cycles, epilogue done at %lld\n", blockIdx.x, t_acc - t_start,
+               clock64() - t_start);
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CS > 1) cluster_sync_all();   // no CTA leaves while a mate may still arrive on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -444,7 +586,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct bt_gemm_ws {
   PFN_encodeTiled encode = nullptr;
-  bool attr_set = false;
+  struct Entry { const void* base; int rows, d, box_rows; CUtensorMap map; };
+  Entry cache[8] = {};
+  int next = 0;
 };
 
 int32_t bt_gemm_ws_create(bt_ctx* ctx) {
@@ -464,6 +608,9 @@ void bt_gemm_ws_destroy(bt_ctx* ctx) {
 }
 
 static int32_t make_tmap(bt_ctx* ctx, CUtensorMap* tm, const __half* base, int rows, int d, int box_rows) {
+  bt_gemm_ws* ws = ctx->gemm;
+  for (const auto& e : ws->cache)
+    if (e.base == base && e.rows == rows && e.d == d && e.box_rows == box_rows) { *tm = e.map; return BT_OK; }
   const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(__half)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
@@ -473,21 +620,72 @@ static int32_t make_tmap(bt_ctx* ctx, CUtensorMap* tm, const __half* base, int r
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BT_CHECK(r == CUDA_SUCCESS, BT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  bt_gemm_ws::Entry& e = ws->cache[ws->next];
+  ws->next = (ws->next + 1) % 8;
+  e.base = base; e.rows = rows; e.d = d; e.box_rows = box_rows; e.map = *tm;
   return BT_OK;
 }
 
-template <int BN, bool kDense>
+template <int BN, bool kDense, int CM, int CN>
 static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep) {
+  constexpr int CS = CM * CN;
   CUtensorMap ta, tb;
-  BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.n, ap.d, BM));
-  BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.m, ap.d, BN));
-  auto kern = assoc_tc_kernel<BN, kDense>;
-  BT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn));
-  const int tiles = ((ap.n + BM - 1) / BM) * ((ap.m + BN - 1) / BN);
-  const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-  kern<<<grid, kTcThreads, TcSmem<BN>::kDyn, ctx->stream>>>(ta, tb, ep, ap.d);
+  BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.a_rows_alloc > 0 ? ap.a_rows_alloc : ap.n, ap.d, BM / CN));  // box = one CTA's slice
+  BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.b_rows_alloc > 0 ? ap.b_rows_alloc : ap.m, ap.d, BN / CM));
+  auto kern = assoc_tc_kernel<BN, kDense, CM, CN>;
+  static int cached_clusters = -1;   // per instantiation: attribute + occupancy query only once
+  if (cached_clusters < 0)
+    BT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn));
+  const int tiles_m = (ap.n + BM - 1) / BM, tiles_n = (ap.m + BN - 1) / BN;
+  const int ctiles = ((tiles_m + CM - 1) / CM) * ((tiles_n + CN - 1) / CN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = TcSmem<BN>::kDyn;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cached_clusters < 0) {
+    int q = ctx->num_sms / CS;
+    if (CS > 1) {
+      cfg.gridDim = dim3(CS);
+      BT_CUDA(cudaOccupancyMaxActiveClusters(&q, kern, &cfg));
+      BT_CHECK(q > 0, BT_ERR_CUDA, "cluster of %d CTAs cannot be scheduled", CS);
+    }
+    cached_clusters = q;
+  }
+  const int max_clusters = cached_clusters;
+  const int nclusters = ctiles < max_clusters ? ctiles : max_clusters;
+  cfg.gridDim = dim3(nclusters * CS);
+  BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
   BT_LAUNCHED(ctx);
   return BT_OK;
+}
+
+// Cluster shape of the association GEMM.  BT_ASSOC_CLUSTER=CMxCN overrides (profiling sweeps).
+static void pick_cluster(int* cm, int* cn) {
+  *cm = 2; *cn = 2;
+  const char* e = getenv("BT_ASSOC_CLUSTER");
+  if (e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { *cm = e[0] - '0'; *cn = e[2] - '0'; }
+}
+
+template <bool kDense>
+static int32_t launch_tc_cluster(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep) {
+  int cm, cn;
+  pick_cluster(&cm, &cn);
+  if (cm == 1 && cn == 1) return launch_tc<256, kDense, 1, 1>(ctx, ap, ep);
+  if (cm == 1 && cn == 2) return launch_tc<256, kDense, 1, 2>(ctx, ap, ep);
+  if (cm == 2 && cn == 1) return launch_tc<256, kDense, 2, 1>(ctx, ap, ep);
+  if (cm == 2 && cn == 2) return launch_tc<256, kDense, 2, 2>(ctx, ap, ep);
+  if (cm == 4 && cn == 2) return launch_tc<256, kDense, 4, 2>(ctx, ap, ep);
+  if (cm == 2 && cn == 4) return launch_tc<256, kDense, 2, 4>(ctx, ap, ep);
+  if (cm == 4 && cn == 1) return launch_tc<256, kDense, 4, 1>(ctx, ap, ep);
+  if (cm == 1 && cn == 4) return launch_tc<256, kDense, 1, 4>(ctx, ap, ep);
+  return bt_fail(ctx, BT_ERR_INVALID, "unsupported BT_ASSOC_CLUSTER %dx%d", cm, cn);
 }
 
 int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
@@ -499,13 +697,14 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   ep.unconf_thresh = ap.unconf_thresh; ep.proximity = ap.proximity; ep.appearance = ap.appearance;
   ep.cand = ap.cand; ep.out_emb = ap.out_emb; ep.out_dists = ap.out_dists;
   ep.dense_stage = ap.dense_stage; ep.n = ap.n; ep.m = ap.m;
+  ep.debug = getenv("BT_ASSOC_DEBUG") != nullptr;
   const bool dense = (ap.out_emb != nullptr) || (ap.out_dists != nullptr);
   if (precision == 0) {
     BT_CHECK(ap.d % BK == 0 && ap.d >= BK, BT_ERR_INVALID,
              "tensor-core similarity needs feat_dim %% 64 == 0 (got %d)", ap.d);
     BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "fp16 operands missing");
-    if (dense) return launch_tc<256, true>(ctx, ap, ep);
-    return launch_tc<256, false>(ctx, ap, ep);
+    if (dense) return launch_tc_cluster<true>(ctx, ap, ep);
+    return launch_tc_cluster<false>(ctx, ap, ep);
   }
   BT_CHECK(ap.a32 && ap.b32, BT_ERR_INVALID, "fp32 operands missing");
   dim3 grid((ap.m + ST - 1) / ST, (ap.n + ST - 1) / ST);

@@ -85,6 +85,7 @@ struct bt_tracker {
   __half* feat16 = nullptr;
   float *curr32 = nullptr, *smooth32 = nullptr;
   uint8_t* row_kind = nullptr;
+  uint8_t* row_kind_cur = nullptr;   // this frame's row kinds inside the packed control block
   // ---- device per-frame buffers ----
   int32_t* det_boxes = nullptr;
   float* det_scores = nullptr;
@@ -101,6 +102,8 @@ struct bt_tracker {
   int32_t *d_birth_slot = nullptr, *d_birth_det = nullptr;
   int32_t *d_lista = nullptr, *d_listb = nullptr;
   int32_t *d_pairs = nullptr, *d_pair_count = nullptr;
+  char* d_ctrl = nullptr;   // packed per-frame control lists (one H2D per phase)
+  char* h_ctrl = nullptr;
   double* d_gather = nullptr;
   int pair_cap = 0;
   // ---- pinned host mirrors ----
@@ -216,10 +219,11 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &t->det_xywh, md * 4));
   BT_TRY(dev_alloc(ctx, &t->det_xywh32, md * 4));
   BT_TRY(dev_alloc(ctx, &t->col_kind, md));
-  for (int s = 0; s < 3; ++s) {
-    BT_TRY(dev_alloc(ctx, &t->x[s], cap));
-    BT_TRY(dev_alloc(ctx, &t->y[s], md));
-  }
+  BT_TRY(dev_alloc(ctx, &t->x[0], 3 * cap));   // one block: a single D2H brings all three stages back
+  t->x[1] = t->x[0] + cap;
+  t->x[2] = t->x[0] + 2 * cap;
+  for (int s = 0; s < 3; ++s) BT_TRY(dev_alloc(ctx, &t->y[s], md));
+  BT_TRY(dev_alloc(ctx, &t->d_ctrl, 16 * (cap + md) + 1024));
   const size_t nupd = cap + md;
   BT_TRY(dev_alloc(ctx, &t->d_pool_idx, cap));
   BT_TRY(dev_alloc(ctx, &t->d_pool_state, cap));
@@ -237,17 +241,18 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &t->d_gather, cap * 64));
 
   size_t pinned_bytes = 0;
-  pinned_bytes += cap + 2 * cap * 4 + 3 * (cap + md) * 4 + md * 4 + 2 * nupd * 4 + 2 * nupd + 2 * md * 4 +
+  pinned_bytes += 16 * (cap + md) + 1024 + cap + 2 * cap * 4 + 3 * (cap + md) * 4 + md * 4 + 2 * nupd * 4 + 2 * nupd + 2 * md * 4 +
                   2 * cap * 4 + (size_t)2 * t->pair_cap * 4 + 64 + cap * 4 * 8 + 64 * 256;
   BT_CUDA(cudaMallocHost(&t->pinned, pinned_bytes));
   char* cur = t->pinned;
   t->h_row_kind = carve<uint8_t>(cur, cap);
   t->h_pool_idx = carve<int32_t>(cur, cap);
   t->h_pool_state = carve<int32_t>(cur, cap);
-  for (int s = 0; s < 3; ++s) {
-    t->h_x[s] = carve<int32_t>(cur, cap);
-    t->h_y[s] = carve<int32_t>(cur, md);
-  }
+  t->h_x[0] = carve<int32_t>(cur, 3 * cap);
+  t->h_x[1] = t->h_x[0] + cap;
+  t->h_x[2] = t->h_x[0] + 2 * cap;
+  for (int s = 0; s < 3; ++s) t->h_y[s] = carve<int32_t>(cur, md);
+  t->h_ctrl = carve<char>(cur, 16 * (cap + md) + 1024);
   t->h_scores = carve<float>(cur, md);
   t->h_upd_track = carve<int32_t>(cur, nupd);
   t->h_upd_det = carve<int32_t>(cur, nupd);
@@ -270,7 +275,7 @@ void bt_tracker_destroy(bt_ctx* ctx) {
   if (!t) return;
   void* ptrs[] = {t->mean, t->cov, t->tlbr, t->tlbr_f32, t->feat16, t->curr32, t->smooth32, t->row_kind,
                   t->det_boxes, t->det_scores, t->det_feat_in, t->det_feat32, t->det_feat16, t->det_tlbr,
-                  t->det_xywh, t->det_xywh32, t->col_kind, t->x[0], t->x[1], t->x[2], t->y[0], t->y[1], t->y[2],
+                  t->det_xywh, t->det_xywh32, t->col_kind, t->x[0], t->d_ctrl, t->y[0], t->y[1], t->y[2],
                   t->d_pool_idx, t->d_pool_state, t->d_upd_track, t->d_upd_det, t->d_upd_f32, t->d_ema_mode,
                   t->d_birth_slot, t->d_birth_det, t->d_lista, t->d_listb, t->d_pairs, t->d_pair_count,
                   t->d_gather};
@@ -371,23 +376,28 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
 
   // ---- Kalman predict over the pool (demo:1426) ---------------------------------------------
   bool all_f32 = n_pool > 0;
-  memset(t->h_row_kind, BT_ROW_NONE, n_rows);
+  // packed control block A: [pool_idx n_pool][pool_state n_pool][row_kind n_rows] -> one H2D
+  int32_t* hA_idx = reinterpret_cast<int32_t*>(t->h_ctrl);
+  int32_t* hA_state = hA_idx + n_pool;
+  uint8_t* hA_kind = reinterpret_cast<uint8_t*>(hA_state + n_pool);
+  const size_t bytesA = sizeof(int32_t) * 2 * n_pool + n_rows;
+  int32_t* dA_idx = reinterpret_cast<int32_t*>(t->d_ctrl);
+  int32_t* dA_state = dA_idx + n_pool;
+  t->row_kind_cur = reinterpret_cast<uint8_t*>(dA_state + n_pool);
+  memset(hA_kind, BT_ROW_NONE, n_rows);
   for (int i = 0; i < n_pool; ++i) {
     const int s = pool[i];
-    t->h_pool_idx[i] = s;
-    t->h_pool_state[i] = meta[s].state;
-    t->h_row_kind[s] = (meta[s].state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
+    hA_idx[i] = s;
+    hA_state[i] = meta[s].state;
+    hA_kind[s] = (meta[s].state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
     all_f32 = all_f32 && meta[s].f32_state;
   }
-  for (int s : unconfirmed) t->h_row_kind[s] = BT_ROW_UNCONFIRMED;
-  if (n_rows > 0)
-    BT_CUDA(cudaMemcpyAsync(t->row_kind, t->h_row_kind, n_rows, cudaMemcpyHostToDevice, st));
+  for (int s : unconfirmed) hA_kind[s] = BT_ROW_UNCONFIRMED;
+  if (bytesA > 0) BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesA, cudaMemcpyHostToDevice, st));
   SEG_BEGIN(BT_SEG_PREDICT);
   if (n_pool > 0) {
-    BT_CUDA(cudaMemcpyAsync(t->d_pool_idx, t->h_pool_idx, sizeof(int32_t) * n_pool, cudaMemcpyHostToDevice, st));
-    BT_CUDA(cudaMemcpyAsync(t->d_pool_state, t->h_pool_state, sizeof(int32_t) * n_pool, cudaMemcpyHostToDevice, st));
-    BT_TRY(btk_kalman_predict(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->d_pool_state, t->d_pool_idx,
-                              n_pool, all_f32 ? 1 : 0));
+    BT_TRY(btk_kalman_predict(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, dA_state, dA_idx, n_pool,
+                              all_f32 ? 1 : 0));
     for (int s : pool) meta[s].f32_state = 0;
   }
   SEG_END(BT_SEG_PREDICT);
@@ -395,7 +405,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   // ---- fused association over slots x detections + the three chained LAP solves -------------
   const bt_cand& cand = *bt_lap_own_cand(ctx);
   if (n_rows > 0) {
-    BT_CUDA(cudaMemsetAsync(cand.cnt, 0, sizeof(int32_t) * 3 * cand.rows_cap, st));
+    BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, st));
     SEG_BEGIN(BT_SEG_ASSOC);
     if (m > 0) {
       bt_assoc_params p;
@@ -403,7 +413,8 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       p.a16 = t->feat16; p.b16 = t->det_feat16;
       p.a32 = t->curr32; p.b32 = t->det_feat32;
       p.n = n_rows; p.m = m; p.d = reid ? D : 0;
-      p.row_tlbr = t->tlbr; p.row_tlbr_f32 = t->tlbr_f32; p.row_kind = t->row_kind;
+      p.a_rows_alloc = t->cap; p.b_rows_alloc = t->max_dets;
+      p.row_tlbr = t->tlbr; p.row_tlbr_f32 = t->tlbr_f32; p.row_kind = t->row_kind_cur;
       p.col_tlbr = t->det_tlbr; p.col_kind = t->col_kind; p.face_sim = nullptr;
       p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
       p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
@@ -413,12 +424,11 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     }
     SEG_END(BT_SEG_ASSOC);
     SEG_BEGIN(BT_SEG_LAP);
-    BT_TRY(btk_lap_solve(ctx, cand, 0, n_rows, m, cfg.match_thresh, nullptr, nullptr, t->x[0], t->y[0]));
-    BT_TRY(btk_lap_solve(ctx, cand, 1, n_rows, m, cfg.second_thresh, t->x[0], nullptr, t->x[1], t->y[1]));
-    BT_TRY(btk_lap_solve(ctx, cand, 2, n_rows, m, cfg.unconfirmed_thresh, nullptr, t->y[0], t->x[2], t->y[2]));
+    const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
+    BT_TRY(btk_lap_solve3(ctx, cand, n_rows, m, th, t->x, t->y));
     SEG_END(BT_SEG_LAP);
-    for (int s = 0; s < 3; ++s)
-      BT_CUDA(cudaMemcpyAsync(t->h_x[s], t->x[s], sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaMemcpyAsync(t->h_x[0], t->x[0], sizeof(int32_t) * ((size_t)2 * t->cap + n_rows),
+                            cudaMemcpyDeviceToHost, st));
   }
   BT_CUDA(cudaStreamSynchronize(st));  // sync 1: assignments (and scores) are on the host
   BT_TRY(prof_collect(ctx, t));
@@ -556,29 +566,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     }
   }
 
-  // ---- device: Kalman update / initiate / features ----------------------------------------------
-  SEG_BEGIN(BT_SEG_UPDATE);
-  if (n_upd > 0) {
-    BT_CUDA(cudaMemcpyAsync(t->d_upd_track, t->h_upd_track, sizeof(int32_t) * n_upd, cudaMemcpyHostToDevice, st));
-    BT_CUDA(cudaMemcpyAsync(t->d_upd_det, t->h_upd_det, sizeof(int32_t) * n_upd, cudaMemcpyHostToDevice, st));
-    BT_CUDA(cudaMemcpyAsync(t->d_upd_f32, t->h_upd_f32, n_upd, cudaMemcpyHostToDevice, st));
-    BT_CUDA(cudaMemcpyAsync(t->d_ema_mode, t->h_ema_mode, n_upd, cudaMemcpyHostToDevice, st));
-  }
-  if (n_match_upd > 0)
-    BT_TRY(btk_kalman_update(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->det_xywh, t->d_upd_track,
-                             t->d_upd_det, t->d_upd_f32, n_match_upd));
-  if (n_births > 0) {
-    BT_CUDA(cudaMemcpyAsync(t->d_birth_slot, t->h_birth_slot, sizeof(int32_t) * n_births, cudaMemcpyHostToDevice, st));
-    BT_CUDA(cudaMemcpyAsync(t->d_birth_det, t->h_birth_det, sizeof(int32_t) * n_births, cudaMemcpyHostToDevice, st));
-    BT_TRY(btk_kalman_initiate(ctx, t->det_xywh32, t->d_birth_det, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->d_birth_slot,
-                               n_births));
-  }
-  if (reid && n_upd > 0)
-    BT_TRY(btk_feature_ema16(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
-                             t->det_feat16, t->d_upd_track, t->d_upd_det, t->d_ema_mode, n_upd, D,
-                             cfg.ema_alpha));
-  SEG_END(BT_SEG_UPDATE);
-
   // ---- merge lists (demo:1629-1636) -----------------------------------------------------------
   std::vector<int> new_tracked;
   for (int s : t->tracked)
@@ -601,22 +588,51 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   for (int s : removed_now) meta[s].in_removed = 1; // removed_stracks.extend
   t->n_removed_total += (int)removed_now.size();
 
-  // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) + result read-back --------------
+  // ---- device: one packed H2D (update lists, births, merged lists), then Kalman update / initiate /
+  //      features / duplicate test / result gather back to back ------------------------------------
   const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
+  int32_t* hB = reinterpret_cast<int32_t*>(t->h_ctrl);
+  int32_t* dB = reinterpret_cast<int32_t*>(t->d_ctrl);
+  size_t o_track = 0, o_det = o_track + n_upd, o_bslot = o_det + n_upd, o_bdet = o_bslot + n_births,
+         o_la = o_bdet + n_births, o_lb = o_la + nt, o_end = o_lb + nl;
+  memcpy(hB + o_track, t->h_upd_track, sizeof(int32_t) * n_upd);
+  memcpy(hB + o_det, t->h_upd_det, sizeof(int32_t) * n_upd);
+  memcpy(hB + o_bslot, t->h_birth_slot, sizeof(int32_t) * n_births);
+  memcpy(hB + o_bdet, t->h_birth_det, sizeof(int32_t) * n_births);
+  if (nt) memcpy(hB + o_la, new_tracked.data(), sizeof(int32_t) * nt);
+  if (nl) memcpy(hB + o_lb, new_lost.data(), sizeof(int32_t) * nl);
+  uint8_t* hB8 = reinterpret_cast<uint8_t*>(hB + o_end);
+  memcpy(hB8, t->h_upd_f32, n_upd);
+  memcpy(hB8 + n_upd, t->h_ema_mode, n_upd);
+  const size_t bytesB = sizeof(int32_t) * o_end + 2 * (size_t)n_upd;
+  if (bytesB > 0) BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesB, cudaMemcpyHostToDevice, st));
+  const int32_t *d_upd_track = dB + o_track, *d_upd_det = dB + o_det, *d_birth_slot = dB + o_bslot,
+                *d_birth_det = dB + o_bdet, *d_lista = dB + o_la, *d_listb = dB + o_lb;
+  const uint8_t* d_upd_f32 = reinterpret_cast<const uint8_t*>(dB + o_end);
+  const uint8_t* d_ema_mode = d_upd_f32 + n_upd;
+  SEG_BEGIN(BT_SEG_UPDATE);
+  if (n_match_upd > 0)
+    BT_TRY(btk_kalman_update(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->det_xywh, d_upd_track, d_upd_det,
+                             d_upd_f32, n_match_upd));
+  if (n_births > 0)
+    BT_TRY(btk_kalman_initiate(ctx, t->det_xywh32, d_birth_det, t->mean, t->cov, t->tlbr, t->tlbr_f32,
+                               d_birth_slot, n_births));
+  if (reid && n_upd > 0)
+    BT_TRY(btk_feature_ema16(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
+                             t->det_feat16, d_upd_track, d_upd_det, d_ema_mode, n_upd, D, cfg.ema_alpha));
+  SEG_END(BT_SEG_UPDATE);
+
+  // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) + result read-back --------------
   int n_pairs = 0;
   SEG_BEGIN(BT_SEG_DUP);
   if (nt > 0) {
-    memcpy(t->h_lista, new_tracked.data(), sizeof(int32_t) * nt);
-    BT_CUDA(cudaMemcpyAsync(t->d_lista, t->h_lista, sizeof(int32_t) * nt, cudaMemcpyHostToDevice, st));
     if (nl > 0) {
-      memcpy(t->h_listb, new_lost.data(), sizeof(int32_t) * nl);
-      BT_CUDA(cudaMemcpyAsync(t->d_listb, t->h_listb, sizeof(int32_t) * nl, cudaMemcpyHostToDevice, st));
       BT_CUDA(cudaMemsetAsync(t->d_pair_count, 0, sizeof(int32_t), st));
-      BT_TRY(btk_iou_pairs_below(ctx, t->tlbr, t->d_lista, nt, t->d_listb, nl, cfg.duplicate_iou_dist,
-                                 t->d_pairs, t->d_pair_count, t->pair_cap));
+      BT_TRY(btk_iou_pairs_below(ctx, t->tlbr, d_lista, nt, d_listb, nl, cfg.duplicate_iou_dist, t->d_pairs,
+                                 t->d_pair_count, t->pair_cap));
       BT_CUDA(cudaMemcpyAsync(t->h_pair_count, t->d_pair_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
-    gather_rows_f64_kernel<<<(nt * 4 + 255) / 256, 256, 0, st>>>(t->tlbr, t->d_lista, nt, 4, t->d_gather);
+    gather_rows_f64_kernel<<<(nt * 4 + 255) / 256, 256, 0, st>>>(t->tlbr, d_lista, nt, 4, t->d_gather);
     BT_LAUNCHED(ctx);
     BT_CUDA(cudaMemcpyAsync(t->h_tlbr, t->d_gather, sizeof(double) * 4 * nt, cudaMemcpyDeviceToHost, st));
   }
