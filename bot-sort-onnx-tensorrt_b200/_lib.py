@@ -28,7 +28,8 @@ EXPORTS = [
     "bt_tracker_reset", "bt_update_arrays", "bt_get_tracks", "bt_get_track_features", "bt_get_matches",
     "bt_profile_enable", "bt_profile_read",
 ]
-SEGMENTS = ("prep", "predict", "assoc", "lap", "update", "dup")
+SEGMENTS = ("prep", "predict", "assoc", "lap", "update", "dup",
+            "host_enqueue1", "host_wait1", "host_lists", "host_wait2", "host_final")
 
 
 class BtConfig(C.Structure):

@@ -402,6 +402,8 @@ int32_t bt_linear_assignment(bt_ctx* ctx, const double* cost, int32_t n, int32_t
   BT_CUDA(cudaMemsetAsync(cand.total, 0, sizeof(int32_t) * 4, ctx->stream));
   BT_TRY(btk_lap_compact_dense(ctx, d_cost, n, m, thresh, cand, 0));
   BT_TRY(btk_lap_solve(ctx, cand, 0, n, m, thresh, nullptr, nullptr, d_x, d_y));
+  // leave the candidate counters zeroed: the tracker path relies on it (its LAP kernel clears its own)
+  BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, ctx->stream));
   BT_TRY(bt_unstage_out(ctx, x, d_x, sizeof(int32_t) * n, loc));
   BT_TRY(bt_unstage_out(ctx, y, d_y, sizeof(int32_t) * m, loc));
   return bt_finish(ctx, loc);

@@ -103,14 +103,29 @@ static inline int32_t bt_out(bt_ctx* ctx, T* dst, size_t count, int32_t loc, T**
 // ---- kernel launchers (device pointers only; enqueue on ctx->stream) --------------------------
 // kalman.cu
 int32_t btk_kalman_initiate(bt_ctx* ctx, const float* xywh, const int32_t* src_idx, double* mean,
-                            double* cov, double* tlbr, float* tlbr_f32, const int32_t* dst_idx, int32_t k);
+                            double* cov, double* tlbr, float* tlbr_f32, const int32_t* dst_idx, int32_t k,
+                            uint8_t* slot_f32 = nullptr);
 int32_t btk_kalman_predict(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
-                           const int32_t* state, const int32_t* idx, int32_t n, int32_t noise_f32);
+                           const int32_t* state, const int32_t* idx, int32_t n, int32_t noise_f32,
+                           uint8_t* slot_f32 = nullptr);
 int32_t btk_kalman_update(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
                           const double* meas, const int32_t* track_idx, const int32_t* meas_idx,
                           const uint8_t* noise_f32, int32_t k);
+// tracker mode: slot g takes the detection x1[g] / x2[g] / x3[g] (first non-negative) as measurement
+int32_t btk_kalman_update_x(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
+                            const double* meas, const int32_t* x1, const int32_t* x2, const int32_t* x3,
+                            uint8_t* slot_f32, int32_t n_slots, double* res_tlbr = nullptr);
 int32_t btk_kalman_project(bt_ctx* ctx, const double* mean, const double* cov, double* pmean,
                            double* pcov, int32_t n);
+// features.cu: EMA of every slot matched by one of the three stages (x arrays), fp16 bank refresh
+int32_t btk_feature_ema_x(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
+                          const __half* det16, const int32_t* x1, const int32_t* x2, const int32_t* x3,
+                          int32_t n_slots, int32_t d, float alpha);
+// iou.cu: pairs (i < j) of live slots (kind != 0) whose IoU distance is below `limit`
+// pair_count and the first small_cap pairs also land in the frame's result block (one D2H per frame)
+int32_t btk_iou_pairs_live(bt_ctx* ctx, const double* tlbr, const float* tlbr_f32, const uint8_t* kind, int32_t n,
+                           double limit, int32_t* pairs, int32_t* pair_count, int32_t pair_cap,
+                           int32_t* pairs_small = nullptr, int32_t small_cap = 0);
 // iou.cu
 int32_t btk_iou_distance(bt_ctx* ctx, const double* a, int32_t n, const double* b, int32_t m,
                          double* out);
@@ -202,7 +217,7 @@ int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n,
 const bt_cand* bt_lap_own_cand(bt_ctx* ctx);
 // the three chained association stages of a frame in ONE launch (lists 0,1,2)
 int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, int32_t n, int32_t m, const double thresh[3],
-                       int32_t* const x[3], int32_t* const y[3]);
+                       int32_t* const x[3], int32_t* const y[3], int32_t* zero_word = nullptr);
 
 // ---- detector side ------------------------------------------------------------------------------
 int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_config& cfg,

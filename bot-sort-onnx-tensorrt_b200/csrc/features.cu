@@ -71,11 +71,20 @@ __global__ void __launch_bounds__(kThreads)
 feature_ema_kernel(float* __restrict__ smooth, float* __restrict__ curr, const float* __restrict__ feat,
                    __half* __restrict__ bank16, const __half* __restrict__ det16,
                    const int32_t* __restrict__ track_idx, const int32_t* __restrict__ feat_idx,
-                   const uint8_t* __restrict__ first, int d, float alpha) {
+                   const uint8_t* __restrict__ first, int d, float alpha, const int32_t* __restrict__ x1,
+                   const int32_t* __restrict__ x2, const int32_t* __restrict__ x3) {
   __shared__ float red[kThreads / 32];
   const int i = blockIdx.x;
-  const size_t t = track_idx ? track_idx[i] : i;
-  const size_t f = feat_idx ? feat_idx[i] : i;
+  size_t t = track_idx ? track_idx[i] : i;
+  size_t f = feat_idx ? feat_idx[i] : i;
+  if (x1) {   // tracker mode: slot i, detection assigned by one of the three stages (block-uniform exit)
+    int z = x1[i];
+    if (z < 0) z = x2[i];
+    if (z < 0) z = x3[i];
+    if (z < 0) return;
+    t = i;
+    f = z;
+  }
   const int mode = first ? first[i] : 0;
   if (bank16 && det16) {
     if ((d & 3) == 0) {
@@ -125,7 +134,17 @@ int32_t btk_feature_ema16(bt_ctx* ctx, float* smooth, float* curr, const float* 
                           const uint8_t* first, int32_t k, int32_t d, float alpha) {
   if (k <= 0) return BT_OK;
   feature_ema_kernel<<<k, kThreads, 0, ctx->stream>>>(smooth, curr, feat, bank16, det16, track_idx,
-                                                      feat_idx, first, d, alpha);
+                                                      feat_idx, first, d, alpha, nullptr, nullptr, nullptr);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
+int32_t btk_feature_ema_x(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
+                          const __half* det16, const int32_t* x1, const int32_t* x2, const int32_t* x3,
+                          int32_t n_slots, int32_t d, float alpha) {
+  if (n_slots <= 0) return BT_OK;
+  feature_ema_kernel<<<n_slots, kThreads, 0, ctx->stream>>>(smooth, curr, feat, bank16, det16, nullptr, nullptr,
+                                                            nullptr, d, alpha, x1, x2, x3);
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

@@ -37,7 +37,7 @@ __device__ __forceinline__ void store_tlbr(double m, int lane, int r, bool activ
 __global__ void __launch_bounds__(kThreads)
 kalman_predict_kernel(double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ tlbr,
                       float* __restrict__ tlbr_f32, const int32_t* __restrict__ state,
-                      const int32_t* __restrict__ idx, int n, int noise_f32) {
+                      const int32_t* __restrict__ idx, int n, int noise_f32, uint8_t* __restrict__ slot_f32) {
   const int gid = blockIdx.x * kThreads + threadIdx.x;
   const int g = gid >> 3;
   const int r = threadIdx.x & 7;
@@ -96,6 +96,7 @@ kalman_predict_kernel(double* __restrict__ mean, double* __restrict__ cov, doubl
     double2* row = reinterpret_cast<double2*>(cov + (size_t)t * 64 + r * 8);
 #pragma unroll
     for (int j = 0; j < 4; ++j) row[j] = make_double2(c[2 * j], c[2 * j + 1]);
+    if (slot_f32 && r == 0) slot_f32[t] = 0;   // the state is float64 from now on
   }
   store_tlbr(m, lane, r, active, t, tlbr, tlbr_f32);
 }
@@ -105,15 +106,31 @@ __global__ void __launch_bounds__(kThreads)
 kalman_update_kernel(double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ tlbr,
                      float* __restrict__ tlbr_f32, const double* __restrict__ meas,
                      const int32_t* __restrict__ track_idx, const int32_t* __restrict__ meas_idx,
-                     const uint8_t* __restrict__ noise_f32, int k) {
+                     const uint8_t* __restrict__ noise_f32, int k, const int32_t* __restrict__ x1,
+                     const int32_t* __restrict__ x2, const int32_t* __restrict__ x3,
+                     uint8_t* __restrict__ slot_f32, double* __restrict__ res_tlbr) {
   const int gid = blockIdx.x * kThreads + threadIdx.x;
   const int g = gid >> 3;
   const int r = threadIdx.x & 7;
   const int lane = threadIdx.x & 31;
   const int base = lane & ~7;
-  const bool active = g < k;
-  const int t = active ? (track_idx ? track_idx[g] : g) : 0;
-  const int zi = active ? (meas_idx ? meas_idx[g] : g) : 0;
+  bool active = g < k;
+  int t = active ? (track_idx ? track_idx[g] : g) : 0;
+  int zi = active ? (meas_idx ? meas_idx[g] : g) : 0;
+  if (x1) {
+    // tracker mode: group g is track slot g, its measurement is whatever detection one of the three
+    // association stages assigned to it (a slot is matched in at most one stage)
+    t = g;
+    zi = -1;
+    if (active) {
+      zi = x1[g];
+      if (zi < 0) zi = x2[g];
+      if (zi < 0) zi = x3[g];
+    }
+    if (res_tlbr && g < k && zi < 0 && r < 4) res_tlbr[(size_t)g * 4 + r] = tlbr[(size_t)g * 4 + r];  // unchanged box
+    active = active && zi >= 0;
+    if (!active) zi = 0;
+  }
 
   double m = 0.0;
   double c[8];
@@ -150,7 +167,9 @@ kalman_update_kernel(double* __restrict__ mean, double* __restrict__ cov, double
   const double h = shfl_d(m, base + 3);
   // innovation covariance noise, demo:253-258 (w,h of the predicted mean)
   double nw, nh;
-  if (active && noise_f32 && noise_f32[g]) {
+  const bool f32 = active && (slot_f32 ? slot_f32[t] != 0 : (noise_f32 && noise_f32[g]));
+  if (active && slot_f32 && r == 0) slot_f32[t] = 0;
+  if (f32) {
     const float sw = __fmul_rn((float)BT_STD_POS, (float)w), sh = __fmul_rn((float)BT_STD_POS, (float)h);
     nw = (double)__fmul_rn(sw, sw);
     nh = (double)__fmul_rn(sh, sh);
@@ -211,13 +230,15 @@ kalman_update_kernel(double* __restrict__ mean, double* __restrict__ cov, double
     for (int j = 0; j < 4; ++j) row[j] = make_double2(c[2 * j], c[2 * j + 1]);
   }
   store_tlbr(m_new, lane, r, active, t, tlbr, tlbr_f32);
+  if (res_tlbr) store_tlbr(m_new, lane, r, active, t, res_tlbr, nullptr);
 }
 
 // KalmanFilter.initiate (demo:166-197) with NumPy>=2 float32 rounding of the float32 measurement path.
 __global__ void __launch_bounds__(kThreads)
 kalman_initiate_kernel(const float* __restrict__ xywh, const int32_t* __restrict__ src_idx,
                        double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ tlbr,
-                       float* __restrict__ tlbr_f32, const int32_t* __restrict__ dst_idx, int k) {
+                       float* __restrict__ tlbr_f32, const int32_t* __restrict__ dst_idx, int k,
+                       uint8_t* __restrict__ slot_f32) {
   const int gid = blockIdx.x * kThreads + threadIdx.x;
   const int g = gid >> 3;
   const int r = threadIdx.x & 7;
@@ -242,6 +263,7 @@ kalman_initiate_kernel(const float* __restrict__ xywh, const int32_t* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       row[j] = make_double2((2 * j == r) ? var : 0.0, (2 * j + 1 == r) ? var : 0.0);
+    if (slot_f32 && r == 0) slot_f32[t] = 1;   // float32 state until the first predict / update (NumPy >= 2)
   }
   store_tlbr(m, lane, r, active, t, tlbr, tlbr_f32);
 }
@@ -265,19 +287,21 @@ inline int blocks_for_tracks(int n) { return (n * 8 + kThreads - 1) / kThreads; 
 }  // namespace
 
 int32_t btk_kalman_initiate(bt_ctx* ctx, const float* xywh, const int32_t* src_idx, double* mean,
-                            double* cov, double* tlbr, float* tlbr_f32, const int32_t* dst_idx, int32_t k) {
+                            double* cov, double* tlbr, float* tlbr_f32, const int32_t* dst_idx, int32_t k,
+                            uint8_t* slot_f32) {
   if (k <= 0) return BT_OK;
-  kalman_initiate_kernel<<<blocks_for_tracks(k), kThreads, 0, ctx->stream>>>(xywh, src_idx, mean, cov,
-                                                                              tlbr, tlbr_f32, dst_idx, k);
+  kalman_initiate_kernel<<<blocks_for_tracks(k), kThreads, 0, ctx->stream>>>(xywh, src_idx, mean, cov, tlbr,
+                                                                              tlbr_f32, dst_idx, k, slot_f32);
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
 int32_t btk_kalman_predict(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
-                           const int32_t* state, const int32_t* idx, int32_t n, int32_t noise_f32) {
+                           const int32_t* state, const int32_t* idx, int32_t n, int32_t noise_f32,
+                           uint8_t* slot_f32) {
   if (n <= 0) return BT_OK;
-  kalman_predict_kernel<<<blocks_for_tracks(n), kThreads, 0, ctx->stream>>>(mean, cov, tlbr, tlbr_f32,
-                                                                             state, idx, n, noise_f32);
+  kalman_predict_kernel<<<blocks_for_tracks(n), kThreads, 0, ctx->stream>>>(mean, cov, tlbr, tlbr_f32, state,
+                                                                             idx, n, noise_f32, slot_f32);
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
@@ -287,7 +311,17 @@ int32_t btk_kalman_update(bt_ctx* ctx, double* mean, double* cov, double* tlbr, 
                           const uint8_t* noise_f32, int32_t k) {
   if (k <= 0) return BT_OK;
   kalman_update_kernel<<<blocks_for_tracks(k), kThreads, 0, ctx->stream>>>(
-      mean, cov, tlbr, tlbr_f32, meas, track_idx, meas_idx, noise_f32, k);
+      mean, cov, tlbr, tlbr_f32, meas, track_idx, meas_idx, noise_f32, k, nullptr, nullptr, nullptr, nullptr, nullptr);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
+int32_t btk_kalman_update_x(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
+                            const double* meas, const int32_t* x1, const int32_t* x2, const int32_t* x3,
+                            uint8_t* slot_f32, int32_t n_slots, double* res_tlbr) {
+  if (n_slots <= 0) return BT_OK;
+  kalman_update_kernel<<<blocks_for_tracks(n_slots), kThreads, 0, ctx->stream>>>(
+      mean, cov, tlbr, tlbr_f32, meas, nullptr, nullptr, nullptr, n_slots, x1, x2, x3, slot_f32, res_tlbr);
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

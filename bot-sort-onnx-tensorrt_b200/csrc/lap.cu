@@ -76,6 +76,8 @@ struct LapParams {
   LapStage st[3];
   int nstages;
   int n, m;
+  int clear_lists;      // tracker mode: leave cnt / segmask / total zeroed for the next frame
+  int32_t* zero_word;   // optional device word to clear (the frame's duplicate-pair counter)
   int debug;   // BT_LAP_DEBUG=1: phase timestamps (ns) by device printf
 };
 
@@ -476,6 +478,7 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
     }
   }
   if (gtid < 24) ws.counters[gtid] = 0;
+  if (gtid == 0 && P.zero_word) *P.zero_word = 0;
   cluster_barrier();
   LAP_T(1);
 
@@ -497,15 +500,18 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
     for (int r = gtid; r < n; r += GT) {
       W.label[r] = kInf;
       int total = 0, valid = 0, last = -1;
-      if (S.row_block == nullptr || S.row_block[r] < 0) {
-        const int32_t* segcnt = cand.cnt + ((size_t)S.list * cand.rows_cap + r) * cand.nseg;
+      const bool row_on = S.row_block == nullptr || S.row_block[r] < 0;
+      unsigned long long mask = cand.segmask[(size_t)S.list * cand.rows_cap + r];
+      if (mask && P.clear_lists) cand.segmask[(size_t)S.list * cand.rows_cap + r] = 0ull;
+      {
+        int32_t* segcnt = cand.cnt + ((size_t)S.list * cand.rows_cap + r) * cand.nseg;
         int32_t* rc = ecol + (size_t)r * cand.stride;
         double* rv = ecost + (size_t)r * cand.stride;
-        unsigned long long mask = cand.segmask[(size_t)S.list * cand.rows_cap + r];
         while (mask) {                          // only the non-empty segments, in ascending order
           const int g = __ffsll((long long)mask) - 1;
           mask &= mask - 1;
-          const int k = segcnt[g];
+          const int k = row_on ? segcnt[g] : 0;
+          if (P.clear_lists) segcnt[g] = 0;
           const int src = g * BT_CAND_SEG;
           for (int e = 0; e < k; ++e) {
             const int c = rc[src + e];
@@ -619,6 +625,7 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
         solve_component(GA, comp, S.thresh, S.col_block, cnt, ecol, ecost, x, y, lane);
     }
     if (stage + 1 < P.nstages) cluster_barrier();   // x / y of this stage gate the next one
+    if (P.clear_lists && gtid == 0) cand.total[S.list] = 0;   // every CTA has read it (barriers above / kernel end)
     LAP_T(6);
     if (P.debug && gtid == 0)
       printf("lap stage %d: n=%d m=%d complex=%d comps=%d | init %llu P1 %llu P2 %llu P3 %llu P4 %llu P5 %llu ns\n", stage, n, m,
@@ -778,8 +785,10 @@ int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n,
 }
 
 int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, int32_t n, int32_t m, const double thresh[3],
-                       int32_t* const x[3], int32_t* const y[3]) {
+                       int32_t* const x[3], int32_t* const y[3], int32_t* zero_word) {
   LapParams P = {};
+  P.clear_lists = 1;
+  P.zero_word = zero_word;
   P.nstages = 3;
   P.n = n;
   P.m = m;

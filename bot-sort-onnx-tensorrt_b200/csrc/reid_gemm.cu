@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 
 namespace {
@@ -46,6 +47,7 @@ struct EpiParams {
   int dense_stage;
   int n, m;
   int debug;   // BT_ASSOC_DEBUG=1: per-CTA phase timestamps via device printf (profiling aid)
+  float sim_gate;  // smallest similarity for which the appearance gate is open
 };
 
 __device__ __forceinline__ double iou_dist_f64(const double* __restrict__ a, const double* __restrict__ b) {
@@ -448,17 +450,20 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint32_t hot = 0;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            float4 cb;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(cb.x), "=f"(cb.y), "=f"(cb.z), "=f"(cb.w)
-                         : "r"(colbase + (uint32_t)c * 16u));
+            float4 cb;   // not volatile: the staged boxes are read-only here, let ptxas batch the loads
+            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                : "=f"(cb.x), "=f"(cb.y), "=f"(cb.z), "=f"(cb.w)
+                : "r"(colbase + (uint32_t)c * 16u));
             const float sim = __uint_as_float(v[c]);
-            const bool ov = (fminf(rb.z, cb.z) > fmaxf(rb.x, cb.x)) && (fminf(rb.w, cb.w) > fmaxf(rb.y, cb.y));
-            const bool app = !((1.0f - sim) > p.appearance);
-            hot |= (uint32_t)(ov || app) << c;
+            // min(r.x2,c.x2) > max(r.x1,c.x1)  <=>  r.x2 > c.x1 and c.x2 > r.x1 for non-degenerate boxes
+            // (degenerate ones only make the screen more permissive): four chained predicate compares
+            const bool ov = (rb.z > cb.x) & (cb.z > rb.x) & (rb.w > cb.y) & (cb.w > rb.y);
+            const bool app = sim >= p.sim_gate;     // == !((1.0f - sim) > appearance), see sim_gate_for()
+            if (ov | app) hot |= 1u << c;
           }
           if (p.face_sim != nullptr) hot = 0xffffffffu;
           hot &= s_colvalid[ch];
+          if (p.debug & 2) hot = 0;
           // Pass 2 (rare): exact float64 IoU + fusion rule + candidate emission for the survivors.
           // Lanes walk their own hot bits in lock-step (lane i handles its k-th survivor while lane j
           // handles its own), so a warp pays max-over-lanes iterations, not the sum.
@@ -575,6 +580,15 @@ assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiP
       }
     }
   }
+}
+
+// Smallest float s with !((1.0f - s) > appearance): `1.0f - s` is monotone in s, so the reference's
+// test `emb_dists > appearance_thresh` (demo:1545) on emb = 1 - sim is exactly `sim < s`.
+static float sim_gate_for(float appearance) {
+  float s = 1.0f - appearance;
+  while ((1.0f - s) > appearance) s = nextafterf(s, 2.0f);
+  while (!((1.0f - nextafterf(s, -2.0f)) > appearance)) s = nextafterf(s, -2.0f);
+  return s;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -697,7 +711,8 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   ep.unconf_thresh = ap.unconf_thresh; ep.proximity = ap.proximity; ep.appearance = ap.appearance;
   ep.cand = ap.cand; ep.out_emb = ap.out_emb; ep.out_dists = ap.out_dists;
   ep.dense_stage = ap.dense_stage; ep.n = ap.n; ep.m = ap.m;
-  ep.debug = getenv("BT_ASSOC_DEBUG") != nullptr;
+  ep.debug = getenv("BT_ASSOC_DEBUG") ? atoi(getenv("BT_ASSOC_DEBUG")) : 0;
+  ep.sim_gate = sim_gate_for(ap.appearance);
   const bool dense = (ap.out_emb != nullptr) || (ap.out_dists != nullptr);
   if (precision == 0) {
     BT_CHECK(ap.d % BK == 0 && ap.d >= BK, BT_ERR_INVALID,

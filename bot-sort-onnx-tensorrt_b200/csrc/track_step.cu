@@ -16,9 +16,12 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <string.h>
 
 namespace {
+
+constexpr int kPairPrefetch = 512;   // duplicate pairs fetched with the first read-back (more: second copy)
 
 struct SlotMeta {
   int32_t state = BT_STATE_NEW;
@@ -40,7 +43,8 @@ struct SlotMeta {
 // (demo:1501: high = score > 0.40; demo:1531: low = 0.1 <= score <= 0.40).
 __global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* __restrict__ scores, int m,
                                 float high, float low, double* __restrict__ tlbr, double* __restrict__ xywh,
-                                float* __restrict__ xywh32, uint8_t* __restrict__ kind) {
+                                float* __restrict__ xywh32, uint8_t* __restrict__ kind,
+                                float* __restrict__ res_scores, int32_t* __restrict__ res_boxes) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   const int4 b = *reinterpret_cast<const int4*>(boxes + (size_t)j * 4);
@@ -54,6 +58,10 @@ __global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* 
   z[0] = cx; z[1] = cy; z[2] = w; z[3] = h;
   *reinterpret_cast<float4*>(xywh32 + (size_t)j * 4) = make_float4(cx, cy, w, h);
   const float s = scores[j];
+  if (res_scores) {   // device-resident inputs: the host reads them back with the frame's result block
+    res_scores[j] = s;
+    *reinterpret_cast<int4*>(res_boxes + (size_t)j * 4) = b;
+  }
   kind[j] = (s > high) ? BT_COL_HIGH : ((s >= low) ? BT_COL_LOW : BT_COL_NONE);
 }
 
@@ -86,6 +94,7 @@ struct bt_tracker {
   float *curr32 = nullptr, *smooth32 = nullptr;
   uint8_t* row_kind = nullptr;
   uint8_t* row_kind_cur = nullptr;   // this frame's row kinds inside the packed control block
+  uint8_t* slot_f32 = nullptr;       // [cap] slot still holds initiate()'s float32 state (NumPy >= 2 quirk)
   // ---- device per-frame buffers ----
   int32_t* det_boxes = nullptr;
   float* det_scores = nullptr;
@@ -104,6 +113,9 @@ struct bt_tracker {
   int32_t *d_pairs = nullptr, *d_pair_count = nullptr;
   char* d_ctrl = nullptr;   // packed per-frame control lists (one H2D per phase)
   char* h_ctrl = nullptr;
+  char* d_res = nullptr;    // packed per-frame result block (one D2H per frame), layout in bt_update_arrays
+  char* h_res = nullptr;
+  size_t res_cap = 0;
   double* d_gather = nullptr;
   int pair_cap = 0;
   // ---- pinned host mirrors ----
@@ -111,7 +123,8 @@ struct bt_tracker {
   uint8_t* h_row_kind = nullptr;
   int32_t *h_pool_idx = nullptr, *h_pool_state = nullptr;
   int32_t *h_x[3] = {nullptr, nullptr, nullptr}, *h_y[3] = {nullptr, nullptr, nullptr};
-  float* h_scores = nullptr;
+  float* h_scores = nullptr;      // this frame's host view of the scores
+  float* h_scores_own = nullptr;  // pinned copy used with host inputs
   int32_t *h_upd_track = nullptr, *h_upd_det = nullptr;
   uint8_t *h_upd_f32 = nullptr, *h_ema_mode = nullptr;
   int32_t *h_birth_slot = nullptr, *h_birth_det = nullptr;
@@ -127,6 +140,10 @@ struct bt_tracker {
   int frame_id = 0;
   int n_removed_total = 0;
   std::vector<int32_t> matches[3];  // flattened (a, b) pairs in the reference's index spaces
+  std::vector<uint8_t> scratch_a, scratch_b;
+  std::vector<int> scratch_pos_t, scratch_pos_l;
+  int32_t *d_bpairs = nullptr, *h_bpairs = nullptr, *h_boxes = nullptr;
+  int bpair_cap = 1 << 16;
   std::vector<double> tlbr_cache;   // tlbr of `tracked` after the frame
   bool tlbr_cache_valid = false;
   // ---- optional segment timing (bt_profile_*) ----
@@ -146,9 +163,17 @@ struct bt_tracker {
     if (t->prof) { BT_CUDA(cudaEventRecord(t->ev[s][1], st)); t->seg_open[s] = true; } \
   } while (0)
 
+static inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define HOST_MARK(seg)                                                \
+  do {                                                                \
+    if (t->prof) { const double n__ = now_ms(); t->prof_ms[seg] += n__ - t_host; t->prof_n[seg] += 1; t_host = n__; } \
+  } while (0)
+
 static int32_t prof_collect(bt_ctx* ctx, bt_tracker* t) {
   if (!t->prof) return BT_OK;
-  for (int s = 0; s < BT_SEG_COUNT; ++s) {
+  for (int s = 0; s < BT_SEG_HOST_ENQUEUE1; ++s) {
     if (!t->seg_open[s]) continue;
     float ms = 0.f;
     BT_CUDA(cudaEventElapsedTime(&ms, t->ev[s][0], t->ev[s][1]));
@@ -210,6 +235,8 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
     BT_CUDA(cudaMemset(t->smooth32, 0, sizeof(float) * cap * D));
   }
   BT_TRY(dev_alloc(ctx, &t->row_kind, cap));
+  BT_TRY(dev_alloc(ctx, &t->slot_f32, cap));
+  BT_CUDA(cudaMemset(t->slot_f32, 0, cap));
   BT_TRY(dev_alloc(ctx, &t->det_boxes, md * 4));
   BT_TRY(dev_alloc(ctx, &t->det_scores, md));
   BT_TRY(dev_alloc(ctx, &t->det_feat_in, md * D));
@@ -219,11 +246,11 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &t->det_xywh, md * 4));
   BT_TRY(dev_alloc(ctx, &t->det_xywh32, md * 4));
   BT_TRY(dev_alloc(ctx, &t->col_kind, md));
-  BT_TRY(dev_alloc(ctx, &t->x[0], 3 * cap));   // one block: a single D2H brings all three stages back
-  t->x[1] = t->x[0] + cap;
-  t->x[2] = t->x[0] + 2 * cap;
+  // x[0..2] point into the per-frame result block (set in bt_update_arrays)
   for (int s = 0; s < 3; ++s) BT_TRY(dev_alloc(ctx, &t->y[s], md));
   BT_TRY(dev_alloc(ctx, &t->d_ctrl, 16 * (cap + md) + 1024));
+  t->res_cap = 8 + 8 * (size_t)kPairPrefetch + 12 * cap + 20 * md + 32 * cap + 512;
+  BT_TRY(dev_alloc(ctx, &t->d_res, t->res_cap));
   const size_t nupd = cap + md;
   BT_TRY(dev_alloc(ctx, &t->d_pool_idx, cap));
   BT_TRY(dev_alloc(ctx, &t->d_pool_state, cap));
@@ -239,9 +266,10 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &t->d_pairs, (size_t)2 * t->pair_cap));
   BT_TRY(dev_alloc(ctx, &t->d_pair_count, 1));
   BT_TRY(dev_alloc(ctx, &t->d_gather, cap * 64));
+  BT_TRY(dev_alloc(ctx, &t->d_bpairs, (size_t)2 * t->bpair_cap));
 
   size_t pinned_bytes = 0;
-  pinned_bytes += 16 * (cap + md) + 1024 + cap + 2 * cap * 4 + 3 * (cap + md) * 4 + md * 4 + 2 * nupd * 4 + 2 * nupd + 2 * md * 4 +
+  pinned_bytes += t->res_cap + 256 + (size_t)8 * t->bpair_cap + md * 16 + 512 + 16 * (cap + md) + 1024 + cap + 2 * cap * 4 + 3 * (cap + md) * 4 + md * 4 + 2 * nupd * 4 + 2 * nupd + 2 * md * 4 +
                   2 * cap * 4 + (size_t)2 * t->pair_cap * 4 + 64 + cap * 4 * 8 + 64 * 256;
   BT_CUDA(cudaMallocHost(&t->pinned, pinned_bytes));
   char* cur = t->pinned;
@@ -253,7 +281,9 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   t->h_x[2] = t->h_x[0] + 2 * cap;
   for (int s = 0; s < 3; ++s) t->h_y[s] = carve<int32_t>(cur, md);
   t->h_ctrl = carve<char>(cur, 16 * (cap + md) + 1024);
-  t->h_scores = carve<float>(cur, md);
+  t->h_res = carve<char>(cur, t->res_cap);
+  t->h_scores_own = carve<float>(cur, md);
+  t->h_scores = t->h_scores_own;
   t->h_upd_track = carve<int32_t>(cur, nupd);
   t->h_upd_det = carve<int32_t>(cur, nupd);
   t->h_upd_f32 = carve<uint8_t>(cur, nupd);
@@ -265,6 +295,8 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   t->h_pairs = carve<int32_t>(cur, (size_t)2 * t->pair_cap);
   t->h_pair_count = carve<int32_t>(cur, 16);
   t->h_tlbr = carve<double>(cur, cap * 4);
+  t->h_bpairs = carve<int32_t>(cur, (size_t)2 * t->bpair_cap);
+  t->h_boxes = carve<int32_t>(cur, md * 4);
   t->meta.assign(cap, SlotMeta());
   t->max_time_lost = (int)(t->cfg.frame_rate / 30.0 * t->cfg.track_buffer);
   return BT_OK;
@@ -273,17 +305,17 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
 void bt_tracker_destroy(bt_ctx* ctx) {
   bt_tracker* t = ctx->trk;
   if (!t) return;
-  void* ptrs[] = {t->mean, t->cov, t->tlbr, t->tlbr_f32, t->feat16, t->curr32, t->smooth32, t->row_kind,
+  void* ptrs[] = {t->mean, t->cov, t->tlbr, t->tlbr_f32, t->feat16, t->curr32, t->smooth32, t->row_kind, t->slot_f32,
                   t->det_boxes, t->det_scores, t->det_feat_in, t->det_feat32, t->det_feat16, t->det_tlbr,
-                  t->det_xywh, t->det_xywh32, t->col_kind, t->x[0], t->d_ctrl, t->y[0], t->y[1], t->y[2],
+                  t->det_xywh, t->det_xywh32, t->col_kind, t->d_ctrl, t->y[0], t->y[1], t->y[2],
                   t->d_pool_idx, t->d_pool_state, t->d_upd_track, t->d_upd_det, t->d_upd_f32, t->d_ema_mode,
                   t->d_birth_slot, t->d_birth_det, t->d_lista, t->d_listb, t->d_pairs, t->d_pair_count,
-                  t->d_gather};
+                  t->d_gather, t->d_bpairs, t->d_res};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (t->pinned) cudaFreeHost(t->pinned);
-  for (auto& pair : t->ev)
-    for (cudaEvent_t e : pair)
+  for (int s = 0; s < BT_SEG_HOST_ENQUEUE1; ++s)
+    for (cudaEvent_t e : t->ev[s])
       if (e) cudaEventDestroy(e);
   delete t;
   ctx->trk = nullptr;
@@ -310,6 +342,8 @@ int32_t bt_tracker_reset(bt_ctx* ctx, const bt_config* cfg) {
   for (auto& m : t->matches) m.clear();
   t->tlbr_cache_valid = false;
   BT_CUDA(cudaMemsetAsync(t->feat16, 0, sizeof(__half) * (size_t)t->cap * t->D, ctx->stream));
+  const bt_cand& cand = *bt_lap_own_cand(ctx);
+  BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, ctx->stream));
   return BT_OK;
 }
 
@@ -330,11 +364,33 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   cudaStream_t st = ctx->stream;
   std::vector<SlotMeta>& meta = t->meta;
 
+  double t_host = now_ms();
   t->frame_id += 1;  // demo:1292
   const int frame_id = t->frame_id;
   t->tlbr_cache_valid = false;
 
   // ---- inputs -> device ---------------------------------------------------------------------
+  // ---- per-frame result block layout (device d_res mirrors pinned h_res) ----
+  //   int32 [0..1]: duplicate-pair count | int32 pairs[2*kPairPrefetch] | x1,x2,x3 [n_rows each]
+  //   | (device inputs only) float scores[m], int32 boxes[4m] | pad to 8 B | double tlbr[4*n_rows]
+  const int n_rows_pre = t->high_water;
+  const bool inputs_on_device = (loc == BT_DEVICE);
+  size_t o_x = 2 + 2 * (size_t)kPairPrefetch, o_sc = o_x + 3 * (size_t)n_rows_pre,
+         o_bx = (o_sc + (inputs_on_device ? m : 0) + 3) & ~size_t(3),   // int4 stores: 16 B aligned
+         o_end_i = o_bx + (inputs_on_device ? 4 * (size_t)m : 0);
+  o_end_i = (o_end_i + 1) & ~size_t(1);
+  const size_t res_bytes = sizeof(int32_t) * o_end_i + sizeof(double) * 4 * n_rows_pre;
+  int32_t* dres_i = reinterpret_cast<int32_t*>(t->d_res);
+  int32_t* hres_i = reinterpret_cast<int32_t*>(t->h_res);
+  for (int s3 = 0; s3 < 3; ++s3) {
+    t->x[s3] = dres_i + o_x + (size_t)s3 * n_rows_pre;
+    t->h_x[s3] = hres_i + o_x + (size_t)s3 * n_rows_pre;
+  }
+  double* dres_tlbr = reinterpret_cast<double*>(dres_i + o_end_i);
+  const double* hres_tlbr = reinterpret_cast<const double*>(hres_i + o_end_i);
+  if (inputs_on_device) t->h_scores = reinterpret_cast<float*>(hres_i + o_sc);
+  else t->h_scores = t->h_scores_own;
+  const int32_t* host_boxes = inputs_on_device ? (hres_i + o_bx) : boxes;
   const int32_t* d_boxes = boxes;
   const float* d_scores = scores;
   const float* d_feats = feats;
@@ -349,13 +405,14 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
         BT_CUDA(cudaMemcpyAsync(t->det_feat_in, feats, sizeof(float) * (size_t)m * D, cudaMemcpyHostToDevice, st));
         d_feats = t->det_feat_in;
       }
-      memcpy(t->h_scores, scores, sizeof(float) * m);
+      memcpy(t->h_scores_own, scores, sizeof(float) * m);
     } else {
-      BT_CUDA(cudaMemcpyAsync(t->h_scores, scores, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
     }
     det_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_boxes, d_scores, m, cfg.track_high_thresh,
                                                      cfg.track_low_thresh, t->det_tlbr, t->det_xywh,
-                                                     t->det_xywh32, t->col_kind);
+                                                     t->det_xywh32, t->col_kind,
+                                                     inputs_on_device ? reinterpret_cast<float*>(dres_i + o_sc) : nullptr,
+                                                     inputs_on_device ? dres_i + o_bx : nullptr);
     BT_LAUNCHED(ctx);
     if (reid)
       BT_TRY(btk_feature_prep(ctx, d_feats, m, D, keep32 || !tensor_path ? t->det_feat32 : nullptr,
@@ -372,7 +429,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
   for (int s : t->lost) pool.push_back(s);  // joint_stracks: ids are unique per slot, no overlap
   const int n_pool = (int)pool.size(), n_unc = (int)unconfirmed.size();
-  const int n_rows = t->high_water;
+  const int n_rows = n_rows_pre;
 
   // ---- Kalman predict over the pool (demo:1426) ---------------------------------------------
   bool all_f32 = n_pool > 0;
@@ -397,7 +454,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   SEG_BEGIN(BT_SEG_PREDICT);
   if (n_pool > 0) {
     BT_TRY(btk_kalman_predict(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, dA_state, dA_idx, n_pool,
-                              all_f32 ? 1 : 0));
+                              all_f32 ? 1 : 0, t->slot_f32));
     for (int s : pool) meta[s].f32_state = 0;
   }
   SEG_END(BT_SEG_PREDICT);
@@ -405,7 +462,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   // ---- fused association over slots x detections + the three chained LAP solves -------------
   const bt_cand& cand = *bt_lap_own_cand(ctx);
   if (n_rows > 0) {
-    BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, st));
+    // the candidate counters are left zeroed by the previous frame's LAP kernel (no memset here)
     SEG_BEGIN(BT_SEG_ASSOC);
     if (m > 0) {
       bt_assoc_params p;
@@ -425,12 +482,32 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     SEG_END(BT_SEG_ASSOC);
     SEG_BEGIN(BT_SEG_LAP);
     const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
-    BT_TRY(btk_lap_solve3(ctx, cand, n_rows, m, th, t->x, t->y));
+    BT_TRY(btk_lap_solve3(ctx, cand, n_rows, m, th, t->x, t->y, dres_i));   // also zeroes the pair counter
     SEG_END(BT_SEG_LAP);
-    BT_CUDA(cudaMemcpyAsync(t->h_x[0], t->x[0], sizeof(int32_t) * ((size_t)2 * t->cap + n_rows),
-                            cudaMemcpyDeviceToHost, st));
+    // The matched tracks' Kalman update and feature EMA are a pure function of the three assignment
+    // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
+    // demo:570-610) while the host is still waiting for / digesting the assignments.
+    SEG_BEGIN(BT_SEG_UPDATE);
+    {
+      BT_TRY(btk_kalman_update_x(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->det_xywh, t->x[0], t->x[1],
+                                 t->x[2], t->slot_f32, n_rows, dres_tlbr));
+      if (reid && m > 0)
+        BT_TRY(btk_feature_ema_x(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
+                                 t->det_feat16, t->x[0], t->x[1], t->x[2], n_rows, D, cfg.ema_alpha));
+    }
+    SEG_END(BT_SEG_UPDATE);
+    // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
+    SEG_BEGIN(BT_SEG_DUP);
+    BT_TRY(btk_iou_pairs_live(ctx, t->tlbr, t->tlbr_f32, t->row_kind_cur, n_rows, cfg.duplicate_iou_dist,
+                              t->d_pairs, dres_i, t->pair_cap, dres_i + 2, kPairPrefetch));
+    SEG_END(BT_SEG_DUP);
   }
+  // ONE read-back per frame: pair count + first pairs, the three assignment vectors, (scores, boxes), boxes of all slots
+  if (n_rows > 0 || (inputs_on_device && m > 0))
+    BT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, res_bytes, cudaMemcpyDeviceToHost, st));
+  HOST_MARK(BT_SEG_HOST_ENQUEUE1);
   BT_CUDA(cudaStreamSynchronize(st));  // sync 1: assignments (and scores) are on the host
+  HOST_MARK(BT_SEG_HOST_WAIT1);
   BT_TRY(prof_collect(ctx, t));
 
   // ---- detection lists (demo:1493-1532) -----------------------------------------------------
@@ -446,11 +523,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   int n_upd = 0;
   auto apply_match = [&](int slot, int det) {
     SlotMeta& tm = meta[slot];
-    t->h_upd_track[n_upd] = slot;
-    t->h_upd_det[n_upd] = det;
-    t->h_upd_f32[n_upd] = tm.f32_state;
-    t->h_ema_mode[n_upd] = 0;
-    ++n_upd;
     tm.f32_state = 0;
     if (tm.state == BT_STATE_TRACKED) {  // STrack.update, demo:586-610
       tm.tracklet_len += 1;
@@ -528,7 +600,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       removed_now.push_back(s);
     }
   }
-  const int n_match_upd = n_upd;
   // births (demo:1614-1621, STrack.activate demo:556-568)
   int n_births = 0;
   for (int j : hi_list) {
@@ -551,11 +622,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     t->h_birth_slot[n_births] = s;
     t->h_birth_det[n_births] = j;
     ++n_births;
-    t->h_upd_track[n_upd] = s;
-    t->h_upd_det[n_upd] = j;
-    t->h_upd_f32[n_upd] = 0;
-    t->h_ema_mode[n_upd] = 2;
-    ++n_upd;
     activated.push_back(s);
   }
   // expiry (demo:1623-1627)
@@ -588,82 +654,99 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   for (int s : removed_now) meta[s].in_removed = 1; // removed_stracks.extend
   t->n_removed_total += (int)removed_now.size();
 
-  // ---- device: one packed H2D (update lists, births, merged lists), then Kalman update / initiate /
-  //      features / duplicate test / result gather back to back ------------------------------------
+  // ---- births on the device: one packed H2D, Kalman initiate + feature adoption --------------------
   const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
-  int32_t* hB = reinterpret_cast<int32_t*>(t->h_ctrl);
-  int32_t* dB = reinterpret_cast<int32_t*>(t->d_ctrl);
-  size_t o_track = 0, o_det = o_track + n_upd, o_bslot = o_det + n_upd, o_bdet = o_bslot + n_births,
-         o_la = o_bdet + n_births, o_lb = o_la + nt, o_end = o_lb + nl;
-  memcpy(hB + o_track, t->h_upd_track, sizeof(int32_t) * n_upd);
-  memcpy(hB + o_det, t->h_upd_det, sizeof(int32_t) * n_upd);
-  memcpy(hB + o_bslot, t->h_birth_slot, sizeof(int32_t) * n_births);
-  memcpy(hB + o_bdet, t->h_birth_det, sizeof(int32_t) * n_births);
-  if (nt) memcpy(hB + o_la, new_tracked.data(), sizeof(int32_t) * nt);
-  if (nl) memcpy(hB + o_lb, new_lost.data(), sizeof(int32_t) * nl);
-  uint8_t* hB8 = reinterpret_cast<uint8_t*>(hB + o_end);
-  memcpy(hB8, t->h_upd_f32, n_upd);
-  memcpy(hB8 + n_upd, t->h_ema_mode, n_upd);
-  const size_t bytesB = sizeof(int32_t) * o_end + 2 * (size_t)n_upd;
-  if (bytesB > 0) BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesB, cudaMemcpyHostToDevice, st));
-  const int32_t *d_upd_track = dB + o_track, *d_upd_det = dB + o_det, *d_birth_slot = dB + o_bslot,
-                *d_birth_det = dB + o_bdet, *d_lista = dB + o_la, *d_listb = dB + o_lb;
-  const uint8_t* d_upd_f32 = reinterpret_cast<const uint8_t*>(dB + o_end);
-  const uint8_t* d_ema_mode = d_upd_f32 + n_upd;
-  SEG_BEGIN(BT_SEG_UPDATE);
-  if (n_match_upd > 0)
-    BT_TRY(btk_kalman_update(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->det_xywh, d_upd_track, d_upd_det,
-                             d_upd_f32, n_match_upd));
-  if (n_births > 0)
+  int n_pairs = hres_i[0];               // live-slot duplicate candidates found before the sync
+  if (n_rows <= 1) n_pairs = 0;
+  BT_CHECK(n_pairs <= t->pair_cap, BT_ERR_CAPACITY, "%d duplicate pairs exceed capacity %d", n_pairs, t->pair_cap);
+  bool need_sync = false;
+  const int32_t* live_pairs = hres_i + 2;
+  if (n_pairs > kPairPrefetch) {
+    BT_CUDA(cudaMemcpyAsync(t->h_pairs, t->d_pairs, sizeof(int32_t) * 2 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    live_pairs = t->h_pairs;
+    need_sync = true;
+  }
+  int n_bpairs = 0;
+  if (n_births > 0) {
+    int32_t* hB = reinterpret_cast<int32_t*>(t->h_ctrl);
+    int32_t* dB = reinterpret_cast<int32_t*>(t->d_ctrl);
+    const bool birth_dup = nl > 0;       // a newborn can duplicate a lost track: test births x lost
+    memcpy(hB, t->h_birth_slot, sizeof(int32_t) * n_births);
+    memcpy(hB + n_births, t->h_birth_det, sizeof(int32_t) * n_births);
+    if (birth_dup) memcpy(hB + 2 * n_births, new_lost.data(), sizeof(int32_t) * nl);
+    uint8_t* hB8 = reinterpret_cast<uint8_t*>(hB + 2 * n_births + (birth_dup ? nl : 0));
+    memset(hB8, 2, n_births);              // feature mode 2: adopt the detection's normalised feature
+    const size_t bytesB = sizeof(int32_t) * (2 * (size_t)n_births + (birth_dup ? nl : 0)) + n_births;
+    BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesB, cudaMemcpyHostToDevice, st));
+    const int32_t *d_birth_slot = dB, *d_birth_det = dB + n_births, *d_listb = dB + 2 * n_births;
+    const uint8_t* d_mode = reinterpret_cast<const uint8_t*>(dB + 2 * n_births + (birth_dup ? nl : 0));
     BT_TRY(btk_kalman_initiate(ctx, t->det_xywh32, d_birth_det, t->mean, t->cov, t->tlbr, t->tlbr_f32,
-                               d_birth_slot, n_births));
-  if (reid && n_upd > 0)
-    BT_TRY(btk_feature_ema16(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
-                             t->det_feat16, d_upd_track, d_upd_det, d_ema_mode, n_upd, D, cfg.ema_alpha));
-  SEG_END(BT_SEG_UPDATE);
-
-  // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) + result read-back --------------
-  int n_pairs = 0;
-  SEG_BEGIN(BT_SEG_DUP);
-  if (nt > 0) {
-    if (nl > 0) {
+                               d_birth_slot, n_births, t->slot_f32));
+    if (reid)
+      BT_TRY(btk_feature_ema16(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
+                               t->det_feat16, d_birth_slot, d_birth_det, d_mode, n_births, D, cfg.ema_alpha));
+    if (birth_dup) {
       BT_CUDA(cudaMemsetAsync(t->d_pair_count, 0, sizeof(int32_t), st));
-      BT_TRY(btk_iou_pairs_below(ctx, t->tlbr, d_lista, nt, d_listb, nl, cfg.duplicate_iou_dist, t->d_pairs,
-                                 t->d_pair_count, t->pair_cap));
+      BT_TRY(btk_iou_pairs_below(ctx, t->tlbr, d_birth_slot, n_births, d_listb, nl, cfg.duplicate_iou_dist,
+                                 t->d_bpairs, t->d_pair_count, t->bpair_cap));
       BT_CUDA(cudaMemcpyAsync(t->h_pair_count, t->d_pair_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    }
-    gather_rows_f64_kernel<<<(nt * 4 + 255) / 256, 256, 0, st>>>(t->tlbr, d_lista, nt, 4, t->d_gather);
-    BT_LAUNCHED(ctx);
-    BT_CUDA(cudaMemcpyAsync(t->h_tlbr, t->d_gather, sizeof(double) * 4 * nt, cudaMemcpyDeviceToHost, st));
-  }
-  SEG_END(BT_SEG_DUP);
-  BT_CUDA(cudaStreamSynchronize(st));  // sync 2: duplicate count + boxes of the returned list
-  BT_TRY(prof_collect(ctx, t));
-  if (nt > 0 && nl > 0) {
-    n_pairs = *t->h_pair_count;
-    BT_CHECK(n_pairs <= t->pair_cap, BT_ERR_CAPACITY, "%d duplicate pairs exceed capacity %d", n_pairs,
-             t->pair_cap);
-    if (n_pairs > 0) {
-      BT_CUDA(cudaMemcpyAsync(t->h_pairs, t->d_pairs, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, st));
-      BT_CUDA(cudaStreamSynchronize(st));
+      need_sync = true;
     }
   }
-  std::vector<uint8_t> dupa(nt, 0), dupb(nl, 0);
-  for (int k = 0; k < n_pairs; ++k) {
-    const int p = t->h_pairs[2 * k], q = t->h_pairs[2 * k + 1];
-    const int timep = meta[new_tracked[p]].frame_id - meta[new_tracked[p]].start_frame;
-    const int timeq = meta[new_lost[q]].frame_id - meta[new_lost[q]].start_frame;
-    if (timep > timeq) dupb[q] = 1;
-    else dupa[p] = 1;
+  HOST_MARK(BT_SEG_HOST_LISTS);
+  if (need_sync) {
+    BT_CUDA(cudaStreamSynchronize(st));  // rare second sync: births next to lost tracks / very many candidates
+    if (n_births > 0 && nl > 0) {
+      n_bpairs = *t->h_pair_count;
+      BT_CHECK(n_bpairs <= t->bpair_cap, BT_ERR_CAPACITY, "%d duplicate pairs exceed capacity %d", n_bpairs,
+               t->bpair_cap);
+      if (n_bpairs > 0) {
+        BT_CUDA(cudaMemcpyAsync(t->h_bpairs, t->d_bpairs, sizeof(int32_t) * 2 * n_bpairs,
+                                cudaMemcpyDeviceToHost, st));
+        BT_CUDA(cudaStreamSynchronize(st));
+      }
+    }
+  }
+  HOST_MARK(BT_SEG_HOST_WAIT2);
+
+  // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) --------------------------------------
+  std::vector<uint8_t>& dupa = t->scratch_a; dupa.assign(nt, 0);
+  std::vector<uint8_t>& dupb = t->scratch_b; dupb.assign(nl, 0);
+  if (n_pairs > 0 || n_bpairs > 0) {
+    std::vector<int>& pos_t = t->scratch_pos_t; pos_t.assign(t->high_water, -1);
+    std::vector<int>& pos_l = t->scratch_pos_l; pos_l.assign(t->high_water, -1);
+    for (int i = 0; i < nt; ++i) pos_t[new_tracked[i]] = i;
+    for (int i = 0; i < nl; ++i) pos_l[new_lost[i]] = i;
+    auto resolve = [&](int p, int q) {   // p: position in tracked, q: position in lost (demo:1669-1677)
+      const int timep = meta[new_tracked[p]].frame_id - meta[new_tracked[p]].start_frame;
+      const int timeq = meta[new_lost[q]].frame_id - meta[new_lost[q]].start_frame;
+      if (timep > timeq) dupb[q] = 1;
+      else dupa[p] = 1;
+    };
+    for (int k = 0; k < n_pairs; ++k) {
+      const int i = live_pairs[2 * k], j = live_pairs[2 * k + 1];
+      if (pos_t[i] >= 0 && pos_l[j] >= 0) resolve(pos_t[i], pos_l[j]);
+      if (pos_t[j] >= 0 && pos_l[i] >= 0) resolve(pos_t[j], pos_l[i]);
+    }
+    for (int k = 0; k < n_bpairs; ++k)     // (birth index, lost position)
+      resolve(pos_t[t->h_birth_slot[t->h_bpairs[2 * k]]], t->h_bpairs[2 * k + 1]);
   }
   t->tracked.clear();
   t->lost.clear();
   t->tlbr_cache.clear();
-  for (int i = 0; i < nt; ++i)
-    if (!dupa[i]) {
-      t->tracked.push_back(new_tracked[i]);
-      for (int c = 0; c < 4; ++c) t->tlbr_cache.push_back(t->h_tlbr[4 * i + c]);
+  for (int i = 0; i < nt; ++i) {
+    if (dupa[i]) continue;
+    const int s = new_tracked[i];
+    t->tracked.push_back(s);
+    const bool born_now = meta[s].f32_state && meta[s].start_frame == frame_id;
+    if (!born_now) {
+      for (int c = 0; c < 4; ++c) t->tlbr_cache.push_back(hres_tlbr[4 * (size_t)s + c]);
+    } else {
+      // a track born this frame in a fresh slot: its box is the detection's (demo:624-648 on initiate's mean)
+      const int32_t* bx = host_boxes + 4 * (size_t)meta[s].det_index;
+      for (int c = 0; c < 4; ++c) t->tlbr_cache.push_back((double)bx[c]);
     }
+  }
   for (int i = 0; i < nl; ++i)
     if (!dupb[i]) t->lost.push_back(new_lost[i]);
   t->tlbr_cache_valid = true;
@@ -682,6 +765,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
   if (freed) std::sort(t->free_slots.begin(), t->free_slots.end(), std::greater<int>());
 
+  HOST_MARK(BT_SEG_HOST_FINAL);
   if (info) {
     info->frame_id = frame_id;
     info->n_tracked = (int)t->tracked.size();
@@ -705,8 +789,8 @@ int32_t bt_profile_enable(bt_ctx* ctx, int32_t on) {
   bt_tracker* t = ctx->trk;
   BT_CUDA(cudaStreamSynchronize(ctx->stream));
   if (on) {
-    for (auto& pair : t->ev)
-      for (cudaEvent_t& e : pair)
+    for (int s = 0; s < BT_SEG_HOST_ENQUEUE1; ++s)
+      for (cudaEvent_t& e : t->ev[s])
         if (!e) BT_CUDA(cudaEventCreate(&e));
     for (int s = 0; s < BT_SEG_COUNT; ++s) { t->prof_ms[s] = 0.0; t->prof_n[s] = 0; t->seg_open[s] = false; }
   }

@@ -97,7 +97,13 @@ enum {
   BT_SEG_LAP = 3,     /* the three LAP solves */
   BT_SEG_UPDATE = 4,  /* Kalman update + initiate + feature EMA */
   BT_SEG_DUP = 5,     /* duplicate test + result gather */
-  BT_SEG_COUNT = 6
+  /* host wall-clock phases of bt_update_arrays (std::chrono), same units (ms) */
+  BT_SEG_HOST_ENQUEUE1 = 6, /* input staging + enqueue up to the LAP */
+  BT_SEG_HOST_WAIT1 = 7,    /* first stream synchronisation */
+  BT_SEG_HOST_LISTS = 8,    /* list bookkeeping + enqueue of update/duplicate kernels */
+  BT_SEG_HOST_WAIT2 = 9,    /* second stream synchronisation */
+  BT_SEG_HOST_FINAL = 10,   /* duplicate resolution, slot recycling */
+  BT_SEG_COUNT = 11
 };
 int32_t bt_profile_enable(bt_ctx* ctx, int32_t on);
 /* accumulated device milliseconds and number of samples of a segment since bt_profile_enable(1) */

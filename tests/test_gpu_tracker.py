@@ -115,3 +115,32 @@ def test_capacity_error(ctx):
     with pytest.raises(ValueError):
         ctx.update_arrays(np.zeros((ctx.max_dets + 1, 4), np.int32), np.zeros(ctx.max_dets + 1, np.float32),
                           np.zeros((ctx.max_dets + 1, 2048), np.float32))
+
+
+def test_device_resident_inputs_match_host_inputs(ctx):
+    """loc = BT_DEVICE (inputs already in HBM, what bench.py's `value` leg times) gives the same tracks
+    as host buffers."""
+    import torch
+    from botsort_b200._lib import BT_DEVICE
+    scene_cfg = SceneConfig(n_ids=150, feat_dim=2048, seed=13, low_frac=0.1, drop_frac=0.1, newcomer_every=4)
+    frames = [SyntheticScene(scene_cfg).next_frame()]
+    sc = SyntheticScene(scene_cfg)
+    frames = [sc.next_frame() for _ in range(8)]
+    ctx.tracker_reset()
+    ref = []
+    for fr in frames:
+        ctx.update_arrays(fr["boxes"], fr["scores"], fr["feats"])
+        ref.append((ctx.get_tracks(0, with_state=True), ctx.get_tracks(1)))
+    ctx.tracker_reset()
+    for fr, (rt, rl) in zip(frames, ref):
+        b = torch.from_numpy(fr["boxes"]).cuda()
+        s = torch.from_numpy(fr["scores"]).cuda()
+        f = torch.from_numpy(fr["feats"]).cuda()
+        torch.cuda.synchronize()
+        ctx.update_arrays_raw(b.data_ptr(), s.data_ptr(), f.data_ptr(), b.shape[0], BT_DEVICE)
+        gt, gl = ctx.get_tracks(0, with_state=True), ctx.get_tracks(1)
+        for key in INT_FIELDS:
+            np.testing.assert_array_equal(gt[key], rt[key])
+            np.testing.assert_array_equal(gl[key], rl[key])
+        np.testing.assert_array_equal(gt["tlbr"], rt["tlbr"])
+        np.testing.assert_array_equal(gt["mean"], rt["mean"])

@@ -11,6 +11,6 @@ os.environ["BT_ASSOC_CLUSTER"] = sys.argv[1] if len(sys.argv) > 1 else "1x1"
 ctx.tracker_reset()
 for i, f in enumerate(frames):
     if i == 4:
-        os.environ["BT_ASSOC_DEBUG"] = "1"; os.environ["BT_LAP_DEBUG"] = "1"
+        os.environ["BT_ASSOC_DEBUG"] = sys.argv[2] if len(sys.argv) > 2 else "1"; os.environ["BT_LAP_DEBUG"] = "1"
     ctx.update_arrays(f["boxes"], f["scores"], f["feats"])
 ctx.sync()
