@@ -26,7 +26,7 @@ EXPORTS = [
     "bt_iou_distance", "bt_embedding_distance", "bt_fused_cost", "bt_fuse_score", "bt_linear_assignment",
     "bt_feature_ema", "bt_default_yolox_config", "bt_yolox_postprocess", "bt_reid_crop_gather",
     "bt_tracker_reset", "bt_update_arrays", "bt_get_tracks", "bt_get_track_features", "bt_get_matches",
-    "bt_profile_enable", "bt_profile_read",
+    "bt_profile_enable", "bt_profile_read", "bt_profile_replay_assoc",
 ]
 SEGMENTS = ("prep", "predict", "assoc", "lap", "update", "dup",
             "host_enqueue1", "host_wait1", "host_lists", "host_wait2", "host_final")
@@ -110,6 +110,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bt_get_matches": [vp, i32, i32, vp, vp],
         "bt_profile_enable": [vp, i32],
         "bt_profile_read": [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
+        "bt_profile_replay_assoc": [vp, i32, C.POINTER(C.c_double)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -182,6 +183,12 @@ class Context:
 
     def profile_enable(self, on: bool = True):
         self._check(self.lib.bt_profile_enable(self.h, int(on)))
+
+    def profile_replay_assoc(self, iters: int = 50) -> float:
+        """Average device ms of one launch of the last frame's association kernel (back-to-back replays)."""
+        ms = C.c_double(0)
+        self._check(self.lib.bt_profile_replay_assoc(self.h, iters, C.byref(ms)))
+        return ms.value / max(1, iters)
 
     def profile_read(self) -> dict:
         """{segment: (total device ms, samples)} accumulated since profile_enable(True)."""

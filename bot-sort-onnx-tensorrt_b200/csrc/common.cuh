@@ -154,12 +154,12 @@ enum { BT_COL_NONE = 0, BT_COL_HIGH = 1, BT_COL_LOW = 2 };
 
 // Candidate lists ("ragged dense" adjacency): list s in {0,1,2} = association stage 1,2,3.
 // Row r owns entries [r*stride, r*stride + cnt[s*rows_cap + r]) of col/cost.
-// A row's region of `stride` entries is cut into `nseg` segments of BT_CAND_SEG columns: the
-// edges of row r found in columns [g*SEG, (g+1)*SEG) are written to
-// [r*stride + g*SEG, r*stride + g*SEG + cnt[list][r][g]).  The tensor-core epilogue owns one
+// A row's region of `stride` entries is cut into segments of `seg` columns: the
+// edges of row r found in columns [g*seg, (g+1)*seg) are written to
+// [r*stride + g*seg, r*stride + g*seg + cnt[list][r][g]).  The tensor-core epilogue owns one
 // (row, segment) pair per thread, so it appends with plain stores and a register counter -- no
 // atomics; the LAP set-up compacts the segments of a row to the front of its region.
-#define BT_CAND_SEG 128
+#define BT_CAND_MAXSEG 64   // segments per row (bits of segmask); cnt row pitch
 struct bt_cand {
   int32_t* cnt;    // [3][rows_cap][nseg]
   int32_t* total;  // [4] per list: non-zero when any edge was emitted (lets the LAP skip empty stages)
@@ -168,8 +168,9 @@ struct bt_cand {
   int32_t* col;    // [3][rows_cap*stride]
   double* cost;    // [3][rows_cap*stride]
   int32_t rows_cap;
-  int32_t stride;  // = round_up(max_dets, BT_CAND_SEG)
-  int32_t nseg;    // = stride / BT_CAND_SEG
+  int32_t stride;  // entries per row >= max_dets + one segment of slack
+  int32_t nseg;    // = BT_CAND_MAXSEG (row pitch of cnt)
+  int32_t seg;     // columns per segment THIS frame: half the association tile width (128 or 112), 128 otherwise
   size_t clear_bytes;  // cnt, total and segmask live in one allocation: one memset of this many bytes at cnt
 };
 
@@ -180,6 +181,8 @@ struct bt_assoc_params {
   const float* a32;    // fp32 variants for the SIMT kernel (may be null when tensor path is used)
   const float* b32;
   int32_t n, m, d;
+  int32_t bn;                          // association tile width (256 or 224); 0 = 256.  Candidate emission
+                                       // requires cand.seg == bn / 2 (btk_assoc_pick_bn)
   int32_t a_rows_alloc, b_rows_alloc;  // rows the operand buffers really hold (0 = n / m): lets the TMA
                                        // descriptors be cached across frames; rows >= n / m are masked
   // epilogue inputs (null => not used)
@@ -199,6 +202,8 @@ struct bt_assoc_params {
   int32_t dense_stage;      // 1 or 3: which fusion rule the dense dump uses
 };
 int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& p, int32_t precision);
+// tile width that minimises (waves x MMA time per tile) for an n x m problem on this GPU
+int32_t btk_assoc_pick_bn(const bt_ctx* ctx, int32_t n, int32_t m);
 int32_t bt_gemm_ws_create(bt_ctx* ctx);
 void bt_gemm_ws_destroy(bt_ctx* ctx);
 

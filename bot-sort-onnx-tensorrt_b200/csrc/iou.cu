@@ -125,22 +125,27 @@ iou_pairs_live_kernel(const double* __restrict__ tlbr, const float* __restrict__
                       const uint8_t* __restrict__ kind, int n, double limit, int32_t* __restrict__ pairs,
                       int32_t* __restrict__ pair_count, int pair_cap, int32_t* __restrict__ pairs_small,
                       int small_cap) {
-  // grid (j tile, i tile) with j tile >= i tile; a thread owns slot i and scans the 256 slots of the j tile
-  if (blockIdx.x < blockIdx.y) return;
-  __shared__ float4 sb[256];
-  __shared__ uint8_t sk[256];
+  // grid (j tile of 64, i tile of 256), only tiles that can hold a pair j > i; a thread owns slot i and
+  // scans the 64 slots of the j tile (hundreds of small blocks: the shared-memory broadcasts of the
+  // j boxes are the cost, spread them over all SMs)
+  constexpr int JT = 64;
+  if ((int)(blockIdx.x + 1) * JT <= (int)blockIdx.y * 256) return;
+  __shared__ float4 sb[JT];
+  __shared__ uint8_t sk[JT];
   const int i = blockIdx.y * 256 + threadIdx.x;
-  const int j0 = blockIdx.x * 256;
+  const int j0 = blockIdx.x * JT;
   const bool live_i = i < n && kind[i] != 0;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live_i) a = *reinterpret_cast<const float4*>(tlbr_f32 + (size_t)i * 4);
   const float area_a = (a.z - a.x) * (a.w - a.y);
   const int jj = j0 + threadIdx.x;
-  sk[threadIdx.x] = (jj < n) ? kind[jj] : 0;
-  sb[threadIdx.x] = (jj < n) ? *reinterpret_cast<const float4*>(tlbr_f32 + (size_t)jj * 4) : a;
+  if (threadIdx.x < JT) {
+    sk[threadIdx.x] = (jj < n) ? kind[jj] : 0;
+    sb[threadIdx.x] = (jj < n) ? *reinterpret_cast<const float4*>(tlbr_f32 + (size_t)jj * 4) : a;
+  }
   __syncthreads();
   if (!live_i) return;
-  const int lim = min(256, n - j0);
+  const int lim = min(JT, n - j0);
 #pragma unroll 4
   for (int k = 0; k < lim; ++k) {
     const int j = j0 + k;
@@ -168,7 +173,7 @@ int32_t btk_iou_pairs_live(bt_ctx* ctx, const double* tlbr, const float* tlbr_f3
                            int32_t* pairs_small, int32_t small_cap) {
   if (n <= 1) return BT_OK;
   const int tiles = (n + 255) / 256;
-  iou_pairs_live_kernel<<<dim3(tiles, tiles), 256, 0, ctx->stream>>>(tlbr, tlbr_f32, kind, n, limit, pairs,
+  iou_pairs_live_kernel<<<dim3((n + 63) / 64, tiles), 256, 0, ctx->stream>>>(tlbr, tlbr_f32, kind, n, limit, pairs,
                                                                       pair_count, pair_cap, pairs_small, small_cap);
   BT_LAUNCHED(ctx);
   return BT_OK;

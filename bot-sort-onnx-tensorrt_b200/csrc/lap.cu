@@ -512,7 +512,7 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
           mask &= mask - 1;
           const int k = row_on ? segcnt[g] : 0;
           if (P.clear_lists) segcnt[g] = 0;
-          const int src = g * BT_CAND_SEG;
+          const int src = g * cand.seg;
           for (int e = 0; e < k; ++e) {
             const int c = rc[src + e];
             if (src + e != total) { rc[total] = c; rv[total] = rv[src + e]; }
@@ -646,8 +646,8 @@ lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double t
   int32_t* segcnt = cand.cnt + ((size_t)list * cand.rows_cap + row) * cand.nseg;
   int count = 0;
   for (int c0 = 0; c0 < m; c0 += 32) {
-    if (c0 > 0 && (c0 % BT_CAND_SEG) == 0) {     // next segment
-      if (lane == 0) segcnt[c0 / BT_CAND_SEG - 1] = count;
+    if (c0 > 0 && (c0 % cand.seg) == 0) {     // next segment (seg is a multiple of 32 here)
+      if (lane == 0) segcnt[c0 / cand.seg - 1] = count;
       count = 0;
     }
     const int c = c0 + lane;
@@ -655,16 +655,16 @@ lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double t
     const bool keep = (c < m) && (v < thresh);
     const unsigned ball = __ballot_sync(0xffffffffu, keep);
     if (keep) {
-      const int pos = (c0 / BT_CAND_SEG) * BT_CAND_SEG + count + __popc(ball & ((1u << lane) - 1));
+      const int pos = (c0 / cand.seg) * cand.seg + count + __popc(ball & ((1u << lane) - 1));
       ecol[pos] = c;
       ecost[pos] = v;
     }
     count += __popc(ball);
   }
-  if (lane == 0) segcnt[(m - 1) / BT_CAND_SEG] = count;
+  if (lane == 0) segcnt[(m - 1) / cand.seg] = count;
   if (lane == 0) {
     atomicAdd(&cand.total[list], 1);   // any non-zero value means "stage not empty"
-    const int nseg_used = (m - 1) / BT_CAND_SEG + 1;
+    const int nseg_used = (m - 1) / cand.seg + 1;
     cand.segmask[(size_t)list * cand.rows_cap + row] = (nseg_used >= 64) ? ~0ull : ((1ull << nseg_used) - 1);
   }
 }
@@ -677,10 +677,11 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
   const int rows = ctx->max_tracks, cols = ctx->max_dets;
   ws->rows = rows;
   ws->cols = cols;
-  const int stride = (cols + BT_CAND_SEG - 1) / BT_CAND_SEG * BT_CAND_SEG;
+  const int stride = (cols + 127) / 128 * 128 + 128;
   ws->cand.rows_cap = rows;
   ws->cand.stride = stride;
-  ws->cand.nseg = stride / BT_CAND_SEG;
+  ws->cand.nseg = BT_CAND_MAXSEG;
+  ws->cand.seg = 128;
   const size_t cnt_ints = (3 * (size_t)rows * ws->cand.nseg + 4 + 1) & ~size_t(1);   // keeps segmask 8 B aligned
   ws->cand.clear_bytes = sizeof(int32_t) * cnt_ints + sizeof(unsigned long long) * 3 * rows;
   BT_CUDA(cudaMalloc(&ws->cand.cnt, ws->cand.clear_bytes));
@@ -690,7 +691,7 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
   BT_CUDA(cudaMalloc(&ws->cand.col, sizeof(int32_t) * 3 * (size_t)rows * stride));
   BT_CUDA(cudaMalloc(&ws->cand.cost, sizeof(double) * 3 * (size_t)rows * stride));
   BT_CUDA(cudaMemset(ws->cand.cnt, 0, ws->cand.clear_bytes));
-  BT_CHECK(ws->cand.nseg <= 64, BT_ERR_CAPACITY, "max_dets %d exceeds %d", cols, 64 * BT_CAND_SEG);
+  BT_CHECK(cols <= BT_CAND_MAXSEG * 112, BT_ERR_CAPACITY, "max_dets %d exceeds %d", cols, BT_CAND_MAXSEG * 112);
 #define BT_LAP_ALLOC(field, type, count) BT_CUDA(cudaMalloc(&ws->field, sizeof(type) * (size_t)(count)))
   BT_LAP_ALLOC(label, int32_t, rows);
   BT_LAP_ALLOC(collabel, int32_t, 3 * (size_t)cols);

@@ -25,6 +25,7 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace {
@@ -48,6 +49,7 @@ struct EpiParams {
   int n, m;
   int debug;   // BT_ASSOC_DEBUG=1: per-CTA phase timestamps via device printf (profiling aid)
   float sim_gate;  // smallest similarity for which the appearance gate is open
+  float iou_gate;  // a pair without open appearance gate needs IoU > 1 - max(stage thresholds); slightly lowered
 };
 
 __device__ __forceinline__ double iou_dist_f64(const double* __restrict__ a, const double* __restrict__ b) {
@@ -76,9 +78,9 @@ __device__ __forceinline__ double fuse_stage3(double iou_d, float sim, float app
 
 // atomic append into the (row, column-segment) sub-list (CUDA-core kernel: several threads share a row)
 __device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int col, double cost) {
-  const int seg = col / BT_CAND_SEG;
+  const int seg = col / c.seg;
   const int k = atomicAdd(c.cnt + ((size_t)list * c.rows_cap + row) * c.nseg + seg, 1);
-  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * BT_CAND_SEG + k;
+  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * c.seg + k;
   c.col[base] = col;
   c.cost[base] = cost;
   atomicAdd(&c.total[list], 1);
@@ -86,7 +88,7 @@ __device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int co
 }
 // plain append: the caller owns (row, segment) exclusively and keeps the count in a register
 __device__ __forceinline__ void emit_owned(const bt_cand& c, int list, int row, int seg, int k, int col, double cost) {
-  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * BT_CAND_SEG + k;
+  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * c.seg + k;
   c.col[base] = col;
   c.cost[base] = cost;
 }
@@ -211,6 +213,30 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// Box -> two 32-bit words of 15-bit integer corners rounded OUTWARD (lo floored, hi ceiled):
+//   .x = (x1 + 1) | (y1 + 1) << 16        .y = x2 | y2 << 16 | 0x80008000
+// Corners outside [0, 32766] are widened to the whole range (the screen then passes and the exact
+// float64 path decides), so the packed test never rejects a pair whose exact IoU is positive.
+__device__ __forceinline__ uint2 pack16_box(double x1, double y1, double x2, double y2, bool is_col) {
+  // Saturation keeps the screen conservative: lowering a lower corner or raising an upper corner only adds
+  // overlaps; upper corners above 32767 meet lower corners saturated to 32766 (test passes); a ROW's negative
+  // corners clamp to 0 because detection corners are >= 0 -- a detection with a negative corner (outside the
+  // reference's domain: YOLOX._postprocess clamps at 0, demo:1009) and NaNs fall back to the whole range.
+  const bool ok = (x1 == x1) && (y1 == y1) && (x2 == x2) && (y2 == y2) && !(is_col && (x1 < 0.0 || y1 < 0.0));
+  const double lx = ok ? fmin(fmax(floor(x1), 0.0), 32766.0) : 0.0, ly = ok ? fmin(fmax(floor(y1), 0.0), 32766.0) : 0.0;
+  const double hx = ok ? fmin(fmax(ceil(x2), 0.0), 32767.0) : 32767.0, hy = ok ? fmin(fmax(ceil(y2), 0.0), 32767.0) : 32767.0;
+  const uint32_t ix1 = (uint32_t)lx, iy1 = (uint32_t)ly, ix2 = (uint32_t)hx, iy2 = (uint32_t)hy;
+  return make_uint2((ix1 + 1u) | ((iy1 + 1u) << 16), ix2 | (iy2 << 16) | 0x80008000u);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile in shared memory, 128-byte swizzle (as written by TMA SWIZZLE_128B):
@@ -237,6 +263,7 @@ constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kEpiWarps = 8;     // two per SM sub-partition: warp w and w+4 share TMEM lane quarter w%4
 constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kQueue = 96;       // survivor records per epilogue warp before a drain
 constexpr int kTcThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN>
@@ -244,11 +271,12 @@ struct TcSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kColF32Off = kStages * kStageBytes;            // float4[BN]  det box fp32
-  static constexpr int kColKindOff = kColF32Off + BN * 16;            // uint8[BN]
-  static constexpr int kColValidOff = kColKindOff + BN;               // uint32[BN/32] bit c: kind != NONE
-  static constexpr int kColF64Off = kColValidOff + 64;                // double[BN][4] det box float64 (exact path)
-  static constexpr int kBarOff = kColF64Off + BN * 32;                // barriers (8B aligned)
+  static constexpr int kColPkOff = kStages * kStageBytes;             // uint2[BN]  packed integer det corners
+  static constexpr int kColKindOff = kColPkOff + BN * 8;              // uint8[BN]
+  static constexpr int kColF64Off = kColKindOff + 256;                // double[BN][4] det box float64 (exact path)
+  static constexpr int kQueueOff = kColF64Off + BN * 32;              // uint2[kEpiWarps][kQueue] survivor records
+  static constexpr int kRowCntOff = kQueueOff + 8 * 96 * 8;           // int[kEpiWarps][32][2]
+  static constexpr int kBarOff = kRowCntOff + 8 * 64 * 4;             // barriers (8B aligned)
   static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
@@ -269,7 +297,6 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int CS = CM * CN;
   constexpr int kASlice = BM / CN, kBSlice = BN / CM;  // rows each CTA loads itself
   static_assert(kASlice % 8 == 0 && kBSlice % 8 == 0, "slices must keep the 8-row swizzle atoms whole");
-  static_assert(BN == 2 * BT_CAND_SEG, "one epilogue thread owns one (row, candidate segment) pair");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -277,13 +304,16 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + kAccStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
-  float4* s_col32 = reinterpret_cast<float4*>(smem + L::kColF32Off);
+  uint2* s_colpk = reinterpret_cast<uint2*>(smem + L::kColPkOff);
   uint8_t* s_colkind = smem + L::kColKindOff;
-  uint32_t* s_colvalid = reinterpret_cast<uint32_t*>(smem + L::kColValidOff);
+  uint2* s_queue = reinterpret_cast<uint2*>(smem + L::kQueueOff);
+  int* s_rowcnt = reinterpret_cast<int*>(smem + L::kRowCntOff);
   double* s_col64 = reinterpret_cast<double*>(smem + L::kColF64Off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long t_start = clock64();
+  unsigned long long g_start = 0;
+  if (p.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
   const int tiles_m = (p.n + BM - 1) / BM, tiles_n = (p.m + BN - 1) / BN;
   const int num_kb = d / BK;
   // cluster geometry: cluster `cid` walks "cluster tiles" of CM x CN output tiles; tiles past the
@@ -388,129 +418,191 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
       const int row = m0 + quarter * 32 + lane;
       int rkind = BT_ROW_NONE;
-      float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
       double rbox[4] = {0.0, 0.0, 0.0, 0.0};
+      uint32_t r2h = 0, r1p = 0;   // packed conservative integer row box (see pack16 below)
+      int rix1 = 0, riy1 = 0, rix2 = 0, riy2 = 0;
+      float r_area_lb = 0.f;
       if (!kDense) {
-        // stage this tile's detection boxes (fp32, exact: integer pixels) and kinds
+        // stage this tile's detection boxes: packed 15-bit integer corners for the screen, float64 for
+        // the exact path, and the score class
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // previous tile's readers are done
         for (int c = et; c < BN; c += kEpiThreads) {
           const int col = n0 + c;
-          float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+          uint2 pk = make_uint2(0x7fff7fffu, 0x80008000u);   // x1+1 = y1+1 = 32767, x2 = y2 = 0: overlaps nothing
           uint8_t ck = BT_COL_NONE;
           double4 cd = make_double4(0.0, 0.0, 0.0, 0.0);
           if (col < p.m) {
             const double2* s = reinterpret_cast<const double2*>(p.col_tlbr + (size_t)col * 4);
             const double2 lo = s[0], hi = s[1];
             cd = make_double4(lo.x, lo.y, hi.x, hi.y);
-            cb = make_float4((float)lo.x, (float)lo.y, (float)hi.x, (float)hi.y);
             ck = p.col_kind[col];
+            if (ck != BT_COL_NONE) pk = pack16_box(lo.x, lo.y, hi.x, hi.y, true);
           }
-          s_col32[c] = cb;
+          s_colpk[c] = pk;
           s_colkind[c] = ck;
           reinterpret_cast<double2*>(s_col64 + c * 4)[0] = make_double2(cd.x, cd.y);
           reinterpret_cast<double2*>(s_col64 + c * 4)[1] = make_double2(cd.z, cd.w);
-          const uint32_t vmask = __ballot_sync(0xffffffffu, ck != BT_COL_NONE);   // c>>5 is warp-uniform
-          if (lane == 0) s_colvalid[c >> 5] = vmask;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (row < p.n) {
           rkind = p.row_kind[row];
-          rb = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
           if (rkind != BT_ROW_NONE) {
             const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (size_t)row * 4);
             const double2 lo = s[0], hi = s[1];
             rbox[0] = lo.x; rbox[1] = lo.y; rbox[2] = hi.x; rbox[3] = hi.y;
+            const uint2 pk = pack16_box(lo.x, lo.y, hi.x, hi.y, false);
+            r1p = pk.x;   // (x1+1) | (y1+1) << 16
+            r2h = pk.y;   // x2 | y2 << 16 | 0x80008000
+            rix1 = (int)(pk.x & 0xffffu) - 1; riy1 = (int)(pk.x >> 16) - 1;
+            rix2 = (int)(pk.y & 0x7fffu); riy2 = (int)((pk.y >> 16) & 0x7fffu);
+            // the integer corners are rounded outward by < 1 px per side: a lower bound of the true area
+            r_area_lb = (float)max(rix2 - rix1 - 2, 0) * (float)max(riy2 - riy1 - 2, 0);
           }
         }
       }
-      int cnt_a = 0, cnt_b = 0;   // edges this thread appended for its row in this column segment
-      const int seg = n0 / BT_CAND_SEG + half;
+      const int seg = n0 / (BN / 2) + half;   // the warp's rows x this column half = one candidate segment per row
+      uint2* my_queue = s_queue + (warp - 2) * kQueue;
+      int* my_rowcnt = s_rowcnt + (warp - 2) * 64;   // [32 rows][2]: edges appended per row (list 0|2, list 1)
+      int qn = 0, dbg_iters = 0, dbg_recs = 0;
+      my_rowcnt[lane * 2] = 0;
+      my_rowcnt[lane * 2 + 1] = 0;
+      __syncwarp();
       mbar_wait(&tmem_full[acc], acc_phase);
       const long long t_acc = clock64();
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int ch = half * (BN / 64); ch < (half + 1) * (BN / 64); ++ch) {
+      constexpr int kHalfCols = BN / 2, kFullChunks = kHalfCols / 32, kTailCols = kHalfCols % 32;
+      static_assert(kTailCols == 0 || kTailCols == 16, "column half must be a multiple of 16");
+      // one chunk = W (32 or 16) accumulator columns of this thread's row, starting at tile column c0
+      // Pass 2b: the exact path, 32 records at a time, one per lane (row data comes by shuffle)
+      auto drain = [&]() {
+        for (int base = 0; base < qn; base += 32) {
+          const bool act = base + lane < qn;
+          const uint2 rec = act ? my_queue[base + lane] : make_uint2(0u, 0u);
+          const int rl = (int)(rec.x & 31u), lc = (int)(rec.x >> 8);
+          double rb4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rb4[k] = __shfl_sync(0xffffffffu, rbox[k], rl);
+          const int rk = __shfl_sync(0xffffffffu, rkind, rl);
+          if (!act) continue;
+          const float sim = __uint_as_float(rec.y);
+          const int grow = row - lane + rl, col = n0 + lc;
+          const int ckind = s_colkind[lc];
+          if (ckind == BT_COL_NONE) continue;
+          const double iou_d = iou_dist_f64(rb4, s_col64 + lc * 4);
+          const float face = p.face_sim ? p.face_sim[(size_t)grow * p.m + col] : 0.0f;
+          if (rk == BT_ROW_UNCONFIRMED) {
+            if (ckind == BT_COL_HIGH) {
+              const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+              if (c3 < p.unconf_thresh) emit_owned(p.cand, 2, grow, seg, atomicAdd(&my_rowcnt[rl * 2], 1), col, c3);
+            }
+          } else if (ckind == BT_COL_HIGH) {
+            const double c1 = fuse_stage1(iou_d, sim, face, p.appearance);
+            if (c1 < p.match_thresh) emit_owned(p.cand, 0, grow, seg, atomicAdd(&my_rowcnt[rl * 2], 1), col, c1);
+          } else if (ckind == BT_COL_LOW && rk == BT_ROW_POOL_TRACKED) {
+            if (iou_d < p.second_thresh) emit_owned(p.cand, 1, grow, seg, atomicAdd(&my_rowcnt[rl * 2 + 1], 1), col, iou_d);
+          }
+        }
+        __syncwarp();
+        qn = 0;
+      };
+      auto do_chunk = [&](auto wtag, const int c0) {
+        constexpr int W = decltype(wtag)::value;
         uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), v);
+        if constexpr (W == 32) tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        else tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
         tmem_ld_wait();
         if (kDense) {
           if (row < p.n) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int col = n0 + ch * 32 + c;
+            for (int c = 0; c < W; ++c) {
+              const int col = n0 + c0 + c;
               if (col < p.m) assoc_dense(p, row, col, __uint_as_float(v[c]));
             }
           }
-        } else if (rkind != BT_ROW_NONE) {
-          // Pass 1 (branch-free, all 32 shared loads independent): which of the 32 pairs can have
-          // a cost below 1?  Conservative fp32 overlap test (row box rounded outward, detection
-          // boxes exact integers: false => exact IoU is 0) OR appearance gate open.
-          const uint32_t colbase = smem_u32(s_col32) + (uint32_t)(ch * 32) * 16u;
-          uint32_t hot = 0;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float4 cb;   // not volatile: the staged boxes are read-only here, let ptxas batch the loads
-            asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                : "=f"(cb.x), "=f"(cb.y), "=f"(cb.z), "=f"(cb.w)
-                : "r"(colbase + (uint32_t)c * 16u));
-            const float sim = __uint_as_float(v[c]);
-            // min(r.x2,c.x2) > max(r.x1,c.x1)  <=>  r.x2 > c.x1 and c.x2 > r.x1 for non-degenerate boxes
-            // (degenerate ones only make the screen more permissive): four chained predicate compares
-            const bool ov = (rb.z > cb.x) & (cb.z > rb.x) & (rb.w > cb.y) & (cb.w > rb.y);
-            const bool app = sim >= p.sim_gate;     // == !((1.0f - sim) > appearance), see sim_gate_for()
-            if (ov | app) hot |= 1u << c;
-          }
-          if (p.face_sim != nullptr) hot = 0xffffffffu;
-          hot &= s_colvalid[ch];
-          if (p.debug & 2) hot = 0;
-          // Pass 2 (rare): exact float64 IoU + fusion rule + candidate emission for the survivors.
-          // Lanes walk their own hot bits in lock-step (lane i handles its k-th survivor while lane j
-          // handles its own), so a warp pays max-over-lanes iterations, not the sum.
-          while (hot) {
-            const int c = __ffs(hot) - 1;
-            hot &= hot - 1;
-            float sim = 0.f;
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (c == k) sim = __uint_as_float(v[k]);
-            const int lc = ch * 32 + c;
-            const int col = n0 + lc;
-            const int ckind = s_colkind[lc];
-            const double iou_d = iou_dist_f64(rbox, s_col64 + lc * 4);
-            const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
-            if (rkind == BT_ROW_UNCONFIRMED) {
-              if (ckind == BT_COL_HIGH) {
-                const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
-                if (c3 < p.unconf_thresh) emit_owned(p.cand, 2, row, seg, cnt_a++, col, c3);
-              }
-            } else if (ckind == BT_COL_HIGH) {
-              const double c1 = fuse_stage1(iou_d, sim, face, p.appearance);
-              if (c1 < p.match_thresh) emit_owned(p.cand, 0, row, seg, cnt_a++, col, c1);
-            } else if (ckind == BT_COL_LOW && rkind == BT_ROW_POOL_TRACKED) {
-              if (iou_d < p.second_thresh) emit_owned(p.cand, 1, row, seg, cnt_b++, col, iou_d);
-            }
-          }
+          return;
         }
-      }
-      if (!kDense && rkind != BT_ROW_NONE) {
-        const int la = (rkind == BT_ROW_UNCONFIRMED) ? 2 : 0;
-        if (cnt_a) {
-          p.cand.cnt[((size_t)la * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_a;
-          atomicAdd(&p.cand.total[la], cnt_a);
-          atomicOr(&p.cand.segmask[(size_t)la * p.cand.rows_cap + row], 1ull << seg);
+        // Pass 1 (branch-free, independent shared loads): which of the W pairs can have a cost below 1?
+        // Integer screen on outward-rounded 15-bit corners, two corners per 32-bit word:
+        //   r.x2 > c.x1 & r.y2 > c.y1  <=>  both half-words of (r2 | 0x80008000) - (c1 + 0x00010001) keep bit 15
+        //   c.x2 > r.x1 & c.y2 > r.y1  <=>  likewise with the roles swapped
+        // (false => the exact IoU is 0), OR the appearance gate is open.
+        const uint32_t colbase = smem_u32(s_colpk) + (uint32_t)c0 * 8u;
+        uint32_t hot_ov = 0, hot = 0;
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+          uint32_t c1p, c2h;   // not volatile: the staged boxes are read-only here, let ptxas batch the loads
+          asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c1p), "=r"(c2h) : "r"(colbase + (uint32_t)c * 8u));
+          const uint32_t both = (r2h - c1p) & (c2h - r1p) & 0x80008000u;
+          if (both == 0x80008000u) hot_ov |= 1u << c;
+          if (__uint_as_float(v[c]) >= p.sim_gate) hot |= 1u << c;   // == !((1.0f - sim) > appearance), sim_gate_for()
         }
-        if (cnt_b) {
-          p.cand.cnt[((size_t)1 * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_b;
-          atomicAdd(&p.cand.total[1], cnt_b);
-          atomicOr(&p.cand.segmask[(size_t)1 * p.cand.rows_cap + row], 1ull << seg);
+        // Pass 1b (cheap, rare): an overlapping pair whose appearance gate is closed only matters if its
+        // IoU can exceed 1 - max(stage threshold): integer upper bound of the intersection against lower
+        // bounds of the areas, no division.
+        hot_ov &= ~hot;
+        if (rkind == BT_ROW_NONE) hot_ov = 0;   // unused slot / row past the matrix edge
+        while (hot_ov) {
+          const int c = __ffs(hot_ov) - 1;
+          hot_ov &= hot_ov - 1;
+          const uint2 pk = s_colpk[c0 + c];
+          const int cx1 = (int)(pk.x & 0xffffu) - 1, cy1 = (int)(pk.x >> 16) - 1;
+          const int cx2 = (int)(pk.y & 0x7fffu), cy2 = (int)((pk.y >> 16) & 0x7fffu);
+          const float inter_ub = (float)(min(rix2, cx2) - max(rix1, cx1)) * (float)(min(riy2, cy2) - max(riy1, cy1));
+          const float c_area_lb = (float)max(cx2 - cx1 - 2, 0) * (float)max(cy2 - cy1 - 2, 0);
+          // IoU <= inter_ub / (areas_lb - inter_ub) < gate  <=>  inter_ub * (1 + gate) < gate * areas_lb
+          if (!(inter_ub * (1.0f + p.iou_gate) * 1.0001f < p.iou_gate * (r_area_lb + c_area_lb))) hot |= 1u << c;
+        }
+        if (p.face_sim != nullptr) hot = (W == 32) ? 0xffffffffu : 0xffffu;
+        if ((p.debug & 2) || rkind == BT_ROW_NONE) hot = 0;
+        // Pass 2a (warp-collective, cheap): survivors go to the warp's shared-memory queue as
+        // (row lane, tile column, similarity) records.
+        while (__any_sync(0xffffffffu, hot != 0)) {
+          ++dbg_iters;
+          const bool has = hot != 0;
+          const int c = has ? __ffs(hot) - 1 : 0;
+          if (has) hot &= hot - 1;
+          float sim = 0.f;
+#pragma unroll
+          for (int k = 0; k < W; ++k)
+            if (c == k) sim = __uint_as_float(v[k]);
+          const uint32_t ball = __ballot_sync(0xffffffffu, has);
+          if (has) my_queue[qn + __popc(ball & ((1u << lane) - 1))] = make_uint2((uint32_t)lane | ((uint32_t)(c0 + c) << 8), __float_as_uint(sim));
+          qn += __popc(ball);
+          dbg_recs += __popc(ball);
+          if (qn > kQueue - 32) { __syncwarp(); drain(); }
+        }
+      };
+#pragma unroll 1
+      for (int ch = 0; ch < kFullChunks; ++ch) do_chunk(std::integral_constant<int, 32>{}, half * kHalfCols + ch * 32);
+      if constexpr (kTailCols == 16) do_chunk(std::integral_constant<int, 16>{}, half * kHalfCols + kFullChunks * 32);
+      if (!kDense) {
+        __syncwarp();
+        drain();
+        const int cnt_a = my_rowcnt[lane * 2], cnt_b = my_rowcnt[lane * 2 + 1];
+        if (rkind != BT_ROW_NONE) {
+          const int la = (rkind == BT_ROW_UNCONFIRMED) ? 2 : 0;
+          if (cnt_a) {
+            p.cand.cnt[((size_t)la * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_a;
+            atomicAdd(&p.cand.total[la], cnt_a);
+            atomicOr(&p.cand.segmask[(size_t)la * p.cand.rows_cap + row], 1ull << seg);
+          }
+          if (cnt_b) {
+            p.cand.cnt[((size_t)1 * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_b;
+            atomicAdd(&p.cand.total[1], cnt_b);
+            atomicOr(&p.cand.segmask[(size_t)1 * p.cand.rows_cap + row], 1ull << seg);
+          }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (p.debug && et == 0 && (blockIdx.x % 37) == 0)
-        printf("cta %d: accumulator ready at %lld cycles, epilogue done at %lld\n", blockIdx.x, t_acc - t_start,
-               clock64() - t_start);
+      if ((p.debug & 8) && lane == 0 && dbg_iters > 24)
+        printf("SLOW cta %d warp %d m0 %d n0 %d: %d enqueue iterations, %d records\n", blockIdx.x, warp, m0, n0, dbg_iters, dbg_recs);
+      if ((p.debug & 4) && et == 0)
+        printf("ALL %d %lld %lld\n", blockIdx.x, t_acc - t_start, clock64() - t_start);
+      if ((p.debug & 1) && et == 0 && (blockIdx.x % 37) == 0)
+        printf("cta %d (BN=%d grid=%d): accumulator ready at %lld cycles, epilogue done at %lld\n", blockIdx.x, BN,
+               gridDim.x, t_acc - t_start, clock64() - t_start);
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
@@ -523,6 +615,12 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (p.debug && threadIdx.x == 0 && (blockIdx.x % 37) == 0) {
+    unsigned long long g_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+    printf("cta %d: globaltimer start %llu end %llu (ns), lifetime %llu ns = %lld cycles\n", blockIdx.x, g_start, g_end,
+           g_end - g_start, clock64() - t_start);
   }
 }
 
@@ -675,22 +773,42 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams
   const int max_clusters = cached_clusters;
   const int nclusters = ctiles < max_clusters ? ctiles : max_clusters;
   cfg.gridDim = dim3(nclusters * CS);
-  BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
+  if (CS == 1) {
+    kern<<<nclusters, kTcThreads, TcSmem<BN>::kDyn, ctx->stream>>>(ta, tb, ep, ap.d);   // no cluster attribute
+  } else {
+    BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
+  }
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
 // Cluster shape of the association GEMM.  BT_ASSOC_CLUSTER=CMxCN overrides (profiling sweeps).
 static void pick_cluster(int* cm, int* cn) {
-  *cm = 2; *cn = 2;
+  *cm = 1; *cn = 1;   // measured: multicast clusters do not pay (the kernel is MMA/epilogue bound, profiles/README.md)
   const char* e = getenv("BT_ASSOC_CLUSTER");
   if (e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { *cm = e[0] - '0'; *cn = e[2] - '0'; }
+}
+
+int32_t btk_assoc_pick_bn(const bt_ctx* ctx, int32_t n, int32_t m) {
+  const char* e = getenv("BT_ASSOC_BN");
+  if (e) return atoi(e) == 224 ? 224 : 256;
+  const int tiles_m = (n + BM - 1) / BM;
+  long best_cost = -1;
+  int best = 256;
+  for (int bn : {256, 224}) {
+    const long tiles = (long)tiles_m * ((m + bn - 1) / bn);
+    const long waves = (tiles + ctx->num_sms - 1) / ctx->num_sms;
+    const long cost = waves * bn;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
 }
 
 template <bool kDense>
 static int32_t launch_tc_cluster(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep) {
   int cm, cn;
   pick_cluster(&cm, &cn);
+  if (ap.bn == 224) return launch_tc<224, kDense, 1, 1>(ctx, ap, ep);
   if (cm == 1 && cn == 1) return launch_tc<256, kDense, 1, 1>(ctx, ap, ep);
   if (cm == 1 && cn == 2) return launch_tc<256, kDense, 1, 2>(ctx, ap, ep);
   if (cm == 2 && cn == 1) return launch_tc<256, kDense, 2, 1>(ctx, ap, ep);
@@ -713,11 +831,19 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   ep.dense_stage = ap.dense_stage; ep.n = ap.n; ep.m = ap.m;
   ep.debug = getenv("BT_ASSOC_DEBUG") ? atoi(getenv("BT_ASSOC_DEBUG")) : 0;
   ep.sim_gate = sim_gate_for(ap.appearance);
+  {
+    double mx = ap.match_thresh > ap.second_thresh ? ap.match_thresh : ap.second_thresh;
+    if (ap.unconf_thresh > mx) mx = ap.unconf_thresh;
+    const double g = (1.0 - mx) * 0.999 - 1e-6;      // safely below the smallest IoU any stage can accept
+    ep.iou_gate = g > 0.0 ? (float)g : 0.0f;
+  }
   const bool dense = (ap.out_emb != nullptr) || (ap.out_dists != nullptr);
   if (precision == 0) {
     BT_CHECK(ap.d % BK == 0 && ap.d >= BK, BT_ERR_INVALID,
              "tensor-core similarity needs feat_dim %% 64 == 0 (got %d)", ap.d);
     BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "fp16 operands missing");
+    BT_CHECK(dense || ap.cand.seg * 2 == (ap.bn ? ap.bn : 256), BT_ERR_STATE,
+             "candidate segment size %d does not match the tile width %d", ap.cand.seg, ap.bn ? ap.bn : 256);
     if (dense) return launch_tc_cluster<true>(ctx, ap, ep);
     return launch_tc_cluster<false>(ctx, ap, ep);
   }

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -63,6 +64,11 @@ __global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* 
     *reinterpret_cast<int4*>(res_boxes + (size_t)j * 4) = b;
   }
   kind[j] = (s > high) ? BT_COL_HIGH : ((s >= low) ? BT_COL_LOW : BT_COL_NONE);
+}
+
+__global__ void clear_words_kernel(int4* __restrict__ p, size_t n16) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) p[i] = make_int4(0, 0, 0, 0);
 }
 
 __global__ void gather_rows_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx, int n,
@@ -140,6 +146,9 @@ struct bt_tracker {
   int frame_id = 0;
   int n_removed_total = 0;
   std::vector<int32_t> matches[3];  // flattened (a, b) pairs in the reference's index spaces
+  bt_assoc_params last_assoc;          // for bt_profile_replay_assoc
+  int last_assoc_precision = 0;
+  bool last_assoc_valid = false;
   std::vector<uint8_t> scratch_a, scratch_b;
   std::vector<int> scratch_pos_t, scratch_pos_l;
   int32_t *d_bpairs = nullptr, *h_bpairs = nullptr, *h_boxes = nullptr;
@@ -460,7 +469,9 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   SEG_END(BT_SEG_PREDICT);
 
   // ---- fused association over slots x detections + the three chained LAP solves -------------
-  const bt_cand& cand = *bt_lap_own_cand(ctx);
+  bt_cand cand = *bt_lap_own_cand(ctx);
+  const int assoc_bn = (reid && tensor_path) ? btk_assoc_pick_bn(ctx, n_rows, m) : 256;
+  cand.seg = assoc_bn / 2;    // one epilogue thread owns one (row, segment) pair; the LAP compaction follows
   if (n_rows > 0) {
     // the candidate counters are left zeroed by the previous frame's LAP kernel (no memset here)
     SEG_BEGIN(BT_SEG_ASSOC);
@@ -471,13 +482,17 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       p.a32 = t->curr32; p.b32 = t->det_feat32;
       p.n = n_rows; p.m = m; p.d = reid ? D : 0;
       p.a_rows_alloc = t->cap; p.b_rows_alloc = t->max_dets;
+      p.bn = assoc_bn;
       p.row_tlbr = t->tlbr; p.row_tlbr_f32 = t->tlbr_f32; p.row_kind = t->row_kind_cur;
       p.col_tlbr = t->det_tlbr; p.col_kind = t->col_kind; p.face_sim = nullptr;
       p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
       p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
       p.appearance = cfg.appearance_thresh;
       p.cand = cand;
-      BT_TRY(btk_assoc(ctx, p, (reid && tensor_path) ? 0 : 1));
+      t->last_assoc = p;
+      t->last_assoc_precision = (reid && tensor_path) ? 0 : 1;
+      t->last_assoc_valid = true;
+      BT_TRY(btk_assoc(ctx, p, t->last_assoc_precision));
     }
     SEG_END(BT_SEG_ASSOC);
     SEG_BEGIN(BT_SEG_LAP);
@@ -795,6 +810,52 @@ int32_t bt_profile_enable(bt_ctx* ctx, int32_t on) {
     for (int s = 0; s < BT_SEG_COUNT; ++s) { t->prof_ms[s] = 0.0; t->prof_n[s] = 0; t->seg_open[s] = false; }
   }
   t->prof = on != 0;
+  return BT_OK;
+}
+
+int32_t bt_profile_replay_assoc(bt_ctx* ctx, int32_t iters, double* total_ms) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  bt_tracker* t = ctx->trk;
+  BT_CHECK(t->last_assoc_valid, BT_ERR_STATE, "no association launch to replay yet");
+  BT_CHECK(iters > 0 && iters <= 1000 && total_ms, BT_ERR_INVALID, "iters must be 1..1000");
+  cudaStream_t st = ctx->stream;
+  const bt_cand& cand = *bt_lap_own_cand(ctx);
+  // The tensor-core kernel's emission is idempotent (every (row, segment) owner rewrites the same
+  // entries and the same count), so its launches can run back to back inside ONE event pair; the
+  // CUDA-core kernel appends with atomics and needs its lists cleared between launches.
+  const bool idempotent = t->last_assoc_precision == 0;
+  cudaEvent_t e0, e1;
+  BT_CUDA(cudaEventCreate(&e0));
+  BT_CUDA(cudaEventCreate(&e1));
+  BT_CUDA(cudaStreamSynchronize(st));
+  double sum = 0.0;
+  if (idempotent) {
+    BT_TRY(btk_assoc(ctx, t->last_assoc, t->last_assoc_precision));   // warm
+    BT_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) BT_TRY(btk_assoc(ctx, t->last_assoc, t->last_assoc_precision));
+    BT_CUDA(cudaEventRecord(e1, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    BT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    sum = ms;
+  } else {
+    for (int i = 0; i < iters; ++i) {
+      BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, st));
+      BT_CUDA(cudaEventRecord(e0, st));
+      BT_TRY(btk_assoc(ctx, t->last_assoc, t->last_assoc_precision));
+      BT_CUDA(cudaEventRecord(e1, st));
+      BT_CUDA(cudaStreamSynchronize(st));
+      float ms = 0.f;
+      BT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      sum += ms;
+    }
+  }
+  BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, st));
+  BT_CUDA(cudaStreamSynchronize(st));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *total_ms = sum;
   return BT_OK;
 }
 

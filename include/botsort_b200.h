@@ -106,6 +106,12 @@ enum {
   BT_SEG_COUNT = 11
 };
 int32_t bt_profile_enable(bt_ctx* ctx, int32_t on);
+/* Re-launches the fused association kernel of the LAST bt_update_arrays frame `iters` times back to
+ * back on the ctx stream (same operands; the tensor-core kernel's candidate emission is idempotent)
+ * inside one CUDA-event pair and returns the elapsed time in *total_ms (per launch: / iters).  Measurement aid for the kernel's
+ * roofline figure: back-to-back launches are not inflated by host enqueue gaps.  The tracker state is
+ * not changed (the candidate lists are left cleared, as the frame step leaves them). */
+int32_t bt_profile_replay_assoc(bt_ctx* ctx, int32_t iters, double* total_ms);
 /* accumulated device milliseconds and number of samples of a segment since bt_profile_enable(1) */
 int32_t bt_profile_read(bt_ctx* ctx, int32_t segment, double* total_ms, int64_t* samples);
 
