@@ -309,6 +309,81 @@ __device__ void solve_component(const SolveArrays& ws, int comp, double thresh,
   }
 }
 
+// One THREAD solves one tiny component (a few rows): same shortest-augmenting-path algorithm as
+// solve_component without the warp machinery -- for 2-3 row components the shuffles and warp
+// barriers of the cooperative version cost far more than the arithmetic.
+__device__ void solve_component_serial(const SolveArrays& ws, int comp, double thresh, const int32_t* cnt,
+                                       const int32_t* ecol, const double* ecost, int32_t* x, int32_t* y) {
+  const int r0 = ws.rowcnt[comp], nr = ws.rowcnt[comp + 1] - r0;
+  const int c0 = ws.colcnt[comp];
+  int32_t* rows = ws.sorted_rows + r0;
+  int32_t* touched = ws.touched + c0;
+  int32_t* treerows = ws.treerows + r0;
+  for (int a = 1; a < nr; ++a) {            // insertion sort: ascending row index (deterministic order)
+    const int key = rows[a];
+    int b = a - 1;
+    while (b >= 0 && rows[b] > key) { rows[b + 1] = rows[b]; --b; }
+    rows[b + 1] = key;
+  }
+  for (int ri = 0; ri < nr; ++ri) {
+    const int i0 = rows[ri];
+    const int sid = i0 + 1;
+    int nT = 0, nTR = 0, i = i0, sink = -1, bestDummyRow = i0;
+    double minVal = 0.0, bestDummy = -ws.u[i0];
+    while (true) {
+      const int deg = cnt[i];
+      const double ui = ws.u[i];
+      const size_t eb = ebase(ws, i);
+      for (int k = 0; k < deg; ++k) {
+        const int c = ecol[eb + k];
+        if (ws.insc[c] == sid) continue;
+        const double r = minVal + (ecost[eb + k] - thresh) - ui - ws.v[c];
+        if (ws.seen[c] != sid) {
+          ws.seen[c] = sid; ws.dist[c] = r; ws.pathrow[c] = i; touched[nT++] = c;
+        } else if (r < ws.dist[c]) {
+          ws.dist[c] = r; ws.pathrow[c] = i;
+        }
+      }
+      MinPair best{DBL_MAX, kInf, 0};
+      for (int k = 0; k < nT; ++k) {
+        const int c = touched[k];
+        if (ws.insc[c] == sid) continue;
+        const MinPair cur{ws.dist[c], c, (y[c] < 0) ? 1 : 0};
+        if (better(cur, best)) best = cur;
+      }
+      if (best.c == kInf || bestDummy <= best.d) { minVal = bestDummy; sink = -2; break; }
+      minVal = best.d;
+      const int j = best.c;
+      ws.insc[j] = sid;
+      if (best.freecol) { sink = j; break; }
+      i = y[j];
+      treerows[nTR++] = i;
+      const double cand_d = minVal - ws.u[i];
+      if (cand_d < bestDummy) { bestDummy = cand_d; bestDummyRow = i; }
+    }
+    for (int k = 0; k < nTR; ++k) { const int r = treerows[k]; ws.u[r] += minVal - ws.dist[x[r]]; }
+    for (int k = 0; k < nT; ++k) { const int c = touched[k]; if (ws.insc[c] == sid) ws.v[c] -= minVal - ws.dist[c]; }
+    ws.u[i0] += minVal;
+    int j;
+    bool go = true;
+    if (sink == -2) {
+      if (bestDummyRow == i0) go = false;
+      j = go ? x[bestDummyRow] : -1;
+      if (go) x[bestDummyRow] = -1;
+    } else {
+      j = sink;
+    }
+    while (go) {
+      const int pi = ws.pathrow[j];
+      y[j] = pi;
+      const int t = x[pi];
+      x[pi] = j;
+      j = t;
+      if (pi == i0) break;
+    }
+  }
+}
+
 // ---- on-chip path for the usual case: a handful of complex rows -------------------------------
 // CTA 0 pulls the complex rows' valid edges into shared memory (CSR, local row ids; a column's
 // local id is the smallest local edge index that touches it), labels components, groups them and
@@ -327,14 +402,45 @@ struct SmallSmem {
   int32_t yl[kSmallEdges], touched[kSmallEdges];
   double v[kSmallEdges], dist[kSmallEdges];
   int changed;
+  int scan_total;
 };
+
+constexpr int kSmallThreads = 128;   // the on-chip path runs on the first four warps of CTA 0
+#define SMALL_SYNC() asm volatile("bar.sync 2, 128;" ::: "memory")
+
+// exclusive scan of a (shared-memory) array of up to a few thousand ints by warp 0; all kSmallThreads call it
+__device__ int small_scan(int32_t* data, int n, int* total_slot) {
+  SMALL_SYNC();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const int val = (i < n) ? data[i] : 0;
+      int incl = val;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < n) data[i] = carry + incl - val;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) *total_slot = carry;
+  }
+  SMALL_SYNC();
+  return *total_slot;
+}
 
 __device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, const LapStage& S, int nC,
                                     const int32_t* cnt, const int32_t* ecol, const double* ecost,
-                                    int32_t* x, int32_t* y, SmallSmem& sm, int32_t* s_warp, int32_t* s_carry) {
+                                    int32_t* x, int32_t* y, SmallSmem& sm, int debug) {
+  unsigned long long ts[8] = {0,0,0,0,0,0,0,0};
+#define ST(i) do { if (debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])); } while (0)
+  ST(0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // S1: valid degree per complex row -> CSR offsets
-  for (int i = tid; i < nC; i += kLapThreads) {
+  for (int i = tid; i < nC; i += kSmallThreads) {
     const int r = W.clist[i];
     sm.rg[i] = r;
     const int deg = cnt[r];
@@ -348,10 +454,11 @@ __device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, con
     sm.u[i] = 0.0;
   }
   if (tid == 0) sm.rstart[nC] = 0;
-  __syncthreads();
-  const int E = block_exclusive_scan(sm.rstart, nC + 1, s_warp, s_carry);
+  SMALL_SYNC();
+  const int E = small_scan(sm.rstart, nC + 1, &sm.scan_total);
+  ST(1);
   // S2: edges; column representative = smallest local edge index touching the column
-  for (int i = tid; i < nC; i += kLapThreads) {
+  for (int i = tid; i < nC; i += kSmallThreads) {
     const int r = sm.rg[i];
     const int deg = cnt[r];
     const int32_t* e = ecol + (size_t)r * cand.stride;
@@ -366,8 +473,8 @@ __device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, con
       ++pos;
     }
   }
-  __syncthreads();
-  for (int e = tid; e < E; e += kLapThreads) {
+  SMALL_SYNC();
+  for (int e = tid; e < E; e += kSmallThreads) {
     const int c = sm.lcl[e];
     const int rep = __ldcg(&W.collabel[c]);
     sm.lcl[e] = rep;
@@ -378,13 +485,14 @@ __device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, con
     sm.insc[e] = 0;
     sm.yl[e] = -1;
   }
-  __syncthreads();
+  SMALL_SYNC();
+  ST(2);
   // S4: components by min-label propagation + pointer jumping (shared memory)
   while (true) {
     if (tid == 0) sm.changed = 0;
-    __syncthreads();
+    SMALL_SYNC();
     bool changed = false;
-    for (int i = tid; i < nC; i += kLapThreads) {
+    for (int i = tid; i < nC; i += kSmallThreads) {
       int lr = sm.rlabel[i];
       const int l0 = lr;
       for (int k = sm.rstart[i]; k < sm.rstart[i] + sm.rdeg[i]; ++k) {
@@ -395,51 +503,64 @@ __device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, con
       }
       if (lr < l0) { atomicMin(&sm.rlabel[i], lr); changed = true; }
     }
-    __syncthreads();
-    for (int i = tid; i < nC; i += kLapThreads) {
+    SMALL_SYNC();
+    for (int i = tid; i < nC; i += kSmallThreads) {
       const int l = sm.rlabel[i];
       const int ll = sm.rlabel[l];
       if (ll < l) { atomicMin(&sm.rlabel[i], ll); changed = true; }
     }
     if (changed) sm.changed = 1;
-    __syncthreads();
+    SMALL_SYNC();
     const int any = sm.changed;
-    __syncthreads();
+    SMALL_SYNC();
     if (!any) break;
   }
+  ST(3);
   // S5: grouping
-  for (int i = tid; i < nC; i += kLapThreads) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
-  for (int i = tid; i <= nC; i += kLapThreads) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
-  __syncthreads();
-  const int ncomp = block_exclusive_scan(sm.isroot, nC, s_warp, s_carry);
-  for (int i = tid; i < nC; i += kLapThreads)
+  for (int i = tid; i < nC; i += kSmallThreads) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
+  for (int i = tid; i <= nC; i += kSmallThreads) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
+  SMALL_SYNC();
+  const int ncomp = small_scan(sm.isroot, nC, &sm.scan_total);
+  for (int i = tid; i < nC; i += kSmallThreads)
     if (sm.rlabel[i] == i) sm.compidx[i] = sm.isroot[i];
-  __syncthreads();
-  for (int i = tid; i < nC; i += kLapThreads) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
-  for (int e = tid; e < E; e += kLapThreads)
+  SMALL_SYNC();
+  for (int i = tid; i < nC; i += kSmallThreads) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
+  for (int e = tid; e < E; e += kSmallThreads)
     if (sm.lcl[e] == e) atomicAdd(&sm.colcnt[sm.compidx[sm.clabel[e]]], 1);
-  __syncthreads();
-  block_exclusive_scan(sm.rowcnt, ncomp + 1, s_warp, s_carry);
-  block_exclusive_scan(sm.colcnt, ncomp + 1, s_warp, s_carry);
-  for (int i = tid; i < nC; i += kLapThreads) {
+  SMALL_SYNC();
+  small_scan(sm.rowcnt, ncomp + 1, &sm.scan_total);
+  small_scan(sm.colcnt, ncomp + 1, &sm.scan_total);
+  for (int i = tid; i < nC; i += kSmallThreads) {
     const int k = sm.compidx[sm.rlabel[i]];
     sm.sorted_rows[sm.rowcnt[k] + atomicAdd(&sm.fill[k], 1)] = i;
   }
-  __syncthreads();
+  SMALL_SYNC();
+  ST(4);
   // S6: one warp per component, everything in shared memory
   const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
                       sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
-  for (int comp = warp; comp < ncomp; comp += kLapThreads / 32)
-    solve_component(A, comp, S.thresh, nullptr, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl, lane);
-  __syncthreads();
+  constexpr int kSerialRows = 6;     // components up to this many rows: one thread each
+  for (int comp = tid; comp < ncomp; comp += kSmallThreads)
+    if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] <= kSerialRows)
+      solve_component_serial(A, comp, S.thresh, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl);
+  __syncwarp();
+  for (int comp = warp; comp < ncomp; comp += kSmallThreads / 32)
+    if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] > kSerialRows)
+      solve_component(A, comp, S.thresh, nullptr, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl, lane);
+  SMALL_SYNC();
+  ST(5);
   // S7: write back with global ids
-  for (int i = tid; i < nC; i += kLapThreads) {
+  for (int i = tid; i < nC; i += kSmallThreads) {
     const int c = sm.xl[i];
     if (c >= 0) {
       x[sm.rg[i]] = sm.cglob[c];
       y[sm.cglob[c]] = sm.rg[i];
     }
   }
+  ST(6);
+  if (debug && threadIdx.x == 0)
+    printf("small path nC=%d E=%d ncomp=%d: S1 %llu S2+3 %llu label %llu group %llu solve %llu write %llu ns\n", nC, E, ncomp,
+           ts[1]-ts[0], ts[2]-ts[1], ts[3]-ts[2], ts[4]-ts[3], ts[5]-ts[4], ts[6]-ts[5]);
 }
 
 __global__ void __launch_bounds__(kLapThreads, 1)
@@ -549,7 +670,7 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
 
     const bool small = nC > 0 && nC <= kSmallRows && W.counters[4] <= kSmallEdges;
     if (small) {
-      if (crank == 0) small_complex_solve(cand, W, S, nC, cnt, ecol, ecost, x, y, sm, s_warp, &s_carry);
+      if (crank == 0 && tid < kSmallThreads) small_complex_solve(cand, W, S, nC, cnt, ecol, ecost, x, y, sm, P.debug);
       LAP_T(4); tq[5] = tq[4];
     } else if (nC > 0) {
       // ---- P3: connected components of the complex part ----
