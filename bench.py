@@ -34,7 +34,8 @@ WORKLOADS = {
     # BASELINE.json configs[0] (CPU-runnable case)
     "c1": dict(n=64, feat_dim=2048, reid=True, desc="64 tracks x 64 dets, 2048-d ReID features, 1 stream/GPU"),
     # per-stream shape of BASELINE.json configs[4]
-    "c5": dict(n=1000, feat_dim=2048, reid=True, desc="1000 tracks x 1000 dets per stream (config-5 stream shape), 1 stream/GPU"),
+    "c5": dict(n=1000, feat_dim=2048, reid=True, streams=4,
+               desc="1000 tracks x 1000 dets per stream, 4 independent streams per GPU (BASELINE config 5: 32 streams over 8 GPUs)"),
 }
 METRIC = "tracks/sec (Kalman+IoU+ReID-dist+LAP per frame)"
 
@@ -139,6 +140,11 @@ def run_reference(args):
         return
     wl = WORKLOADS[args.workload]
     n = wl["n"]
+    try:    # torchrun exports OMP_NUM_THREADS=1: give NumPy/BLAS every host core back for the CPU arm
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     iou_rows = None
     if n > 600:
         iou_rows = args.ref_rows           # bounded sample of the pure-Python IoU loop
@@ -188,21 +194,29 @@ def run_ours(args):
     n, D, reid = wl["n"], wl["feat_dim"], wl["reid"]
     K, W = args.steps, max(args.warmup, 3)
 
+    from concurrent.futures import ThreadPoolExecutor
+    from botsort_b200.sharding import shard_streams
+    S = int(wl.get("streams", 1))                       # independent video streams on THIS GPU
+    my_streams = shard_streams(S * world, world, rank)  # global stream ids of this rank (no data-path collective)
     cap = (n + n // 8 + 255) // 128 * 128
-    ctx = bs.Context(max_tracks=cap, max_dets=cap, feat_dim=D, device=local)
+    ctxs = [bs.Context(max_tracks=cap, max_dets=cap, feat_dim=D, device=local) for _ in my_streams]
+    ctx = ctxs[0]
     cfg = ctx.default_config()
     cfg.with_reid = 1 if reid else 0
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    cu_streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)) for c in ctxs]
+    pool = ThreadPoolExecutor(max_workers=S) if S > 1 else None
 
-    # independent stream per rank (weak scaling: every GPU tracks its own video stream)
+    # every stream has its own synthetic scene (weak scaling: each GPU tracks its own video streams)
     n_frames = 1 + W + K
-    frames = make_frames(wl, n_frames, seed=1234 + rank)
-    boxes_h = [torch.from_numpy(f["boxes"]).pin_memory() for f in frames]
-    scores_h = [torch.from_numpy(f["scores"]).pin_memory() for f in frames]
-    feats_h = [torch.from_numpy(f["feats"]).pin_memory() for f in frames] if reid else [None] * n_frames
-    boxes_d = [b.cuda(non_blocking=True) for b in boxes_h]
-    scores_d = [s.cuda(non_blocking=True) for s in scores_h]
-    feats_d = [f.cuda(non_blocking=True) for f in feats_h] if reid else [None] * n_frames
+    data = []
+    for sid in my_streams:
+        frames = make_frames(wl, n_frames, seed=1234 + sid)
+        bh = [torch.from_numpy(f["boxes"]).pin_memory() for f in frames]
+        sh = [torch.from_numpy(f["scores"]).pin_memory() for f in frames]
+        fh = [torch.from_numpy(f["feats"]).pin_memory() for f in frames] if reid else [None] * n_frames
+        data.append(dict(bh=bh, sh=sh, fh=fh, bd=[b.cuda(non_blocking=True) for b in bh],
+                         sd=[x.cuda(non_blocking=True) for x in sh],
+                         fd=[f.cuda(non_blocking=True) for f in fh] if reid else [None] * n_frames))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     torch.cuda.synchronize()
 
@@ -212,41 +226,56 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i, loc):
-        b, s, f = (boxes_d, scores_d, feats_d) if loc == BT_DEVICE else (boxes_h, scores_h, feats_h)
-        ctx.update_arrays_raw(b[i].data_ptr(), s[i].data_ptr(), f[i].data_ptr() if reid else 0,
-                              b[i].shape[0], loc)
+    def step_one(k, i, loc, read_back=False, events=None):
+        d, c = data[k], ctxs[k]
+        b, s, f = (d["bd"], d["sd"], d["fd"]) if loc == BT_DEVICE else (d["bh"], d["sh"], d["fh"])
+        if events is not None:
+            events[0].record(cu_streams[k])
+        c.update_arrays_raw(b[i].data_ptr(), s[i].data_ptr(), f[i].data_ptr() if reid else 0, b[i].shape[0], loc)
+        nbytes = 0
+        if read_back:
+            res = c.get_tracks(0)                       # ids + boxes of the returned list, on the host
+            nbytes = res["tlbr"].nbytes + res["ids"].nbytes
+        if events is not None:
+            events[1].record(cu_streams[k])
+        return nbytes
+
+    def step(i, loc, read_back=False, events=None):
+        """One frame for every stream of this rank (threads: ctypes releases the GIL, the ctx streams overlap)."""
+        if pool is None:
+            return step_one(0, i, loc, read_back, None if events is None else events[0])
+        futs = [pool.submit(step_one, k, i, loc, read_back, None if events is None else events[k]) for k in range(S)]
+        return sum(f.result() for f in futs)
 
     def run_pass(loc, read_back, profile=False):
         """frame 0 = births (untimed), W warm-up frames, then K timed frames.  Returns per-step device
         ms (CUDA events on the ctx stream), per-step wall ms, matched-track counts."""
-        ctx.tracker_reset(cfg)
+        for c in ctxs:
+            c.tracker_reset(cfg)
         step(0, loc)
         for i in range(1, 1 + W):
             step(i, loc)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
+              for _ in range(K)]
         wall = []
         d2h = 0
         barrier()
         if profile:
-            ctx.profile_enable(True)        # segment events only around the K timed steps
-        launches0 = ctx.launch_count
+            ctx.profile_enable(True)        # segment events only around the K timed steps (first stream)
+        launches0 = sum(c.launch_count for c in ctxs)
         for k in range(K):
             flush.zero_()                                   # L2 flush between timed steps (untimed)
             torch.cuda.synchronize()
             i = 1 + W + k
             t0 = time.perf_counter()
-            ev[k][0].record(stream)
-            step(i, loc)
-            if read_back:
-                res = ctx.get_tracks(0)                     # ids + boxes of the returned list, on the host
-                d2h = res["tlbr"].nbytes + res["ids"].nbytes
-            ev[k][1].record(stream)
-            ctx.sync()
+            d2h = step(i, loc, read_back, ev[k])
+            for c in ctxs:
+                c.sync()
             wall.append(1e3 * (time.perf_counter() - t0))
-        launches = ctx.launch_count - launches0
+        launches = sum(c.launch_count for c in ctxs) - launches0
         barrier()
-        dev = [a.elapsed_time(b) for a, b in ev]
+        # a step ends when its slowest stream ends (the streams of a step start together)
+        dev = [max(a.elapsed_time(b) for a, b in evk) for evk in ev]
         return dev, wall, launches, d2h
 
     sampler = ClockSampler(local)
@@ -273,9 +302,9 @@ def run_ours(args):
 
     from botsort_b200.sharding import aggregate_throughput, max_over_ranks
     total_dev_ms, total_e2e_ms = max_over_ranks([sum(dev_ms), sum(e2e_wall)], device="cuda")
-    value = aggregate_throughput(n, world, K, total_dev_ms)
-    e2e_value = aggregate_throughput(n, world, K, total_e2e_ms)
-    h2d_bytes = n * (16 + 4) + (n * D * 4 if reid else 0)
+    value = aggregate_throughput(n * S, world, K, total_dev_ms)
+    e2e_value = aggregate_throughput(n * S, world, K, total_e2e_ms)
+    h2d_bytes = S * (n * (16 + 4) + (n * D * 4 if reid else 0))
 
     if rank == 0:
         peaks = {}
@@ -328,7 +357,7 @@ def run_ours(args):
             "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 Kalman/IoU/LAP, fp16-in/fp32-acc tcgen05 ReID similarity" if reid else "f64",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "tracks": n, "dets": n, "feat_dim": D, "streams_per_gpu": 1,
+            "config": {"workload": wl["desc"], "tracks": n, "dets": n, "feat_dim": D, "streams_per_gpu": S,
                        "live_tracks_end": n_live,
                        "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the ctx stream, summed",
                        "sharding": "independent video streams, one per GPU, no data-path collective"},
@@ -342,7 +371,8 @@ def run_ours(args):
             "clocks": clocks,
         }
         print(json.dumps(line))
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 
