@@ -119,6 +119,9 @@ struct bt_tracker {
   int32_t *d_pairs = nullptr, *d_pair_count = nullptr;
   char* d_ctrl = nullptr;   // packed per-frame control lists (one H2D per phase)
   char* h_ctrl = nullptr;
+  cudaStream_t st2 = nullptr;   // side stream: work that is independent of the main chain runs beside it
+  cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  bool overlap = true;
   char* d_res = nullptr;    // packed per-frame result block (one D2H per frame), layout in bt_update_arrays
   char* h_res = nullptr;
   size_t res_cap = 0;
@@ -150,6 +153,9 @@ struct bt_tracker {
   int last_assoc_precision = 0;
   bool last_assoc_valid = false;
   std::vector<uint8_t> scratch_a, scratch_b;
+  std::vector<int> v_unconfirmed, v_pool, v_hi_pos, v_lo_pos, v_hi_list, v_lo_list, v_activated, v_refind, v_lost_now,
+      v_removed_now, v_r_tracked, v_u_det_pos, v_new_tracked, v_new_lost, v_tmp;
+  std::vector<uint8_t> v_det_taken, v_pool_matched;
   std::vector<int> scratch_pos_t, scratch_pos_l;
   int32_t *d_bpairs = nullptr, *h_bpairs = nullptr, *h_boxes = nullptr;
   int bpair_cap = 1 << 16;
@@ -308,6 +314,10 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   t->h_boxes = carve<int32_t>(cur, md * 4);
   t->meta.assign(cap, SlotMeta());
   t->max_time_lost = (int)(t->cfg.frame_rate / 30.0 * t->cfg.track_buffer);
+  BT_CUDA(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&t->ev_fork1, &t->ev_join1, &t->ev_fork2, &t->ev_join2})
+    BT_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  t->overlap = getenv("BT_NO_OVERLAP") == nullptr;
   return BT_OK;
 }
 
@@ -323,6 +333,9 @@ void bt_tracker_destroy(bt_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (t->pinned) cudaFreeHost(t->pinned);
+  for (cudaEvent_t e : {t->ev_fork1, t->ev_join1, t->ev_fork2, t->ev_join2})
+    if (e) cudaEventDestroy(e);
+  if (t->st2) cudaStreamDestroy(t->st2);
   for (int s = 0; s < BT_SEG_HOST_ENQUEUE1; ++s)
     for (cudaEvent_t e : t->ev[s])
       if (e) cudaEventDestroy(e);
@@ -431,7 +444,8 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   SEG_END(BT_SEG_PREP);
 
   // ---- split lists (demo:1415-1423) -------------------------------------------------------------
-  std::vector<int> unconfirmed, pool;
+  std::vector<int>& unconfirmed = t->v_unconfirmed; unconfirmed.clear();
+  std::vector<int>& pool = t->v_pool; pool.clear();
   for (int s : t->tracked) {
     if (!meta[s].activated) unconfirmed.push_back(s);
     else pool.push_back(s);
@@ -459,15 +473,32 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     all_f32 = all_f32 && meta[s].f32_state;
   }
   for (int s : unconfirmed) hA_kind[s] = BT_ROW_UNCONFIRMED;
-  if (bytesA > 0) BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesA, cudaMemcpyHostToDevice, st));
+  // The control block + Kalman predict do not depend on the detection prep: they run on the side
+  // stream next to it and join before the association kernel (single stream while profiling, so that
+  // the per-segment events stay meaningful).
+  const bool overlap = t->overlap && !t->prof;
+  cudaStream_t sp = overlap ? t->st2 : st;
+  if (overlap) {
+    BT_CUDA(cudaEventRecord(t->ev_fork1, st));       // everything already queued on the main stream
+    BT_CUDA(cudaStreamWaitEvent(t->st2, t->ev_fork1, 0));
+  }
+  if (bytesA > 0) BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesA, cudaMemcpyHostToDevice, sp));
   SEG_BEGIN(BT_SEG_PREDICT);
   if (n_pool > 0) {
-    BT_TRY(btk_kalman_predict(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, dA_state, dA_idx, n_pool,
-                              all_f32 ? 1 : 0, t->slot_f32));
+    ctx->stream = sp;
+    const int32_t rc = btk_kalman_predict(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, dA_state, dA_idx, n_pool,
+                                          all_f32 ? 1 : 0, t->slot_f32);
+    ctx->stream = st;
+    BT_TRY(rc);
     for (int s : pool) meta[s].f32_state = 0;
   }
   SEG_END(BT_SEG_PREDICT);
+  if (overlap) {
+    BT_CUDA(cudaEventRecord(t->ev_join1, t->st2));
+    BT_CUDA(cudaStreamWaitEvent(st, t->ev_join1, 0));
+  }
 
+  bool ema_pending = false;
   // ---- fused association over slots x detections + the three chained LAP solves -------------
   bt_cand cand = *bt_lap_own_cand(ctx);
   const int assoc_bn = (reid && tensor_path) ? btk_assoc_pick_bn(ctx, n_rows, m) : 256;
@@ -506,9 +537,19 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     {
       BT_TRY(btk_kalman_update_x(ctx, t->mean, t->cov, t->tlbr, t->tlbr_f32, t->det_xywh, t->x[0], t->x[1],
                                  t->x[2], t->slot_f32, n_rows, dres_tlbr));
-      if (reid && m > 0)
-        BT_TRY(btk_feature_ema_x(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
-                                 t->det_feat16, t->x[0], t->x[1], t->x[2], n_rows, D, cfg.ema_alpha));
+      if (reid && m > 0) {
+        // the feature EMA only needs the assignment vectors: side stream, next to update + duplicate test
+        if (overlap) {
+          BT_CUDA(cudaEventRecord(t->ev_fork2, st));
+          BT_CUDA(cudaStreamWaitEvent(t->st2, t->ev_fork2, 0));
+          ctx->stream = t->st2;
+        }
+        const int32_t rc = btk_feature_ema_x(ctx, t->smooth32, t->curr32, keep32 ? t->det_feat32 : nullptr, t->feat16,
+                                             t->det_feat16, t->x[0], t->x[1], t->x[2], n_rows, D, cfg.ema_alpha);
+        ctx->stream = st;
+        BT_TRY(rc);
+        if (overlap) { BT_CUDA(cudaEventRecord(t->ev_join2, t->st2)); ema_pending = true; }
+      }
     }
     SEG_END(BT_SEG_UPDATE);
     // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
@@ -522,19 +563,26 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     BT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, res_bytes, cudaMemcpyDeviceToHost, st));
   HOST_MARK(BT_SEG_HOST_ENQUEUE1);
   BT_CUDA(cudaStreamSynchronize(st));  // sync 1: assignments (and scores) are on the host
+  if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join2));   // the side stream's EMA (usually done already)
   HOST_MARK(BT_SEG_HOST_WAIT1);
   BT_TRY(prof_collect(ctx, t));
 
   // ---- detection lists (demo:1493-1532) -----------------------------------------------------
   const float* sc = t->h_scores;
-  std::vector<int> hi_pos(m, -1), lo_pos(m, -1), hi_list, lo_list;
+  std::vector<int>& hi_pos = t->v_hi_pos; hi_pos.assign(m, -1);
+  std::vector<int>& lo_pos = t->v_lo_pos; lo_pos.assign(m, -1);
+  std::vector<int>& hi_list = t->v_hi_list; hi_list.clear();
+  std::vector<int>& lo_list = t->v_lo_list; lo_list.clear();
   for (int j = 0; j < m; ++j) {
     if (sc[j] > cfg.track_high_thresh) { hi_pos[j] = (int)hi_list.size(); hi_list.push_back(j); }
     else if (sc[j] >= cfg.track_low_thresh) { lo_pos[j] = (int)lo_list.size(); lo_list.push_back(j); }
   }
-  std::vector<uint8_t> det_taken(m, 0);
+  std::vector<uint8_t>& det_taken = t->v_det_taken; det_taken.assign(m, 0);
 
-  std::vector<int> activated, refind, lost_now, removed_now;
+  std::vector<int>& activated = t->v_activated; activated.clear();
+  std::vector<int>& refind = t->v_refind; refind.clear();
+  std::vector<int>& lost_now = t->v_lost_now; lost_now.clear();
+  std::vector<int>& removed_now = t->v_removed_now; removed_now.clear();
   int n_upd = 0;
   auto apply_match = [&](int slot, int det) {
     SlotMeta& tm = meta[slot];
@@ -556,7 +604,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
 
   for (auto& mm : t->matches) mm.clear();
   // first association (demo:1556-1566): matches in ascending pool order
-  std::vector<uint8_t> pool_matched(n_pool, 0);
+  std::vector<uint8_t>& pool_matched = t->v_pool_matched; pool_matched.assign(n_pool, 0);
   for (int i = 0; i < n_pool; ++i) {
     const int s = pool[i];
     const int j = (n_rows > 0) ? t->h_x[0][s] : -1;
@@ -568,7 +616,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
   // the state test of stage 2 (demo:1569) reads the state BEFORE stage-1 updates touch the
   // unmatched tracks, which they never do; build r_tracked first, then apply stage 1.
-  std::vector<int> r_tracked;
+  std::vector<int>& r_tracked = t->v_r_tracked; r_tracked.clear();
   for (int i = 0; i < n_pool; ++i)
     if (!pool_matched[i] && meta[pool[i]].state == BT_STATE_TRACKED) r_tracked.push_back(pool[i]);
   for (int i = 0; i < n_pool; ++i)
@@ -590,7 +638,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     }
   }
   // unconfirmed (demo:1588-1612): detections = unmatched high detections, in order
-  std::vector<int> u_det_pos(m, -1);
+  std::vector<int>& u_det_pos = t->v_u_det_pos; u_det_pos.assign(m, -1);
   {
     int k = 0;
     for (int j : hi_list)
@@ -648,19 +696,19 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
 
   // ---- merge lists (demo:1629-1636) -----------------------------------------------------------
-  std::vector<int> new_tracked;
+  std::vector<int>& new_tracked = t->v_new_tracked; new_tracked.clear();
   for (int s : t->tracked)
     if (meta[s].state == BT_STATE_TRACKED) { new_tracked.push_back(s); meta[s].mark = 1; }
   for (int s : activated)
     if (!meta[s].mark) { new_tracked.push_back(s); meta[s].mark = 1; }
   for (int s : refind)
     if (!meta[s].mark) { new_tracked.push_back(s); meta[s].mark = 1; }
-  std::vector<int> new_lost;
+  std::vector<int>& new_lost = t->v_new_lost; new_lost.clear();
   for (int s : t->lost)
     if (!meta[s].mark) new_lost.push_back(s);       // sub_stracks(lost, tracked)
   for (int s : lost_now) new_lost.push_back(s);     // extend(lost_stracks)
   {
-    std::vector<int> tmp;
+    std::vector<int>& tmp = t->v_tmp; tmp.clear();
     for (int s : new_lost)
       if (!meta[s].in_removed) tmp.push_back(s);    // sub_stracks(lost, removed) BEFORE this frame's removals
     new_lost.swap(tmp);
@@ -748,20 +796,23 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
   t->tracked.clear();
   t->lost.clear();
-  t->tlbr_cache.clear();
+  t->tlbr_cache.resize(4 * (size_t)nt);
+  size_t n_out = 0;
   for (int i = 0; i < nt; ++i) {
     if (dupa[i]) continue;
     const int s = new_tracked[i];
     t->tracked.push_back(s);
+    double* dst = t->tlbr_cache.data() + 4 * n_out++;
     const bool born_now = meta[s].f32_state && meta[s].start_frame == frame_id;
     if (!born_now) {
-      for (int c = 0; c < 4; ++c) t->tlbr_cache.push_back(hres_tlbr[4 * (size_t)s + c]);
+      memcpy(dst, hres_tlbr + 4 * (size_t)s, 4 * sizeof(double));
     } else {
-      // a track born this frame in a fresh slot: its box is the detection's (demo:624-648 on initiate's mean)
+      // a track born this frame: its box is the detection's (demo:624-648 on initiate's mean)
       const int32_t* bx = host_boxes + 4 * (size_t)meta[s].det_index;
-      for (int c = 0; c < 4; ++c) t->tlbr_cache.push_back((double)bx[c]);
+      for (int c = 0; c < 4; ++c) dst[c] = (double)bx[c];
     }
   }
+  t->tlbr_cache.resize(4 * n_out);
   for (int i = 0; i < nl; ++i)
     if (!dupb[i]) t->lost.push_back(new_lost[i]);
   t->tlbr_cache_valid = true;
