@@ -164,6 +164,10 @@ struct bt_cand {
   int32_t* cnt;    // [3][rows_cap][nseg]
   int32_t* total;  // [4] per list: non-zero when any edge was emitted (lets the LAP skip empty stages)
   unsigned long long* segmask;  // [3][rows_cap] bit g: segment g of the row is non-empty (nseg <= 64)
+  int32_t* rowdeg;  // [3][rows_cap] edges emitted for the row      } maintained by the emitters with fire-and-forget
+  int32_t* indeg;   // [3][cols_cap] edges emitted into the column  } atomics: the LAP classifies rows without
+  int32_t* rowcol;  // [3][rows_cap] a column of the row (THE column when rowdeg == 1)   touching the edge lists
+  int32_t cols_cap;
   int32_t* deg;    // [3][rows_cap]  row degree after compaction (written by the LAP set-up)
   int32_t* col;    // [3][rows_cap*stride]
   double* cost;    // [3][rows_cap*stride]

@@ -34,7 +34,6 @@ struct bt_lap_ws {
   bt_cand cand;            // ctx-wide candidate lists (3 lists)
   int32_t* label = nullptr;     // [rows]
   int32_t* collabel = nullptr;  // [cols]
-  int32_t* indeg = nullptr;     // [cols]  valid in-degree
   int32_t* nvalid = nullptr;    // [rows]  valid out-degree
   int32_t* onlycol = nullptr;   // [rows]  a valid column of the row (the only one when nvalid == 1)
   int32_t* clist = nullptr;     // [rows]  complex rows
@@ -588,7 +587,6 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
     for (int c = gtid; c < m; c += GT) {
       S.y[c] = -1;
       ws.collabel[co + c] = kInf;
-      ws.indeg[co + c] = 0;
       ws.v[co + c] = 0.0;
       ws.seen[co + c] = 0;
       ws.insc[co + c] = 0;
@@ -607,7 +605,7 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
     const LapStage S = P.st[stage];
     if (cand.total[S.list] == 0) continue;   // nothing was emitted for this stage (cluster-uniform)
     bt_lap_ws W = ws;                          // this stage's slices of the scratch arrays
-    W.collabel += (size_t)stage * ws.cols; W.indeg += (size_t)stage * ws.cols; W.v += (size_t)stage * ws.cols;
+    W.collabel += (size_t)stage * ws.cols; W.v += (size_t)stage * ws.cols;
     W.seen += (size_t)stage * ws.cols; W.insc += (size_t)stage * ws.cols; W.u += (size_t)stage * ws.rows;
     W.counters += stage * 8;
     int32_t* cnt = cand.deg + (size_t)S.list * cand.rows_cap;
@@ -616,56 +614,56 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
     int32_t* x = S.x;
     int32_t* y = S.y;
 
-    // ---- P1: compact the row's segments (in place, ascending copy), valid degree, column in-degree ----
-    int my_valid = 0, my_last = -1;   // the thread's first row stays in registers for P2
+    // ---- P1: classify every row from the emitters' degree bookkeeping (no edge traversal for the bulk):
+    //      isolated edges (row degree 1, column in-degree 1) are final; rows with several candidates or a
+    //      contested column are "complex": only those have their segments compacted ----
+    const int32_t* indeg = cand.indeg + (size_t)S.list * cand.cols_cap;
     for (int r = gtid; r < n; r += GT) {
       W.label[r] = kInf;
-      int total = 0, valid = 0, last = -1;
+      const size_t ri = (size_t)S.list * cand.rows_cap + r;
+      const int deg = cand.rowdeg[ri];
+      if (deg == 0) continue;                      // nothing was emitted for this row
+      const int col1 = cand.rowcol[ri];
       const bool row_on = S.row_block == nullptr || S.row_block[r] < 0;
-      unsigned long long mask = cand.segmask[(size_t)S.list * cand.rows_cap + r];
-      if (mask && P.clear_lists) cand.segmask[(size_t)S.list * cand.rows_cap + r] = 0ull;
-      {
-        int32_t* segcnt = cand.cnt + ((size_t)S.list * cand.rows_cap + r) * cand.nseg;
-        int32_t* rc = ecol + (size_t)r * cand.stride;
-        double* rv = ecost + (size_t)r * cand.stride;
-        while (mask) {                          // only the non-empty segments, in ascending order
-          const int g = __ffsll((long long)mask) - 1;
-          mask &= mask - 1;
-          const int k = row_on ? segcnt[g] : 0;
-          if (P.clear_lists) segcnt[g] = 0;
-          const int src = g * cand.seg;
-          for (int e = 0; e < k; ++e) {
-            const int c = rc[src + e];
-            if (src + e != total) { rc[total] = c; rv[total] = rv[src + e]; }
-            ++total;
-            if (edge_ok(S.col_block, c)) { ++valid; last = c; atomicAdd(&W.indeg[c], 1); }
-          }
+      if (P.clear_lists) cand.rowdeg[ri] = 0;
+      const bool col1_ok = edge_ok(S.col_block, col1);
+      const bool contested1 = deg == 1 && row_on && col1_ok && indeg[col1] != 1;
+      const bool need_edges = row_on && (deg > 1 || contested1);
+      int total = 0, valid = 0;
+      unsigned long long mask = cand.segmask[ri];
+      if (P.clear_lists) cand.segmask[ri] = 0ull;
+      int32_t* segcnt = cand.cnt + ri * cand.nseg;
+      int32_t* rc = ecol + (size_t)r * cand.stride;
+      double* rv = ecost + (size_t)r * cand.stride;
+      while (mask) {                               // only the non-empty segments, in ascending order
+        const int g = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const int k = need_edges ? segcnt[g] : 0;  // complex rows: compact in place (ascending copy)
+        if (P.clear_lists) segcnt[g] = 0;
+        const int src = g * cand.seg;
+        for (int e = 0; e < k; ++e) {
+          const int c = rc[src + e];
+          if (src + e != total) { rc[total] = c; rv[total] = rv[src + e]; }
+          ++total;
+          if (edge_ok(S.col_block, c)) ++valid;
         }
       }
       cnt[r] = total;
-      if (r == gtid) { my_valid = valid; my_last = last; }
-      else { W.nvalid[r] = valid; W.onlycol[r] = last; }
-    }
-    cluster_barrier();
-    LAP_T(2);
-
-    // ---- P2: isolated edges are final; everything else is "complex" ----
-    for (int r = gtid; r < n; r += GT) {
-      const int valid = (r == gtid) ? my_valid : W.nvalid[r];
-      if (valid == 0) continue;
-      const int c = (r == gtid) ? my_last : W.onlycol[r];
-      if (valid == 1 && W.indeg[c] == 1) {
-        x[r] = c;
-        y[c] = r;
-      } else {
-        const int pos = atomicAdd(&W.counters[0], 1);
-        atomicAdd(&W.counters[4], valid);            // valid edges of the complex part
-        W.clist[pos] = r;
-        W.label[r] = r;
+      if (!row_on) continue;
+      if (deg == 1 && !contested1) {               // isolated edge, or its only column is taken already
+        if (col1_ok) { x[r] = col1; y[col1] = r; }
+        continue;
       }
+      if (valid == 0) continue;
+      const int pos = atomicAdd(&W.counters[0], 1);
+      atomicAdd(&W.counters[4], valid);            // valid edges of the complex part
+      W.clist[pos] = r;
+      W.label[r] = r;
     }
     cluster_barrier();
     const int nC = W.counters[0];
+    if (P.clear_lists)                              // every read of the in-degrees is behind us
+      for (int c = gtid; c < cand.cols_cap; c += GT) cand.indeg[(size_t)S.list * cand.cols_cap + c] = 0;
     LAP_T(3);
 
     const bool small = nC > 0 && nC <= kSmallRows && W.counters[4] <= kSmallEdges;
@@ -765,7 +763,7 @@ lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double t
   int32_t* ecol = cand.col + ((size_t)list * cand.rows_cap + row) * cand.stride;
   double* ecost = cand.cost + ((size_t)list * cand.rows_cap + row) * cand.stride;
   int32_t* segcnt = cand.cnt + ((size_t)list * cand.rows_cap + row) * cand.nseg;
-  int count = 0;
+  int count = 0, rowtotal = 0;
   for (int c0 = 0; c0 < m; c0 += 32) {
     if (c0 > 0 && (c0 % cand.seg) == 0) {     // next segment (seg is a multiple of 32 here)
       if (lane == 0) segcnt[c0 / cand.seg - 1] = count;
@@ -779,9 +777,13 @@ lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double t
       const int pos = (c0 / cand.seg) * cand.seg + count + __popc(ball & ((1u << lane) - 1));
       ecol[pos] = c;
       ecost[pos] = v;
+      atomicAdd(&cand.indeg[(size_t)list * cand.cols_cap + c], 1);
+      cand.rowcol[(size_t)list * cand.rows_cap + row] = c;
     }
     count += __popc(ball);
+    rowtotal += __popc(ball);
   }
+  if (lane == 0) cand.rowdeg[(size_t)list * cand.rows_cap + row] = rowtotal;
   if (lane == 0) segcnt[(m - 1) / cand.seg] = count;
   if (lane == 0) {
     atomicAdd(&cand.total[list], 1);   // any non-zero value means "stage not empty"
@@ -804,10 +806,15 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
   ws->cand.nseg = BT_CAND_MAXSEG;
   ws->cand.seg = 128;
   const size_t cnt_ints = (3 * (size_t)rows * ws->cand.nseg + 4 + 1) & ~size_t(1);   // keeps segmask 8 B aligned
-  ws->cand.clear_bytes = sizeof(int32_t) * cnt_ints + sizeof(unsigned long long) * 3 * rows;
+  ws->cand.cols_cap = cols;
+  ws->cand.clear_bytes = sizeof(int32_t) * cnt_ints + sizeof(unsigned long long) * 3 * rows +
+                         sizeof(int32_t) * 3 * ((size_t)rows + cols);
   BT_CUDA(cudaMalloc(&ws->cand.cnt, ws->cand.clear_bytes));
   ws->cand.total = ws->cand.cnt + 3 * (size_t)rows * ws->cand.nseg;   // cleared by the same memset as cnt
   ws->cand.segmask = reinterpret_cast<unsigned long long*>(ws->cand.cnt + cnt_ints);
+  ws->cand.rowdeg = reinterpret_cast<int32_t*>(ws->cand.segmask + 3 * (size_t)rows);
+  ws->cand.indeg = ws->cand.rowdeg + 3 * (size_t)rows;
+  BT_CUDA(cudaMalloc(&ws->cand.rowcol, sizeof(int32_t) * 3 * (size_t)rows));
   BT_CUDA(cudaMalloc(&ws->cand.deg, sizeof(int32_t) * 3 * rows));
   BT_CUDA(cudaMalloc(&ws->cand.col, sizeof(int32_t) * 3 * (size_t)rows * stride));
   BT_CUDA(cudaMalloc(&ws->cand.cost, sizeof(double) * 3 * (size_t)rows * stride));
@@ -816,7 +823,6 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
 #define BT_LAP_ALLOC(field, type, count) BT_CUDA(cudaMalloc(&ws->field, sizeof(type) * (size_t)(count)))
   BT_LAP_ALLOC(label, int32_t, rows);
   BT_LAP_ALLOC(collabel, int32_t, 3 * (size_t)cols);
-  BT_LAP_ALLOC(indeg, int32_t, 3 * (size_t)cols);
   BT_LAP_ALLOC(nvalid, int32_t, rows);
   BT_LAP_ALLOC(onlycol, int32_t, rows);
   BT_LAP_ALLOC(clist, int32_t, rows);
@@ -844,7 +850,7 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
 void bt_lap_ws_destroy(bt_ctx* ctx) {
   bt_lap_ws* ws = ctx->lap;
   if (!ws) return;
-  void* ptrs[] = {ws->cand.cnt, ws->cand.deg, ws->cand.col, ws->cand.cost, ws->label, ws->collabel, ws->indeg,
+  void* ptrs[] = {ws->cand.cnt, ws->cand.rowcol, ws->cand.deg, ws->cand.col, ws->cand.cost, ws->label, ws->collabel,
                   ws->nvalid, ws->onlycol, ws->clist, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
                   ws->sorted_rows, ws->counters, ws->u, ws->v, ws->dist, ws->pathrow, ws->seen, ws->insc,
                   ws->touched, ws->treerows, ws->x, ws->y};

@@ -76,6 +76,12 @@ __device__ __forceinline__ double fuse_stage3(double iou_d, float sim, float app
   return fmin(iou_d, (double)emb);
 }
 
+// degree bookkeeping for the LAP's row classification (no return value needed: RED atomics)
+__device__ __forceinline__ void note_edge(const bt_cand& c, int list, int row, int col) {
+  atomicAdd(&c.rowdeg[(size_t)list * c.rows_cap + row], 1);
+  atomicAdd(&c.indeg[(size_t)list * c.cols_cap + col], 1);
+  c.rowcol[(size_t)list * c.rows_cap + row] = col;
+}
 // atomic append into the (row, column-segment) sub-list (CUDA-core kernel: several threads share a row)
 __device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int col, double cost) {
   const int seg = col / c.seg;
@@ -85,12 +91,14 @@ __device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int co
   c.cost[base] = cost;
   atomicAdd(&c.total[list], 1);
   if (k == 0) atomicOr(&c.segmask[(size_t)list * c.rows_cap + row], 1ull << seg);
+  note_edge(c, list, row, col);
 }
 // plain append: the caller owns (row, segment) exclusively and keeps the count in a register
 __device__ __forceinline__ void emit_owned(const bt_cand& c, int list, int row, int seg, int k, int col, double cost) {
   const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * c.seg + k;
   c.col[base] = col;
   c.cost[base] = cost;
+  note_edge(c, list, row, col);
 }
 
 // exact path for one (row, col) pair that survived the cheap rejection test
