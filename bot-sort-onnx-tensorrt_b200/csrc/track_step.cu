@@ -120,7 +120,7 @@ struct bt_tracker {
   char* d_ctrl = nullptr;   // packed per-frame control lists (one H2D per phase)
   char* h_ctrl = nullptr;
   cudaStream_t st2 = nullptr;   // side stream: work that is independent of the main chain runs beside it
-  cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr, ev_x = nullptr;
   bool overlap = true;
   char* d_res = nullptr;    // packed per-frame result block (one D2H per frame), layout in bt_update_arrays
   char* h_res = nullptr;
@@ -315,7 +315,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   t->meta.assign(cap, SlotMeta());
   t->max_time_lost = (int)(t->cfg.frame_rate / 30.0 * t->cfg.track_buffer);
   BT_CUDA(cudaStreamCreateWithFlags(&t->st2, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&t->ev_fork1, &t->ev_join1, &t->ev_fork2, &t->ev_join2})
+  for (cudaEvent_t* e : {&t->ev_fork1, &t->ev_join1, &t->ev_fork2, &t->ev_join2, &t->ev_x})
     BT_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   t->overlap = getenv("BT_NO_OVERLAP") == nullptr;
   return BT_OK;
@@ -333,7 +333,7 @@ void bt_tracker_destroy(bt_ctx* ctx) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (t->pinned) cudaFreeHost(t->pinned);
-  for (cudaEvent_t e : {t->ev_fork1, t->ev_join1, t->ev_fork2, t->ev_join2})
+  for (cudaEvent_t e : {t->ev_fork1, t->ev_join1, t->ev_fork2, t->ev_join2, t->ev_x})
     if (e) cudaEventDestroy(e);
   if (t->st2) cudaStreamDestroy(t->st2);
   for (int s = 0; s < BT_SEG_HOST_ENQUEUE1; ++s)
@@ -397,11 +397,15 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   //   | (device inputs only) float scores[m], int32 boxes[4m] | pad to 8 B | double tlbr[4*n_rows]
   const int n_rows_pre = t->high_water;
   const bool inputs_on_device = (loc == BT_DEVICE);
-  size_t o_x = 2 + 2 * (size_t)kPairPrefetch, o_sc = o_x + 3 * (size_t)n_rows_pre,
-         o_bx = (o_sc + (inputs_on_device ? m : 0) + 3) & ~size_t(3),   // int4 stores: 16 B aligned
-         o_end_i = o_bx + (inputs_on_device ? 4 * (size_t)m : 0);
-  o_end_i = (o_end_i + 1) & ~size_t(1);
-  const size_t res_bytes = sizeof(int32_t) * o_end_i + sizeof(double) * 4 * n_rows_pre;
+  //   part A (read back right after the LAP, the host starts its list bookkeeping on it while the GPU
+  //           still runs update / EMA / duplicate test): x1,x2,x3 [n_rows each] | scores[m], boxes[4m]
+  //   part B (read back at the end): pair count (2 ints) | pairs[2*kPairPrefetch] | tlbr[4*n_rows] f64
+  const size_t o_x = 0, o_sc = o_x + 3 * (size_t)n_rows_pre,
+               o_bx = (o_sc + (inputs_on_device ? m : 0) + 3) & ~size_t(3),   // int4 stores: 16 B aligned
+               o_hdr = (o_bx + (inputs_on_device ? 4 * (size_t)m : 0) + 3) & ~size_t(3),
+               o_pairs = o_hdr + 2, o_end_i = (o_pairs + 2 * (size_t)kPairPrefetch + 1) & ~size_t(1);
+  const size_t bytesA_res = sizeof(int32_t) * o_hdr;
+  const size_t bytesB_res = sizeof(int32_t) * (o_end_i - o_hdr) + sizeof(double) * 4 * n_rows_pre;
   int32_t* dres_i = reinterpret_cast<int32_t*>(t->d_res);
   int32_t* hres_i = reinterpret_cast<int32_t*>(t->h_res);
   for (int s3 = 0; s3 < 3; ++s3) {
@@ -498,7 +502,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     BT_CUDA(cudaStreamWaitEvent(st, t->ev_join1, 0));
   }
 
-  bool ema_pending = false;
+  bool ema_pending = false, part_a_sent = false;
   // ---- fused association over slots x detections + the three chained LAP solves -------------
   bt_cand cand = *bt_lap_own_cand(ctx);
   const int assoc_bn = (reid && tensor_path) ? btk_assoc_pick_bn(ctx, n_rows, m) : 256;
@@ -528,8 +532,11 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     SEG_END(BT_SEG_ASSOC);
     SEG_BEGIN(BT_SEG_LAP);
     const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
-    BT_TRY(btk_lap_solve3(ctx, cand, n_rows, m, th, t->x, t->y, dres_i));   // also zeroes the pair counter
+    BT_TRY(btk_lap_solve3(ctx, cand, n_rows, m, th, t->x, t->y, dres_i + o_hdr));   // also zeroes the pair counter
     SEG_END(BT_SEG_LAP);
+    BT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, bytesA_res, cudaMemcpyDeviceToHost, st));   // part A
+    BT_CUDA(cudaEventRecord(t->ev_x, st));
+    part_a_sent = true;
     // The matched tracks' Kalman update and feature EMA are a pure function of the three assignment
     // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
     // demo:570-610) while the host is still waiting for / digesting the assignments.
@@ -555,17 +562,21 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
     SEG_BEGIN(BT_SEG_DUP);
     BT_TRY(btk_iou_pairs_live(ctx, t->tlbr, t->tlbr_f32, t->row_kind_cur, n_rows, cfg.duplicate_iou_dist,
-                              t->d_pairs, dres_i, t->pair_cap, dres_i + 2, kPairPrefetch));
+                              t->d_pairs, dres_i + o_hdr, t->pair_cap, dres_i + o_pairs, kPairPrefetch));
     SEG_END(BT_SEG_DUP);
   }
-  // ONE read-back per frame: pair count + first pairs, the three assignment vectors, (scores, boxes), boxes of all slots
-  if (n_rows > 0 || (inputs_on_device && m > 0))
-    BT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, res_bytes, cudaMemcpyDeviceToHost, st));
+  if (!part_a_sent && inputs_on_device && m > 0) {     // no tracks yet: only scores / boxes come back
+    BT_CUDA(cudaMemcpyAsync(t->h_res, t->d_res, bytesA_res, cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaEventRecord(t->ev_x, st));
+    part_a_sent = true;
+  }
+  if (n_rows > 0)                                      // part B: pair count + first pairs, boxes of all slots
+    BT_CUDA(cudaMemcpyAsync(t->h_res + bytesA_res, t->d_res + bytesA_res, bytesB_res, cudaMemcpyDeviceToHost, st));
   HOST_MARK(BT_SEG_HOST_ENQUEUE1);
-  BT_CUDA(cudaStreamSynchronize(st));  // sync 1: assignments (and scores) are on the host
-  if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join2));   // the side stream's EMA (usually done already)
+  // wait only for the assignments (+ scores / boxes): the list bookkeeping below overlaps the GPU's
+  // update / EMA / duplicate-test tail
+  if (part_a_sent) BT_CUDA(cudaEventSynchronize(t->ev_x));
   HOST_MARK(BT_SEG_HOST_WAIT1);
-  BT_TRY(prof_collect(ctx, t));
 
   // ---- detection lists (demo:1493-1532) -----------------------------------------------------
   const float* sc = t->h_scores;
@@ -719,11 +730,14 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
 
   // ---- births on the device: one packed H2D, Kalman initiate + feature adoption --------------------
   const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
-  int n_pairs = hres_i[0];               // live-slot duplicate candidates found before the sync
+  BT_CUDA(cudaStreamSynchronize(st));    // the frame's device work is complete, part B is on the host
+  if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join2));   // the side stream's EMA (usually done already)
+  BT_TRY(prof_collect(ctx, t));
+  int n_pairs = hres_i[o_hdr];           // live-slot duplicate candidates found by the device
   if (n_rows <= 1) n_pairs = 0;
   BT_CHECK(n_pairs <= t->pair_cap, BT_ERR_CAPACITY, "%d duplicate pairs exceed capacity %d", n_pairs, t->pair_cap);
   bool need_sync = false;
-  const int32_t* live_pairs = hres_i + 2;
+  const int32_t* live_pairs = hres_i + o_pairs;
   if (n_pairs > kPairPrefetch) {
     BT_CUDA(cudaMemcpyAsync(t->h_pairs, t->d_pairs, sizeof(int32_t) * 2 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
     live_pairs = t->h_pairs;
