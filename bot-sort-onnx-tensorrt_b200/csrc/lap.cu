@@ -383,6 +383,44 @@ __device__ void solve_component_serial(const SolveArrays& ws, int comp, double t
   }
 }
 
+// Components of two or three rows (by far the most common complex case: two tracks competing for one
+// or two detections) are solved by exhaustive enumeration in registers: every row takes one of its
+// edges or stays unmatched, columns must be distinct, minimise sum (cost - thresh).
+__device__ void solve_component_enum(const SolveArrays& ws, int comp, double thresh, const int32_t* cnt,
+                                     const int32_t* ecol, const double* ecost, int32_t* x, int32_t* y) {
+  const int r0 = ws.rowcnt[comp], nr = ws.rowcnt[comp + 1] - r0;
+  int rows[3], deg[3];
+  size_t eb[3];
+  for (int a = 0; a < 3; ++a) {
+    rows[a] = (a < nr) ? ws.sorted_rows[r0 + a] : -1;
+    deg[a] = (a < nr) ? cnt[rows[a]] : 0;
+    eb[a] = (a < nr) ? ebase(ws, rows[a]) : 0;
+  }
+  double best = 0.0;                 // everything unmatched
+  int bk[3] = {-1, -1, -1};
+  for (int k0 = -1; k0 < deg[0]; ++k0) {
+    const int c0 = k0 < 0 ? -1 : ecol[eb[0] + k0];
+    const double w0 = k0 < 0 ? 0.0 : ecost[eb[0] + k0] - thresh;
+    for (int k1 = -1; k1 < deg[1]; ++k1) {
+      const int c1 = k1 < 0 ? -1 : ecol[eb[1] + k1];
+      if (c1 >= 0 && c1 == c0) continue;
+      const double w1 = w0 + (k1 < 0 ? 0.0 : ecost[eb[1] + k1] - thresh);
+      for (int k2 = -1; k2 < deg[2]; ++k2) {
+        const int c2 = k2 < 0 ? -1 : ecol[eb[2] + k2];
+        if (c2 >= 0 && (c2 == c0 || c2 == c1)) continue;
+        const double w2 = w1 + (k2 < 0 ? 0.0 : ecost[eb[2] + k2] - thresh);
+        if (w2 < best) { best = w2; bk[0] = k0; bk[1] = k1; bk[2] = k2; }
+      }
+    }
+  }
+  for (int a = 0; a < nr; ++a)
+    if (bk[a] >= 0) {
+      const int c = ecol[eb[a] + bk[a]];
+      x[rows[a]] = c;
+      y[c] = rows[a];
+    }
+}
+
 // ---- on-chip path for the usual case: a handful of complex rows -------------------------------
 // CTA 0 pulls the complex rows' valid edges into shared memory (CSR, local row ids; a column's
 // local id is the smallest local edge index that touches it), labels components, groups them and
@@ -539,9 +577,11 @@ __device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, con
   const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
                       sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
   constexpr int kSerialRows = 6;     // components up to this many rows: one thread each
-  for (int comp = tid; comp < ncomp; comp += kSmallThreads)
-    if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] <= kSerialRows)
-      solve_component_serial(A, comp, S.thresh, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl);
+  for (int comp = tid; comp < ncomp; comp += kSmallThreads) {
+    const int nr = sm.rowcnt[comp + 1] - sm.rowcnt[comp];
+    if (nr <= 3) solve_component_enum(A, comp, S.thresh, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl);
+    else if (nr <= kSerialRows) solve_component_serial(A, comp, S.thresh, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl);
+  }
   __syncwarp();
   for (int comp = warp; comp < ncomp; comp += kSmallThreads / 32)
     if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] > kSerialRows)
@@ -661,6 +701,7 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
       W.label[r] = r;
     }
     cluster_barrier();
+    LAP_T(2);
     const int nC = W.counters[0];
     if (P.clear_lists)                              // every read of the in-degrees is behind us
       for (int c = gtid; c < cand.cols_cap; c += GT) cand.indeg[(size_t)S.list * cand.cols_cap + c] = 0;
@@ -747,8 +788,8 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
     if (P.clear_lists && gtid == 0) cand.total[S.list] = 0;   // every CTA has read it (barriers above / kernel end)
     LAP_T(6);
     if (P.debug && gtid == 0)
-      printf("lap stage %d: n=%d m=%d complex=%d comps=%d | init %llu P1 %llu P2 %llu P3 %llu P4 %llu P5 %llu ns\n", stage, n, m,
-             nC, W.counters[1], tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3], tq[5] - tq[4], tq[6] - tq[5]);
+      printf("lap stage %d: n=%d m=%d complex=%d comps=%d | init %llu classify %llu clear %llu complex-part %llu tail %llu ns\n", stage, n, m,
+             nC, W.counters[1], tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[5] - tq[3], tq[6] - tq[5]);
     LAP_T(1);
   }
 }
