@@ -144,3 +144,55 @@ def test_device_resident_inputs_match_host_inputs(ctx):
             np.testing.assert_array_equal(gl[key], rl[key])
         np.testing.assert_array_equal(gt["tlbr"], rt["tlbr"])
         np.testing.assert_array_equal(gt["mean"], rt["mean"])
+
+
+def test_two_contexts_interleaved(ctx):
+    """Independent video streams = independent bt_ctx objects (own CUDA stream, own id counter):
+    interleaving two trackers frame by frame gives the same tracks as running each alone."""
+    import botsort_b200 as bs
+    cfgs = [SceneConfig(n_ids=60, feat_dim=2048, seed=21, low_frac=0.1, drop_frac=0.1),
+            SceneConfig(n_ids=45, feat_dim=2048, seed=22, low_frac=0.2, drop_frac=0.05, newcomer_every=2)]
+    seqs = []
+    for c in cfgs:
+        sc = SyntheticScene(c)
+        seqs.append([sc.next_frame() for _ in range(10)])
+    alone = []
+    for seq in seqs:
+        ctx.tracker_reset()
+        out = []
+        for fr in seq:
+            ctx.update_arrays(fr["boxes"], fr["scores"], fr["feats"])
+            out.append(ctx.get_tracks(0))
+        alone.append(out)
+    a = bs.Context(max_tracks=256, max_dets=256, feat_dim=2048)
+    b = bs.Context(max_tracks=256, max_dets=256, feat_dim=2048)
+    try:
+        for k in range(10):
+            for c, seq, ref in ((a, seqs[0], alone[0]), (b, seqs[1], alone[1])):
+                fr = seq[k]
+                c.update_arrays(fr["boxes"], fr["scores"], fr["feats"])
+                got = c.get_tracks(0)
+                np.testing.assert_array_equal(got["ids"], ref[k]["ids"])
+                np.testing.assert_array_equal(got["tlbr"], ref[k]["tlbr"])
+    finally:
+        a.close()
+        b.close()
+
+
+def test_replay_hook_leaves_state_untouched(ctx):
+    """bt_profile_replay_assoc (bench.py's roofline measurement) must not disturb the tracker."""
+    scene = SyntheticScene(SceneConfig(n_ids=300, feat_dim=2048, seed=31))
+    frames = [scene.next_frame() for _ in range(6)]
+    outs = []
+    for use_replay in (False, True):
+        ctx.tracker_reset()
+        res = []
+        for fr in frames:
+            ctx.update_arrays(fr["boxes"], fr["scores"], fr["feats"])
+            if use_replay:
+                assert ctx.profile_replay_assoc(3) > 0
+            res.append(ctx.get_tracks(0, with_state=True))
+        outs.append(res)
+    for r0, r1 in zip(*outs):
+        np.testing.assert_array_equal(r0["ids"], r1["ids"])
+        np.testing.assert_array_equal(r0["mean"], r1["mean"])
