@@ -122,6 +122,7 @@ struct bt_tracker {
   cudaStream_t st2 = nullptr;   // side stream: work that is independent of the main chain runs beside it
   cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr, ev_x = nullptr;
   bool overlap = true;
+  bool host_debug = false;
   char* d_res = nullptr;    // packed per-frame result block (one D2H per frame), layout in bt_update_arrays
   char* h_res = nullptr;
   size_t res_cap = 0;
@@ -318,6 +319,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   for (cudaEvent_t* e : {&t->ev_fork1, &t->ev_join1, &t->ev_fork2, &t->ev_join2, &t->ev_x})
     BT_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   t->overlap = getenv("BT_NO_OVERLAP") == nullptr;
+  t->host_debug = getenv("BT_HOST_DEBUG") != nullptr;
   return BT_OK;
 }
 
@@ -614,6 +616,9 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   };
 
   for (auto& mm : t->matches) mm.clear();
+  double dbg_t[8]; int dbg_n = 0;
+  const bool dbg_host = t->host_debug;
+  if (dbg_host) dbg_t[dbg_n++] = now_ms();
   // first association (demo:1556-1566): matches in ascending pool order
   std::vector<uint8_t>& pool_matched = t->v_pool_matched; pool_matched.assign(n_pool, 0);
   for (int i = 0; i < n_pool; ++i) {
@@ -632,6 +637,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     if (!pool_matched[i] && meta[pool[i]].state == BT_STATE_TRACKED) r_tracked.push_back(pool[i]);
   for (int i = 0; i < n_pool; ++i)
     if (pool_matched[i]) apply_match(pool[i], t->h_x[0][pool[i]]);
+  if (dbg_host) dbg_t[dbg_n++] = now_ms();
   // second association (demo:1568-1586)
   for (int i = 0; i < (int)r_tracked.size(); ++i) {
     const int s = r_tracked[i];
@@ -674,6 +680,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       removed_now.push_back(s);
     }
   }
+  if (dbg_host) dbg_t[dbg_n++] = now_ms();
   // births (demo:1614-1621, STrack.activate demo:556-568)
   int n_births = 0;
   for (int j : hi_list) {
@@ -706,6 +713,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     }
   }
 
+  if (dbg_host) dbg_t[dbg_n++] = now_ms();
   // ---- merge lists (demo:1629-1636) -----------------------------------------------------------
   std::vector<int>& new_tracked = t->v_new_tracked; new_tracked.clear();
   for (int s : t->tracked)
@@ -728,6 +736,12 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   for (int s : removed_now) meta[s].in_removed = 1; // removed_stracks.extend
   t->n_removed_total += (int)removed_now.size();
 
+  if (dbg_host) {
+    dbg_t[dbg_n++] = now_ms();
+    fprintf(stderr, "host lists: detlists %.1f stage1 %.1f stage2+3 %.1f births+expiry %.1f merge %.1f us\n",
+            1e3 * (dbg_t[0] - t_host), 1e3 * (dbg_t[1] - dbg_t[0]), 1e3 * (dbg_t[2] - dbg_t[1]),
+            1e3 * (dbg_t[3] - dbg_t[2]), 1e3 * (dbg_t[4] - dbg_t[3]));
+  }
   // ---- births on the device: one packed H2D, Kalman initiate + feature adoption --------------------
   const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
   BT_CUDA(cudaStreamSynchronize(st));    // the frame's device work is complete, part B is on the host

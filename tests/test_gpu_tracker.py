@@ -196,3 +196,40 @@ def test_replay_hook_leaves_state_untouched(ctx):
     for r0, r1 in zip(*outs):
         np.testing.assert_array_equal(r0["ids"], r1["ids"])
         np.testing.assert_array_equal(r0["mean"], r1["mean"])
+
+
+def test_very_crowded_scene_large_components(ctx):
+    """Boxes packed so tightly that the candidate graph is a few huge components (the LAP's global-memory
+    path: > 512 complex rows / > 2048 edges), IoU-only and with features."""
+    for with_reid in (False, True):
+        infos = _run(ctx, SceneConfig(n_ids=700, feat_dim=2048, seed=17, pitch_x=12.0, pitch_y=16.0, walk=1.0,
+                                      size_jitter=0.5, low_frac=0.1, drop_frac=0.05, with_features=with_reid),
+                     frames=4, with_reid=with_reid)
+        assert infos[-1]["n_pool"] >= 600
+
+
+def test_out_of_range_coordinates(ctx):
+    """Coordinates beyond the 15-bit integer screen of the association epilogue (and negative track boxes)
+    must fall back to the exact path, never lose a candidate."""
+    ctx.tracker_reset()
+    oracle = O.OracleBoTSORT()
+    rng = np.random.default_rng(3)
+    n = 40
+    base = np.stack([rng.uniform(0, 200, n), rng.uniform(0, 200, n)], axis=1)
+    base[: n // 2] += 40000.0                      # half of the scene far beyond 32767 px
+    wh = np.stack([rng.uniform(30, 60, n), rng.uniform(50, 90, n)], axis=1)
+    feats_id = rng.standard_normal((n, 2048)).astype(np.float32)
+    feats_id /= np.linalg.norm(feats_id, axis=1, keepdims=True)
+    vel = np.zeros_like(base)
+    vel[n // 2:] = -25.0                            # the near half drifts out of the frame: negative track boxes
+    for k in range(8):
+        pos = base + vel * k + rng.uniform(-2, 2, base.shape)
+        boxes = np.hstack([np.maximum(pos, 0), np.maximum(pos + wh, 1)]).astype(np.int32)
+        keep = (boxes[:, 2] > boxes[:, 0] + 4) & (boxes[:, 3] > boxes[:, 1] + 4)
+        perm = rng.permutation(np.nonzero(keep)[0])
+        f = feats_id[perm] + 0.005 * rng.standard_normal((len(perm), 2048)).astype(np.float32)
+        f /= np.linalg.norm(f, axis=1, keepdims=True)
+        scores = np.full(len(perm), 0.95, np.float32)
+        oracle.update_arrays(boxes[perm], scores, f.astype(np.float32))
+        ctx.update_arrays(boxes[perm], scores, f.astype(np.float32))
+        _compare_frame(ctx, oracle, k + 1)
