@@ -184,7 +184,12 @@ static inline double now_ms() {
 }
 #define HOST_MARK(seg)                                                \
   do {                                                                \
-    if (t->prof) { const double n__ = now_ms(); t->prof_ms[seg] += n__ - t_host; t->prof_n[seg] += 1; t_host = n__; } \
+    if (t->prof || t->host_debug) {                                   \
+      const double n__ = now_ms();                                    \
+      if (t->prof) { t->prof_ms[seg] += n__ - t_host; t->prof_n[seg] += 1; } \
+      hphase[seg - BT_SEG_HOST_ENQUEUE1] = n__ - t_host;              \
+      t_host = n__;                                                   \
+    }                                                                 \
   } while (0)
 
 static int32_t prof_collect(bt_ctx* ctx, bt_tracker* t) {
@@ -389,6 +394,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   std::vector<SlotMeta>& meta = t->meta;
 
   double t_host = now_ms();
+  double hphase[5] = {0, 0, 0, 0, 0};
   t->frame_id += 1;  // demo:1292
   const int frame_id = t->frame_id;
   t->tlbr_cache_valid = false;
@@ -744,7 +750,9 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   }
   // ---- births on the device: one packed H2D, Kalman initiate + feature adoption --------------------
   const int nt = (int)new_tracked.size(), nl = (int)new_lost.size();
+  HOST_MARK(BT_SEG_HOST_LISTS);
   BT_CUDA(cudaStreamSynchronize(st));    // the frame's device work is complete, part B is on the host
+  HOST_MARK(BT_SEG_HOST_WAIT2);
   if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join2));   // the side stream's EMA (usually done already)
   BT_TRY(prof_collect(ctx, t));
   int n_pairs = hres_i[o_hdr];           // live-slot duplicate candidates found by the device
@@ -784,7 +792,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       need_sync = true;
     }
   }
-  HOST_MARK(BT_SEG_HOST_LISTS);
   if (need_sync) {
     BT_CUDA(cudaStreamSynchronize(st));  // rare second sync: births next to lost tracks / very many candidates
     if (n_births > 0 && nl > 0) {
@@ -798,7 +805,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       }
     }
   }
-  HOST_MARK(BT_SEG_HOST_WAIT2);
 
   // ---- remove_duplicate_stracks (demo:1637, demo:1665-1680) --------------------------------------
   std::vector<uint8_t>& dupa = t->scratch_a; dupa.assign(nt, 0);
@@ -860,6 +866,9 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   if (freed) std::sort(t->free_slots.begin(), t->free_slots.end(), std::greater<int>());
 
   HOST_MARK(BT_SEG_HOST_FINAL);
+  if (t->host_debug)
+    fprintf(stderr, "frame %d host phases (us): enqueue %.1f wait_x %.1f lists+births %.1f wait_end %.1f final %.1f\n", frame_id,
+            1e3 * hphase[0], 1e3 * hphase[1], 1e3 * hphase[2], 1e3 * hphase[3], 1e3 * hphase[4]);
   if (info) {
     info->frame_id = frame_id;
     info->n_tracked = (int)t->tracked.size();

@@ -8,8 +8,17 @@ scene = SyntheticScene(SceneConfig(n_ids=n, feat_dim=2048, seed=1))
 frames = [scene.next_frame() for _ in range(4)]
 ctx = bs.Context(max_tracks=n + 256, max_dets=n + 256, feat_dim=2048)
 ctx.tracker_reset()
+import torch
+from botsort_b200._lib import BT_DEVICE
 for f in frames:
     ctx.update_arrays(f["boxes"], f["scores"], f["feats"])
+if os.environ.get("BT_HOST_DEBUG"):
+    fl = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for k in range(6):
+        f = scene.next_frame()
+        b_, s_, f_ = (torch.from_numpy(f[k2]).cuda() for k2 in ("boxes", "scores", "feats"))
+        fl.zero_(); torch.cuda.synchronize()
+        ctx.update_arrays_raw(b_.data_ptr(), s_.data_ptr(), f_.data_ptr(), b_.shape[0], BT_DEVICE)
 if len(sys.argv) > 1:
     os.environ["BT_ASSOC_DEBUG"] = sys.argv[1]
 for k in range(3):
