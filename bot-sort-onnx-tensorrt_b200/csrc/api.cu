@@ -154,6 +154,7 @@ int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t 
   c->feat_dim = feat_dim;
   c->flags = flags;
   c->num_sms = prop.multiProcessorCount;
+  c->pdl = getenv("BT_NO_PDL") ? 0 : 1;
   ctx = c;
   int32_t s = BT_OK;
   auto fail = [&](int32_t code) {

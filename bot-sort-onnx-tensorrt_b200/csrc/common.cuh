@@ -19,6 +19,7 @@ struct bt_ctx {
   int max_tracks = 0, max_dets = 0, feat_dim = 0;
   uint32_t flags = 0;
   int num_sms = 148;
+  int pdl = 1;   // programmatic dependent launch between the frame step's kernels (BT_NO_PDL=1 turns it off)
   std::string err;
   int64_t launches = 0;
   // bump arena for the stand-alone entry points (device) and a pinned mirror for small results
@@ -34,6 +35,29 @@ struct bt_ctx {
 };
 
 int32_t bt_fail(bt_ctx* ctx, int32_t code, const char* fmt, ...);
+
+#ifdef __CUDACC__
+// Box -> two 32-bit words of 15-bit integer corners rounded OUTWARD, the operands of the association
+// kernel's two-subtraction overlap screen:
+//   .x = (x1 + 1) | (y1 + 1) << 16        .y = x2 | y2 << 16 | 0x80008000
+// Saturation keeps the screen conservative: lowering a lower corner or raising an upper corner only adds
+// overlaps; upper corners above 32767 meet lower corners saturated to 32766 (test passes); a ROW's negative
+// corners clamp to 0 because detection corners are >= 0 -- a detection with a negative corner (outside the
+// reference's domain: YOLOX._postprocess clamps at 0, demo:1009) and NaNs fall back to the whole range, so
+// the packed test never rejects a pair whose exact IoU is positive.
+__device__ __forceinline__ uint2 bt_pack16_corners(int lx, int ly, int hx, int hy, bool whole) {
+  const uint32_t ix1 = whole ? 0u : (uint32_t)min(max(lx, 0), 32766), iy1 = whole ? 0u : (uint32_t)min(max(ly, 0), 32766);
+  const uint32_t ix2 = whole ? 32767u : (uint32_t)min(max(hx, 0), 32767), iy2 = whole ? 32767u : (uint32_t)min(max(hy, 0), 32767);
+  return make_uint2((ix1 + 1u) | ((iy1 + 1u) << 16), ix2 | (iy2 << 16) | 0x80008000u);
+}
+// from an fp32 interval (lower corners rounded down, upper corners rounded up): integer conversions and
+// integer clamps only -- fp64 rounding / compares crawl next to a running tcgen05 main loop
+__device__ __forceinline__ uint2 bt_pack16_f32(float x1, float y1, float x2, float y2, bool is_col) {
+  const bool nan = (x1 != x1) || (y1 != y1) || (x2 != x2) || (y2 != y2);
+  const bool whole = nan || (is_col && (x1 < 0.0f || y1 < 0.0f));
+  return bt_pack16_corners(__float2int_rd(x1), __float2int_rd(y1), __float2int_ru(x2), __float2int_ru(y2), whole);
+}
+#endif
 extern thread_local std::string g_bt_create_error;
 
 #define BT_CUDA(expr)                                                                              \
@@ -195,6 +219,7 @@ struct bt_assoc_params {
   const uint8_t* row_kind;  // [n]
   const double* col_tlbr;   // [m,4]
   const uint8_t* col_kind;  // [m]
+  const uint2* col_pk;      // [m] packed 15-bit integer corners (bt_pack16_*), or null: packed in the kernel
   const float* face_sim;    // [n,m] or null
   // thresholds
   double match_thresh, second_thresh, unconf_thresh, proximity;

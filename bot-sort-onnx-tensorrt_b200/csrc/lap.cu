@@ -638,6 +638,9 @@ lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
   }
   if (gtid < 24) ws.counters[gtid] = 0;
   if (gtid == 0 && P.zero_word) *P.zero_word = 0;
+  // Everything above touches only this kernel's own outputs and scratch, so under programmatic
+  // dependent launch it runs while the emitting kernel drains; the candidate lists are read below.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   cluster_barrier();
   LAP_T(1);
 
@@ -930,13 +933,15 @@ static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const LapParams& P) 
                                  (int)sizeof(SmallSmem)));
     attr_done = true;
   }
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = nctas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->pdl ? 2 : 1;
   BT_CUDA(cudaLaunchKernelEx(&cfg, lap_cluster_kernel, cand, *ctx->lap, P));
   BT_LAUNCHED(ctx);
   return BT_OK;

@@ -39,6 +39,7 @@ struct EpiParams {
   const uint8_t* row_kind;
   const double* col_tlbr;
   const uint8_t* col_kind;
+  const uint2* col_pk;
   const float* face_sim;
   double match_thresh, second_thresh, unconf_thresh, proximity;
   float appearance;
@@ -47,7 +48,11 @@ struct EpiParams {
   double* out_dists;
   int dense_stage;
   int n, m;
-  int debug;   // BT_ASSOC_DEBUG=1: per-CTA phase timestamps via device printf (profiling aid)
+  // BT_ASSOC_DEBUG bits (profiling / bisection aids of the tensor-core kernel, device printf):
+  //   1 sampled CTA timestamps   2 similarity pass off   4 every CTA's timestamps   16 epilogue phase times
+  //   32 no box pass (every pair evaluated by the similarity pass)   64 no early TMA prologue
+  //   1024 globaltimer go/end of every epilogue warp
+  int debug;
   float sim_gate;  // smallest similarity for which the appearance gate is open
   float iou_gate;  // a pair without open appearance gate needs IoU > 1 - max(stage thresholds); slightly lowered
 };
@@ -93,12 +98,12 @@ __device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int co
   if (k == 0) atomicOr(&c.segmask[(size_t)list * c.rows_cap + row], 1ull << seg);
   note_edge(c, list, row, col);
 }
-// plain append: the caller owns (row, segment) exclusively and keeps the count in a register
-__device__ __forceinline__ void emit_owned(const bt_cand& c, int list, int row, int seg, int k, int col, double cost) {
+// tensor-core kernel: the owner of (row, segment) adds the row degree once, at the end of its tile
+__device__ __forceinline__ void emit_owned_tc(const bt_cand& c, int list, int row, int seg, int k, int col, double cost) {
   const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * c.seg + k;
   c.col[base] = col;
   c.cost[base] = cost;
-  note_edge(c, list, row, col);
+  atomicAdd(&c.indeg[(size_t)list * c.cols_cap + col], 1);
 }
 
 // exact path for one (row, col) pair that survived the cheap rejection test
@@ -119,6 +124,37 @@ __device__ __noinline__ void assoc_exact(const EpiParams& p, int row, int col, f
       if (iou_d < p.second_thresh) emit(p.cand, 1, row, col, iou_d);
     }
   }
+}
+
+// Similarity pass of the tensor-core kernel for a pair that is not in the warp's shared-memory slots:
+// evaluates it from scratch; if the box pass spilled edges of this row straight to the list (more than
+// kPreSlots of them) the pair is looked up there first and re-costed in place.
+// Returns 1 when a new edge was appended at position `k_next` of the caller's (row, seg) sub-list.
+__device__ __noinline__ int open_pair_slow(const EpiParams& p, double r0, double r1, double r2, double r3,
+                                           const double* __restrict__ cbox, int list, int row, int seg, int col,
+                                           float sim, int k_next, int scan_from) {
+  const double rb[4] = {r0, r1, r2, r3};
+  const size_t eb = ((size_t)list * p.cand.rows_cap + row) * (size_t)p.cand.stride + (size_t)seg * p.cand.seg;
+  int k_found = -1;
+  if (scan_from >= 0)
+    for (int j = scan_from; j < k_next; ++j)
+      if (p.cand.col[eb + j] == col) k_found = j;
+  const double iou_d = iou_dist_f64(rb, cbox);
+  double cost = iou_d;
+  if (list == 0) {
+    const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
+    cost = fuse_stage1(iou_d, sim, face, p.appearance);
+  } else if (list == 2) {
+    cost = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+  }
+  if (k_found >= 0) {
+    if (cost != iou_d) p.cand.cost[eb + k_found] = cost;
+    return 0;
+  }
+  const double thr = list == 0 ? p.match_thresh : (list == 1 ? p.second_thresh : p.unconf_thresh);
+  if (!(cost < thr)) return 0;
+  emit_owned_tc(p.cand, list, row, seg, k_next, col, cost);
+  return 1;
 }
 
 __device__ __forceinline__ void assoc_dense(const EpiParams& p, int row, int col, float sim) {
@@ -230,22 +266,21 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
       : "r"(taddr)
       : "memory");
 }
-// Box -> two 32-bit words of 15-bit integer corners rounded OUTWARD (lo floored, hi ceiled):
-//   .x = (x1 + 1) | (y1 + 1) << 16        .y = x2 | y2 << 16 | 0x80008000
-// Corners outside [0, 32766] are widened to the whole range (the screen then passes and the exact
-// float64 path decides), so the packed test never rejects a pair whose exact IoU is positive.
+// float64 box -> packed corners (common.cuh) through a directed-rounding fp32 interval: 4 conversions
 __device__ __forceinline__ uint2 pack16_box(double x1, double y1, double x2, double y2, bool is_col) {
-  // Saturation keeps the screen conservative: lowering a lower corner or raising an upper corner only adds
-  // overlaps; upper corners above 32767 meet lower corners saturated to 32766 (test passes); a ROW's negative
-  // corners clamp to 0 because detection corners are >= 0 -- a detection with a negative corner (outside the
-  // reference's domain: YOLOX._postprocess clamps at 0, demo:1009) and NaNs fall back to the whole range.
-  const bool ok = (x1 == x1) && (y1 == y1) && (x2 == x2) && (y2 == y2) && !(is_col && (x1 < 0.0 || y1 < 0.0));
-  const double lx = ok ? fmin(fmax(floor(x1), 0.0), 32766.0) : 0.0, ly = ok ? fmin(fmax(floor(y1), 0.0), 32766.0) : 0.0;
-  const double hx = ok ? fmin(fmax(ceil(x2), 0.0), 32767.0) : 32767.0, hy = ok ? fmin(fmax(ceil(y2), 0.0), 32767.0) : 32767.0;
-  const uint32_t ix1 = (uint32_t)lx, iy1 = (uint32_t)ly, ix2 = (uint32_t)hx, iy2 = (uint32_t)hy;
-  return make_uint2((ix1 + 1u) | ((iy1 + 1u) << 16), ix2 | (iy2 << 16) | 0x80008000u);
+  return bt_pack16_f32(__double2float_rd(x1), __double2float_rd(y1), __double2float_ru(x2), __double2float_ru(y2), is_col);
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.wait::ld with the loaded registers as in/out operands so that the compiler cannot move a use of them
+// above the wait when loads are software-pipelined.
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 
 // K-major operand tile in shared memory, 128-byte swizzle (as written by TMA SWIZZLE_128B):
 // rows of 64 fp16 = 128 B, 8-row groups 1024 B apart.  sm_100 descriptor: start>>4 [0,14),
@@ -271,7 +306,7 @@ constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kEpiWarps = 8;     // two per SM sub-partition: warp w and w+4 share TMEM lane quarter w%4
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kQueue = 96;       // survivor records per epilogue warp before a drain
+constexpr int kPreSlots = 4;     // pairs per row and tile half whose box-pass result is remembered in shared memory
 constexpr int kTcThreads = 64 + kEpiThreads;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 template <int BN>
@@ -282,9 +317,9 @@ struct TcSmem {
   static constexpr int kColPkOff = kStages * kStageBytes;             // uint2[BN]  packed integer det corners
   static constexpr int kColKindOff = kColPkOff + BN * 8;              // uint8[BN]
   static constexpr int kColF64Off = kColKindOff + 256;                // double[BN][4] det box float64 (exact path)
-  static constexpr int kQueueOff = kColF64Off + BN * 32;              // uint2[kEpiWarps][kQueue] survivor records
-  static constexpr int kRowCntOff = kQueueOff + 8 * 96 * 8;           // int[kEpiWarps][32][2]
-  static constexpr int kBarOff = kRowCntOff + 8 * 64 * 4;             // barriers (8B aligned)
+  static constexpr int kPreIouOff = kColF64Off + BN * 32;             // double[kEpiWarps][kPreSlots][32] IoU distance of box-pass edges
+  static constexpr int kPreKeyOff = kPreIouOff + 8 * 4 * 32 * 8;      // uint32[kEpiWarps][kPreSlots][32] their (column, position, list)
+  static constexpr int kBarOff = kPreKeyOff + 8 * 4 * 32 * 4;         // barriers (8B aligned)
   static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
   static constexpr int kTotal = kTmemPtrOff + 16;
@@ -300,7 +335,7 @@ struct TcSmem {
 template <int BN, bool kDense, int CM, int CN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                EpiParams p, int d) {
+                const __grid_constant__ EpiParams p, int d) {   // grid constant: &p (open_pair_slow) needs no local copy
   using L = TcSmem<BN>;
   constexpr int CS = CM * CN;
   constexpr int kASlice = BM / CN, kBSlice = BN / CM;  // rows each CTA loads itself
@@ -314,8 +349,8 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   uint2* s_colpk = reinterpret_cast<uint2*>(smem + L::kColPkOff);
   uint8_t* s_colkind = smem + L::kColKindOff;
-  uint2* s_queue = reinterpret_cast<uint2*>(smem + L::kQueueOff);
-  int* s_rowcnt = reinterpret_cast<int*>(smem + L::kRowCntOff);
+  double* s_preiou = reinterpret_cast<double*>(smem + L::kPreIouOff);
+  uint32_t* s_prekey = reinterpret_cast<uint32_t*>(smem + L::kPreKeyOff);
   double* s_col64 = reinterpret_cast<double*>(smem + L::kColF64Off);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,14 +373,33 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
   for (int i = 0; i < CM; ++i) col_mask |= (uint16_t)(1u << (i * CN + rn));
 
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as SMs free
+  // up (it blocks in its own griddepcontrol.wait until this grid has completed and flushed).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  int pro_kb = 0;   // k-blocks of the first tile already requested by the prologue below
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    // a slot is free again when every CTA that receives my slices has consumed it
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CM + CN - 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (CS == 1 && cid < num_ctiles && !(p.debug & 64)) {
+      // the pipeline's first kStages loads do not wait for anybody: request them before the TMEM
+      // allocation and the CTA-wide sync so that their latency overlaps the rest of the ramp
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // the operands come from the previous kernels
+      const int m0 = (cid / ctiles_n) * BM, n0 = (cid % ctiles_n) * BN;
+      pro_kb = num_kb < kStages ? num_kb : kStages;
+      for (int kb = 0; kb < pro_kb; ++kb) {
+        mbar_expect_tx(&full_bar[kb], L::kStageBytes);
+        uint8_t* sa = smem + kb * L::kStageBytes;
+        tma_load_2d(sa, &tmap_a, kb * BK, m0, &full_bar[kb]);
+        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, n0, &full_bar[kb]);
+      }
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
-      // a slot is free again when every CTA that receives my slices has consumed it
-      for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CM + CN - 1); }
       for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -365,11 +419,12 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = pro_kb % kStages;
+      uint32_t phase = pro_kb == kStages ? 1u : 0u;
+      if (CS > 1) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
         const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = (ct == cid) ? pro_kb : 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);   // the whole stage lands here (own + mates' slices)
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -422,6 +477,10 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
     int acc = 0;
     uint32_t acc_phase = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // boxes / kinds / candidate lists belong to earlier kernels
+    const long long t_go = clock64();
+    unsigned long long g_go = 0;
+    if (p.debug & 1024) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_go));
     for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
       const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
       const int row = m0 + quarter * 32 + lane;
@@ -430,182 +489,312 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t r2h = 0, r1p = 0;   // packed conservative integer row box (see pack16 below)
       int rix1 = 0, riy1 = 0, rix2 = 0, riy2 = 0;
       float r_area_lb = 0.f;
+      long long t_s1 = 0, t_s2 = 0, t_s3 = 0, t_rl = 0;
       if (!kDense) {
-        // stage this tile's detection boxes: packed 15-bit integer corners for the screen, float64 for
-        // the exact path, and the score class
+        // All global loads of the tile first, in one batch and without dependent chains: while the TMA
+        // pipeline is streaming, an ordinary load queues behind ~4 stages of operand traffic (measured
+        // 3-6 k cycles per round trip), so the row kind -> row box dependency of the obvious code and the
+        // separate detection-box round trip cost ~14 k cycles (profiles/README.md).
+        const int c = et, col = n0 + et;          // BN <= kEpiThreads: one detection per thread
+        double2 rlo = make_double2(0.0, 0.0), rhi = rlo, clo = rlo, chi = rlo;
+        float4 r32 = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint2 cpk = make_uint2(0u, 0u);
+        uint8_t ck = BT_COL_NONE;
+        if (row < p.n) {
+          const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (size_t)row * 4);
+          rkind = p.row_kind[row];
+          rlo = s[0]; rhi = s[1];
+          if (p.row_tlbr_f32) r32 = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
+        }
+        if (c < BN && col < p.m) {
+          const double2* s = reinterpret_cast<const double2*>(p.col_tlbr + (size_t)col * 4);
+          ck = p.col_kind[col];
+          clo = s[0]; chi = s[1];
+          if (p.col_pk) cpk = p.col_pk[col];
+        }
+        // stage the detection boxes: packed 15-bit integer corners for the screen, float64 for the exact
+        // path, and the score class
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // previous tile's readers are done
-        for (int c = et; c < BN; c += kEpiThreads) {
-          const int col = n0 + c;
+        t_s1 = clock64();
+        if (c < BN) {
           uint2 pk = make_uint2(0x7fff7fffu, 0x80008000u);   // x1+1 = y1+1 = 32767, x2 = y2 = 0: overlaps nothing
-          uint8_t ck = BT_COL_NONE;
-          double4 cd = make_double4(0.0, 0.0, 0.0, 0.0);
-          if (col < p.m) {
-            const double2* s = reinterpret_cast<const double2*>(p.col_tlbr + (size_t)col * 4);
-            const double2 lo = s[0], hi = s[1];
-            cd = make_double4(lo.x, lo.y, hi.x, hi.y);
-            ck = p.col_kind[col];
-            if (ck != BT_COL_NONE) pk = pack16_box(lo.x, lo.y, hi.x, hi.y, true);
-          }
+          if (ck != BT_COL_NONE) pk = p.col_pk ? cpk : pack16_box(clo.x, clo.y, chi.x, chi.y, true);
           s_colpk[c] = pk;
           s_colkind[c] = ck;
-          reinterpret_cast<double2*>(s_col64 + c * 4)[0] = make_double2(cd.x, cd.y);
-          reinterpret_cast<double2*>(s_col64 + c * 4)[1] = make_double2(cd.z, cd.w);
+          reinterpret_cast<double2*>(s_col64 + c * 4)[0] = clo;
+          reinterpret_cast<double2*>(s_col64 + c * 4)[1] = chi;
         }
+        t_s2 = clock64();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (row < p.n) {
-          rkind = p.row_kind[row];
-          if (rkind != BT_ROW_NONE) {
-            const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (size_t)row * 4);
-            const double2 lo = s[0], hi = s[1];
-            rbox[0] = lo.x; rbox[1] = lo.y; rbox[2] = hi.x; rbox[3] = hi.y;
-            const uint2 pk = pack16_box(lo.x, lo.y, hi.x, hi.y, false);
-            r1p = pk.x;   // (x1+1) | (y1+1) << 16
-            r2h = pk.y;   // x2 | y2 << 16 | 0x80008000
-            rix1 = (int)(pk.x & 0xffffu) - 1; riy1 = (int)(pk.x >> 16) - 1;
-            rix2 = (int)(pk.y & 0x7fffu); riy2 = (int)((pk.y >> 16) & 0x7fffu);
-            // the integer corners are rounded outward by < 1 px per side: a lower bound of the true area
-            r_area_lb = (float)max(rix2 - rix1 - 2, 0) * (float)max(riy2 - riy1 - 2, 0);
+        t_s3 = clock64();
+        if (p.debug & 16) {
+          asm volatile("" ::"d"(rlo.x), "d"(rhi.y), "r"(rkind) : "memory");   // the row loads have landed
+          t_rl = clock64();
+        }
+        if (rkind != BT_ROW_NONE) {
+          rbox[0] = rlo.x; rbox[1] = rlo.y; rbox[2] = rhi.x; rbox[3] = rhi.y;
+          const uint2 pk = p.row_tlbr_f32 ? bt_pack16_f32(r32.x, r32.y, r32.z, r32.w, false)
+                                          : pack16_box(rlo.x, rlo.y, rhi.x, rhi.y, false);
+          r1p = pk.x;   // (x1+1) | (y1+1) << 16
+          r2h = pk.y;   // x2 | y2 << 16 | 0x80008000
+          rix1 = (int)(pk.x & 0xffffu) - 1; riy1 = (int)(pk.x >> 16) - 1;
+          rix2 = (int)(pk.y & 0x7fffu); riy2 = (int)((pk.y >> 16) & 0x7fffu);
+          // the integer corners are rounded outward by < 1 px per side: a lower bound of the true area
+          r_area_lb = (float)max(rix2 - rix1 - 2, 0) * (float)max(riy2 - riy1 - 2, 0);
+        }
+      }
+      const long long t_rows = clock64();
+      const int seg = n0 / (BN / 2) + half;   // the warp's rows x this column half = one candidate segment per row
+      double* my_preiou = s_preiou + (warp - 2) * (kPreSlots * 32);     // [slot][lane]
+      uint32_t* my_prekey = s_prekey + (warp - 2) * (kPreSlots * 32);
+      // This lane owns (row, seg) of every candidate list: counts live in registers, appends need no atomics.
+      int cnt_a = 0, cnt_b = 0;   // edges appended so far: list 0 (or 2 for an unconfirmed row) | list 1
+      my_prekey[lane] = 0u; my_prekey[32 + lane] = 0u;   // slots 0 / 1 are read unconditionally by the exact pass
+      int npre = 0;               // box-pass candidates waiting in shared memory (<= kPreSlots)
+      int last_a = 0, last_b = 0; // column of the latest edge per list (the row's only column if its degree stays 1)
+      int spill_a = -1, spill_b = -1;   // 0 once the box pass wrote edges of a crowded row straight to the list
+      int dbg_open = 0;
+      const int la = (rkind == BT_ROW_UNCONFIRMED) ? 2 : 0;
+      const double thr_a = (rkind == BT_ROW_UNCONFIRMED) ? p.unconf_thresh : p.match_thresh;
+      // candidate list a (row, detection class) pair belongs to: demo:1539-1556 (0), demo:1569-1571 (1), demo:1593-1604 (2)
+      auto list_of = [&](const int ckind) -> int {
+        if (ckind == BT_COL_HIGH) return la;
+        if (ckind == BT_COL_LOW && rkind == BT_ROW_POOL_TRACKED) return 1;
+        return -1;
+      };
+      constexpr int kHalfCols = BN / 2, kFullChunks = kHalfCols / 32, kTailCols = kHalfCols % 32;
+      constexpr int kChunks = kFullChunks + (kTailCols ? 1 : 0);
+      static_assert(kTailCols == 0 || kTailCols == 16, "column half must be a multiple of 16");
+      static_assert(BN <= kEpiThreads, "one staged detection per epilogue thread");
+      // ---- Box pass, in the shadow of the MMA main loop (it needs no accumulator).  With the
+      // appearance gate closed the cost of a pair is its IoU distance in every stage, so every edge that
+      // exists without the similarity is found, evaluated in float64 and appended here:
+      //  1. integer screen on outward-rounded 15-bit corners, two corners per 32-bit word:
+      //       r.x2 > c.x1 & r.y2 > c.y1  <=>  both half-words of (r2 | 0x80008000) - (c1 + 0x00010001) keep bit 15
+      //       c.x2 > r.x1 & c.y2 > r.y1  <=>  likewise with the roles swapped     (false => the exact IoU is 0)
+      //  2. for the few overlapping pairs an integer upper bound of the intersection against lower bounds
+      //     of the areas (no division): the IoU must be able to reach 1 - max(stage threshold)
+      //  3. exact float64 IoU distance against the stage threshold.
+      // (With real face similarities the gate is not a function of the body similarity alone: everything
+      // is left to the similarity pass.)
+      const bool all_open = p.face_sim != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
+      if (!kDense && !all_open && rkind != BT_ROW_NONE) {
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          const int W = (ch < kFullChunks) ? 32 : kTailCols;
+          const int c0 = half * kHalfCols + ch * 32;
+          const uint32_t colbase = smem_u32(s_colpk) + (uint32_t)c0 * 8u;
+          uint32_t hot_ov = 0;
+#pragma unroll
+          for (int c = 0; c < W; c += 2) {
+            // two detections per 16-byte load; volatile + memory clobber: must stay below the staging
+            // barrier (bar.sync 1) -- a plain asm was hoisted above it by the compiler
+            uint32_t a1, a2, b1, b2;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a1), "=r"(a2), "=r"(b1), "=r"(b2)
+                         : "r"(colbase + (uint32_t)c * 8u) : "memory");
+            if (((r2h - a1) & (a2 - r1p) & 0x80008000u) == 0x80008000u) hot_ov |= 1u << c;
+            if (((r2h - b1) & (b2 - r1p) & 0x80008000u) == 0x80008000u) hot_ov |= 2u << c;
+          }
+          while (hot_ov) {
+            const int lc = c0 + __ffs(hot_ov) - 1;
+            hot_ov &= hot_ov - 1;
+            const uint2 pk = s_colpk[lc];
+            const int cx1 = (int)(pk.x & 0xffffu) - 1, cy1 = (int)(pk.x >> 16) - 1;
+            const int cx2 = (int)(pk.y & 0x7fffu), cy2 = (int)((pk.y >> 16) & 0x7fffu);
+            const float inter_ub = (float)(min(rix2, cx2) - max(rix1, cx1)) * (float)(min(riy2, cy2) - max(riy1, cy1));
+            const float c_area_lb = (float)max(cx2 - cx1 - 2, 0) * (float)max(cy2 - cy1 - 2, 0);
+            // IoU <= inter_ub / (areas_lb - inter_ub) < gate  <=>  inter_ub * (1 + gate) < gate * areas_lb
+            if (inter_ub * (1.0f + p.iou_gate) * 1.0001f < p.iou_gate * (r_area_lb + c_area_lb)) continue;
+            const int list = list_of(s_colkind[lc]);
+            if (list < 0) continue;
+            if (npre < kPreSlots) {
+              // remembered in shared memory; the float64 IoU waits until the main loop is over (FP64
+              // instructions crawl next to a running tcgen05 pipeline: ~5 k cycles per evaluation here,
+              // ~300 afterwards, and they slow the MMAs down -- profiles/README.md)
+              my_prekey[npre * 32 + lane] = (uint32_t)lc | ((uint32_t)(list == 1) << 16);
+              ++npre;
+              continue;
+            }
+            // crowded row (more than kPreSlots box candidates in this half tile): evaluate now, straight to the list
+            const double iou_d = iou_dist_f64(rbox, s_col64 + lc * 4);
+            if (!(iou_d < (list == 1 ? p.second_thresh : thr_a))) continue;
+            const int k = (list == 1) ? cnt_b++ : cnt_a++;
+            if (list == 1) { last_b = n0 + lc; spill_b = 0; } else { last_a = n0 + lc; spill_a = 0; }
+            emit_owned_tc(p.cand, list, row, seg, k, n0 + lc, iou_d);
           }
         }
       }
-      const int seg = n0 / (BN / 2) + half;   // the warp's rows x this column half = one candidate segment per row
-      uint2* my_queue = s_queue + (warp - 2) * kQueue;
-      int* my_rowcnt = s_rowcnt + (warp - 2) * 64;   // [32 rows][2]: edges appended per row (list 0|2, list 1)
-      int qn = 0, dbg_iters = 0, dbg_recs = 0;
-      my_rowcnt[lane * 2] = 0;
-      my_rowcnt[lane * 2 + 1] = 0;
       __syncwarp();
+      const long long t_shadow = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
       const long long t_acc = clock64();
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-      constexpr int kHalfCols = BN / 2, kFullChunks = kHalfCols / 32, kTailCols = kHalfCols % 32;
-      static_assert(kTailCols == 0 || kTailCols == 16, "column half must be a multiple of 16");
-      // one chunk = W (32 or 16) accumulator columns of this thread's row, starting at tile column c0
-      // Pass 2b: the exact path, 32 records at a time, one per lane (row data comes by shuffle)
-      auto drain = [&]() {
-        for (int base = 0; base < qn; base += 32) {
-          const bool act = base + lane < qn;
-          const uint2 rec = act ? my_queue[base + lane] : make_uint2(0u, 0u);
-          const int rl = (int)(rec.x & 31u), lc = (int)(rec.x >> 8);
-          double rb4[4];
+      uint32_t va[32], vb[32];
+      auto issue = [&](const int ch, uint32_t (&v)[32]) {
+        const uint32_t c0 = (uint32_t)(half * kHalfCols + ch * 32);
+        if (ch < kFullChunks) tmem_ld_32x32b_x32(taddr + c0, v);
+        else tmem_ld_32x32b_x16(taddr + c0, v);
+      };
+      // ---- Similarity pass.  A pair whose appearance gate is open (sim >= sim_gate, == !((1.0f - sim) >
+      // appearance), sim_gate_for()) gets the fused cost: an edge of the box pass is overwritten in place,
+      // otherwise the pair is evaluated from scratch.  Lane-local, no shuffles: the lane owns its row.
+      auto open_pair = [&](const int lc, const float sim) {
+        const int list = list_of(s_colkind[lc]);
+        if (list < 0) return;
+        const uint32_t want = (uint32_t)lc | ((uint32_t)(list == 1) << 16);
+        bool found = false;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) rb4[k] = __shfl_sync(0xffffffffu, rbox[k], rl);
-          const int rk = __shfl_sync(0xffffffffu, rkind, rl);
-          if (!act) continue;
-          const float sim = __uint_as_float(rec.y);
-          const int grow = row - lane + rl, col = n0 + lc;
-          const int ckind = s_colkind[lc];
-          if (ckind == BT_COL_NONE) continue;
-          const double iou_d = iou_dist_f64(rb4, s_col64 + lc * 4);
-          const float face = p.face_sim ? p.face_sim[(size_t)grow * p.m + col] : 0.0f;
-          if (rk == BT_ROW_UNCONFIRMED) {
-            if (ckind == BT_COL_HIGH) {
-              const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
-              if (c3 < p.unconf_thresh) emit_owned(p.cand, 2, grow, seg, atomicAdd(&my_rowcnt[rl * 2], 1), col, c3);
-            }
-          } else if (ckind == BT_COL_HIGH) {
-            const double c1 = fuse_stage1(iou_d, sim, face, p.appearance);
-            if (c1 < p.match_thresh) emit_owned(p.cand, 0, grow, seg, atomicAdd(&my_rowcnt[rl * 2], 1), col, c1);
-          } else if (ckind == BT_COL_LOW && rk == BT_ROW_POOL_TRACKED) {
-            if (iou_d < p.second_thresh) emit_owned(p.cand, 1, grow, seg, atomicAdd(&my_rowcnt[rl * 2 + 1], 1), col, iou_d);
+        for (int j = 0; j < kPreSlots; ++j) {
+          if (j < npre && my_prekey[j * 32 + lane] == want) {
+            // an edge of the box pass whose gate turned out open (slots exist only without a face term)
+            const double iou_d = my_preiou[j * 32 + lane];
+            if (list == 0) my_preiou[j * 32 + lane] = fuse_stage1(iou_d, sim, 0.0f, p.appearance);
+            if (list == 2) my_preiou[j * 32 + lane] = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+            found = true;
           }
         }
-        __syncwarp();
-        qn = 0;
+        if (found) return;
+        const int cnt = (list == 1) ? cnt_b : cnt_a;
+        const int added = open_pair_slow(p, rbox[0], rbox[1], rbox[2], rbox[3], s_col64 + lc * 4, list, row, seg, n0 + lc, sim,
+                                         cnt, (list == 1) ? spill_b : spill_a);
+        if (added) { if (list == 1) { ++cnt_b; last_b = n0 + lc; } else { ++cnt_a; last_a = n0 + lc; } }
       };
-      auto do_chunk = [&](auto wtag, const int c0) {
-        constexpr int W = decltype(wtag)::value;
-        uint32_t v[32];
-        if constexpr (W == 32) tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
-        else tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (kDense) {
+      long long t_l0 = 0, t_l1 = 0;
+      if (kDense) {
+#pragma unroll 1
+        for (int ch = 0; ch < kChunks; ++ch) {
+          issue(ch, va);
+          tmem_ld_wait_dep(va);
+          const int W = (ch < kFullChunks) ? 32 : kTailCols;
           if (row < p.n) {
 #pragma unroll
-            for (int c = 0; c < W; ++c) {
-              const int col = n0 + c0 + c;
-              if (col < p.m) assoc_dense(p, row, col, __uint_as_float(v[c]));
+            for (int c = 0; c < 32; ++c) {
+              const int col = n0 + half * kHalfCols + ch * 32 + c;
+              if (c < W && col < p.m) assoc_dense(p, row, col, __uint_as_float(va[c]));
             }
           }
-          return;
         }
-        // Pass 1 (branch-free, independent shared loads): which of the W pairs can have a cost below 1?
-        // Integer screen on outward-rounded 15-bit corners, two corners per 32-bit word:
-        //   r.x2 > c.x1 & r.y2 > c.y1  <=>  both half-words of (r2 | 0x80008000) - (c1 + 0x00010001) keep bit 15
-        //   c.x2 > r.x1 & c.y2 > r.y1  <=>  likewise with the roles swapped
-        // (false => the exact IoU is 0), OR the appearance gate is open.
-        const uint32_t colbase = smem_u32(s_colpk) + (uint32_t)c0 * 8u;
-        uint32_t hot_ov = 0, hot = 0;
+      } else {
+        // phase A: chunk maxima, TMEM loads software-pipelined, no branches
+        uint32_t gatebits = 0;
+        issue(0, va);
 #pragma unroll
-        for (int c = 0; c < W; ++c) {
-          uint32_t c1p, c2h;   // not volatile: the staged boxes are read-only here, let ptxas batch the loads
-          asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c1p), "=r"(c2h) : "r"(colbase + (uint32_t)c * 8u));
-          const uint32_t both = (r2h - c1p) & (c2h - r1p) & 0x80008000u;
-          if (both == 0x80008000u) hot_ov |= 1u << c;
-          if (__uint_as_float(v[c]) >= p.sim_gate) hot |= 1u << c;   // == !((1.0f - sim) > appearance), sim_gate_for()
-        }
-        // Pass 1b (cheap, rare): an overlapping pair whose appearance gate is closed only matters if its
-        // IoU can exceed 1 - max(stage threshold): integer upper bound of the intersection against lower
-        // bounds of the areas, no division.
-        hot_ov &= ~hot;
-        if (rkind == BT_ROW_NONE) hot_ov = 0;   // unused slot / row past the matrix edge
-        while (hot_ov) {
-          const int c = __ffs(hot_ov) - 1;
-          hot_ov &= hot_ov - 1;
-          const uint2 pk = s_colpk[c0 + c];
-          const int cx1 = (int)(pk.x & 0xffffu) - 1, cy1 = (int)(pk.x >> 16) - 1;
-          const int cx2 = (int)(pk.y & 0x7fffu), cy2 = (int)((pk.y >> 16) & 0x7fffu);
-          const float inter_ub = (float)(min(rix2, cx2) - max(rix1, cx1)) * (float)(min(riy2, cy2) - max(riy1, cy1));
-          const float c_area_lb = (float)max(cx2 - cx1 - 2, 0) * (float)max(cy2 - cy1 - 2, 0);
-          // IoU <= inter_ub / (areas_lb - inter_ub) < gate  <=>  inter_ub * (1 + gate) < gate * areas_lb
-          if (!(inter_ub * (1.0f + p.iou_gate) * 1.0001f < p.iou_gate * (r_area_lb + c_area_lb))) hot |= 1u << c;
-        }
-        if (p.face_sim != nullptr) hot = (W == 32) ? 0xffffffffu : 0xffffu;
-        if ((p.debug & 2) || rkind == BT_ROW_NONE) hot = 0;
-        // Pass 2a (warp-collective, cheap): survivors go to the warp's shared-memory queue as
-        // (row lane, tile column, similarity) records.
-        while (__any_sync(0xffffffffu, hot != 0)) {
-          ++dbg_iters;
-          const bool has = hot != 0;
-          const int c = has ? __ffs(hot) - 1 : 0;
-          if (has) hot &= hot - 1;
-          float sim = 0.f;
+        for (int ch = 0; ch < kChunks; ++ch) {
+          uint32_t (&cur)[32] = (ch & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
+          tmem_ld_wait_dep(cur);
+          if (p.debug & 16) { if (ch == 0) t_l0 = clock64(); if (ch == 1) t_l1 = clock64(); }
+          if (ch + 1 < kChunks) issue(ch + 1, nxt);
+          const int G = ((ch < kFullChunks) ? 32 : kTailCols) / 4;
+          float m4[8];
 #pragma unroll
-          for (int k = 0; k < W; ++k)
-            if (c == k) sim = __uint_as_float(v[k]);
-          const uint32_t ball = __ballot_sync(0xffffffffu, has);
-          if (has) my_queue[qn + __popc(ball & ((1u << lane) - 1))] = make_uint2((uint32_t)lane | ((uint32_t)(c0 + c) << 8), __float_as_uint(sim));
-          qn += __popc(ball);
-          dbg_recs += __popc(ball);
-          if (qn > kQueue - 32) { __syncwarp(); drain(); }
+          for (int g = 0; g < G; ++g)
+            m4[g] = fmaxf(fmaxf(__uint_as_float(cur[4 * g]), __uint_as_float(cur[4 * g + 1])),
+                          fmaxf(__uint_as_float(cur[4 * g + 2]), __uint_as_float(cur[4 * g + 3])));
+          float mx = m4[0];
+          if (G == 8) mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+          else mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          if (mx >= p.sim_gate) gatebits |= 1u << ch;
         }
-      };
-#pragma unroll 1
-      for (int ch = 0; ch < kFullChunks; ++ch) do_chunk(std::integral_constant<int, 32>{}, half * kHalfCols + ch * 32);
-      if constexpr (kTailCols == 16) do_chunk(std::integral_constant<int, 16>{}, half * kHalfCols + kFullChunks * 32);
-      if (!kDense) {
-        __syncwarp();
-        drain();
-        const int cnt_a = my_rowcnt[lane * 2], cnt_b = my_rowcnt[lane * 2 + 1];
-        if (rkind != BT_ROW_NONE) {
-          const int la = (rkind == BT_ROW_UNCONFIRMED) ? 2 : 0;
-          if (cnt_a) {
-            p.cand.cnt[((size_t)la * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_a;
-            atomicAdd(&p.cand.total[la], cnt_a);
-            atomicOr(&p.cand.segmask[(size_t)la * p.cand.rows_cap + row], 1ull << seg);
+        if (all_open) gatebits = (1u << kChunks) - 1u;
+        // exact pass: float64 IoU distance of the remembered candidates, all lanes at once; slots 0 and 1
+        // are evaluated together (two independent dependency chains), slots 2.. only if some row has them
+        {
+          const uint32_t k0 = my_prekey[lane], k1 = my_prekey[32 + lane];
+          const double d0 = iou_dist_f64(rbox, s_col64 + (k0 & 0xffu) * 4);
+          const double d1 = iou_dist_f64(rbox, s_col64 + (k1 & 0xffu) * 4);
+          if (npre > 0) my_preiou[lane] = d0;
+          if (npre > 1) my_preiou[32 + lane] = d1;
+          if (__any_sync(0xffffffffu, npre > 2)) {
+#pragma unroll
+            for (int j = 2; j < kPreSlots; ++j)
+              if (j < npre) my_preiou[j * 32 + lane] = iou_dist_f64(rbox, s_col64 + (my_prekey[j * 32 + lane] & 0xffu) * 4);
           }
-          if (cnt_b) {
-            p.cand.cnt[((size_t)1 * p.cand.rows_cap + row) * p.cand.nseg + seg] = cnt_b;
-            atomicAdd(&p.cand.total[1], cnt_b);
-            atomicOr(&p.cand.segmask[(size_t)1 * p.cand.rows_cap + row], 1ull << seg);
+        }
+        if ((p.debug & 2) || rkind == BT_ROW_NONE) gatebits = 0;
+        // phase B: only chunks in which some row of the warp has an open gate are looked at again.
+        // One rolled loop (one copy of the code: it runs once or twice per warp and would otherwise be
+        // fetched cold every time); the tail chunk is loaded 32 wide and masked.
+        uint32_t need = __reduce_or_sync(0xffffffffu, gatebits);
+        while (need) {                          // warp-uniform
+          const int ch = __ffs(need) - 1;
+          need &= need - 1;
+          tmem_ld_32x32b_x32(taddr + (uint32_t)(half * kHalfCols + ch * 32), va);
+          tmem_ld_wait_dep(va);
+          if ((gatebits >> ch) & 1u) {
+            uint32_t hot = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (__uint_as_float(va[c]) >= p.sim_gate) hot |= 1u << c;
+            if (all_open) hot = 0xffffffffu;
+            if (ch >= kFullChunks) hot &= (1u << kTailCols) - 1u;
+            while (hot) {
+              const int c = __ffs(hot) - 1;
+              hot &= hot - 1;
+              // va[c] by a 5-level select tree on the bits of c
+              uint32_t s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) s16[i] = (c & 16) ? va[i + 16] : va[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s8[i] = (c & 8) ? s16[i + 8] : s16[i];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) s4[i] = (c & 4) ? s8[i + 4] : s8[i];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) s2[i] = (c & 2) ? s4[i + 2] : s4[i];
+              const float sim = __uint_as_float((c & 1) ? s2[1] : s2[0]);
+              open_pair(half * kHalfCols + ch * 32 + c, sim);
+              ++dbg_open;
+            }
           }
+          __syncwarp();
+        }
+      }
+      const long long t_chunks = clock64();
+      if (!kDense && rkind != BT_ROW_NONE) {
+        // the remembered edges go out with their final cost, then the (row, segment) bookkeeping the LAP
+        // kernel classifies rows with: segment count, row degree, the row's column if it has only one
+#pragma unroll
+        for (int j = 0; j < kPreSlots; ++j) {
+          if (j < npre) {
+            const uint32_t key = my_prekey[j * 32 + lane];
+            const double cost = my_preiou[j * 32 + lane];
+            const int col = n0 + (int)(key & 0xffu);
+            if ((key >> 16) & 1u) {
+              if (cost < p.second_thresh) { emit_owned_tc(p.cand, 1, row, seg, cnt_b++, col, cost); last_b = col; }
+            } else if (cost < thr_a) {
+              emit_owned_tc(p.cand, la, row, seg, cnt_a++, col, cost);
+              last_a = col;
+            }
+          }
+        }
+        if (cnt_a) {
+          const size_t ri = (size_t)la * p.cand.rows_cap + row;
+          p.cand.cnt[ri * p.cand.nseg + seg] = cnt_a;
+          atomicAdd(&p.cand.total[la], cnt_a);
+          atomicOr(&p.cand.segmask[ri], 1ull << seg);
+          atomicAdd(&p.cand.rowdeg[ri], cnt_a);
+          if (cnt_a == 1) p.cand.rowcol[ri] = last_a;
+        }
+        if (cnt_b) {
+          const size_t ri = (size_t)1 * p.cand.rows_cap + row;
+          p.cand.cnt[ri * p.cand.nseg + seg] = cnt_b;
+          atomicAdd(&p.cand.total[1], cnt_b);
+          atomicOr(&p.cand.segmask[ri], 1ull << seg);
+          atomicAdd(&p.cand.rowdeg[ri], cnt_b);
+          if (cnt_b == 1) p.cand.rowcol[ri] = last_b;
         }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if ((p.debug & 8) && lane == 0 && dbg_iters > 24)
-        printf("SLOW cta %d warp %d m0 %d n0 %d: %d enqueue iterations, %d records\n", blockIdx.x, warp, m0, n0, dbg_iters, dbg_recs);
+      if ((p.debug & 16) && lane == 0 && (blockIdx.x % 37) == 0)
+        printf("EPI cta %d warp %d: go %lld bar1 +%lld staged +%lld bar2 +%lld rowloads +%lld rows +%lld box pass done +%lld acc +%lld ld0 +%lld ld1 +%lld sim pass +%lld tail +%lld (lane 0: box edges %d, open pairs %d)\n", blockIdx.x,
+               warp, t_go - t_start, t_s1 - t_go, t_s2 - t_go, t_s3 - t_go, t_rl - t_go, t_rows - t_go, t_shadow - t_go, t_acc - t_go, t_l0 - t_acc, t_l1 - t_l0, t_chunks - t_acc, clock64() - t_chunks, npre, dbg_open);
+      if ((p.debug & 1024) && lane == 0) {
+        unsigned long long g_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        printf("GT %d %d %llu %llu %lld\n", blockIdx.x, warp, g_go, g_end, clock64() - t_go);
+      }
       if ((p.debug & 4) && et == 0)
         printf("ALL %d %lld %lld\n", blockIdx.x, t_acc - t_start, clock64() - t_start);
       if ((p.debug & 1) && et == 0 && (blockIdx.x % 37) == 0)
@@ -762,7 +951,7 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = TcSmem<BN>::kDyn;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CS;
   attr[0].val.clusterDim.y = 1;
@@ -782,10 +971,12 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams
   const int nclusters = ctiles < max_clusters ? ctiles : max_clusters;
   cfg.gridDim = dim3(nclusters * CS);
   if (CS == 1) {
-    kern<<<nclusters, kTcThreads, TcSmem<BN>::kDyn, ctx->stream>>>(ta, tb, ep, ap.d);   // no cluster attribute
-  } else {
-    BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
+    // no cluster attribute; may start its ramp under the previous kernel's tail (griddepcontrol.wait inside)
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = ctx->pdl ? 1 : 0;
   }
+  BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
@@ -832,7 +1023,7 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   if (ap.n <= 0 || ap.m <= 0) return BT_OK;
   EpiParams ep;
   ep.row_tlbr = ap.row_tlbr; ep.row_tlbr_f32 = ap.row_tlbr_f32; ep.row_kind = ap.row_kind;
-  ep.col_tlbr = ap.col_tlbr; ep.col_kind = ap.col_kind; ep.face_sim = ap.face_sim;
+  ep.col_tlbr = ap.col_tlbr; ep.col_kind = ap.col_kind; ep.col_pk = ap.col_pk; ep.face_sim = ap.face_sim;
   ep.match_thresh = ap.match_thresh; ep.second_thresh = ap.second_thresh;
   ep.unconf_thresh = ap.unconf_thresh; ep.proximity = ap.proximity; ep.appearance = ap.appearance;
   ep.cand = ap.cand; ep.out_emb = ap.out_emb; ep.out_dists = ap.out_dists;

@@ -44,7 +44,7 @@ struct SlotMeta {
 // (demo:1501: high = score > 0.40; demo:1531: low = 0.1 <= score <= 0.40).
 __global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* __restrict__ scores, int m,
                                 float high, float low, double* __restrict__ tlbr, double* __restrict__ xywh,
-                                float* __restrict__ xywh32, uint8_t* __restrict__ kind,
+                                float* __restrict__ xywh32, uint8_t* __restrict__ kind, uint2* __restrict__ pk,
                                 float* __restrict__ res_scores, int32_t* __restrict__ res_boxes) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
@@ -64,6 +64,16 @@ __global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* 
     *reinterpret_cast<int4*>(res_boxes + (size_t)j * 4) = b;
   }
   kind[j] = (s > high) ? BT_COL_HIGH : ((s >= low) ? BT_COL_LOW : BT_COL_NONE);
+  // packed integer corners for the association kernel's overlap screen, from the same float32 values
+  pk[j] = bt_pack16_f32(x1, y1, w + x1, h + y1, true);
+}
+
+// debugging aid (BT_DEBUG_DELAY_SIDE=<us>): holds the side stream back so that a missing
+// dependency between the two streams shows up as a wrong result instead of a rare flake
+__global__ void debug_spin_kernel(long long ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while ((long long)(t1 - t0) < ns);
 }
 
 __global__ void clear_words_kernel(int4* __restrict__ p, size_t n16) {
@@ -110,6 +120,7 @@ struct bt_tracker {
   double *det_tlbr = nullptr, *det_xywh = nullptr;
   float* det_xywh32 = nullptr;
   uint8_t* col_kind = nullptr;
+  uint2* col_pk = nullptr;     // packed integer corners of the detections (association overlap screen)
   int32_t *x[3] = {nullptr, nullptr, nullptr}, *y[3] = {nullptr, nullptr, nullptr};
   int32_t *d_pool_idx = nullptr, *d_pool_state = nullptr;
   int32_t *d_upd_track = nullptr, *d_upd_det = nullptr;
@@ -122,6 +133,7 @@ struct bt_tracker {
   cudaStream_t st2 = nullptr;   // side stream: work that is independent of the main chain runs beside it
   cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr, ev_x = nullptr;
   bool overlap = true;
+  int debug_delay_us = 0;
   bool host_debug = false;
   char* d_res = nullptr;    // packed per-frame result block (one D2H per frame), layout in bt_update_arrays
   char* h_res = nullptr;
@@ -267,6 +279,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &t->det_xywh, md * 4));
   BT_TRY(dev_alloc(ctx, &t->det_xywh32, md * 4));
   BT_TRY(dev_alloc(ctx, &t->col_kind, md));
+  BT_TRY(dev_alloc(ctx, &t->col_pk, md));
   // x[0..2] point into the per-frame result block (set in bt_update_arrays)
   for (int s = 0; s < 3; ++s) BT_TRY(dev_alloc(ctx, &t->y[s], md));
   BT_TRY(dev_alloc(ctx, &t->d_ctrl, 16 * (cap + md) + 1024));
@@ -324,6 +337,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   for (cudaEvent_t* e : {&t->ev_fork1, &t->ev_join1, &t->ev_fork2, &t->ev_join2, &t->ev_x})
     BT_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   t->overlap = getenv("BT_NO_OVERLAP") == nullptr;
+  t->debug_delay_us = getenv("BT_DEBUG_DELAY_SIDE") ? atoi(getenv("BT_DEBUG_DELAY_SIDE")) : 0;
   t->host_debug = getenv("BT_HOST_DEBUG") != nullptr;
   return BT_OK;
 }
@@ -333,7 +347,7 @@ void bt_tracker_destroy(bt_ctx* ctx) {
   if (!t) return;
   void* ptrs[] = {t->mean, t->cov, t->tlbr, t->tlbr_f32, t->feat16, t->curr32, t->smooth32, t->row_kind, t->slot_f32,
                   t->det_boxes, t->det_scores, t->det_feat_in, t->det_feat32, t->det_feat16, t->det_tlbr,
-                  t->det_xywh, t->det_xywh32, t->col_kind, t->d_ctrl, t->y[0], t->y[1], t->y[2],
+                  t->det_xywh, t->det_xywh32, t->col_kind, t->col_pk, t->d_ctrl, t->y[0], t->y[1], t->y[2],
                   t->d_pool_idx, t->d_pool_state, t->d_upd_track, t->d_upd_det, t->d_upd_f32, t->d_ema_mode,
                   t->d_birth_slot, t->d_birth_det, t->d_lista, t->d_listb, t->d_pairs, t->d_pair_count,
                   t->d_gather, t->d_bpairs, t->d_res};
@@ -444,7 +458,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     }
     det_prep_kernel<<<(m + 255) / 256, 256, 0, st>>>(d_boxes, d_scores, m, cfg.track_high_thresh,
                                                      cfg.track_low_thresh, t->det_tlbr, t->det_xywh,
-                                                     t->det_xywh32, t->col_kind,
+                                                     t->det_xywh32, t->col_kind, t->col_pk,
                                                      inputs_on_device ? reinterpret_cast<float*>(dres_i + o_sc) : nullptr,
                                                      inputs_on_device ? dres_i + o_bx : nullptr);
     BT_LAUNCHED(ctx);
@@ -494,6 +508,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     BT_CUDA(cudaEventRecord(t->ev_fork1, st));       // everything already queued on the main stream
     BT_CUDA(cudaStreamWaitEvent(t->st2, t->ev_fork1, 0));
   }
+  if (t->debug_delay_us > 0) debug_spin_kernel<<<1, 1, 0, sp>>>(1000ll * t->debug_delay_us);
   if (bytesA > 0) BT_CUDA(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, bytesA, cudaMemcpyHostToDevice, sp));
   SEG_BEGIN(BT_SEG_PREDICT);
   if (n_pool > 0) {
@@ -527,7 +542,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
       p.a_rows_alloc = t->cap; p.b_rows_alloc = t->max_dets;
       p.bn = assoc_bn;
       p.row_tlbr = t->tlbr; p.row_tlbr_f32 = t->tlbr_f32; p.row_kind = t->row_kind_cur;
-      p.col_tlbr = t->det_tlbr; p.col_kind = t->col_kind; p.face_sim = nullptr;
+      p.col_tlbr = t->det_tlbr; p.col_kind = t->col_kind; p.col_pk = t->col_pk; p.face_sim = nullptr;
       p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
       p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
       p.appearance = cfg.appearance_thresh;

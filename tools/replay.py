@@ -21,5 +21,6 @@ if os.environ.get("BT_HOST_DEBUG"):
         ctx.update_arrays_raw(b_.data_ptr(), s_.data_ptr(), f_.data_ptr(), b_.shape[0], BT_DEVICE)
 if len(sys.argv) > 1:
     os.environ["BT_ASSOC_DEBUG"] = sys.argv[1]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 for k in range(3):
-    print("replay avg us:", 1e3 * ctx.profile_replay_assoc(50), flush=True)
+    print("replay avg us:", 1e3 * ctx.profile_replay_assoc(iters), flush=True)
