@@ -325,10 +325,14 @@ def run_ours(args):
                                     if peaks else "fallback 1590 (B200_PROFILING.md)"),
                     "algorithmic_flops": flops, "avg_launch_ms": assoc_avg_ms,
                     "how": "one CUDA-event pair around 50 back-to-back launches of the last frame's kernel on the ctx "
-                           "stream (bt_profile_replay_assoc), divided by 50",
+                           "stream (bt_profile_replay_assoc), divided by 50; launched as in the step (programmatic "
+                           "dependent launch: a launch's ramp overlaps its predecessor's tail)",
                     "in_step_event_ms": assoc_in_step_ms,
                     "in_step_note": "events bracketing the same launch inside the step also count host enqueue gaps",
-                    "traffic": None}
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
+                    # kernel on this workload (profiles/r01_ncu_assoc_tc_v3_details.csv); other workloads: not captured
+                    "traffic": (16927232.0 if (n_rows, n, D) == (2000, 2000, 2048) else None),
+                    "traffic_unit": "bytes/launch (algorithmic: the two fp16 operands once = %d)" % (2 * (n_rows + n) * D)}
         else:
             nbytes = 32.0 * (n_rows + n) + 0.0      # boxes in, candidate edges out (sparse)
             peak = peaks.get("hbm_gbs", 6650.0)

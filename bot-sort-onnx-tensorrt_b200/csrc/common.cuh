@@ -37,6 +37,25 @@ struct bt_ctx {
 int32_t bt_fail(bt_ctx* ctx, int32_t code, const char* fmt, ...);
 
 #ifdef __CUDACC__
+// Launch on ctx->stream, optionally as a programmatic dependent of the stream's previous kernel: the grid
+// may then be scheduled before that kernel has completed, and must execute griddepcontrol.wait
+// (bt_grid_dependency_wait) before it touches anything the earlier kernels of the stream produce -- and at
+// the latest before it exits, so that completion stays ordered for its own dependents.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t bt_launch(bt_ctx* ctx, bool dependent, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                    size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (dependent && ctx->pdl) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void bt_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void bt_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Box -> two 32-bit words of 15-bit integer corners rounded OUTWARD, the operands of the association
 // kernel's two-subtraction overlap screen:
 //   .x = (x1 + 1) | (y1 + 1) << 16        .y = x2 | y2 << 16 | 0x80008000
@@ -162,7 +181,7 @@ int32_t btk_iou_pairs_below(bt_ctx* ctx, const double* tlbr, const int32_t* a_id
 // features.cu
 // det_prep: normalise rows, write fp32 normalised copy (optional) + fp16 copy; also boxes -> tlbr/xywh
 int32_t btk_feature_prep(bt_ctx* ctx, const float* feat, int32_t m, int32_t d, float* out_f32,
-                         __half* out_f16, int32_t normalise);
+                         __half* out_f16, int32_t normalise, int32_t dependent = 0);
 int32_t btk_feature_ema(bt_ctx* ctx, float* smooth, float* curr, const float* feat,
                         const int32_t* track_idx, const int32_t* feat_idx, const uint8_t* first,
                         int32_t k, int32_t d, float alpha);

@@ -62,6 +62,9 @@ feature_prep_kernel(const float* __restrict__ feat, int d, float* __restrict__ o
       if (out_f16) out_f16[row * d + i] = __float2half_rn(v);
     }
   }
+  // Launched as a programmatic dependent of det_prep (frame step): nothing above reads what det_prep
+  // writes, so the two run side by side; completion stays ordered behind it for the association kernel.
+  bt_grid_dependency_wait();
 }
 
 // mode (first[i]): 0 = EMA (demo:499-502), 1 = first call on a raw feature: smooth = feat/||feat||,
@@ -122,9 +125,9 @@ feature_ema_kernel(float* __restrict__ smooth, float* __restrict__ curr, const f
 }  // namespace
 
 int32_t btk_feature_prep(bt_ctx* ctx, const float* feat, int32_t m, int32_t d, float* out_f32,
-                         __half* out_f16, int32_t normalise) {
+                         __half* out_f16, int32_t normalise, int32_t dependent) {
   if (m <= 0) return BT_OK;
-  feature_prep_kernel<<<m, kThreads, 0, ctx->stream>>>(feat, d, out_f32, out_f16, normalise);
+  BT_CUDA(bt_launch(ctx, dependent != 0, feature_prep_kernel, dim3(m), dim3(kThreads), 0, feat, d, out_f32, out_f16, normalise));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

@@ -129,6 +129,7 @@ iou_pairs_live_kernel(const double* __restrict__ tlbr, const float* __restrict__
   // scans the 64 slots of the j tile (hundreds of small blocks: the shared-memory broadcasts of the
   // j boxes are the cost, spread them over all SMs)
   constexpr int JT = 64;
+  bt_grid_dependency_wait();   // programmatic dependent of the Kalman update that writes the boxes
   if ((int)(blockIdx.x + 1) * JT <= (int)blockIdx.y * 256) return;
   __shared__ float4 sb[JT];
   __shared__ uint8_t sk[JT];
@@ -173,8 +174,8 @@ int32_t btk_iou_pairs_live(bt_ctx* ctx, const double* tlbr, const float* tlbr_f3
                            int32_t* pairs_small, int32_t small_cap) {
   if (n <= 1) return BT_OK;
   const int tiles = (n + 255) / 256;
-  iou_pairs_live_kernel<<<dim3((n + 63) / 64, tiles), 256, 0, ctx->stream>>>(tlbr, tlbr_f32, kind, n, limit, pairs,
-                                                                      pair_count, pair_cap, pairs_small, small_cap);
+  BT_CUDA(bt_launch(ctx, true, iou_pairs_live_kernel, dim3((n + 63) / 64, tiles), dim3(256), 0, tlbr, tlbr_f32, kind, n,
+                    limit, pairs, pair_count, pair_cap, pairs_small, small_cap));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

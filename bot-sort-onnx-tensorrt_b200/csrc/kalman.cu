@@ -109,6 +109,7 @@ kalman_update_kernel(double* __restrict__ mean, double* __restrict__ cov, double
                      const uint8_t* __restrict__ noise_f32, int k, const int32_t* __restrict__ x1,
                      const int32_t* __restrict__ x2, const int32_t* __restrict__ x3,
                      uint8_t* __restrict__ slot_f32, double* __restrict__ res_tlbr) {
+  bt_grid_launch_dependents();   // frame step: the duplicate test is queued behind this kernel and waits for its boxes
   const int gid = blockIdx.x * kThreads + threadIdx.x;
   const int g = gid >> 3;
   const int r = threadIdx.x & 7;

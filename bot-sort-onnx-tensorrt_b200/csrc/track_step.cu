@@ -46,6 +46,7 @@ __global__ void det_prep_kernel(const int32_t* __restrict__ boxes, const float* 
                                 float high, float low, double* __restrict__ tlbr, double* __restrict__ xywh,
                                 float* __restrict__ xywh32, uint8_t* __restrict__ kind, uint2* __restrict__ pk,
                                 float* __restrict__ res_scores, int32_t* __restrict__ res_boxes) {
+  bt_grid_launch_dependents();   // feature_prep does not read anything written here: let it start right away
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   const int4 b = *reinterpret_cast<const int4*>(boxes + (size_t)j * 4);
@@ -464,7 +465,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     BT_LAUNCHED(ctx);
     if (reid)
       BT_TRY(btk_feature_prep(ctx, d_feats, m, D, keep32 || !tensor_path ? t->det_feat32 : nullptr,
-                              t->det_feat16, 1));
+                              t->det_feat16, 1, /*dependent of det_prep=*/1));
   }
 
   SEG_END(BT_SEG_PREP);
