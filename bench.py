@@ -247,7 +247,7 @@ def run_ours(args):
         futs = [pool.submit(step_one, k, i, loc, read_back, None if events is None else events[k]) for k in range(S)]
         return sum(f.result() for f in futs)
 
-    def run_pass(loc, read_back, profile=False):
+    def run_pass(loc, read_back, profile=False, l2_flush=True):
         """frame 0 = births (untimed), W warm-up frames, then K timed frames.  Returns per-step device
         ms (CUDA events on the ctx stream), per-step wall ms, matched-track counts."""
         for c in ctxs:
@@ -264,7 +264,8 @@ def run_ours(args):
             ctx.profile_enable(True)        # segment events only around the K timed steps (first stream)
         launches0 = sum(c.launch_count for c in ctxs)
         for k in range(K):
-            flush.zero_()                                   # L2 flush between timed steps (untimed)
+            if l2_flush:
+                flush.zero_()                               # L2 flush between timed steps (untimed)
             torch.cuda.synchronize()
             i = 1 + W + k
             t0 = time.perf_counter()
@@ -284,6 +285,9 @@ def run_ours(args):
     # ---- device-resident pass (value) with segment profiling ----
     run_pass(BT_DEVICE, read_back=False)                     # untimed: first-launch / module-load costs
     dev_ms, _, launches, _ = run_pass(BT_DEVICE, read_back=False)   # `value`: no event bracketing inside
+    # the other admissible protocol: no flush, every step reads a detection frame it has never touched (the
+    # 1+W+K frames together exceed L2) while the tracker's own state stays as warm as it is in a running stream
+    dev_ms_warm, _, _, _ = run_pass(BT_DEVICE, read_back=False, l2_flush=False)
     run_pass(BT_DEVICE, read_back=False, profile=True)       # same steps again with per-kernel CUDA events
     prof = ctx.profile_read()
     ctx.profile_enable(False)
@@ -301,7 +305,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     from botsort_b200.sharding import aggregate_throughput, max_over_ranks
-    total_dev_ms, total_e2e_ms = max_over_ranks([sum(dev_ms), sum(e2e_wall)], device="cuda")
+    total_dev_ms, total_e2e_ms, total_warm_ms = max_over_ranks([sum(dev_ms), sum(e2e_wall), sum(dev_ms_warm)], device="cuda")
     value = aggregate_throughput(n * S, world, K, total_dev_ms)
     e2e_value = aggregate_throughput(n * S, world, K, total_e2e_ms)
     h2d_bytes = S * (n * (16 + 4) + (n * D * 4 if reid else 0))
@@ -368,6 +372,13 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": total_e2e_ms / K,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "how": "bt_update_arrays on pinned host buffers + bt_get_tracks read-back, wall clock per step"},
+            "value_inputs_larger_than_l2": {
+                "value": aggregate_throughput(n * S, world, K, total_warm_ms), "unit": "tracks/s",
+                "ms_per_step": total_warm_ms / K,
+                "note": "same K steps without the L2 flush: each step's detection frame (%.1f MB) is one of %d distinct "
+                        "device-resident frames (%.0f MB in total, larger than L2) and has not been touched since its "
+                        "upload; the tracker's own state stays warm as in a running stream"
+                        % (h2d_bytes / S / 1e6, n_frames, n_frames * h2d_bytes / S / 1e6)},
             "gpu_launches": int(launches),
             "segments_ms": segs,
             "roofline": roof,

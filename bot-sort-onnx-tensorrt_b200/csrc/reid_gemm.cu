@@ -858,11 +858,39 @@ assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiP
     }
     __syncthreads();
   }
+  // candidate mode: the same integer overlap screen as the tensor-core kernel decides which pairs can
+  // have a cost below 1 at all (boxes overlap, or the appearance gate is open); only those reach the
+  // float64 path
+  uint2 cpk[4];
+  int ckind[4];
+  if (!kDense) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + tx * 4 + j;
+      ckind[j] = BT_COL_NONE;
+      cpk[j] = make_uint2(0x7fff7fffu, 0x80008000u);
+      if (col < p.m) {
+        ckind[j] = p.col_kind[col];
+        if (p.col_pk) cpk[j] = p.col_pk[col];
+        else { const double* c = p.col_tlbr + (size_t)col * 4; cpk[j] = pack16_box(c[0], c[1], c[2], c[3], true); }
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = row0 + ty * 4 + i;
     if (row >= p.n) continue;
     const int rkind = (!kDense) ? p.row_kind[row] : 0;
+    uint2 rpk = make_uint2(0u, 0u);
+    if (!kDense && rkind != BT_ROW_NONE) {
+      if (p.row_tlbr_f32) {
+        const float4 r = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
+        rpk = bt_pack16_f32(r.x, r.y, r.z, r.w, false);
+      } else {
+        const double* r = p.row_tlbr + (size_t)row * 4;
+        rpk = pack16_box(r[0], r[1], r[2], r[3], false);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = col0 + tx * 4 + j;
@@ -870,8 +898,9 @@ assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiP
       if (kDense) {
         assoc_dense(p, row, col, acc[i][j]);
       } else {
-        const int ckind = p.col_kind[col];
-        if (rkind != BT_ROW_NONE && ckind != BT_COL_NONE) assoc_exact(p, row, col, acc[i][j], rkind, ckind);
+        if (rkind == BT_ROW_NONE || ckind[j] == BT_COL_NONE) continue;
+        const bool overlap = ((rpk.y - cpk[j].x) & (cpk[j].y - rpk.x) & 0x80008000u) == 0x80008000u;
+        if (overlap || acc[i][j] >= p.sim_gate || p.face_sim != nullptr) assoc_exact(p, row, col, acc[i][j], rkind, ckind[j]);
       }
     }
   }
