@@ -261,6 +261,7 @@ __device__ void solve_component(const SolveArrays& ws, int comp, double thresh,
         }
         minVal = best.d;
         const int j = best.c;
+        __syncwarp();                       // every lane's scan reads of insc[] are behind us (racecheck: WAR)
         if (lane == 0) ws.insc[j] = sid;
         __syncwarp();
         if (best.freecol) { sink = j; break; }
