@@ -18,7 +18,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 constexpr int kYoloThreads = 1024;
 constexpr int kMaxClasses = 4;
-constexpr int kKeepCap = 64;  // >= max_per_class
+constexpr int kKeepCap = 64;   // >= max_per_class
+constexpr int kNmsFast = 1024; // sorted candidates per class whose boxes are staged in shared memory
 
 struct YoloScratch {
   unsigned long long* keys;  // [classes][anchors] (score bits << 32) | (0xffffffff - anchor)
@@ -39,17 +40,26 @@ __device__ __forceinline__ float iou_f32(const float4& a, const float4& b) {
   return inter / (area1 + area2 - inter);
 }
 
+__device__ __forceinline__ int key_anchor(unsigned long long key) {
+  return (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+}
+
+// Dynamic shared memory: [classes][anchors] suppression flags | [classes][kNmsFast] sorted boxes (first
+// used as the sort's key staging area).
 __global__ void __launch_bounds__(kYoloThreads)
 yolox_post_kernel(const float* __restrict__ raw, bt_yolox_config cfg, int anchors, YoloScratch sc,
-                  double* __restrict__ out, int max_out, int32_t* __restrict__ out_count) {
+                  double* __restrict__ out, int max_out, int32_t* __restrict__ out_count, int supp_bytes) {
   __shared__ int s_cnt[kMaxClasses];
   __shared__ int s_keep_idx[kMaxClasses][kKeepCap];
   __shared__ int s_nkeep[kMaxClasses];
   __shared__ int s_cursor[kMaxClasses];
-  extern __shared__ unsigned char s_supp_raw[];  // [classes][anchors] suppression flags
+  __shared__ int s_pass[kMaxClasses];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  unsigned char* s_supp_raw = s_dyn;
+  float4* s_boxes = reinterpret_cast<float4*>(s_dyn + supp_bytes);
   const int tid = threadIdx.x;
   const int C = cfg.num_classes, ch = 5 + C;
-  if (tid < kMaxClasses) { s_cnt[tid] = 0; s_nkeep[tid] = 0; s_cursor[tid] = 0; }
+  if (tid < kMaxClasses) { s_cnt[tid] = 0; s_nkeep[tid] = 0; s_cursor[tid] = 0; s_pass[tid] = 0; }
   __syncthreads();
 
   // ---- decode + candidate selection ----
@@ -78,76 +88,120 @@ yolox_post_kernel(const float* __restrict__ raw, bt_yolox_config cfg, int anchor
   }
   __syncthreads();
 
-  // ---- per class: rank sort (descending score, ties: lower anchor first), greedy NMS ----
+  // ---- per class (one group of 256 threads each): rank sort (descending score, ties: lower anchor
+  //      first), then greedy NMS: one sweep of the group per kept box, boxes and suppression flags in
+  //      shared memory, two barriers per sweep (pick + broadcast | suppress). ----
   const int group = tid >> 8, gt = tid & 255;  // 4 groups of 256 threads
+#define GROUP_SYNC() asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory")
   for (int c = group; c < C; c += kYoloThreads / 256) {
     const int n = s_cnt[c];
     const unsigned long long* keys = sc.keys + (size_t)c * anchors;
     unsigned long long* sorted = sc.sorted + (size_t)c * anchors;
     unsigned char* supp = s_supp_raw + (size_t)c * anchors;
-    for (int i = gt; i < n; i += 256) {
-      const unsigned long long k = keys[i];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) rank += (keys[j] > k);
-      sorted[rank] = k;
-      supp[i] = 0;
+    float4* sbox = s_boxes + (size_t)c * kNmsFast;
+    constexpr int kStage = kNmsFast * 2;                     // u64 keys that fit into the (not yet used) box area
+    constexpr int kPer = (kStage + 255) / 256;
+    if (n <= kStage) {
+      unsigned long long* skey = reinterpret_cast<unsigned long long*>(sbox);
+      for (int i = gt; i < n; i += 256) skey[i] = keys[i];
+      GROUP_SYNC();
+      unsigned long long mine[kPer];
+      int myrank[kPer];
+#pragma unroll
+      for (int t = 0; t < kPer; ++t) {
+        const int i = gt + t * 256;
+        if (i < n) {
+          const unsigned long long k = skey[i];
+          int rank = 0;
+          for (int j = 0; j < n; ++j) rank += (skey[j] > k);
+          mine[t] = k; myrank[t] = rank;
+          supp[i] = 0;
+        }
+      }
+      GROUP_SYNC();                                          // everybody is done reading the staged keys
+#pragma unroll
+      for (int t = 0; t < kPer; ++t) {
+        const int i = gt + t * 256;
+        if (i < n) {
+          sorted[myrank[t]] = mine[t];
+          if (myrank[t] < kNmsFast) sbox[myrank[t]] = sc.boxes[key_anchor(mine[t])];
+        }
+      }
+    } else {
+      for (int i = gt; i < n; i += 256) {
+        const unsigned long long k = keys[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (keys[j] > k);
+        sorted[rank] = k;
+        supp[i] = 0;
+      }
+      GROUP_SYNC();
+      for (int i = gt; i < n && i < kNmsFast; i += 256) sbox[i] = sc.boxes[key_anchor(sorted[i])];
     }
-    asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+    GROUP_SYNC();
+    auto box_of = [&](int j) -> float4 { return j < kNmsFast ? sbox[j] : sc.boxes[key_anchor(sorted[j])]; };
+    int next = 0;                                            // thread 0: where the search for the next survivor starts
     while (true) {
       if (gt == 0) {
-        int i = s_cursor[c];
+        int i = next;
         while (i < n && supp[i]) ++i;
-        s_cursor[c] = i;
         if (i < n && s_nkeep[c] < cfg.max_per_class) {
           s_keep_idx[c][s_nkeep[c]] = i;
           s_nkeep[c] += 1;
+          s_cursor[c] = i;
+          next = i + 1;
         } else {
           s_cursor[c] = n;  // done
         }
       }
-      asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+      GROUP_SYNC();
       const int i = s_cursor[c];
       if (i >= n) break;
-      const int ai = (int)(0xffffffffu - (unsigned)(sorted[i] & 0xffffffffull));
-      const float4 bi = sc.boxes[ai];
-      for (int j = i + 1 + gt; j < n; j += 256) {
-        if (supp[j]) continue;
-        const int aj = (int)(0xffffffffu - (unsigned)(sorted[j] & 0xffffffffull));
-        if (iou_f32(bi, sc.boxes[aj]) > cfg.nms_iou_thresh) supp[j] = 1;
+      if (s_nkeep[c] < cfg.max_per_class) {                  // the last kept box suppresses nobody that matters
+        const float4 bi = box_of(i);
+        for (int j = i + 1 + gt; j < n; j += 256)
+          if (!supp[j] && iou_f32(bi, box_of(j)) > cfg.nms_iou_thresh) supp[j] = 1;
       }
-      asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
-      if (gt == 0) s_cursor[c] = i + 1;
-      asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+      GROUP_SYNC();
     }
   }
+#undef GROUP_SYNC
   __syncthreads();
 
-  // ---- YOLOX._postprocess (demo:1001-1027): score filter, rescale, truncate; class-major order ----
+  // ---- YOLOX._postprocess (demo:1001-1027): score filter, rescale, truncate; class-major order.
+  //      One thread per kept box; the boxes of a class are sorted by score, so the ones that pass the
+  //      score filter are a prefix of its list and the output position is a prefix sum over classes. ----
+  const int pc = tid / kKeepCap, pk = tid % kKeepCap;
+  bool pass = false;
+  float score = 0.f;
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pc < C && pk < s_nkeep[pc]) {
+    const unsigned long long key = sc.sorted[(size_t)pc * anchors + s_keep_idx[pc][pk]];
+    score = __uint_as_float((unsigned)(key >> 32));
+    pass = score > cfg.post_score_thresh;
+    b = sc.boxes[key_anchor(key)];
+    if (pass) atomicAdd(&s_pass[pc], 1);
+  }
+  __syncthreads();
+  if (pass) {
+    int pos = pk;
+    for (int c = 0; c < pc; ++c) pos += s_pass[c];
+    if (pos < max_out) {
+      const float inw = (float)cfg.in_w, inh = (float)cfg.in_h;
+      const float imw = (float)cfg.img_w, imh = (float)cfg.img_h;
+      // float32 multiply then divide, truncation toward zero (demo:1009-1012)
+      const int x_min = (int)__fdiv_rn(__fmul_rn(fmaxf(0.f, b.x), imw), inw);
+      const int y_min = (int)__fdiv_rn(__fmul_rn(fmaxf(0.f, b.y), imh), inh);
+      const int x_max = (int)__fdiv_rn(__fmul_rn(fminf(b.z, inw), imw), inw);
+      const int y_max = (int)__fdiv_rn(__fmul_rn(fminf(b.w, inh), imh), inh);
+      double* o = out + (size_t)pos * 6;
+      o[0] = (double)pc; o[1] = (double)score;
+      o[2] = (double)x_min; o[3] = (double)y_min; o[4] = (double)x_max; o[5] = (double)y_max;
+    }
+  }
   if (tid == 0) {
     int n_out = 0;
-    for (int c = 0; c < C; ++c) {
-      const unsigned long long* sorted = sc.sorted + (size_t)c * anchors;
-      for (int k = 0; k < s_nkeep[c]; ++k) {
-        const unsigned long long key = sorted[s_keep_idx[c][k]];
-        const float score = __uint_as_float((unsigned)(key >> 32));
-        if (!(score > cfg.post_score_thresh)) continue;
-        const int a = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
-        const float4 b = sc.boxes[a];
-        const float inw = (float)cfg.in_w, inh = (float)cfg.in_h;
-        const float imw = (float)cfg.img_w, imh = (float)cfg.img_h;
-        // float32 multiply then divide, truncation toward zero (demo:1009-1012)
-        const int x_min = (int)__fdiv_rn(__fmul_rn(fmaxf(0.f, b.x), imw), inw);
-        const int y_min = (int)__fdiv_rn(__fmul_rn(fmaxf(0.f, b.y), imh), inh);
-        const int x_max = (int)__fdiv_rn(__fmul_rn(fminf(b.z, inw), imw), inw);
-        const int y_max = (int)__fdiv_rn(__fmul_rn(fminf(b.w, inh), imh), inh);
-        if (n_out < max_out) {
-          double* o = out + (size_t)n_out * 6;
-          o[0] = (double)c; o[1] = (double)score;
-          o[2] = (double)x_min; o[3] = (double)y_min; o[4] = (double)x_max; o[5] = (double)y_max;
-        }
-        ++n_out;
-      }
-    }
+    for (int c = 0; c < C; ++c) n_out += s_pass[c];
     *out_count = n_out < max_out ? n_out : max_out;
   }
 }
@@ -225,15 +279,17 @@ int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_conf
            "input size must be a positive multiple of 32");
   const int anchors = (cfg.in_h / 8) * (cfg.in_w / 8) + (cfg.in_h / 16) * (cfg.in_w / 16) +
                       (cfg.in_h / 32) * (cfg.in_w / 32);
-  const size_t smem = (size_t)cfg.num_classes * anchors;
-  BT_CHECK(smem <= 200 * 1024, BT_ERR_CAPACITY, "too many anchors (%d) for the single-CTA NMS", anchors);
+  const size_t supp_bytes = ((size_t)cfg.num_classes * anchors + 15) & ~size_t(15);
+  const size_t smem = supp_bytes + (size_t)kMaxClasses * kNmsFast * sizeof(float4);
+  BT_CHECK(smem <= 220 * 1024, BT_ERR_CAPACITY, "too many anchors (%d) for the single-CTA NMS", anchors);
   YoloScratch sc;
   BT_TRY(bt_arena(ctx, (size_t)cfg.num_classes * anchors, &sc.keys));
   BT_TRY(bt_arena(ctx, (size_t)cfg.num_classes * anchors, &sc.sorted));
   BT_TRY(bt_arena(ctx, (size_t)anchors, &sc.boxes));
   sc.counts = nullptr;
   BT_CUDA(cudaFuncSetAttribute(yolox_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  yolox_post_kernel<<<1, kYoloThreads, smem, ctx->stream>>>(raw, cfg, anchors, sc, out_boxes, max_out, out_count);
+  yolox_post_kernel<<<1, kYoloThreads, smem, ctx->stream>>>(raw, cfg, anchors, sc, out_boxes, max_out, out_count,
+                                                            (int)supp_bytes);
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

@@ -55,3 +55,29 @@ def test_reid_crop_gather(ctx, seed):
     got = ctx.reid_crop_gather(frame, boxes)
     ref = Dn.crop_preprocess(frame, boxes)
     np.testing.assert_array_equal(got, ref)
+
+
+def test_yolox_postprocess_beyond_the_on_chip_window(ctx):
+    """More candidates than the kernel's shared-memory window (1024 boxes per class), and the head of the list is a pile of
+    near-identical boxes: one is kept, the rest must be suppressed, and the greedy selection has to
+    continue over the remaining candidates exactly like ONNX NonMaxSuppression."""
+    rng = np.random.default_rng(11)
+    raw = Dn.synth_yolox_head(rng, [(100.4, 80.3, 220.6, 300.7), (400.2, 120.6, 520.3, 400.4)], [0, 1], [0.95, 0.9], clutter=2500)
+    gx, gy, st = Dn.yolox_grid(480, 640)
+    dup = np.nonzero(st == 8)[0][100:800]                      # 700 anchors that all decode to (almost) one box
+    cx, cy, w, h = 320.0, 240.0, 150.0, 260.0
+    raw[dup, 0] = (cx + rng.uniform(-1, 1, len(dup))) / 8 - gx[dup]
+    raw[dup, 1] = (cy + rng.uniform(-1, 1, len(dup))) / 8 - gy[dup]
+    raw[dup, 2] = np.log(w / 8)
+    raw[dup, 3] = np.log(h / 8)
+    p = np.linspace(0.999, 0.97, len(dup))                     # the highest scores of class 2
+    raw[dup, 4] = np.log(p / (1 - p))
+    raw[dup, 5:] = -6.0
+    raw[dup, 7] = np.log(p / (1 - p))
+    raw = raw.astype(np.float32)
+    got = ctx.yolox_postprocess(raw)
+    ref = Dn.yolox_postprocess(raw, img_h=480, img_w=640)
+    assert got.shape == ref.shape and len(ref) > 60
+    assert np.array_equal(got[:, [0, 2, 3, 4, 5]], ref[:, [0, 2, 3, 4, 5]])
+    np.testing.assert_allclose(got[:, 1], ref[:, 1], atol=2e-6)
+    assert (ref[:, 0] == 2).sum() >= 2                         # the duplicate pile collapsed, clutter of class 2 followed
