@@ -187,6 +187,17 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    if local_world > 1 and hasattr(os, "sched_setaffinity"):
+        # one rank per GPU on one host: give every rank its own slice of the host cores so that the ranks'
+        # enqueue / bookkeeping threads (they are on the frame's critical path) do not migrate onto each other
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // local_world)
+        mine = cores[local * per:(local + 1) * per] or cores
+        try:
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
