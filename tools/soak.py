@@ -14,7 +14,9 @@ from test_gpu_tracker import _compare_frame
 
 n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-ctx = bs.Context(max_tracks=1024, max_dets=1024, feat_dim=256,
+BIG = bool(os.environ.get("SOAK_BIG"))     # SOAK_BIG=1: 300-2200 identities, 2048-d features, a few frames each
+D = 2048 if BIG else 256
+ctx = bs.Context(max_tracks=2304 if BIG else 1024, max_dets=2304 if BIG else 1024, feat_dim=D,
                  flags=1 if os.environ.get("SOAK_SIMT") else 0)   # SOAK_SIMT=1: fp32 CUDA-core similarity (BT_FLAG_SIMT_SIM)
 bad = []
 t0 = time.time()
@@ -22,9 +24,9 @@ frames_total = 0
 for seed in range(first, first + n_seeds):
     rng = np.random.default_rng(seed)
     with_reid = bool(rng.random() < 0.7)
-    n_ids = int(rng.integers(8, 400))
+    n_ids = int(rng.integers(300, 2200)) if BIG else int(rng.integers(8, 400))
     pitch = float(rng.uniform(22, 80))
-    sc = SceneConfig(n_ids=n_ids, feat_dim=256, seed=seed, pitch_x=pitch, pitch_y=pitch * 1.7,
+    sc = SceneConfig(n_ids=n_ids, feat_dim=D, seed=seed, pitch_x=pitch, pitch_y=pitch * 1.7,
                      low_frac=float(rng.uniform(0, 0.3)), drop_frac=float(rng.uniform(0, 0.25)),
                      mid_frac=float(rng.uniform(0, 0.1)), walk=float(rng.uniform(1, 8)),
                      newcomer_every=int(rng.integers(2, 9)), with_features=with_reid)
@@ -33,7 +35,7 @@ for seed in range(first, first + n_seeds):
     ctx.tracker_reset(cfg)
     scene = SyntheticScene(sc)
     oracle = O.OracleBoTSORT(mode="vectorized", lap_solver="jv", use_features=with_reid)
-    frames = int(rng.integers(15, 45))
+    frames = int(rng.integers(4, 9)) if BIG else int(rng.integers(15, 45))
     status = "ok"
     for k in range(frames):
         fr = scene.next_frame()
