@@ -129,7 +129,6 @@ void bt_default_yolox_config(bt_yolox_config* cfg) {
 
 int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t feat_dim, uint32_t flags,
                   bt_ctx** out) {
-  bt_ctx* ctx = nullptr;
   if (!out) return bt_fail(nullptr, BT_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (max_tracks <= 0 || max_dets <= 0 || feat_dim <= 0)
@@ -155,7 +154,6 @@ int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t 
   c->flags = flags;
   c->num_sms = prop.multiProcessorCount;
   c->pdl = getenv("BT_NO_PDL") ? 0 : 1;
-  ctx = c;
   int32_t s = BT_OK;
   auto fail = [&](int32_t code) {
     g_bt_create_error = c->err;
@@ -170,7 +168,6 @@ int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t 
   if ((s = bt_lap_ws_create(c)) != BT_OK) return fail(s);
   if ((s = bt_gemm_ws_create(c)) != BT_OK) return fail(s);
   if ((s = bt_tracker_create(c)) != BT_OK) return fail(s);
-  (void)ctx;
   *out = c;
   return BT_OK;
 }

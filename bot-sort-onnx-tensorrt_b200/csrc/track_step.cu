@@ -77,11 +77,6 @@ __global__ void debug_spin_kernel(long long ns) {
   do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while ((long long)(t1 - t0) < ns);
 }
 
-__global__ void clear_words_kernel(int4* __restrict__ p, size_t n16) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n16) p[i] = make_int4(0, 0, 0, 0);
-}
-
 __global__ void gather_rows_f64_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx, int n,
                                        int width, double* __restrict__ dst) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,7 +613,6 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
   std::vector<int>& refind = t->v_refind; refind.clear();
   std::vector<int>& lost_now = t->v_lost_now; lost_now.clear();
   std::vector<int>& removed_now = t->v_removed_now; removed_now.clear();
-  int n_upd = 0;
   auto apply_match = [&](int slot, int det) {
     SlotMeta& tm = meta[slot];
     tm.f32_state = 0;
