@@ -30,36 +30,54 @@ feature_prep_kernel(const float* __restrict__ feat, int d, float* __restrict__ o
   __shared__ float red[kThreads / 32];
   const size_t row = blockIdx.x;
   const float* src = feat + row * d;
+  constexpr int kHold = 4;               // float4 per thread kept in registers: rows up to 4096 floats are read once
+  const bool vec = (d & 3) == 0;
+  const bool held = vec && d <= kThreads * 4 * kHold;
+  float4 v[kHold];
   float ss = 0.f;
-  if ((d & 3) == 0) {
+  if (held) {
+#pragma unroll
+    for (int t = 0; t < kHold; ++t) {
+      const int i = (threadIdx.x + t * kThreads) * 4;
+      v[t] = (i < d) ? __ldg(reinterpret_cast<const float4*>(src + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < kHold; ++t) ss += v[t].x * v[t].x + v[t].y * v[t].y + v[t].z * v[t].z + v[t].w * v[t].w;
+  } else if (vec) {
     for (int i = threadIdx.x * 4; i < d; i += kThreads * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(src + i);
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      const float4 w = *reinterpret_cast<const float4*>(src + i);
+      ss += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
     }
   } else {
     for (int i = threadIdx.x; i < d; i += kThreads) ss += src[i] * src[i];
   }
   float norm = 1.f;
   if (normalise) norm = sqrtf(block_sum(ss, red));
-  if ((d & 3) == 0) {
-    for (int i = threadIdx.x * 4; i < d; i += kThreads * 4) {
-      float4 v = *reinterpret_cast<const float4*>(src + i);
-      if (normalise) { v.x /= norm; v.y /= norm; v.z /= norm; v.w /= norm; }
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * d + i) = v;
-      if (out_f16) {
-        __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(out_f16 + row * d + i) = pk;
-      }
+  auto put = [&](int i, float4 w) {
+    if (normalise) { w.x /= norm; w.y /= norm; w.z /= norm; w.w /= norm; }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * d + i) = w;
+    if (out_f16) {
+      __half2 h0 = __floats2half2_rn(w.x, w.y), h1 = __floats2half2_rn(w.z, w.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(out_f16 + row * d + i) = pk;
     }
+  };
+  if (held) {
+#pragma unroll
+    for (int t = 0; t < kHold; ++t) {
+      const int i = (threadIdx.x + t * kThreads) * 4;
+      if (i < d) put(i, v[t]);
+    }
+  } else if (vec) {
+    for (int i = threadIdx.x * 4; i < d; i += kThreads * 4) put(i, *reinterpret_cast<const float4*>(src + i));
   } else {
     for (int i = threadIdx.x; i < d; i += kThreads) {
-      float v = src[i];
-      if (normalise) v /= norm;
-      if (out_f32) out_f32[row * d + i] = v;
-      if (out_f16) out_f16[row * d + i] = __float2half_rn(v);
+      float w = src[i];
+      if (normalise) w /= norm;
+      if (out_f32) out_f32[row * d + i] = w;
+      if (out_f16) out_f16[row * d + i] = __float2half_rn(w);
     }
   }
   // Launched as a programmatic dependent of det_prep (frame step): nothing above reads what det_prep
@@ -100,7 +118,39 @@ feature_ema_kernel(float* __restrict__ smooth, float* __restrict__ curr, const f
   }
   if (!smooth && !curr) return;
   const float one_minus = (float)(1.0 - (double)alpha);
-  // pass 1: new smooth (unnormalised) kept in registers (d <= 8 * kThreads) else recomputed
+  constexpr int kHold = 4;               // float4 per thread kept in registers: rows up to 4096 floats are read once
+  if ((d & 3) == 0 && d <= kThreads * 4 * kHold) {
+    float4 xv[kHold], sv[kHold];
+#pragma unroll
+    for (int k = 0; k < kHold; ++k) {
+      const int j = (threadIdx.x + k * kThreads) * 4;
+      xv[k] = (j < d) ? __ldg(reinterpret_cast<const float4*>(feat + f * d + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sv[k] = xv[k];
+      if (mode == 0 && j < d) {
+        const float4 o = *reinterpret_cast<const float4*>(smooth + t * d + j);
+        sv[k].x = __fadd_rn(__fmul_rn(alpha, o.x), __fmul_rn(one_minus, xv[k].x));
+        sv[k].y = __fadd_rn(__fmul_rn(alpha, o.y), __fmul_rn(one_minus, xv[k].y));
+        sv[k].z = __fadd_rn(__fmul_rn(alpha, o.z), __fmul_rn(one_minus, xv[k].z));
+        sv[k].w = __fadd_rn(__fmul_rn(alpha, o.w), __fmul_rn(one_minus, xv[k].w));
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kHold; ++k) ss += sv[k].x * sv[k].x + sv[k].y * sv[k].y + sv[k].z * sv[k].z + sv[k].w * sv[k].w;
+    float norm = 1.f;
+    if (mode != 2) norm = sqrtf(block_sum(ss, red));
+#pragma unroll
+    for (int k = 0; k < kHold; ++k) {
+      const int j = (threadIdx.x + k * kThreads) * 4;
+      if (j >= d) continue;
+      float4 o = sv[k];
+      if (mode != 2) { o.x /= norm; o.y /= norm; o.z /= norm; o.w /= norm; }
+      if (smooth) *reinterpret_cast<float4*>(smooth + t * d + j) = o;
+      if (curr) *reinterpret_cast<float4*>(curr + t * d + j) = (mode == 1) ? o : xv[k];
+    }
+    return;
+  }
+  // generic sizes: two passes, the new smooth is recomputed in the second
   float ss = 0.f;
   for (int j = threadIdx.x; j < d; j += kThreads) {
     const float x = feat[f * d + j];
