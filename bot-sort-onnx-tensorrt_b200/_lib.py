@@ -340,18 +340,29 @@ class Context:
 
     def get_tracks(self, which: int = 0, with_state: bool = False) -> dict:
         n = C.c_int32(0)
-        self._check(self.lib.bt_get_tracks(self.h, which, 0, C.byref(n), *([None] * 11)))
-        k = n.value
-        out = {name: np.empty(k, np.int32) for name in
-               ("ids", "state", "activated", "frame_id", "start_frame", "tracklet_len", "det_index")}
-        out["score"] = np.empty(k, np.float32)
-        out["tlbr"] = np.empty((k, 4), np.float64)
-        mean = np.empty((k, 8), np.float64) if with_state else None
-        cov = np.empty((k, 8, 8), np.float64) if with_state else None
-        self._check(self.lib.bt_get_tracks(
-            self.h, which, k, C.byref(n), _ptr(out["ids"]), _ptr(out["state"]), _ptr(out["activated"]),
-            _ptr(out["frame_id"]), _ptr(out["start_frame"]), _ptr(out["tracklet_len"]), _ptr(out["det_index"]),
-            _ptr(out["score"]), _ptr(out["tlbr"]), _ptr(mean), _ptr(cov)))
+        hints = self.__dict__.setdefault("_list_size_hint", [0, 0])
+        k = hints[which]                    # steady state: the list is as long as last time -> one call
+        for attempt in range(2):
+            out = {name: np.empty(k, np.int32) for name in
+                   ("ids", "state", "activated", "frame_id", "start_frame", "tracklet_len", "det_index")}
+            out["score"] = np.empty(k, np.float32)
+            out["tlbr"] = np.empty((k, 4), np.float64)
+            mean = np.empty((k, 8), np.float64) if with_state else None
+            cov = np.empty((k, 8, 8), np.float64) if with_state else None
+            st = self.lib.bt_get_tracks(
+                self.h, which, k, C.byref(n), _ptr(out["ids"]), _ptr(out["state"]), _ptr(out["activated"]),
+                _ptr(out["frame_id"]), _ptr(out["start_frame"]), _ptr(out["tracklet_len"]), _ptr(out["det_index"]),
+                _ptr(out["score"]), _ptr(out["tlbr"]), _ptr(mean), _ptr(cov))
+            if attempt == 0 and n.value > k and st in (BT_OK, BT_ERR_CAPACITY):
+                k = n.value                 # the list grew: the library reported its length, size the buffers again
+                continue
+            self._check(st)
+            break
+        hints[which] = cnt = n.value
+        if cnt < k:
+            out = {name: a[:cnt] for name, a in out.items()}
+            mean = None if mean is None else mean[:cnt]
+            cov = None if cov is None else cov[:cnt]
         if with_state:
             out["mean"], out["cov"] = mean, cov
         return out
