@@ -44,3 +44,26 @@ def test_random_scenes_match_the_oracle(flags):
                 _compare_frame(ctx, oracle, k + 1)
     finally:
         ctx.close()
+
+
+def test_wide_tiles_of_the_association_kernel(monkeypatch):
+    """The tile width of the association GEMM is picked per launch (224 or 256 columns; 256 only wins for
+    2017-2304 detections): force the 256-column variant of the candidate path through a few scenes."""
+    monkeypatch.setenv("BT_ASSOC_BN", "256")
+    ctx = bs.Context(max_tracks=1024, max_dets=1024, feat_dim=256)
+    try:
+        for seed in (1001, 1020, 1034):
+            sc, with_reid, frames = _scene_for(seed)
+            cfg = ctx.default_config()
+            cfg.with_reid = 1 if with_reid else 0
+            ctx.tracker_reset(cfg)
+            scene = SyntheticScene(sc)
+            oracle = O.OracleBoTSORT(mode="vectorized", lap_solver="jv", use_features=with_reid)
+            for k in range(frames):
+                fr = scene.next_frame()
+                feats = fr["feats"] if with_reid else None
+                oracle.update_arrays(fr["boxes"], fr["scores"], feats)
+                ctx.update_arrays(fr["boxes"], fr["scores"], feats)
+                _compare_frame(ctx, oracle, k + 1)
+    finally:
+        ctx.close()
