@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kThreads)
 kalman_predict_kernel(double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ tlbr,
                       float* __restrict__ tlbr_f32, const int32_t* __restrict__ state,
                       const int32_t* __restrict__ idx, int n, int noise_f32, uint8_t* __restrict__ slot_f32) {
+  bt_grid_launch_dependents();   // frame step: the association kernel behind this one sets itself up meanwhile
   const int gid = blockIdx.x * kThreads + threadIdx.x;
   const int g = gid >> 3;
   const int r = threadIdx.x & 7;

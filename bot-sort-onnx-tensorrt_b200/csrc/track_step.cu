@@ -129,6 +129,8 @@ struct bt_tracker {
   cudaStream_t st2 = nullptr;   // side stream: work that is independent of the main chain runs beside it
   cudaEvent_t ev_fork1 = nullptr, ev_join1 = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr, ev_x = nullptr;
   bool overlap = true;
+  bool predict_side = false;  // BT_PREDICT_SIDE=1: control block + Kalman predict on the side stream (measured: the four
+                              // event calls cost the host more than the 5 us kernel costs the main stream)
   int debug_delay_us = 0;
   bool host_debug = false;
   char* d_res = nullptr;    // packed per-frame result block (one D2H per frame), layout in bt_update_arrays
@@ -333,6 +335,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   for (cudaEvent_t* e : {&t->ev_fork1, &t->ev_join1, &t->ev_fork2, &t->ev_join2, &t->ev_x})
     BT_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   t->overlap = getenv("BT_NO_OVERLAP") == nullptr;
+  t->predict_side = getenv("BT_PREDICT_SIDE") != nullptr;
   t->debug_delay_us = getenv("BT_DEBUG_DELAY_SIDE") ? atoi(getenv("BT_DEBUG_DELAY_SIDE")) : 0;
   t->host_debug = getenv("BT_HOST_DEBUG") != nullptr;
   return BT_OK;
@@ -495,12 +498,13 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     all_f32 = all_f32 && meta[s].f32_state;
   }
   for (int s : unconfirmed) hA_kind[s] = BT_ROW_UNCONFIRMED;
-  // The control block + Kalman predict do not depend on the detection prep: they run on the side
-  // stream next to it and join before the association kernel (single stream while profiling, so that
-  // the per-segment events stay meaningful).
+  // The control block + Kalman predict do not depend on the detection prep; they can run on the side
+  // stream next to it and join before the association kernel (BT_PREDICT_SIDE=1), but by default they
+  // stay on the main stream: the GPU is waiting for the host's launches at this point of the frame.
   const bool overlap = t->overlap && !t->prof;
-  cudaStream_t sp = overlap ? t->st2 : st;
-  if (overlap) {
+  const bool overlap_predict = overlap && t->predict_side;
+  cudaStream_t sp = overlap_predict ? t->st2 : st;
+  if (overlap_predict) {
     BT_CUDA(cudaEventRecord(t->ev_fork1, st));       // everything already queued on the main stream
     BT_CUDA(cudaStreamWaitEvent(t->st2, t->ev_fork1, 0));
   }
@@ -516,7 +520,7 @@ int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores,
     for (int s : pool) meta[s].f32_state = 0;
   }
   SEG_END(BT_SEG_PREDICT);
-  if (overlap) {
+  if (overlap_predict) {
     BT_CUDA(cudaEventRecord(t->ev_join1, t->st2));
     BT_CUDA(cudaStreamWaitEvent(st, t->ev_join1, 0));
   }
