@@ -18,14 +18,19 @@ BT_HOST, BT_DEVICE = 0, 1
 BT_OK, BT_ERR_INVALID, BT_ERR_CUDA, BT_ERR_CAPACITY, BT_ERR_STATE = 0, -1, -2, -3, -4
 BT_FLAG_SIMT_SIM = 1 << 0
 BT_FLAG_NO_F32_FEATURES = 1 << 1
+BT_F32, BT_F16 = 0, 1
+BT_MAX_BATCH = 32
 
 # every symbol include/botsort_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "bt_version", "bt_last_error", "bt_default_config", "bt_create", "bt_destroy", "bt_sync", "bt_stream",
+    "bt_version", "bt_last_error", "bt_default_config", "bt_create", "bt_create_streams", "bt_num_streams",
+    "bt_destroy", "bt_sync", "bt_stream",
     "bt_launch_count", "bt_kalman_initiate", "bt_kalman_multi_predict", "bt_kalman_update", "bt_kalman_project",
     "bt_iou_distance", "bt_embedding_distance", "bt_fused_cost", "bt_fuse_score", "bt_linear_assignment",
     "bt_feature_ema", "bt_default_yolox_config", "bt_yolox_postprocess", "bt_reid_crop_gather",
-    "bt_tracker_reset", "bt_update_arrays", "bt_get_tracks", "bt_get_track_features", "bt_get_matches",
+    "bt_tracker_reset", "bt_tracker_reset_stream", "bt_update_arrays", "bt_update_streams", "bt_submit_streams",
+    "bt_step_streams", "bt_input_buffers", "bt_get_tracks", "bt_get_tracks_stream", "bt_get_track_features",
+    "bt_get_track_features_stream", "bt_get_matches", "bt_get_matches_stream",
     "bt_profile_enable", "bt_profile_read", "bt_profile_replay_assoc",
 ]
 SEGMENTS = ("prep", "predict", "assoc", "lap", "update", "dup",
@@ -34,10 +39,11 @@ SEGMENTS = ("prep", "predict", "assoc", "lap", "update", "dup",
 
 class BtConfig(C.Structure):
     _fields_ = [
-        ("track_high_thresh", C.c_float), ("track_low_thresh", C.c_float), ("new_track_thresh", C.c_float),
+        ("track_high_thresh", C.c_double), ("track_low_thresh", C.c_double), ("new_track_thresh", C.c_double),
         ("match_thresh", C.c_double), ("second_thresh", C.c_double), ("unconfirmed_thresh", C.c_double),
-        ("proximity_thresh", C.c_double), ("appearance_thresh", C.c_float), ("duplicate_iou_dist", C.c_double),
-        ("track_buffer", C.c_int32), ("frame_rate", C.c_int32), ("ema_alpha", C.c_float), ("with_reid", C.c_int32),
+        ("proximity_thresh", C.c_double), ("appearance_thresh", C.c_double), ("duplicate_iou_dist", C.c_double),
+        ("ema_alpha", C.c_double),
+        ("track_buffer", C.c_int32), ("frame_rate", C.c_int32), ("with_reid", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -52,10 +58,10 @@ class BtYoloxConfig(C.Structure):
 class BtFrameInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "frame_id", "n_tracked", "n_lost", "n_removed_total", "n_pool", "n_high", "n_low", "n_unconfirmed",
-        "n_matches1", "n_matches2", "n_matches3", "n_births")]
+        "n_matches1", "n_matches2", "n_matches3", "n_births", "n_births_skipped")] + [("reserved", C.c_int32 * 3)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
 _lib = None
@@ -82,6 +88,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.bt_default_yolox_config.argtypes = [C.POINTER(BtYoloxConfig)]
     lib.bt_create.restype = i32
     lib.bt_create.argtypes = [i32, i32, i32, i32, C.c_uint32, C.POINTER(vp)]
+    lib.bt_create_streams.restype = i32
+    lib.bt_create_streams.argtypes = [i32, i32, i32, i32, i32, C.c_uint32, C.POINTER(vp)]
+    lib.bt_num_streams.restype = i32
+    lib.bt_num_streams.argtypes = [vp]
     lib.bt_destroy.restype = i32
     lib.bt_destroy.argtypes = [vp]
     lib.bt_sync.restype = i32
@@ -104,10 +114,18 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bt_yolox_postprocess": [vp, vp, C.POINTER(BtYoloxConfig), vp, i32, vp, i32],
         "bt_reid_crop_gather": [vp, vp, i32, i32, vp, i32, i32, i32, vp, i32],
         "bt_tracker_reset": [vp, C.POINTER(BtConfig)],
+        "bt_tracker_reset_stream": [vp, i32, C.POINTER(BtConfig)],
         "bt_update_arrays": [vp, vp, vp, vp, i32, i32, C.POINTER(BtFrameInfo)],
+        "bt_update_streams": [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp],
+        "bt_submit_streams": [vp, i32, vp, vp, vp, vp, vp, i32, vp, i32],
+        "bt_step_streams": [vp, i32, vp, vp],
+        "bt_input_buffers": [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
         "bt_get_tracks": [vp, i32, i32, vp] + [vp] * 11,
+        "bt_get_tracks_stream": [vp, i32, i32, i32, vp] + [vp] * 11,
         "bt_get_track_features": [vp, i32, i32, vp, vp],
+        "bt_get_track_features_stream": [vp, i32, i32, i32, vp, vp],
         "bt_get_matches": [vp, i32, i32, vp, vp],
+        "bt_get_matches_stream": [vp, i32, i32, i32, vp, vp],
         "bt_profile_enable": [vp, i32],
         "bt_profile_read": [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "bt_profile_replay_assoc": [vp, i32, C.POINTER(C.c_double)],
@@ -140,15 +158,16 @@ class Context:
     """One bt_ctx: a CUDA device + stream + workspaces + one tracker.  Host-buffer (NumPy) API."""
 
     def __init__(self, max_tracks: int = 4096, max_dets: int = 4096, feat_dim: int = 2048, device: int = 0,
-                 flags: int = 0):
+                 flags: int = 0, n_streams: int = 1):
         self.lib = load_library()
         h = C.c_void_p()
-        st = self.lib.bt_create(device, max_tracks, max_dets, feat_dim, flags, C.byref(h))
+        st = self.lib.bt_create_streams(device, n_streams, max_tracks, max_dets, feat_dim, flags, C.byref(h))
         if st != BT_OK:
             msg = self.lib.bt_last_error(None).decode()
             raise BotsortError(f"bt_create failed ({st}): {msg}")
         self.h = h
         self.max_tracks, self.max_dets, self.feat_dim, self.device = max_tracks, max_dets, feat_dim, device
+        self.n_streams = n_streams
 
     def close(self):
         if getattr(self, "h", None):
@@ -320,28 +339,105 @@ class Context:
         self.lib.bt_default_config(C.byref(cfg))
         return cfg
 
-    def tracker_reset(self, cfg: Optional[BtConfig] = None):
-        self._check(self.lib.bt_tracker_reset(self.h, None if cfg is None else C.byref(cfg)))
+    def tracker_reset(self, cfg: Optional[BtConfig] = None, stream: int = -1):
+        """Reset one video stream's tracker (stream >= 0) or all of them (default)."""
+        self._check(self.lib.bt_tracker_reset_stream(self.h, stream, None if cfg is None else C.byref(cfg)))
 
-    def update_arrays(self, boxes, scores, feats=None) -> dict:
-        b = _arr(boxes, np.int32, (-1, 4))
-        s = _arr(scores, np.float32, (-1,))
-        f = None if feats is None else _arr(feats, np.float32, (b.shape[0], self.feat_dim))
-        info = BtFrameInfo()
-        self._check(self.lib.bt_update_arrays(self.h, _ptr(b), _ptr(s), _ptr(f), b.shape[0], BT_HOST, C.byref(info)))
-        return info.as_dict()
+    @staticmethod
+    def _feat_array(feats, m, d):
+        """float16 arrays are passed through as they are (BT_F16), everything else as float32 (BT_F32)."""
+        if feats is None:
+            return None, BT_F32
+        a = np.asarray(feats)
+        if a.dtype == np.float16:
+            return np.ascontiguousarray(a).reshape(m, d), BT_F16
+        return _arr(a, np.float32, (m, d)), BT_F32
+
+    def update_arrays(self, boxes, scores, feats=None, face_sim=None, stream: int = 0) -> dict:
+        """One BoTSORT.update of video stream `stream` on detector / encoder outputs (NumPy arrays)."""
+        return self.update_streams([stream], [boxes], [scores], [feats],
+                                   None if face_sim is None else [face_sim])[0]
+
+    def _pack_batch(self, stream_ids, boxes, scores, feats, face_sims):
+        n = len(stream_ids)
+        ids = (C.c_int32 * n)(*[int(s) for s in stream_ids])
+        keep, bp, sp, fp, mp, xp = [], (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_int32 * n)(), (C.c_void_p * n)()
+        dtype = None
+        for k in range(n):
+            b = _arr(boxes[k], np.int32, (-1, 4))
+            s = _arr(scores[k], np.float32, (-1,))
+            m = b.shape[0]
+            f, dt = self._feat_array(None if feats is None else feats[k], m, self.feat_dim)
+            if f is not None:
+                if dtype is not None and dt != dtype:
+                    raise ValueError("one batch cannot mix float16 and float32 features")
+                dtype = dt
+            x = None if (face_sims is None or face_sims[k] is None) else _arr(face_sims[k], np.float32)
+            keep += [b, s, f, x]
+            bp[k], sp[k], mp[k] = b.ctypes.data, s.ctypes.data, m
+            fp[k] = None if f is None else f.ctypes.data
+            xp[k] = None if x is None else x.ctypes.data
+        return n, ids, bp, sp, fp, mp, (BT_F32 if dtype is None else dtype), (None if face_sims is None else xp), keep
+
+    def update_streams(self, stream_ids, boxes, scores, feats=None, face_sims=None) -> list:
+        """One frame step for several video streams of this ctx at once (one launch per kernel)."""
+        n, ids, bp, sp, fp, mp, dtype, xp, keep = self._pack_batch(stream_ids, boxes, scores, feats, face_sims)
+        infos = (BtFrameInfo * n)()
+        self._check(self.lib.bt_update_streams(self.h, n, ids, bp, sp, fp, mp, dtype, xp, BT_HOST, infos))
+        return [infos[k].as_dict() for k in range(n)]
+
+    def submit_streams(self, stream_ids, boxes, scores, feats=None, face_sims=None):
+        """Start moving one frame of inputs in (returns at once); the arrays must stay alive until the
+        matching step_streams returns -- the returned handle keeps them referenced."""
+        n, ids, bp, sp, fp, mp, dtype, xp, keep = self._pack_batch(stream_ids, boxes, scores, feats, face_sims)
+        self._check(self.lib.bt_submit_streams(self.h, n, ids, bp, sp, fp, mp, dtype, xp, BT_HOST))
+        return keep
+
+    def step_streams(self, stream_ids) -> list:
+        n = len(stream_ids)
+        ids = (C.c_int32 * n)(*[int(s) for s in stream_ids])
+        infos = (BtFrameInfo * n)()
+        self._check(self.lib.bt_step_streams(self.h, n, ids, infos))
+        return [infos[k].as_dict() for k in range(n)]
+
+    def input_buffers(self, stream: int = 0):
+        """Device pointers (boxes int32, scores float32, feats float16) the next submit of `stream` reads in place."""
+        b, s, f = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.lib.bt_input_buffers(self.h, stream, C.byref(b), C.byref(s), C.byref(f)))
+        return int(b.value), int(s.value), int(f.value)
 
     def update_arrays_raw(self, boxes_ptr: int, scores_ptr: int, feats_ptr: int, m: int, loc: int,
-                          info: Optional[BtFrameInfo] = None):
-        """Pointer-level call (pinned host or device buffers), used by bench.py."""
-        self._check(self.lib.bt_update_arrays(self.h, C.c_void_p(boxes_ptr), C.c_void_p(scores_ptr),
-                                              C.c_void_p(feats_ptr) if feats_ptr else None, m, loc,
-                                              None if info is None else C.byref(info)))
+                          info: Optional[BtFrameInfo] = None, dtype: int = BT_F32, stream: int = 0):
+        """Pointer-level call (pinned host or device buffers) for one stream, used by bench.py."""
+        self.update_streams_raw([stream], [boxes_ptr], [scores_ptr], [feats_ptr], [m], loc, dtype,
+                                None if info is None else C.pointer(info))
 
-    def get_tracks(self, which: int = 0, with_state: bool = False) -> dict:
+    def _raw_arrays(self, stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms):
+        n = len(stream_ids)
+        ids = (C.c_int32 * n)(*stream_ids)
+        bp = (C.c_void_p * n)(*boxes_ptrs)
+        sp = (C.c_void_p * n)(*scores_ptrs)
+        fp = (C.c_void_p * n)(*[p or None for p in feats_ptrs])
+        mp = (C.c_int32 * n)(*ms)
+        return n, ids, bp, sp, fp, mp
+
+    def update_streams_raw(self, stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms, loc, dtype=BT_F32, infos=None):
+        n, ids, bp, sp, fp, mp = self._raw_arrays(stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms)
+        self._check(self.lib.bt_update_streams(self.h, n, ids, bp, sp, fp, mp, dtype, None, loc, infos))
+
+    def submit_streams_raw(self, stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms, loc, dtype=BT_F32):
+        n, ids, bp, sp, fp, mp = self._raw_arrays(stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms)
+        self._check(self.lib.bt_submit_streams(self.h, n, ids, bp, sp, fp, mp, dtype, None, loc))
+
+    def step_streams_raw(self, stream_ids, infos=None):
+        n = len(stream_ids)
+        ids = (C.c_int32 * n)(*stream_ids)
+        self._check(self.lib.bt_step_streams(self.h, n, ids, infos))
+
+    def get_tracks(self, which: int = 0, with_state: bool = False, stream: int = 0) -> dict:
         n = C.c_int32(0)
-        hints = self.__dict__.setdefault("_list_size_hint", [0, 0])
-        k = hints[which]                    # steady state: the list is as long as last time -> one call
+        hints = self.__dict__.setdefault("_list_size_hint", {})
+        k = hints.get((stream, which), 0)   # steady state: the list is as long as last time -> one call
         for attempt in range(2):
             out = {name: np.empty(k, np.int32) for name in
                    ("ids", "state", "activated", "frame_id", "start_frame", "tracklet_len", "det_index")}
@@ -349,8 +445,8 @@ class Context:
             out["tlbr"] = np.empty((k, 4), np.float64)
             mean = np.empty((k, 8), np.float64) if with_state else None
             cov = np.empty((k, 8, 8), np.float64) if with_state else None
-            st = self.lib.bt_get_tracks(
-                self.h, which, k, C.byref(n), _ptr(out["ids"]), _ptr(out["state"]), _ptr(out["activated"]),
+            st = self.lib.bt_get_tracks_stream(
+                self.h, stream, which, k, C.byref(n), _ptr(out["ids"]), _ptr(out["state"]), _ptr(out["activated"]),
                 _ptr(out["frame_id"]), _ptr(out["start_frame"]), _ptr(out["tracklet_len"]), _ptr(out["det_index"]),
                 _ptr(out["score"]), _ptr(out["tlbr"]), _ptr(mean), _ptr(cov))
             if attempt == 0 and n.value > k and st in (BT_OK, BT_ERR_CAPACITY):
@@ -358,7 +454,7 @@ class Context:
                 continue
             self._check(st)
             break
-        hints[which] = cnt = n.value
+        hints[(stream, which)] = cnt = n.value
         if cnt < k:
             out = {name: a[:cnt] for name, a in out.items()}
             mean = None if mean is None else mean[:cnt]
@@ -367,19 +463,19 @@ class Context:
             out["mean"], out["cov"] = mean, cov
         return out
 
-    def get_track_features(self, which: int = 0):
+    def get_track_features(self, which: int = 0, stream: int = 0):
         n = C.c_int32(0)
-        self._check(self.lib.bt_get_tracks(self.h, which, 0, C.byref(n), *([None] * 11)))
+        self._check(self.lib.bt_get_tracks_stream(self.h, stream, which, 0, C.byref(n), *([None] * 11)))
         k = n.value
         curr = np.empty((k, self.feat_dim), np.float32)
         smooth = np.empty((k, self.feat_dim), np.float32)
-        self._check(self.lib.bt_get_track_features(self.h, which, k, _ptr(curr), _ptr(smooth)))
+        self._check(self.lib.bt_get_track_features_stream(self.h, stream, which, k, _ptr(curr), _ptr(smooth)))
         return curr, smooth
 
-    def get_matches(self, stage: int) -> np.ndarray:
+    def get_matches(self, stage: int, stream: int = 0) -> np.ndarray:
         n = C.c_int32(0)
-        self._check(self.lib.bt_get_matches(self.h, stage, 0, C.byref(n), None))
+        self._check(self.lib.bt_get_matches_stream(self.h, stream, stage, 0, C.byref(n), None))
         pairs = np.empty((n.value, 2), np.int32)
         if n.value:
-            self._check(self.lib.bt_get_matches(self.h, stage, n.value, C.byref(n), _ptr(pairs)))
+            self._check(self.lib.bt_get_matches_stream(self.h, stream, stage, n.value, C.byref(n), _ptr(pairs)))
         return pairs

@@ -20,9 +20,10 @@ LIB_NAME = "libbotsort_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["api.cu", "kalman.cu", "iou.cu", "features.cu", "reid_gemm.cu", "lap.cu", "track_step.cu",
-           "detector_side.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(REPO, "include", "botsort_b200.h")]
+SOURCES = ["api.cu", "kalman.cu", "iou.cu", "features.cu", "frame_kernels.cu", "reid_gemm.cu", "lap.cu",
+           "track_step.cu", "detector_side.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kalman_dev.cuh"),
+           os.path.join(REPO, "include", "botsort_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -100,19 +100,20 @@ int32_t bt_version(void) { return BT_VERSION; }
 const char* bt_last_error(const bt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_bt_create_error.c_str(); }
 
 void bt_default_config(bt_config* cfg) {
-  cfg->track_high_thresh = 0.40f;
-  cfg->track_low_thresh = 0.1f;
-  cfg->new_track_thresh = 0.9f;
+  cfg->track_high_thresh = 0.40;
+  cfg->track_low_thresh = 0.1;
+  cfg->new_track_thresh = 0.9;
   cfg->match_thresh = 0.8;
   cfg->second_thresh = 0.5;
   cfg->unconfirmed_thresh = 0.7;
   cfg->proximity_thresh = 0.5;
-  cfg->appearance_thresh = 0.25f;
+  cfg->appearance_thresh = 0.25;
   cfg->duplicate_iou_dist = 0.15;
+  cfg->ema_alpha = 0.9;
   cfg->track_buffer = 300;
   cfg->frame_rate = 30;
-  cfg->ema_alpha = 0.9f;
   cfg->with_reid = 1;
+  cfg->reserved = 0;
 }
 
 void bt_default_yolox_config(bt_yolox_config* cfg) {
@@ -129,10 +130,19 @@ void bt_default_yolox_config(bt_yolox_config* cfg) {
 
 int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t feat_dim, uint32_t flags,
                   bt_ctx** out) {
+  return bt_create_streams(device, 1, max_tracks, max_dets, feat_dim, flags, out);
+}
+
+int32_t bt_num_streams(const bt_ctx* ctx) { return ctx ? ctx->n_streams : 0; }
+
+int32_t bt_create_streams(int32_t device, int32_t n_streams, int32_t max_tracks, int32_t max_dets, int32_t feat_dim,
+                          uint32_t flags, bt_ctx** out) {
   if (!out) return bt_fail(nullptr, BT_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (max_tracks <= 0 || max_dets <= 0 || feat_dim <= 0)
     return bt_fail(nullptr, BT_ERR_INVALID, "max_tracks, max_dets, feat_dim must be positive");
+  if (n_streams < 1 || n_streams > 1024)
+    return bt_fail(nullptr, BT_ERR_INVALID, "n_streams must be 1..1024");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count <= 0)
@@ -149,8 +159,9 @@ int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t 
   bt_ctx* c = new bt_ctx();
   c->device = device;
   c->max_tracks = (max_tracks + 127) / 128 * 128;
-  c->max_dets = max_dets;
+  c->max_dets = (max_dets + 3) / 4 * 4;   // keeps every stream's detection rows 16-byte aligned
   c->feat_dim = feat_dim;
+  c->n_streams = n_streams;
   c->flags = flags;
   c->num_sms = prop.multiProcessorCount;
   c->pdl = getenv("BT_NO_PDL") ? 0 : 1;
@@ -160,7 +171,8 @@ int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t 
     bt_destroy(c);
     return code;
   };
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     bt_fail(c, BT_ERR_CUDA, "cudaStreamCreate failed");
     return fail(BT_ERR_CUDA);
   }
@@ -176,12 +188,14 @@ int32_t bt_destroy(bt_ctx* ctx) {
   if (!ctx) return BT_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   bt_tracker_destroy(ctx);
   bt_gemm_ws_destroy(ctx);
   bt_lap_ws_destroy(ctx);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return BT_OK;
 }
@@ -330,7 +344,14 @@ static int32_t assoc_dense_common(bt_ctx* ctx, const double* trk_tlbr, int32_t n
   if (out_dists) BT_TRY(bt_out(ctx, out_dists, nm, loc, &d_dists));
   bt_assoc_params p;
   memset(&p, 0, sizeof(p));
-  p.a32 = d_a; p.b32 = d_b; p.n = n; p.m = m; p.d = d;
+  p.count = 1;
+  p.n[0] = n; p.m[0] = m; p.d = d;
+  p.a_rows_alloc = n; p.b_rows_alloc = m;
+  p.face_sim[0] = d_face;
+  // fp16 operands round unit-norm rows of few components coarsely (d = 64: up to 5e-4 on the similarity):
+  // below 512 components the CUDA-core fp32 kernel is both exact and fast enough
+  if (precision == 0 && (d < 512 || d % 64 != 0)) precision = 1;
+  if (precision == 1) { p.a32 = d_a; p.b32 = d_b; }
   if (precision == 0) {
     __half *a16, *b16;
     BT_TRY(bt_arena(ctx, fa, &a16));
@@ -339,12 +360,12 @@ static int32_t assoc_dense_common(bt_ctx* ctx, const double* trk_tlbr, int32_t n
     BT_TRY(btk_feature_prep(ctx, d_b, m, d, nullptr, b16, 0));
     p.a16 = a16; p.b16 = b16;
   }
-  p.row_tlbr = d_rt; p.col_tlbr = d_ct; p.face_sim = d_face;
+  p.row_tlbr = d_rt; p.col_tlbr = d_ct;
   bt_config cfg;
   bt_default_config(&cfg);
   p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
   p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
-  p.appearance = cfg.appearance_thresh;
+  p.appearance = (float)cfg.appearance_thresh;
   p.cand.cnt = nullptr;
   p.out_emb = d_emb; p.out_dists = d_dists; p.dense_stage = stage;
   BT_TRY(btk_assoc(ctx, p, precision));
@@ -395,11 +416,11 @@ int32_t bt_linear_assignment(bt_ctx* ctx, const double* cost, int32_t n, int32_t
   }
   BT_TRY(bt_out(ctx, x, (size_t)n, loc, &d_x));
   BT_TRY(bt_out(ctx, y, (size_t)m, loc, &d_y));
+  // video stream 0's candidate lists serve the stand-alone solver (its tracker keeps them zeroed between frames)
   const bt_cand& cand = *bt_lap_own_cand(ctx);
-  if (n > 0) BT_CUDA(cudaMemsetAsync(cand.cnt, 0, sizeof(int32_t) * (size_t)n * cand.nseg, ctx->stream));
-  BT_CUDA(cudaMemsetAsync(cand.total, 0, sizeof(int32_t) * 4, ctx->stream));
+  BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, ctx->stream));
   BT_TRY(btk_lap_compact_dense(ctx, d_cost, n, m, thresh, cand, 0));
-  BT_TRY(btk_lap_solve(ctx, cand, 0, n, m, thresh, nullptr, nullptr, d_x, d_y));
+  BT_TRY(btk_lap_solve(ctx, cand, 0, n, m, thresh, d_x, d_y));
   // leave the candidate counters zeroed: the tracker path relies on it (its LAP kernel clears its own)
   BT_CUDA(cudaMemsetAsync(cand.cnt, 0, cand.clear_bytes, ctx->stream));
   BT_TRY(bt_unstage_out(ctx, x, d_x, sizeof(int32_t) * n, loc));
@@ -426,7 +447,9 @@ int32_t bt_feature_ema(bt_ctx* ctx, float* smooth, float* curr, const float* fea
   if (first) BT_TRY(bt_in(ctx, first, (size_t)k, loc, &d_first));
   float* d_s = const_cast<float*>(d_s_in);
   float* d_c = const_cast<float*>(d_c_in);
-  BT_TRY(btk_feature_ema(ctx, d_s, d_c, d_f, track_idx, feat_idx, d_first, k, d, alpha));
+  // alpha and 1 - alpha are rounded to float32 separately (NEP 50 weak Python floats, demo:473, demo:499-501)
+  const double alpha_d = (alpha == 0.9f) ? 0.9 : (double)alpha;
+  BT_TRY(btk_feature_ema(ctx, d_s, d_c, d_f, track_idx, feat_idx, d_first, k, d, (float)alpha_d, (float)(1.0 - alpha_d)));
   BT_TRY(bt_unstage_out(ctx, smooth, d_s, sizeof(float) * kd, loc));
   BT_TRY(bt_unstage_out(ctx, curr, d_c, sizeof(float) * kd, loc));
   return bt_finish(ctx, loc);

@@ -17,6 +17,8 @@ struct bt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   int max_tracks = 0, max_dets = 0, feat_dim = 0;
+  int n_streams = 1;             // video streams (trackers) of this ctx: a leading batch dimension of every kernel
+  cudaStream_t copy_stream = nullptr;   // input staging of bt_submit_streams (overlaps the frame step)
   uint32_t flags = 0;
   int num_sms = 148;
   int pdl = 1;   // programmatic dependent launch between the frame step's kernels (BT_NO_PDL=1 turns it off)
@@ -143,8 +145,88 @@ static inline int32_t bt_out(bt_ctx* ctx, T* dst, size_t count, int32_t loc, T**
 #define BT_STD_POS (1.0 / 20)
 #define BT_STD_VEL (1.0 / 160)
 
+// ---- reference cost fusion (shared by the association epilogue and the LAP's exact re-costing) ----
+#ifdef __CUDACC__
+// bbox_iou, demo:1695-1713, as a distance
+__device__ __forceinline__ double bt_iou_dist_f64(const double* __restrict__ a, const double* __restrict__ b) {
+  const double ixmin = fmax(a[0], b[0]), iymin = fmax(a[1], b[1]);
+  const double ixmax = fmin(a[2], b[2]), iymax = fmin(a[3], b[3]);
+  if (ixmax <= ixmin || iymax <= iymin) return 1.0;
+  const double inter = (ixmax - ixmin) * (iymax - iymin);
+  const double area1 = (a[2] - a[0]) * (a[3] - a[1]);
+  const double area2 = (b[2] - b[0]) * (b[3] - b[1]);
+  return 1.0 - inter / (area1 + area2 - inter);
+}
+// first association, demo:1539-1554
+__device__ __forceinline__ double bt_fuse_stage1(double iou_d, float sim, float face, float appearance) {
+  float emb = 1.0f - sim;
+  const float face_emb = 1.0f - face;
+  if (fminf(emb, face_emb) > appearance) emb = 1.0f;
+  return fmin(iou_d, (double)emb);
+}
+// unconfirmed tracks, demo:1599-1602
+__device__ __forceinline__ double bt_fuse_stage3(double iou_d, float sim, float appearance, double proximity) {
+  float emb = 1.0f - fmaxf(0.0f, sim);
+  if (emb > appearance) emb = 1.0f;
+  if (iou_d > proximity) emb = 1.0f;
+  return fmin(iou_d, (double)emb);
+}
+#endif
+
+// ---- batch of video streams served by one launch ------------------------------------------------
+// Per-slot arrays of the track store are indexed by the global slot gs = stream * max_tracks + slot,
+// per-detection arrays by gd = stream * max_dets + j; the frame's control segment (pool list, states,
+// row kinds) of batch entry k starts ctrl_off[k] bytes into the packed control block and its results
+// land in result region k.
+struct bt_batch {
+  int32_t count;
+  int32_t sid[BT_MAX_BATCH];       // video stream of batch entry k
+  int32_t m[BT_MAX_BATCH];         // detections this frame
+  int32_t n_rows[BT_MAX_BATCH];    // slots in use (high-water mark) = rows of the association problem
+  int32_t n_pool[BT_MAX_BATCH];    // pool tracks (Kalman predict)
+  int32_t ctrl_off[BT_MAX_BATCH];  // byte offset of the control segment: [pool_idx n_pool][pool_state n_pool][row_kind n_rows (pad 4)][pool_pos n_rows]
+  uint8_t noise_f32[BT_MAX_BATCH]; // every pooled mean is still float32 (NumPy >= 2 quirk, frame 2)
+  uint8_t parity[BT_MAX_BATCH];    // which half of the double-buffered inputs holds this frame
+  uint8_t want_norm[BT_MAX_BATCH]; // detection feature norms are needed (unconfirmed rows exist)
+};
+static inline int bt_batch_max(const int32_t* v, int count) {
+  int mx = 0;
+  for (int k = 0; k < count; ++k) mx = v[k] > mx ? v[k] : mx;
+  return mx;
+}
+
+// Device-side track store + per-frame buffers of a ctx (track_step.cu owns the allocations).
+struct bt_store {
+  int32_t S, cap, md, D;
+  // per slot (gs)
+  double *mean, *cov, *tlbr;
+  float* tlbr_f32;
+  __half* feat16;      // raw fp16 feature of the track's latest detection = A operand of the similarity GEMM
+  float* norm;         // its L2 norm: body_curr_feature = feat16 / norm (demo:497-502)
+  float* curr32;       // fp32 ingest only: the normalised fp32 current feature (exact re-costing + exposed state)
+  float* smooth32;     // EMA feature (A10), optional
+  uint8_t* slot_f32;
+  // per detection (gd), per input parity where noted
+  int32_t* det_boxes;  // [2][S*md][4]
+  float* det_scores;   // [2][S*md]
+  __half* det16;       // [2][S*md][D] raw fp16 features = B operand
+  float* det32;        // [2][S*md][D] fp32 ingest staging (allocated on first use)
+  float* det_norm;     // [S*md] L2 norms of the detection rows (when computed)
+  double *det_tlbr, *det_xywh;
+  float* det_xywh32;
+  uint8_t* col_kind;
+  uint2* col_pk;
+  // per batch entry
+  char* ctrl;          // packed control block
+  char* res;           // result regions part A (read back right after the LAP): x1,x2,x3 [cap each] | scores[md] | boxes[4 md]
+  char* resB;          // result regions part B (read back at the end): pair count (2 ints) | pairs[2*prefetch] | tlbr[4*cap] f64
+  int32_t* y;          // [BT_MAX_BATCH][3][md]
+  int32_t* pairs;      // [BT_MAX_BATCH][2*pair_cap] duplicate candidates beyond the prefetch
+  int32_t pair_cap;
+};
+
 // ---- kernel launchers (device pointers only; enqueue on ctx->stream) --------------------------
-// kalman.cu
+// kalman.cu (stand-alone entry points)
 int32_t btk_kalman_initiate(bt_ctx* ctx, const float* xywh, const int32_t* src_idx, double* mean,
                             double* cov, double* tlbr, float* tlbr_f32, const int32_t* dst_idx, int32_t k,
                             uint8_t* slot_f32 = nullptr);
@@ -154,21 +236,8 @@ int32_t btk_kalman_predict(bt_ctx* ctx, double* mean, double* cov, double* tlbr,
 int32_t btk_kalman_update(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
                           const double* meas, const int32_t* track_idx, const int32_t* meas_idx,
                           const uint8_t* noise_f32, int32_t k);
-// tracker mode: slot g takes the detection x1[g] / x2[g] / x3[g] (first non-negative) as measurement
-int32_t btk_kalman_update_x(bt_ctx* ctx, double* mean, double* cov, double* tlbr, float* tlbr_f32,
-                            const double* meas, const int32_t* x1, const int32_t* x2, const int32_t* x3,
-                            uint8_t* slot_f32, int32_t n_slots, double* res_tlbr = nullptr);
 int32_t btk_kalman_project(bt_ctx* ctx, const double* mean, const double* cov, double* pmean,
                            double* pcov, int32_t n);
-// features.cu: EMA of every slot matched by one of the three stages (x arrays), fp16 bank refresh
-int32_t btk_feature_ema_x(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
-                          const __half* det16, const int32_t* x1, const int32_t* x2, const int32_t* x3,
-                          int32_t n_slots, int32_t d, float alpha);
-// iou.cu: pairs (i < j) of live slots (kind != 0) whose IoU distance is below `limit`
-// pair_count and the first small_cap pairs also land in the frame's result block (one D2H per frame)
-int32_t btk_iou_pairs_live(bt_ctx* ctx, const double* tlbr, const float* tlbr_f32, const uint8_t* kind, int32_t n,
-                           double limit, int32_t* pairs, int32_t* pair_count, int32_t pair_cap,
-                           int32_t* pairs_small = nullptr, int32_t small_cap = 0);
 // iou.cu
 int32_t btk_iou_distance(bt_ctx* ctx, const double* a, int32_t n, const double* b, int32_t m,
                          double* out);
@@ -177,31 +246,68 @@ int32_t btk_fuse_score(bt_ctx* ctx, const double* d, const double* s, int32_t n,
 int32_t btk_iou_pairs_below(bt_ctx* ctx, const double* tlbr, const int32_t* a_idx, int32_t n,
                             const int32_t* b_idx, int32_t m, double limit, int32_t* pairs,
                             int32_t* pair_count, int32_t pair_cap);
-
-// features.cu
-// det_prep: normalise rows, write fp32 normalised copy (optional) + fp16 copy; also boxes -> tlbr/xywh
+// features.cu (stand-alone entry points)
 int32_t btk_feature_prep(bt_ctx* ctx, const float* feat, int32_t m, int32_t d, float* out_f32,
                          __half* out_f16, int32_t normalise, int32_t dependent = 0);
 int32_t btk_feature_ema(bt_ctx* ctx, float* smooth, float* curr, const float* feat,
                         const int32_t* track_idx, const int32_t* feat_idx, const uint8_t* first,
-                        int32_t k, int32_t d, float alpha);
-// same, and also refreshes the fp16 bank row (GEMM A operand): bank16[track_idx[i]] = det16[feat_idx[i]]
-int32_t btk_feature_ema16(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
-                          const __half* det16, const int32_t* track_idx, const int32_t* feat_idx,
-                          const uint8_t* first, int32_t k, int32_t d, float alpha);
+                        int32_t k, int32_t d, float alpha, float one_minus_alpha);
+
+// result-block layout of one batch entry's regions (part A: int32 offsets; part B: int32 offsets + the byte
+// offset of the float64 boxes)
+struct bt_res_layout {
+  size_t o_x, o_sc, o_bx, o_endA, stride;           // part A, regions `stride` bytes apart
+  size_t o_hdr, o_pairs, o_tlbr_bytes, strideB;     // part B, regions `strideB` bytes apart
+};
+// frame_kernels.cu: the per-frame launches of the tracker, all with a leading video-stream dimension
+struct bt_frame_cfg {
+  double high, low;            // score classes (demo:1501, demo:1531)
+  float alpha, one_minus_alpha;
+  double dup_limit;
+  int32_t device_inputs;       // scores / boxes are echoed into the result block
+  int32_t f16_inputs;          // the frame's features came as fp16 (det16 holds them as they are)
+  int32_t keep_smooth;
+  int32_t prefetch_pairs;      // duplicate pairs kept in the result block
+};
+// fp32 ingest: det32 rows -> det16 (raw, round to nearest) + L2 norms
+int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b);
+// detection prep (boxes -> tlbr / xywh / score class / packed corners) + batched Kalman predict of every
+// stream's pool + (optional) detection feature norms: one launch
+int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
+// Kalman update + feature EMA of every slot matched by one of the three stages: one launch
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, int32_t with_feat);
+// duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
+int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
+// births of one stream: Kalman initiate + feature adoption from the frame's detections
+int32_t btk_frame_births(bt_ctx* ctx, const bt_store& st, int32_t sid, int32_t parity, const int32_t* d_slot,
+                         const int32_t* d_det, int32_t n_births, const bt_frame_cfg& fc, int32_t with_feat);
+bt_res_layout bt_res_layout_for(int cap, int md, int prefetch_pairs);
+// gathers of list read-backs
+int32_t btk_gather_rows_f64(bt_ctx* ctx, const double* src, const int32_t* idx, int32_t n, int32_t width, double* dst);
+int32_t btk_gather_rows_f32(bt_ctx* ctx, const float* src, const int32_t* idx, int32_t n, int32_t width, float* dst);
+// curr feature of fp16 stores: dst[i] = float(feat16[idx[i]]) / norm[idx[i]]
+int32_t btk_gather_curr_f16(bt_ctx* ctx, const __half* feat16, const float* norm, const int32_t* idx, int32_t n,
+                            int32_t d, float* dst);
 
 // ---- association (reid_gemm.cu) ----------------------------------------------------------------
 // Row kinds / column kinds of the fused association kernel.
 enum { BT_ROW_NONE = 0, BT_ROW_POOL_TRACKED = 1, BT_ROW_POOL_OTHER = 2, BT_ROW_UNCONFIRMED = 3 };
 enum { BT_COL_NONE = 0, BT_COL_HIGH = 1, BT_COL_LOW = 2 };
+// flag bits in the column field of an emitted candidate edge (and of rowcol):
+//   SIM   the cost comes from the (fp16 tensor-core) similarity: the LAP re-costs it exactly when the row
+//         competes with others (SURVEY hard part 2)
+//   AMBIG the appearance gate is within the tensor-core error of opening / closing: always re-costed
+#define BT_EDGE_SIM 0x40000000
+#define BT_EDGE_AMBIG 0x20000000
+#define BT_EDGE_COLMASK 0x1fffffff
 
-// Candidate lists ("ragged dense" adjacency): list s in {0,1,2} = association stage 1,2,3.
+// Candidate lists ("ragged dense" adjacency) of ONE video stream: list s in {0,1,2} = association stage 1,2,3.
 // Row r owns entries [r*stride, r*stride + cnt[s*rows_cap + r]) of col/cost.
 // A row's region of `stride` entries is cut into segments of `seg` columns: the
 // edges of row r found in columns [g*seg, (g+1)*seg) are written to
 // [r*stride + g*seg, r*stride + g*seg + cnt[list][r][g]).  The tensor-core epilogue owns one
 // (row, segment) pair per thread, so it appends with plain stores and a register counter -- no
-// atomics; the LAP set-up compacts the segments of a row to the front of its region.
+// atomics; the LAP set-up gathers the segments of the rows it has to look at.
 #define BT_CAND_MAXSEG 64   // segments per row (bits of segmask); cnt row pitch
 struct bt_cand {
   int32_t* cnt;    // [3][rows_cap][nseg]
@@ -209,68 +315,120 @@ struct bt_cand {
   unsigned long long* segmask;  // [3][rows_cap] bit g: segment g of the row is non-empty (nseg <= 64)
   int32_t* rowdeg;  // [3][rows_cap] edges emitted for the row      } maintained by the emitters with fire-and-forget
   int32_t* indeg;   // [3][cols_cap] edges emitted into the column  } atomics: the LAP classifies rows without
-  int32_t* rowcol;  // [3][rows_cap] a column of the row (THE column when rowdeg == 1)   touching the edge lists
+  int32_t* rowcol;  // [3][rows_cap] a column of the row (THE column when rowdeg == 1), with flag bits
   int32_t cols_cap;
-  int32_t* deg;    // [3][rows_cap]  row degree after compaction (written by the LAP set-up)
+  int32_t* deg;    // [3][rows_cap]  row degree after compaction (large-problem path of the LAP)
   int32_t* col;    // [3][rows_cap*stride]
   double* cost;    // [3][rows_cap*stride]
   int32_t rows_cap;
   int32_t stride;  // entries per row >= max_dets + one segment of slack
   int32_t nseg;    // = BT_CAND_MAXSEG (row pitch of cnt)
   int32_t seg;     // columns per segment THIS frame: half the association tile width (128 or 112), 128 otherwise
-  size_t clear_bytes;  // cnt, total and segmask live in one allocation: one memset of this many bytes at cnt
+  size_t clear_bytes;  // cnt, total, segmask, rowdeg, indeg live in one allocation: one memset of this many bytes at cnt
+  // element strides from one video stream's lists to the next (0: single set)
+  size_t s_cnt, s_rowcol, s_deg, s_edges;
 };
+// the lists of video stream `sid` (all streams' lists are slices of the same allocations)
+static __host__ __device__ __forceinline__ bt_cand bt_cand_of(const bt_cand& base, int sid) {
+  bt_cand c = base;
+  char* p = reinterpret_cast<char*>(base.cnt) + (size_t)sid * base.s_cnt;
+  c.cnt = reinterpret_cast<int32_t*>(p);
+  c.total = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(base.total) + (size_t)sid * base.s_cnt);
+  c.segmask = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base.segmask) + (size_t)sid * base.s_cnt);
+  c.rowdeg = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(base.rowdeg) + (size_t)sid * base.s_cnt);
+  c.indeg = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(base.indeg) + (size_t)sid * base.s_cnt);
+  c.rowcol = base.rowcol + (size_t)sid * base.s_rowcol;
+  c.deg = base.deg + (size_t)sid * base.s_deg;
+  c.col = base.col + (size_t)sid * base.s_edges;
+  c.cost = base.cost + (size_t)sid * base.s_edges;
+  return c;
+}
 
 struct bt_assoc_params {
-  // operands
-  const __half* a16;   // [n, d] track-side features (bank rows = slots)
-  const __half* b16;   // [m, d] detection features
-  const float* a32;    // fp32 variants for the SIMT kernel (may be null when tensor path is used)
+  // operands (row-major, K contiguous).  Tensor-core path: fp16; CUDA-core path: a32/b32 (fp32) or a16/b16
+  const __half* a16;   // [a_rows_alloc, d] track-side features (bank rows = global slots)
+  const __half* b16;   // [b_rows_alloc, d] detection features
+  const float* a32;
   const float* b32;
-  int32_t n, m, d;
+  int32_t d;
   int32_t bn;                          // association tile width (256 or 224); 0 = 256.  Candidate emission
                                        // requires cand.seg == bn / 2 (btk_assoc_pick_bn)
-  int32_t a_rows_alloc, b_rows_alloc;  // rows the operand buffers really hold (0 = n / m): lets the TMA
-                                       // descriptors be cached across frames; rows >= n / m are masked
-  // epilogue inputs (null => not used)
-  const double* row_tlbr;   // [n,4]
-  const float* row_tlbr_f32;// [n,4] conservative fp32 interval (lo down, hi up)
-  const uint8_t* row_kind;  // [n]
-  const double* col_tlbr;   // [m,4]
-  const uint8_t* col_kind;  // [m]
-  const uint2* col_pk;      // [m] packed 15-bit integer corners (bt_pack16_*), or null: packed in the kernel
-  const float* face_sim;    // [n,m] or null
+  int32_t a_rows_alloc, b_rows_alloc;  // rows the operand buffers really hold: lets the TMA descriptors be
+                                       // cached across frames; rows past a stream's n / m are masked
+  int32_t operands_early;              // the operands were complete before the previous kernel of the stream
+                                       // started: the TMA / MMA warps need not wait for it (PDL)
+  // the batch: problem k has n[k] rows starting at operand row a_row0[k] and m[k] columns at b_row0[k]
+  int32_t count;
+  int32_t n[BT_MAX_BATCH], m[BT_MAX_BATCH];
+  int32_t a_row0[BT_MAX_BATCH], b_row0[BT_MAX_BATCH];
+  int32_t row0[BT_MAX_BATCH], col0[BT_MAX_BATCH];   // first entry of the problem in the row / column side arrays
+  int32_t kind_off[BT_MAX_BATCH];                   // byte offset of the problem's row_kind array in row_kind_base
+  int32_t cand_sid[BT_MAX_BATCH];                   // which slice of `cand`
+  const float* face_sim[BT_MAX_BATCH];              // [n_pool, m] or null
+  int32_t pos_off[BT_MAX_BATCH];                    // byte offset of pool_pos (row -> face_sim row) in row_kind_base
+  // epilogue inputs (null => not used), indexed by row0[k] + r / col0[k] + c
+  const double* row_tlbr;   // [.,4]
+  const float* row_tlbr_f32;// [.,4] conservative fp32 interval (lo down, hi up)
+  const float* row_norm;    // [.] sim = acc / row_norm (null: 1)
+  const char* row_kind_base;
+  const double* col_tlbr;   // [.,4]
+  const uint8_t* col_kind;  // [.]
+  const uint2* col_pk;      // [.] packed 15-bit integer corners (bt_pack16_*), or null: packed in the kernel
+  const float* col_norm;    // [.] detection feature norms: unconfirmed rows use sim / col_norm (demo:1593-1599); null: 1
   // thresholds
   double match_thresh, second_thresh, unconf_thresh, proximity;
   float appearance;
+  float gate_band;          // half-width of the ambiguous band around the appearance gate (similarity units)
   // outputs
   bt_cand cand;             // candidate emission (cnt==null => off)
-  float* out_emb;           // [n,m] 1-max(0,sim)   (dense dump, null => off)
-  double* out_dists;        // [n,m] fused cost      (dense dump, null => off)
+  float* out_emb;           // [n,m] 1-max(0,sim)   (dense dump of problem 0, null => off)
+  double* out_dists;        // [n,m] fused cost      (dense dump of problem 0, null => off)
   int32_t dense_stage;      // 1 or 3: which fusion rule the dense dump uses
 };
 int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& p, int32_t precision);
-// tile width that minimises (waves x MMA time per tile) for an n x m problem on this GPU
-int32_t btk_assoc_pick_bn(const bt_ctx* ctx, int32_t n, int32_t m);
+// tile width that minimises (waves x MMA time per tile) for a batch of n[k] x m[k] problems on this GPU
+int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m, int32_t count);
 int32_t bt_gemm_ws_create(bt_ctx* ctx);
 void bt_gemm_ws_destroy(bt_ctx* ctx);
 
 // ---- LAP (lap.cu) -------------------------------------------------------------------------------
 int32_t bt_lap_ws_create(bt_ctx* ctx);
 void bt_lap_ws_destroy(bt_ctx* ctx);
-// dense cost -> candidate list `list` of ctx->lap's own bt_cand
+// dense cost -> candidate list `list` of ctx->lap's own bt_cand (video stream 0's slice)
 int32_t btk_lap_compact_dense(bt_ctx* ctx, const double* cost, int32_t n, int32_t m, double thresh,
                               const bt_cand& cand, int32_t list);
-// Solve list `list`: rows [0,n), cols [0,m).  row_block/col_block: optional int32 arrays, an edge
-// is valid only if row_block[r] < 0 and col_block[c] < 0 (results of an earlier stage).
-// x[n], y[m] outputs (device).
+// Solve list `list`: rows [0,n), cols [0,m).  x[n], y[m] outputs (device).
 int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n, int32_t m,
-                      double thresh, const int32_t* row_block, const int32_t* col_block, int32_t* x,
-                      int32_t* y);
+                      double thresh, int32_t* x, int32_t* y);
 const bt_cand* bt_lap_own_cand(bt_ctx* ctx);
-// the three chained association stages of a frame in ONE launch (lists 0,1,2)
-int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, int32_t n, int32_t m, const double thresh[3],
-                       int32_t* const x[3], int32_t* const y[3], int32_t* zero_word = nullptr);
+// Exact re-costing of flagged edges inside the LAP (SURVEY hard part 2): what it needs to evaluate a
+// (row, column) pair from scratch in fp32 / fp64.
+struct bt_refine {
+  int32_t enabled, d, f16;                 // f16: features are the raw fp16 rows + norms; else fp32 rows
+  const __half* a16; const float* a_norm;  // per global slot
+  const float* a32;                        // per global slot (normalised fp32 current feature)
+  const __half* b16; const float* b32;     // per global detection of the frame's parity
+  const float* b_norm;                     // per global detection (stage 3 only)
+  const double* row_tlbr; const double* col_tlbr;
+  const char* ctrl;                        // control block (pool_pos for the face term)
+  double proximity; float appearance;
+};
+// the three chained association stages of a frame, one CTA per video stream, ONE launch (lists 0,1,2)
+struct bt_lap_batch {
+  int32_t count;
+  int32_t sid[BT_MAX_BATCH], n[BT_MAX_BATCH], m[BT_MAX_BATCH];
+  int32_t row0[BT_MAX_BATCH], col0[BT_MAX_BATCH];       // global slot / detection of row 0 / column 0
+  int32_t in0[BT_MAX_BATCH];                            // row of column 0 in the (double-buffered) detection feature buffers
+  int32_t pos_off[BT_MAX_BATCH];
+  const float* face_sim[BT_MAX_BATCH];
+  int32_t* x[BT_MAX_BATCH];         // x1,x2,x3 [n_x_stride each]
+  int32_t x_stride[BT_MAX_BATCH];
+  int32_t* y[BT_MAX_BATCH];         // y1,y2,y3 [y_stride each]
+  int32_t y_stride;
+  int32_t* zero_word[BT_MAX_BATCH]; // device word to clear (the frame's duplicate-pair counter)
+};
+int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& b, const double thresh[3],
+                       const bt_refine& rf);
 
 // ---- detector side ------------------------------------------------------------------------------
 int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_config& cfg,

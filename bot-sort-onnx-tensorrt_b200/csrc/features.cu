@@ -1,8 +1,7 @@
-// ReID feature kernels: per-detection normalisation + fp16 staging for the tensor-core
-// similarity GEMM, and the batched feature EMA of STrack.update_body_features
-// (demo:492-502; demo = /root/reference/demo_bottrack_onnx_tflite.py).
-// One CTA per feature row (2048 floats = 8 KB: 256 threads x 2 float4), block reduction for
-// the L2 norm; HBM-bound: prep 4d in + (4d + 2d) out per detection, EMA 3*4*d B per match.
+// Stand-alone ReID feature kernels behind bt_embedding_distance / bt_fused_cost (fp32 -> fp16 operand
+// staging, optional row normalisation) and bt_feature_ema (STrack.update_body_features, demo:492-502;
+// demo = /root/reference/demo_bottrack_onnx_tflite.py).  One CTA per feature row.  The tracker's own
+// per-frame feature work is fused into frame_kernels.cu.
 #include "common.cuh"
 
 namespace {
@@ -86,71 +85,17 @@ feature_prep_kernel(const float* __restrict__ feat, int d, float* __restrict__ o
 }
 
 // mode (first[i]): 0 = EMA (demo:499-502), 1 = first call on a raw feature: smooth = feat/||feat||,
-// 2 = adopt an already-normalised detection feature (birth: smooth = curr = feat).
-// Optionally also refreshes the fp16 bank row used as the GEMM A operand.
+// 2 = adopt an already-normalised feature (smooth = curr = feat).  Stand-alone entry point
+// (bt_feature_ema); the tracker's own EMA runs inside frame_post_kernel (frame_kernels.cu).
 __global__ void __launch_bounds__(kThreads)
 feature_ema_kernel(float* __restrict__ smooth, float* __restrict__ curr, const float* __restrict__ feat,
-                   __half* __restrict__ bank16, const __half* __restrict__ det16,
                    const int32_t* __restrict__ track_idx, const int32_t* __restrict__ feat_idx,
-                   const uint8_t* __restrict__ first, int d, float alpha, const int32_t* __restrict__ x1,
-                   const int32_t* __restrict__ x2, const int32_t* __restrict__ x3) {
+                   const uint8_t* __restrict__ first, int d, float alpha, float one_minus) {
   __shared__ float red[kThreads / 32];
   const int i = blockIdx.x;
-  size_t t = track_idx ? track_idx[i] : i;
-  size_t f = feat_idx ? feat_idx[i] : i;
-  if (x1) {   // tracker mode: slot i, detection assigned by one of the three stages (block-uniform exit)
-    int z = x1[i];
-    if (z < 0) z = x2[i];
-    if (z < 0) z = x3[i];
-    if (z < 0) return;
-    t = i;
-    f = z;
-  }
+  const size_t t = track_idx ? track_idx[i] : i;
+  const size_t f = feat_idx ? feat_idx[i] : i;
   const int mode = first ? first[i] : 0;
-  if (bank16 && det16) {
-    if ((d & 3) == 0) {
-      const uint2* s = reinterpret_cast<const uint2*>(det16 + f * d);
-      uint2* o = reinterpret_cast<uint2*>(bank16 + t * d);
-      for (int j = threadIdx.x; j < d / 4; j += kThreads) o[j] = s[j];
-    } else {
-      for (int j = threadIdx.x; j < d; j += kThreads) bank16[t * d + j] = det16[f * d + j];
-    }
-  }
-  if (!smooth && !curr) return;
-  const float one_minus = (float)(1.0 - (double)alpha);
-  constexpr int kHold = 4;               // float4 per thread kept in registers: rows up to 4096 floats are read once
-  if ((d & 3) == 0 && d <= kThreads * 4 * kHold) {
-    float4 xv[kHold], sv[kHold];
-#pragma unroll
-    for (int k = 0; k < kHold; ++k) {
-      const int j = (threadIdx.x + k * kThreads) * 4;
-      xv[k] = (j < d) ? __ldg(reinterpret_cast<const float4*>(feat + f * d + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      sv[k] = xv[k];
-      if (mode == 0 && j < d) {
-        const float4 o = *reinterpret_cast<const float4*>(smooth + t * d + j);
-        sv[k].x = __fadd_rn(__fmul_rn(alpha, o.x), __fmul_rn(one_minus, xv[k].x));
-        sv[k].y = __fadd_rn(__fmul_rn(alpha, o.y), __fmul_rn(one_minus, xv[k].y));
-        sv[k].z = __fadd_rn(__fmul_rn(alpha, o.z), __fmul_rn(one_minus, xv[k].z));
-        sv[k].w = __fadd_rn(__fmul_rn(alpha, o.w), __fmul_rn(one_minus, xv[k].w));
-      }
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < kHold; ++k) ss += sv[k].x * sv[k].x + sv[k].y * sv[k].y + sv[k].z * sv[k].z + sv[k].w * sv[k].w;
-    float norm = 1.f;
-    if (mode != 2) norm = sqrtf(block_sum(ss, red));
-#pragma unroll
-    for (int k = 0; k < kHold; ++k) {
-      const int j = (threadIdx.x + k * kThreads) * 4;
-      if (j >= d) continue;
-      float4 o = sv[k];
-      if (mode != 2) { o.x /= norm; o.y /= norm; o.z /= norm; o.w /= norm; }
-      if (smooth) *reinterpret_cast<float4*>(smooth + t * d + j) = o;
-      if (curr) *reinterpret_cast<float4*>(curr + t * d + j) = (mode == 1) ? o : xv[k];
-    }
-    return;
-  }
-  // generic sizes: two passes, the new smooth is recomputed in the second
   float ss = 0.f;
   for (int j = threadIdx.x; j < d; j += kThreads) {
     const float x = feat[f * d + j];
@@ -182,28 +127,12 @@ int32_t btk_feature_prep(bt_ctx* ctx, const float* feat, int32_t m, int32_t d, f
   return BT_OK;
 }
 
-int32_t btk_feature_ema16(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
-                          const __half* det16, const int32_t* track_idx, const int32_t* feat_idx,
-                          const uint8_t* first, int32_t k, int32_t d, float alpha) {
-  if (k <= 0) return BT_OK;
-  feature_ema_kernel<<<k, kThreads, 0, ctx->stream>>>(smooth, curr, feat, bank16, det16, track_idx,
-                                                      feat_idx, first, d, alpha, nullptr, nullptr, nullptr);
-  BT_LAUNCHED(ctx);
-  return BT_OK;
-}
-
-int32_t btk_feature_ema_x(bt_ctx* ctx, float* smooth, float* curr, const float* feat, __half* bank16,
-                          const __half* det16, const int32_t* x1, const int32_t* x2, const int32_t* x3,
-                          int32_t n_slots, int32_t d, float alpha) {
-  if (n_slots <= 0) return BT_OK;
-  feature_ema_kernel<<<n_slots, kThreads, 0, ctx->stream>>>(smooth, curr, feat, bank16, det16, nullptr, nullptr,
-                                                            nullptr, d, alpha, x1, x2, x3);
-  BT_LAUNCHED(ctx);
-  return BT_OK;
-}
-
 int32_t btk_feature_ema(bt_ctx* ctx, float* smooth, float* curr, const float* feat,
                         const int32_t* track_idx, const int32_t* feat_idx, const uint8_t* first,
-                        int32_t k, int32_t d, float alpha) {
-  return btk_feature_ema16(ctx, smooth, curr, feat, nullptr, nullptr, track_idx, feat_idx, first, k, d, alpha);
+                        int32_t k, int32_t d, float alpha, float one_minus_alpha) {
+  if (k <= 0) return BT_OK;
+  feature_ema_kernel<<<k, kThreads, 0, ctx->stream>>>(smooth, curr, feat, track_idx, feat_idx, first, d, alpha,
+                                                      one_minus_alpha);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
 }

@@ -117,68 +117,7 @@ iou_pairs_below_kernel(const double* __restrict__ tlbr, const int32_t* __restric
   }
 }
 
-// All pairs i < j of live slots closer than `limit` (IoU distance).  remove_duplicate_stracks
-// (demo:1665-1680) only looks at tracked x lost pairs; both lists are subsets of the live slots, so the
-// host filters this (tiny) superset by list membership without a second round trip.
-__global__ void __launch_bounds__(256)
-iou_pairs_live_kernel(const double* __restrict__ tlbr, const float* __restrict__ tlbr_f32,
-                      const uint8_t* __restrict__ kind, int n, double limit, int32_t* __restrict__ pairs,
-                      int32_t* __restrict__ pair_count, int pair_cap, int32_t* __restrict__ pairs_small,
-                      int small_cap) {
-  // grid (j tile of 64, i tile of 256), only tiles that can hold a pair j > i; a thread owns slot i and
-  // scans the 64 slots of the j tile (hundreds of small blocks: the shared-memory broadcasts of the
-  // j boxes are the cost, spread them over all SMs)
-  constexpr int JT = 64;
-  bt_grid_dependency_wait();   // programmatic dependent of the Kalman update that writes the boxes
-  if ((int)(blockIdx.x + 1) * JT <= (int)blockIdx.y * 256) return;
-  __shared__ float4 sb[JT];
-  __shared__ uint8_t sk[JT];
-  const int i = blockIdx.y * 256 + threadIdx.x;
-  const int j0 = blockIdx.x * JT;
-  const bool live_i = i < n && kind[i] != 0;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (live_i) a = *reinterpret_cast<const float4*>(tlbr_f32 + (size_t)i * 4);
-  const float area_a = (a.z - a.x) * (a.w - a.y);
-  const int jj = j0 + threadIdx.x;
-  if (threadIdx.x < JT) {
-    sk[threadIdx.x] = (jj < n) ? kind[jj] : 0;
-    sb[threadIdx.x] = (jj < n) ? *reinterpret_cast<const float4*>(tlbr_f32 + (size_t)jj * 4) : a;
-  }
-  __syncthreads();
-  if (!live_i) return;
-  const int lim = min(JT, n - j0);
-#pragma unroll 4
-  for (int k = 0; k < lim; ++k) {
-    const int j = j0 + k;
-    const float4 b = sb[k];
-    // fp32 screen on the outward-rounded boxes: a pair this far from IoU 0.5 cannot reach 1 - limit
-    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x), ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
-    const float inter = iw * ih;
-    const float area_b = (b.z - b.x) * (b.w - b.y);
-    if (iw <= 0.f || ih <= 0.f || j <= i || sk[k] == 0 || inter < 0.5f * fmaxf(area_a, area_b)) continue;
-    const double* pa = tlbr + (size_t)i * 4;
-    const double* pb = tlbr + (size_t)j * 4;
-    const Box A{pa[0], pa[1], pa[2], pa[3]}, B{pb[0], pb[1], pb[2], pb[3]};
-    if (1.0 - iou_of(A, B) < limit) {
-      const int slot = atomicAdd(pair_count, 1);
-      if (slot < pair_cap) { pairs[2 * slot] = i; pairs[2 * slot + 1] = j; }
-      if (slot < small_cap) { pairs_small[2 * slot] = i; pairs_small[2 * slot + 1] = j; }
-    }
-  }
-}
-
 }  // namespace
-
-int32_t btk_iou_pairs_live(bt_ctx* ctx, const double* tlbr, const float* tlbr_f32, const uint8_t* kind, int32_t n,
-                           double limit, int32_t* pairs, int32_t* pair_count, int32_t pair_cap,
-                           int32_t* pairs_small, int32_t small_cap) {
-  if (n <= 1) return BT_OK;
-  const int tiles = (n + 255) / 256;
-  BT_CUDA(bt_launch(ctx, true, iou_pairs_live_kernel, dim3((n + 63) / 64, tiles), dim3(256), 0, tlbr, tlbr_f32, kind, n,
-                    limit, pairs, pair_count, pair_cap, pairs_small, small_cap));
-  BT_LAUNCHED(ctx);
-  return BT_OK;
-}
 
 int32_t btk_iou_distance(bt_ctx* ctx, const double* a, int32_t n, const double* b, int32_t m,
                          double* out) {

@@ -8,42 +8,43 @@
 // thresh/2 and solved exactly, which is the same as minimising  sum_matched (c_ij - thresh):
 // a max-weight (not perfect) bipartite matching over the edges with c_ij < thresh.  Instead of
 // the dense 4000 x 4000 float64 matrix of the reference (128 MB at 2000 x 2000) this solver
-// works on the *candidate edge lists* the association epilogue emits:
-// ONE kernel launch (`lap_cluster_kernel`) solves up to three chained association stages.  It runs
-// as a single thread-block cluster (up to 8 CTAs x 1024 threads) so that the phases below can be
-// separated by hardware cluster barriers instead of kernel boundaries:
-//   P1  per row: compact the (row, column-segment) sub-lists, count valid edges, column in-degrees
-//   P2  isolated edges (row degree 1, column in-degree 1) are matched on the spot -- the bulk of a
-//       tracking scene; the remaining "complex" rows are collected
-//   P3  connected components of the complex part: min-label propagation + pointer jumping
-//   P4  component row lists / scratch slices by block scans (CTA 0)
-//   P5  one warp per component: exact shortest-augmenting-path assignment (Jonker-Volgenant /
-//       Crouse formulation, float64 duals) where every row owns a private zero-cost dummy column
-//       ("stay unmatched"); lanes parallelise the edge relaxations and the minimum scans.
-// Stage 2 is masked by stage 1's matched rows and stage 3 by stage 1's matched columns, so the
-// three solves of a frame chain inside the launch.  A single giant component (dense adversarial
-// cost matrix) is still solved exactly, just slower.
+// works on the *candidate edge lists* the association epilogue emits.
+// ONE launch (`lap_stream_kernel`), ONE CTA of 1024 threads per video stream, solves the frame's three
+// chained association stages (stage 2 masked by stage 1's matched rows, stage 3 by stage 1's matched
+// columns); phases are separated by block barriers:
+//   P1  every row is classified from the emitters' degree bookkeeping: isolated edges (row degree 1,
+//       column in-degree 1) are matched on the spot -- the bulk of a tracking scene
+//   S2  the remaining "complex" rows' edges are gathered into shared memory (warp per row)
+//   S3  edges whose cost carries the tensor-core similarity are re-costed exactly (fp32 operands,
+//       float64 accumulation; SURVEY hard part 2) -- so a near-tie between two tracks is decided by the
+//       same numbers the reference sees, not by fp16 rounding
+//   S4+ exact shortest-augmenting-path assignment (Jonker-Volgenant / Crouse formulation, float64 duals,
+//       a private zero-cost dummy column per row = "stay unmatched"): a handful of rows by one warp, more
+//       by labelling connected components (min-label propagation + pointer jumping) and solving them in
+//       parallel (enumeration for <= 3 rows, one thread for <= 6, one warp above).
+// Complex parts that do not fit on chip (> 512 rows, > 4096 edges, > 2560 detections: a crowded scene, a
+// dense adversarial matrix) take the same algorithm over global scratch: slower, still exact.
 // Ties between equal-cost optima are broken by lowest index, lap's own tie-breaking is not
 // reproducible without its sources: "bit-exact" is defined on inputs with a unique optimum.
 #include "common.cuh"
 
 #include <float.h>
 #include <stdlib.h>
+#include <mutex>
 
 struct bt_lap_ws {
-  bt_cand cand;            // ctx-wide candidate lists (3 lists)
+  bt_cand cand;            // ctx-wide candidate lists (3 lists per video stream)
+  // scratch of the large-problem path, one slice per video stream (rows_stride / cols_stride entries apart)
   int32_t* label = nullptr;     // [rows]
   int32_t* collabel = nullptr;  // [cols]
-  int32_t* nvalid = nullptr;    // [rows]  valid out-degree
-  int32_t* onlycol = nullptr;   // [rows]  a valid column of the row (the only one when nvalid == 1)
   int32_t* clist = nullptr;     // [rows]  complex rows
   int32_t* compidx = nullptr;   // [rows]  component index of a root row (indexed by row)
   int32_t* isroot = nullptr;    // [rows]  scan scratch (indexed by clist position)
   int32_t* rowcnt = nullptr;    // [rows+1] per component -> exclusive scan = row_start
   int32_t* colcnt = nullptr;    // [rows+1] per component -> exclusive scan = col_start
-  int32_t* fill = nullptr;      // [rows]
+  int32_t* fill = nullptr;      // [rows+1]
   int32_t* sorted_rows = nullptr;  // [rows]
-  int32_t* counters = nullptr;     // [8]: 0 ncomplex, 1 ncomp, 2/3 changed flags
+  int32_t* counters = nullptr;     // [8]: 1 ncomp, 2/3 changed flags
   double* u = nullptr;             // [rows]
   double* v = nullptr;             // [cols]
   double* dist = nullptr;          // [cols]
@@ -55,38 +56,24 @@ struct bt_lap_ws {
   int32_t* x = nullptr;            // [rows] own outputs for the dense API
   int32_t* y = nullptr;            // [cols]
   int rows = 0, cols = 0;
+  int rows_stride = 0, cols_stride = 0;
 };
 
 namespace {
 
 constexpr int kLapThreads = 1024;
-constexpr int kLapMaxCtas = 8;
 constexpr int kInf = 0x7fffffff;
 
-struct LapStage {
-  int list;
-  double thresh;
-  const int32_t* row_block;  // edge valid only if row_block[r] < 0 (nullptr: all rows)
-  const int32_t* col_block;  // edge valid only if col_block[c] < 0
-  int32_t* x;
-  int32_t* y;
-};
 struct LapParams {
-  LapStage st[3];
-  int nstages;
-  int n, m;
-  int clear_lists;      // tracker mode: leave cnt / segmask / total zeroed for the next frame
-  int32_t* zero_word;   // optional device word to clear (the frame's duplicate-pair counter)
-  int debug;   // BT_LAP_DEBUG=1: phase timestamps (ns) by device printf
+  int nstages;          // 1 (stand-alone: list `list0`) or 3 (the frame's chained stages: lists 0, 1, 2)
+  int list0;
+  double thresh[3];
+  int clear_lists;      // tracker mode: leave cnt / segmask / rowdeg / indeg / total zeroed for the next frame
+  int debug;            // BT_LAP_DEBUG=1: phase timestamps (ns) by device printf
 };
 
 __device__ __forceinline__ bool edge_ok(const int32_t* __restrict__ col_block, int c) {
   return col_block == nullptr || col_block[c] < 0;
-}
-
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // exclusive scan of data[0..n) in place by ONE CTA, returns total
@@ -176,7 +163,9 @@ __device__ void solve_component(const SolveArrays& ws, int comp, double thresh,
         MinPair oth{__shfl_xor_sync(0xffffffffu, best.d, o), __shfl_xor_sync(0xffffffffu, best.c, o), 0};
         if (better(oth, best)) best = oth;
       }
-      if (lane == 0 && best.c != kInf) { x[r] = best.c; y[best.c] = r; }
+      // (an edge that does not beat "stay unmatched" -- a column blocked by an earlier stage, a re-costed
+      //  edge that turned out too expensive -- is no match)
+      if (lane == 0 && best.c != kInf && best.d < thresh) { x[r] = best.c; y[best.c] = r; }
       return;
     }
 
@@ -422,378 +411,455 @@ __device__ void solve_component_enum(const SolveArrays& ws, int comp, double thr
     }
 }
 
-// ---- on-chip path for the usual case: a handful of complex rows -------------------------------
-// CTA 0 pulls the complex rows' valid edges into shared memory (CSR, local row ids; a column's
-// local id is the smallest local edge index that touches it), labels components, groups them and
-// lets its 32 warps solve them -- all with shared-memory latencies instead of L2 round trips.
+// ---- exact re-costing of flagged edges (SURVEY hard part 2) ----------------------------------------------
+// One warp evaluates one (row, column) pair from scratch: exact float64 IoU distance, the similarity as the
+// reference sees it (fp32 values, accumulated in float64: within one ulp of the true dot product, where
+// the reference's sgemm is within a few), the face term, and the stage's fusion rule.  The tensor-core
+// similarity decided WHICH pairs exist; this decides what they cost whenever the cost can matter.
+__device__ double refine_cost(const bt_refine& rf, const bt_lap_batch& B, int k, int list, int row, int col, int lane) {
+  const size_t gs = (size_t)B.row0[k] + row, gd = (size_t)B.col0[k] + col, gi = (size_t)B.in0[k] + col;
+  const int D = rf.d;
+  double acc = 0.0;
+  if (rf.f16) {
+    const __half* a = rf.a16 + gs * D;
+    const __half* b = rf.b16 + gi * D;
+    if ((D & 7) == 0) {
+      for (int i = lane * 8; i < D; i += 256) {
+        const uint4 qa = *reinterpret_cast<const uint4*>(a + i), qb = *reinterpret_cast<const uint4*>(b + i);
+        const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+        const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+          acc += (double)(fa.x * fb.x) + (double)(fa.y * fb.y);     // fp16 x fp16 is exact in fp32
+        }
+      }
+    } else {
+      for (int i = lane; i < D; i += 32) acc += (double)(__half2float(a[i]) * __half2float(b[i]));
+    }
+  } else {
+    const float* a = rf.a32 + gs * D;
+    const float* b = rf.b32 + gi * D;
+    if ((D & 3) == 0) {
+      for (int i = lane * 4; i < D; i += 128) {
+        const float4 fa = *reinterpret_cast<const float4*>(a + i), fb = *reinterpret_cast<const float4*>(b + i);
+        acc += (double)fa.x * fb.x + (double)fa.y * fb.y + (double)fa.z * fb.z + (double)fa.w * fb.w;
+      }
+    } else {
+      for (int i = lane; i < D; i += 32) acc += (double)a[i] * b[i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  float sim;
+  if (rf.f16) {
+    const float na = rf.a_norm[gs];
+    sim = na > 0.f ? (float)(acc / (double)na) : 0.f;
+  } else {
+    sim = (float)acc;
+  }
+  if (list == 2 && rf.b_norm) {      // stage 3 compares the NORMALISED detection feature (demo:1593-1599)
+    const float nb = rf.b_norm[gd];
+    sim = nb > 0.f ? sim / nb : 0.f;
+  }
+  const double iou_d = bt_iou_dist_f64(rf.row_tlbr + gs * 4, rf.col_tlbr + gd * 4);
+  if (list == 2) return bt_fuse_stage3(iou_d, sim, rf.appearance, rf.proximity);
+  float face = 0.f;
+  if (B.face_sim[k]) {
+    const int pr = reinterpret_cast<const int32_t*>(rf.ctrl + B.pos_off[k])[row];
+    if (pr >= 0) face = B.face_sim[k][(size_t)pr * B.m[k] + col];
+  }
+  return bt_fuse_stage1(iou_d, sim, face, rf.appearance);
+}
+
+// ---- on-chip path for the usual case: up to a few hundred complex rows -----------------------------------
+// The CTA pulls the complex rows' edges into shared memory (CSR, local row ids in ascending row order,
+// GLOBAL column ids: the per-column solver state of up to kSmallCols detections lives in shared memory
+// too), re-costs the flagged ones, and solves: a handful of rows by one warp directly, more by labelling
+// connected components and solving them in parallel.
 constexpr int kSmallRows = 512;
-constexpr int kSmallEdges = 2048;
+constexpr int kSmallEdges = 4096;
+constexpr int kSmallCols = 2560;
+constexpr int kOneWarpRows = 16;
+constexpr double kBlockedCost = 1.0e300;   // an edge whose column an earlier stage took: never beats staying unmatched
 
 struct SmallSmem {
   int32_t rg[kSmallRows], rdeg[kSmallRows], rstart[kSmallRows + 1], rlabel[kSmallRows], xl[kSmallRows];
   int32_t sorted_rows[kSmallRows], treerows[kSmallRows], compidx[kSmallRows], isroot[kSmallRows];
   int32_t rowcnt[kSmallRows + 1], colcnt[kSmallRows + 1], fill[kSmallRows + 1];
+  unsigned long long rmask[kSmallRows];
   double u[kSmallRows];
-  int32_t lcl[kSmallEdges];
+  int32_t ecol[kSmallEdges];
   double ecst[kSmallEdges];
-  int32_t cglob[kSmallEdges], clabel[kSmallEdges], pathrow[kSmallEdges], seen[kSmallEdges], insc[kSmallEdges];
-  int32_t yl[kSmallEdges], touched[kSmallEdges];
-  double v[kSmallEdges], dist[kSmallEdges];
-  int changed;
-  int scan_total;
+  int32_t rlist[kSmallEdges];
+  double v[kSmallCols], dist[kSmallCols];
+  int32_t pathrow[kSmallCols], seen[kSmallCols], insc[kSmallCols], yl[kSmallCols], clabel[kSmallCols], touched[kSmallCols];
+  int32_t s_warp[32];
+  int32_t s_carry;
+  int nC, nE, nR, changed, big;
 };
 
-constexpr int kSmallThreads = 128;   // the on-chip path runs on the first four warps of CTA 0
-#define SMALL_SYNC() asm volatile("bar.sync 2, 128;" ::: "memory")
-
-// exclusive scan of a (shared-memory) array of up to a few thousand ints by warp 0; all kSmallThreads call it
-__device__ int small_scan(int32_t* data, int n, int* total_slot) {
-  SMALL_SYNC();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int carry = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const int val = (i < n) ? data[i] : 0;
-      int incl = val;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (i < n) data[i] = carry + incl - val;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) *total_slot = carry;
-  }
-  SMALL_SYNC();
-  return *total_slot;
-}
-
-__device__ void small_complex_solve(const bt_cand& cand, const bt_lap_ws& W, const LapStage& S, int nC,
-                                    const int32_t* cnt, const int32_t* ecol, const double* ecost,
-                                    int32_t* x, int32_t* y, SmallSmem& sm, int debug) {
-  unsigned long long ts[8] = {0,0,0,0,0,0,0,0};
-#define ST(i) do { if (debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])); } while (0)
-  ST(0);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // S1: valid degree per complex row -> CSR offsets
-  for (int i = tid; i < nC; i += kSmallThreads) {
-    const int r = W.clist[i];
-    sm.rg[i] = r;
-    const int deg = cnt[r];
-    const int32_t* e = ecol + (size_t)r * cand.stride;
-    int v = 0;
-    for (int k = 0; k < deg; ++k) v += edge_ok(S.col_block, e[k]) ? 1 : 0;
-    sm.rdeg[i] = v;
-    sm.rstart[i] = v;
-    sm.rlabel[i] = i;
-    sm.xl[i] = -1;
-    sm.u[i] = 0.0;
-  }
-  if (tid == 0) sm.rstart[nC] = 0;
-  SMALL_SYNC();
-  const int E = small_scan(sm.rstart, nC + 1, &sm.scan_total);
-  ST(1);
-  // S2: edges; column representative = smallest local edge index touching the column
-  for (int i = tid; i < nC; i += kSmallThreads) {
-    const int r = sm.rg[i];
-    const int deg = cnt[r];
-    const int32_t* e = ecol + (size_t)r * cand.stride;
-    const double* w = ecost + (size_t)r * cand.stride;
-    int pos = sm.rstart[i];
-    for (int k = 0; k < deg; ++k) {
-      const int c = e[k];
-      if (!edge_ok(S.col_block, c)) continue;
-      sm.lcl[pos] = c;               // global column for now
-      sm.ecst[pos] = w[k];
-      atomicMin(&W.collabel[c], pos);
-      ++pos;
-    }
-  }
-  SMALL_SYNC();
-  for (int e = tid; e < E; e += kSmallThreads) {
-    const int c = sm.lcl[e];
-    const int rep = __ldcg(&W.collabel[c]);
-    sm.lcl[e] = rep;
-    if (rep == e) sm.cglob[e] = c;
-    sm.clabel[e] = kInf;
-    sm.v[e] = 0.0;
-    sm.seen[e] = 0;
-    sm.insc[e] = 0;
-    sm.yl[e] = -1;
-  }
-  SMALL_SYNC();
-  ST(2);
-  // S4: components by min-label propagation + pointer jumping (shared memory)
-  while (true) {
-    if (tid == 0) sm.changed = 0;
-    SMALL_SYNC();
-    bool changed = false;
-    for (int i = tid; i < nC; i += kSmallThreads) {
-      int lr = sm.rlabel[i];
-      const int l0 = lr;
-      for (int k = sm.rstart[i]; k < sm.rstart[i] + sm.rdeg[i]; ++k) {
-        const int c = sm.lcl[k];
-        const int lc = sm.clabel[c];
-        if (lc < lr) lr = lc;
-        else if (lc > lr) { atomicMin(&sm.clabel[c], lr); changed = true; }
-      }
-      if (lr < l0) { atomicMin(&sm.rlabel[i], lr); changed = true; }
-    }
-    SMALL_SYNC();
-    for (int i = tid; i < nC; i += kSmallThreads) {
-      const int l = sm.rlabel[i];
-      const int ll = sm.rlabel[l];
-      if (ll < l) { atomicMin(&sm.rlabel[i], ll); changed = true; }
-    }
-    if (changed) sm.changed = 1;
-    SMALL_SYNC();
-    const int any = sm.changed;
-    SMALL_SYNC();
-    if (!any) break;
-  }
-  ST(3);
-  // S5: grouping
-  for (int i = tid; i < nC; i += kSmallThreads) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
-  for (int i = tid; i <= nC; i += kSmallThreads) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
-  SMALL_SYNC();
-  const int ncomp = small_scan(sm.isroot, nC, &sm.scan_total);
-  for (int i = tid; i < nC; i += kSmallThreads)
-    if (sm.rlabel[i] == i) sm.compidx[i] = sm.isroot[i];
-  SMALL_SYNC();
-  for (int i = tid; i < nC; i += kSmallThreads) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
-  for (int e = tid; e < E; e += kSmallThreads)
-    if (sm.lcl[e] == e) atomicAdd(&sm.colcnt[sm.compidx[sm.clabel[e]]], 1);
-  SMALL_SYNC();
-  small_scan(sm.rowcnt, ncomp + 1, &sm.scan_total);
-  small_scan(sm.colcnt, ncomp + 1, &sm.scan_total);
-  for (int i = tid; i < nC; i += kSmallThreads) {
-    const int k = sm.compidx[sm.rlabel[i]];
-    sm.sorted_rows[sm.rowcnt[k] + atomicAdd(&sm.fill[k], 1)] = i;
-  }
-  SMALL_SYNC();
-  ST(4);
-  // S6: one warp per component, everything in shared memory
-  const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
-                      sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
-  constexpr int kSerialRows = 6;     // components up to this many rows: one thread each
-  for (int comp = tid; comp < ncomp; comp += kSmallThreads) {
-    const int nr = sm.rowcnt[comp + 1] - sm.rowcnt[comp];
-    if (nr <= 3) solve_component_enum(A, comp, S.thresh, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl);
-    else if (nr <= kSerialRows) solve_component_serial(A, comp, S.thresh, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl);
-  }
-  __syncwarp();
-  for (int comp = warp; comp < ncomp; comp += kSmallThreads / 32)
-    if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] > kSerialRows)
-      solve_component(A, comp, S.thresh, nullptr, sm.rdeg, sm.lcl, sm.ecst, sm.xl, sm.yl, lane);
-  SMALL_SYNC();
-  ST(5);
-  // S7: write back with global ids
-  for (int i = tid; i < nC; i += kSmallThreads) {
-    const int c = sm.xl[i];
-    if (c >= 0) {
-      x[sm.rg[i]] = sm.cglob[c];
-      y[sm.cglob[c]] = sm.rg[i];
-    }
-  }
-  ST(6);
-  if (debug && threadIdx.x == 0)
-    printf("small path nC=%d E=%d ncomp=%d: S1 %llu S2+3 %llu label %llu group %llu solve %llu write %llu ns\n", nC, E, ncomp,
-           ts[1]-ts[0], ts[2]-ts[1], ts[3]-ts[2], ts[4]-ts[3], ts[5]-ts[4], ts[6]-ts[5]);
-}
-
+// One CTA per video stream solves the (up to three chained) association stages of its frame.
 __global__ void __launch_bounds__(kLapThreads, 1)
-lap_cluster_kernel(bt_cand cand, bt_lap_ws ws, LapParams P) {
-  __shared__ int32_t s_warp[32];
-  __shared__ int32_t s_carry;
+lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ bt_lap_batch B, LapParams P,
+                  const __grid_constant__ bt_refine rf) {
   extern __shared__ __align__(16) unsigned char lap_dyn_smem[];
   SmallSmem& sm = *reinterpret_cast<SmallSmem*>(lap_dyn_smem);
-  uint32_t nctas, crank;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nctas));
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int gtid = (int)crank * kLapThreads + tid;
-  const int GT = (int)nctas * kLapThreads;
-  const int gwarp = gtid >> 5, nwarps = GT >> 5;
-  const int n = P.n, m = P.m;
+  const int kb = blockIdx.x;
+  const int sid = B.sid[kb];
+  const int n = B.n[kb], m = B.m[kb];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int GT = kLapThreads, NW = kLapThreads / 32;
+  const bt_cand cand = bt_cand_of(cand_base, sid);
+  bt_lap_ws W = ws_base;
+  {
+    const size_t ro = (size_t)sid * ws_base.rows_stride, co = (size_t)sid * ws_base.cols_stride;
+    W.label += ro; W.clist += ro; W.compidx += ro; W.isroot += ro; W.rowcnt += ro + sid; W.colcnt += ro + sid;
+    W.fill += ro + sid; W.sorted_rows += ro; W.u += ro; W.treerows += ro;
+    W.collabel += co; W.v += co; W.dist += co; W.pathrow += co; W.seen += co; W.insc += co; W.touched += co;
+    W.counters += (size_t)sid * 8;
+  }
   unsigned long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define LAP_T(i) do { if (P.debug && gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[i])); } while (0)
+#define LAP_T(i) do { if (P.debug && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[i])); } while (0)
   LAP_T(0);
 
-  // ---- P0 (all stages at once): outputs and per-stage scratch ----
-  for (int stage = 0; stage < P.nstages; ++stage) {
-    const LapStage S = P.st[stage];
-    const size_t co = (size_t)stage * ws.cols, ro = (size_t)stage * ws.rows;
-    for (int c = gtid; c < m; c += GT) {
-      S.y[c] = -1;
-      ws.collabel[co + c] = kInf;
-      ws.v[co + c] = 0.0;
-      ws.seen[co + c] = 0;
-      ws.insc[co + c] = 0;
-    }
-    for (int r = gtid; r < n; r += GT) {
-      S.x[r] = -1;
-      ws.u[ro + r] = 0.0;
-    }
+  // ---- P0: outputs (this kernel's own) ----
+  for (int s = 0; s < P.nstages; ++s) {
+    int32_t* x = B.x[kb] + (size_t)s * B.x_stride[kb];
+    int32_t* y = B.y[kb] + (size_t)s * B.y_stride;
+    for (int r = tid; r < n; r += GT) x[r] = -1;
+    for (int c = tid; c < m; c += GT) y[c] = -1;
   }
-  if (gtid < 24) ws.counters[gtid] = 0;
-  if (gtid == 0 && P.zero_word) *P.zero_word = 0;
-  // Everything above touches only this kernel's own outputs and scratch, so under programmatic
-  // dependent launch it runs while the emitting kernel drains; the candidate lists are read below.
+  if (tid == 0 && B.zero_word[kb]) *B.zero_word[kb] = 0;
+  // Everything above touches only this kernel's own outputs, so under programmatic dependent launch it
+  // runs while the emitting kernel drains; the candidate lists are read below.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  cluster_barrier();
+  __syncthreads();
   LAP_T(1);
 
   for (int stage = 0; stage < P.nstages; ++stage) {
-    const LapStage S = P.st[stage];
-    if (cand.total[S.list] == 0) continue;   // nothing was emitted for this stage (cluster-uniform)
-    bt_lap_ws W = ws;                          // this stage's slices of the scratch arrays
-    W.collabel += (size_t)stage * ws.cols; W.v += (size_t)stage * ws.cols;
-    W.seen += (size_t)stage * ws.cols; W.insc += (size_t)stage * ws.cols; W.u += (size_t)stage * ws.rows;
-    W.counters += stage * 8;
-    int32_t* cnt = cand.deg + (size_t)S.list * cand.rows_cap;
-    int32_t* ecol = cand.col + (size_t)S.list * cand.rows_cap * cand.stride;
-    double* ecost = cand.cost + (size_t)S.list * cand.rows_cap * cand.stride;
-    int32_t* x = S.x;
-    int32_t* y = S.y;
+    const int list = P.nstages == 1 ? P.list0 : stage;
+    if (cand.total[list] == 0) continue;   // nothing was emitted for this stage (CTA-uniform)
+    const double thresh = P.thresh[stage];
+    int32_t* x = B.x[kb] + (size_t)stage * B.x_stride[kb];
+    int32_t* y = B.y[kb] + (size_t)stage * B.y_stride;
+    // stage 2 (demo:1568-1571): rows unmatched in stage 1; stage 3 (demo:1588-1604): columns unmatched in stage 1
+    const int32_t* row_block = (P.nstages == 3 && stage == 1) ? B.x[kb] : nullptr;
+    const int32_t* col_block = (P.nstages == 3 && stage == 2) ? B.y[kb] : nullptr;
+    int32_t* segcnt_all = cand.cnt + (size_t)list * cand.rows_cap * cand.nseg;
+    int32_t* ecol = cand.col + (size_t)list * cand.rows_cap * cand.stride;
+    double* ecost = cand.cost + (size_t)list * cand.rows_cap * cand.stride;
+    int32_t* indeg = cand.indeg + (size_t)list * cand.cols_cap;
+    if (tid == 0) { sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.big = 0; }
+    __syncthreads();
 
     // ---- P1: classify every row from the emitters' degree bookkeeping (no edge traversal for the bulk):
-    //      isolated edges (row degree 1, column in-degree 1) are final; rows with several candidates or a
-    //      contested column are "complex": only those have their segments compacted ----
-    const int32_t* indeg = cand.indeg + (size_t)S.list * cand.cols_cap;
-    for (int r = gtid; r < n; r += GT) {
-      W.label[r] = kInf;
-      const size_t ri = (size_t)S.list * cand.rows_cap + r;
+    //      isolated edges (row degree 1, column in-degree 1, gate decision not in doubt) are final; rows
+    //      with several candidates, a contested column or an ambiguous gate are "complex" ----
+    for (int r = tid; r < n; r += GT) {
+      const size_t ri = (size_t)list * cand.rows_cap + r;
       const int deg = cand.rowdeg[ri];
       if (deg == 0) continue;                      // nothing was emitted for this row
-      const int col1 = cand.rowcol[ri];
-      const bool row_on = S.row_block == nullptr || S.row_block[r] < 0;
-      if (P.clear_lists) cand.rowdeg[ri] = 0;
-      const bool col1_ok = edge_ok(S.col_block, col1);
-      const bool contested1 = deg == 1 && row_on && col1_ok && indeg[col1] != 1;
-      const bool need_edges = row_on && (deg > 1 || contested1);
-      int total = 0, valid = 0;
-      unsigned long long mask = cand.segmask[ri];
-      if (P.clear_lists) cand.segmask[ri] = 0ull;
-      int32_t* segcnt = cand.cnt + ri * cand.nseg;
-      int32_t* rc = ecol + (size_t)r * cand.stride;
-      double* rv = ecost + (size_t)r * cand.stride;
-      while (mask) {                               // only the non-empty segments, in ascending order
-        const int g = __ffsll((long long)mask) - 1;
-        mask &= mask - 1;
-        const int k = need_edges ? segcnt[g] : 0;  // complex rows: compact in place (ascending copy)
-        if (P.clear_lists) segcnt[g] = 0;
-        const int src = g * cand.seg;
-        for (int e = 0; e < k; ++e) {
-          const int c = rc[src + e];
-          if (src + e != total) { rc[total] = c; rv[total] = rv[src + e]; }
-          ++total;
-          if (edge_ok(S.col_block, c)) ++valid;
+      const int rc = cand.rowcol[ri];
+      const int col1 = rc & BT_EDGE_COLMASK;
+      const unsigned long long mask = cand.segmask[ri];
+      if (P.clear_lists) { cand.rowdeg[ri] = 0; cand.segmask[ri] = 0ull; }
+      const bool row_on = row_block == nullptr || row_block[r] < 0;
+      bool complex_row = row_on;
+      if (row_on && deg == 1) {
+        const bool col_ok = edge_ok(col_block, col1);
+        if (!col_ok) complex_row = false;            // its only column is taken already
+        else if (indeg[col1] == 1 && !(rc & BT_EDGE_AMBIG)) {
+          x[r] = col1; y[col1] = r;                  // isolated edge
+          complex_row = false;
         }
       }
-      cnt[r] = total;
-      if (!row_on) continue;
-      if (deg == 1 && !contested1) {               // isolated edge, or its only column is taken already
-        if (col1_ok) { x[r] = col1; y[col1] = r; }
+      if (!complex_row) {
+        if (P.clear_lists) {                          // leave the segment counters zeroed
+          unsigned long long mm = mask;
+          while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
+        }
         continue;
       }
-      if (valid == 0) continue;
-      const int pos = atomicAdd(&W.counters[0], 1);
-      atomicAdd(&W.counters[4], valid);            // valid edges of the complex part
-      W.clist[pos] = r;
-      W.label[r] = r;
+      const int kc = atomicAdd(&sm.nC, 1);
+      const int e0 = atomicAdd(&sm.nE, deg);
+      W.clist[kc] = r;
+      if (kc < kSmallRows && e0 + deg <= kSmallEdges) {
+        sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0; sm.rmask[kc] = mask;
+      } else {
+        sm.big = 1;
+      }
     }
-    cluster_barrier();
+    __syncthreads();
     LAP_T(2);
-    const int nC = W.counters[0];
+    const int nC = sm.nC;
     if (P.clear_lists)                              // every read of the in-degrees is behind us
-      for (int c = gtid; c < cand.cols_cap; c += GT) cand.indeg[(size_t)S.list * cand.cols_cap + c] = 0;
-    LAP_T(3);
+      for (int c = tid; c < cand.cols_cap; c += GT) indeg[c] = 0;
+    const bool big = sm.big != 0 || m > kSmallCols;
+    int dbg_ncomp = 0;
 
-    const bool small = nC > 0 && nC <= kSmallRows && W.counters[4] <= kSmallEdges;
-    if (small) {
-      if (crank == 0 && tid < kSmallThreads) small_complex_solve(cand, W, S, nC, cnt, ecol, ecost, x, y, sm, P.debug);
-      LAP_T(4); tq[5] = tq[4];
+    if (nC > 0 && !big) {
+      // ---- S1: ascending row order (deterministic tie-breaking), by rank ----
+      {
+        int my_r = 0, my_deg = 0, my_start = 0, rank = 0;
+        unsigned long long my_mask = 0;
+        if (tid < nC) {
+          my_r = sm.rg[tid]; my_deg = sm.rdeg[tid]; my_start = sm.rstart[tid]; my_mask = sm.rmask[tid];
+          for (int j = 0; j < nC; ++j) rank += (sm.rg[j] < my_r) ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid < nC) { sm.rg[rank] = my_r; sm.rdeg[rank] = my_deg; sm.rstart[rank] = my_start; sm.rmask[rank] = my_mask; }
+      }
+      // per-column solver state (global column ids)
+      for (int c = tid; c < m; c += GT) { sm.v[c] = 0.0; sm.seen[c] = 0; sm.insc[c] = 0; sm.yl[c] = -1; sm.clabel[c] = kInf; }
+      __syncthreads();
+      // ---- S2: gather the rows' segments into the shared-memory CSR: one warp per row, lanes over segments ----
+      for (int i = warp; i < nC; i += NW) {
+        const int r = sm.rg[i];
+        const size_t ri = (size_t)list * cand.rows_cap + r;
+        const unsigned long long mask = sm.rmask[i];
+        int32_t* segcnt = cand.cnt + ri * cand.nseg;
+        const int g0 = lane, g1 = lane + 32;
+        int k0 = ((mask >> g0) & 1ull) ? segcnt[g0] : 0;
+        int k1 = ((mask >> g1) & 1ull) ? segcnt[g1] : 0;
+        if (P.clear_lists) { if ((mask >> g0) & 1ull) segcnt[g0] = 0; if ((mask >> g1) & 1ull) segcnt[g1] = 0; }
+        int p0 = k0, p1 = k1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t0 = __shfl_up_sync(0xffffffffu, p0, o), t1 = __shfl_up_sync(0xffffffffu, p1, o);
+          if (lane >= o) { p0 += t0; p1 += t1; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, p0, 31);
+        p0 -= k0; p1 += tot0 - k1;
+        const int e0 = sm.rstart[i];
+        const int32_t* rc = ecol + (size_t)r * cand.stride;
+        const double* rv = ecost + (size_t)r * cand.stride;
+        for (int half = 0; half < 2; ++half) {
+          const int kk = half ? k1 : k0, dst0 = e0 + (half ? p1 : p0), src0 = (half ? g1 : g0) * cand.seg;
+          for (int j = 0; j < kk; ++j) {
+            const int colf = rc[src0 + j];
+            const int col = colf & BT_EDGE_COLMASK;
+            const bool ok = edge_ok(col_block, col);
+            sm.ecol[dst0 + j] = col;
+            sm.ecst[dst0 + j] = ok ? rv[src0 + j] : kBlockedCost;
+            if (ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG))) sm.rlist[atomicAdd(&sm.nR, 1)] = (i << 12) | (dst0 + j);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- S3: exact re-costing of the flagged edges, one warp each ----
+      {
+        const int nR = sm.nR;
+        for (int q = warp; q < nR; q += NW) {
+          const int i = sm.rlist[q] >> 12, e = sm.rlist[q] & 4095;
+          const double c = refine_cost(rf, B, kb, list, sm.rg[i], sm.ecol[e], lane);
+          if (lane == 0) sm.ecst[e] = c;
+        }
+      }
+      for (int i = tid; i < nC; i += GT) { sm.xl[i] = -1; sm.u[i] = 0.0; sm.rlabel[i] = i; }
+      __syncthreads();
+      LAP_T(3);
+      const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
+                          sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
+      if (nC <= kOneWarpRows) {
+        // ---- a handful of rows: one warp runs the shortest-augmenting-path solver over all of them ----
+        if (warp == 0) {
+          if (lane < nC) sm.sorted_rows[lane] = lane;
+          if (lane == 0) { sm.rowcnt[0] = 0; sm.rowcnt[1] = nC; sm.colcnt[0] = 0; sm.colcnt[1] = 0; }
+          __syncwarp();
+          solve_component(A, 0, thresh, nullptr, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl, lane);
+        }
+        dbg_ncomp = 1;
+      } else {
+        // ---- S4: components by min-label propagation + pointer jumping (shared memory) ----
+        while (true) {
+          if (tid == 0) sm.changed = 0;
+          __syncthreads();
+          bool changed = false;
+          for (int i = tid; i < nC; i += GT) {
+            int lr = sm.rlabel[i];
+            const int l0 = lr;
+            for (int q = sm.rstart[i]; q < sm.rstart[i] + sm.rdeg[i]; ++q) {
+              const int c = sm.ecol[q];
+              const int lc = sm.clabel[c];
+              if (lc < lr) lr = lc;
+              else if (lc > lr) { atomicMin(&sm.clabel[c], lr); changed = true; }
+            }
+            if (lr < l0) { atomicMin(&sm.rlabel[i], lr); changed = true; }
+          }
+          __syncthreads();
+          for (int i = tid; i < nC; i += GT) {
+            const int l = sm.rlabel[i];
+            const int ll = sm.rlabel[l];
+            if (ll < l) { atomicMin(&sm.rlabel[i], ll); changed = true; }
+          }
+          if (changed) sm.changed = 1;
+          __syncthreads();
+          const int any = sm.changed;
+          __syncthreads();
+          if (!any) break;
+        }
+        // ---- S5: grouping ----
+        for (int i = tid; i < nC; i += GT) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
+        for (int i = tid; i <= nC; i += GT) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
+        __syncthreads();
+        const int ncomp = block_exclusive_scan(sm.isroot, nC, sm.s_warp, &sm.s_carry);
+        for (int i = tid; i < nC; i += GT)
+          if (sm.rlabel[i] == i) sm.compidx[i] = sm.isroot[i];
+        __syncthreads();
+        for (int i = tid; i < nC; i += GT) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
+        for (int c = tid; c < m; c += GT)
+          if (sm.clabel[c] != kInf) atomicAdd(&sm.colcnt[sm.compidx[sm.clabel[c]]], 1);
+        __syncthreads();
+        block_exclusive_scan(sm.rowcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+        block_exclusive_scan(sm.colcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+        for (int i = tid; i < nC; i += GT) {
+          const int q = sm.compidx[sm.rlabel[i]];
+          sm.sorted_rows[sm.rowcnt[q] + atomicAdd(&sm.fill[q], 1)] = i;
+        }
+        __syncthreads();
+        // ---- S6: tiny components one thread each, the others one warp each ----
+        constexpr int kSerialRows = 6;
+        for (int comp = tid; comp < ncomp; comp += GT) {
+          const int nr = sm.rowcnt[comp + 1] - sm.rowcnt[comp];
+          if (nr <= 3) solve_component_enum(A, comp, thresh, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl);
+          else if (nr <= kSerialRows) solve_component_serial(A, comp, thresh, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl);
+        }
+        __syncwarp();
+        for (int comp = warp; comp < ncomp; comp += NW)
+          if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] > kSerialRows)
+            solve_component(A, comp, thresh, nullptr, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl, lane);
+        dbg_ncomp = ncomp;
+      }
+      __syncthreads();
+      // ---- S7: write back ----
+      for (int i = tid; i < nC; i += GT) {
+        const int c = sm.xl[i];
+        if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
+      }
     } else if (nC > 0) {
-      // ---- P3: connected components of the complex part ----
+      // ---- large complex part (a crowded scene, a dense cost matrix, more detections than the on-chip
+      //      arrays hold): same algorithm over global scratch ----
+      int32_t* cnt = cand.deg + (size_t)list * cand.rows_cap;
+      for (int c = tid; c < m; c += GT) { W.collabel[c] = kInf; W.v[c] = 0.0; W.seen[c] = 0; W.insc[c] = 0; }
+      for (int r = tid; r < n; r += GT) { W.u[r] = 0.0; W.label[r] = kInf; }
+      if (tid < 8) W.counters[tid] = 0;
+      __syncthreads();
+      // compact the complex rows' segments in place (ascending copy), one thread per row
+      for (int i = tid; i < nC; i += GT) {
+        const int r = W.clist[i];
+        const size_t ri = (size_t)list * cand.rows_cap + r;
+        // rows that made it into the on-chip arrays still have their segment mask in shared memory; the
+        // others lost it with the clearing above -- walk all segments of those
+        unsigned long long mask = ~0ull;
+        int32_t* segcnt = cand.cnt + ri * cand.nseg;
+        int32_t* rc = ecol + (size_t)r * cand.stride;
+        double* rv = ecost + (size_t)r * cand.stride;
+        int total = 0;
+        for (int g = 0; g < cand.nseg; ++g) {
+          if (!((mask >> g) & 1ull)) continue;
+          const int kk = segcnt[g];
+          if (kk == 0) continue;
+          if (P.clear_lists) segcnt[g] = 0;
+          const int src = g * cand.seg;
+          for (int e = 0; e < kk; ++e) {
+            if (src + e != total) { rc[total] = rc[src + e]; rv[total] = rv[src + e]; }
+            ++total;
+          }
+        }
+        cnt[r] = total;
+        W.label[r] = r;
+      }
+      __syncthreads();
+      // exact re-costing of the flagged edges: one warp per row, flagged edges one after the other
+      for (int i = warp; i < nC; i += NW) {
+        const int r = W.clist[i];
+        const int deg = cnt[r];
+        int32_t* rc = ecol + (size_t)r * cand.stride;
+        double* rv = ecost + (size_t)r * cand.stride;
+        for (int q0 = 0; q0 < deg; q0 += 32) {
+          const int q = q0 + lane;
+          const int colf = q < deg ? rc[q] : 0;
+          const bool ok = q < deg && edge_ok(col_block, colf & BT_EDGE_COLMASK);
+          unsigned todo = __ballot_sync(0xffffffffu, ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG)));
+          while (todo) {
+            const int bsrc = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int col = __shfl_sync(0xffffffffu, colf, bsrc) & BT_EDGE_COLMASK;
+            const double c = refine_cost(rf, B, kb, list, r, col, lane);
+            if (lane == bsrc) rv[q] = c;
+          }
+          if (q < deg) rc[q] = colf & BT_EDGE_COLMASK;
+        }
+      }
+      __syncthreads();
+      // components of the complex part
       for (int iter = 0;; ++iter) {
         int32_t* flag = &W.counters[2 + (iter & 1)];
         bool changed = false;
-        for (int i = gtid; i < nC; i += GT) {
+        for (int i = tid; i < nC; i += GT) {
           const int r = W.clist[i];
           int lr = W.label[r];
           const int l0 = lr;
           const int deg = cnt[r];
           const int32_t* e = ecol + (size_t)r * cand.stride;
-          for (int k = 0; k < deg; ++k) {
-            const int c = e[k];
-            if (!edge_ok(S.col_block, c)) continue;
+          for (int q = 0; q < deg; ++q) {
+            const int c = e[q];
+            if (!edge_ok(col_block, c)) continue;
             const int lc = W.collabel[c];
             if (lc < lr) lr = lc;
             else if (lc > lr) { atomicMin(&W.collabel[c], lr); changed = true; }
           }
           if (lr < l0) { atomicMin(&W.label[r], lr); changed = true; }
         }
-        cluster_barrier();
-        for (int i = gtid; i < nC; i += GT) {
+        __syncthreads();
+        for (int i = tid; i < nC; i += GT) {
           const int r = W.clist[i];
           const int l = W.label[r];
           const int ll = W.label[l];
           if (ll < l) { atomicMin(&W.label[r], ll); changed = true; }
         }
         if (changed) *flag = 1;
-        if (gtid == 0) W.counters[2 + ((iter + 1) & 1)] = 0;   // the other flag, for the next round
-        cluster_barrier();
+        if (tid == 0) W.counters[2 + ((iter + 1) & 1)] = 0;   // the other flag, for the next round
+        __syncthreads();
         if (*flag == 0) break;
       }
-
-      LAP_T(4);
-      // ---- P4: component bookkeeping (CTA 0) ----
-      if (crank == 0) {
-        for (int i = tid; i < nC; i += kLapThreads) {
-          const int r = W.clist[i];
-          W.isroot[i] = (W.label[r] == r) ? 1 : 0;
-        }
-        for (int i = tid; i <= nC; i += kLapThreads) { W.rowcnt[i] = 0; W.colcnt[i] = 0; W.fill[i] = 0; }
-        __syncthreads();
-        const int ncomp = block_exclusive_scan(W.isroot, nC, s_warp, &s_carry);
-        for (int i = tid; i < nC; i += kLapThreads) {
-          const int r = W.clist[i];
-          if (W.label[r] == r) W.compidx[r] = W.isroot[i];
-        }
-        __syncthreads();
-        for (int i = tid; i < nC; i += kLapThreads) atomicAdd(&W.rowcnt[W.compidx[W.label[W.clist[i]]]], 1);
-        for (int c = tid; c < m; c += kLapThreads) {
-          const int l = W.collabel[c];
-          if (l != kInf) atomicAdd(&W.colcnt[W.compidx[l]], 1);
-        }
-        if (tid == 0) W.counters[1] = ncomp;
-        __syncthreads();
-        block_exclusive_scan(W.rowcnt, ncomp + 1, s_warp, &s_carry);
-        block_exclusive_scan(W.colcnt, ncomp + 1, s_warp, &s_carry);
-        for (int i = tid; i < nC; i += kLapThreads) {
-          const int r = W.clist[i];
-          const int k = W.compidx[W.label[r]];
-          W.sorted_rows[W.rowcnt[k] + atomicAdd(&W.fill[k], 1)] = r;
-        }
+      // component bookkeeping
+      for (int i = tid; i < nC; i += GT) W.isroot[i] = (W.label[W.clist[i]] == W.clist[i]) ? 1 : 0;
+      for (int i = tid; i <= nC; i += GT) { W.rowcnt[i] = 0; W.colcnt[i] = 0; W.fill[i] = 0; }
+      __syncthreads();
+      const int ncomp = block_exclusive_scan(W.isroot, nC, sm.s_warp, &sm.s_carry);
+      for (int i = tid; i < nC; i += GT) {
+        const int r = W.clist[i];
+        if (W.label[r] == r) W.compidx[r] = W.isroot[i];
       }
-      cluster_barrier();
-      LAP_T(5);
-
-      // ---- P5: one warp per component ----
-      const int ncomp = W.counters[1];
+      __syncthreads();
+      for (int i = tid; i < nC; i += GT) atomicAdd(&W.rowcnt[W.compidx[W.label[W.clist[i]]]], 1);
+      for (int c = tid; c < m; c += GT) {
+        const int l = W.collabel[c];
+        if (l != kInf) atomicAdd(&W.colcnt[W.compidx[l]], 1);
+      }
+      __syncthreads();
+      block_exclusive_scan(W.rowcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+      block_exclusive_scan(W.colcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+      for (int i = tid; i < nC; i += GT) {
+        const int r = W.clist[i];
+        const int q = W.compidx[W.label[r]];
+        W.sorted_rows[W.rowcnt[q] + atomicAdd(&W.fill[q], 1)] = r;
+      }
+      __syncthreads();
       const SolveArrays GA{W.rowcnt, W.colcnt, W.sorted_rows, W.touched, W.treerows, W.u, W.v, W.dist,
                            W.pathrow, W.seen, W.insc, nullptr, (size_t)cand.stride};
-      for (int comp = gwarp; comp < ncomp; comp += nwarps)
-        solve_component(GA, comp, S.thresh, S.col_block, cnt, ecol, ecost, x, y, lane);
+      for (int comp = warp; comp < ncomp; comp += NW)
+        solve_component(GA, comp, thresh, col_block, cnt, ecol, ecost, x, y, lane);
+      dbg_ncomp = ncomp;
     }
-    if (stage + 1 < P.nstages) cluster_barrier();   // x / y of this stage gate the next one
-    if (P.clear_lists && gtid == 0) cand.total[S.list] = 0;   // every CTA has read it (barriers above / kernel end)
-    LAP_T(6);
-    if (P.debug && gtid == 0)
-      printf("lap stage %d: n=%d m=%d complex=%d comps=%d | init %llu classify %llu clear %llu complex-part %llu tail %llu ns\n", stage, n, m,
-             nC, W.counters[1], tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[5] - tq[3], tq[6] - tq[5]);
+    __syncthreads();                                  // x / y of this stage gate the next one
+    if (P.clear_lists && tid == 0) cand.total[list] = 0;
+    LAP_T(4);
+    if (P.debug && tid == 0)
+      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d comps=%d big=%d | init %llu classify %llu gather+recost %llu solve %llu ns\n",
+             sid, stage, n, m, nC, sm.nE, sm.nR, dbg_ncomp, (int)big, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3]);
     LAP_T(1);
   }
 }
@@ -837,39 +903,48 @@ lap_compact_dense_kernel(const double* __restrict__ cost, int n, int m, double t
   }
 }
 
+
 }  // namespace
 
 int32_t bt_lap_ws_create(bt_ctx* ctx) {
   auto* ws = new bt_lap_ws();
   ctx->lap = ws;
-  const int rows = ctx->max_tracks, cols = ctx->max_dets;
+  const int rows = ctx->max_tracks, cols = ctx->max_dets, S = ctx->n_streams;
   ws->rows = rows;
   ws->cols = cols;
+  ws->rows_stride = rows;
+  ws->cols_stride = cols;
   const int stride = (cols + 127) / 128 * 128 + 128;
-  ws->cand.rows_cap = rows;
-  ws->cand.stride = stride;
-  ws->cand.nseg = BT_CAND_MAXSEG;
-  ws->cand.seg = 128;
-  const size_t cnt_ints = (3 * (size_t)rows * ws->cand.nseg + 4 + 1) & ~size_t(1);   // keeps segmask 8 B aligned
-  ws->cand.cols_cap = cols;
-  ws->cand.clear_bytes = sizeof(int32_t) * cnt_ints + sizeof(unsigned long long) * 3 * rows +
-                         sizeof(int32_t) * 3 * ((size_t)rows + cols);
-  BT_CUDA(cudaMalloc(&ws->cand.cnt, ws->cand.clear_bytes));
-  ws->cand.total = ws->cand.cnt + 3 * (size_t)rows * ws->cand.nseg;   // cleared by the same memset as cnt
-  ws->cand.segmask = reinterpret_cast<unsigned long long*>(ws->cand.cnt + cnt_ints);
-  ws->cand.rowdeg = reinterpret_cast<int32_t*>(ws->cand.segmask + 3 * (size_t)rows);
-  ws->cand.indeg = ws->cand.rowdeg + 3 * (size_t)rows;
-  BT_CUDA(cudaMalloc(&ws->cand.rowcol, sizeof(int32_t) * 3 * (size_t)rows));
-  BT_CUDA(cudaMalloc(&ws->cand.deg, sizeof(int32_t) * 3 * rows));
-  BT_CUDA(cudaMalloc(&ws->cand.col, sizeof(int32_t) * 3 * (size_t)rows * stride));
-  BT_CUDA(cudaMalloc(&ws->cand.cost, sizeof(double) * 3 * (size_t)rows * stride));
-  BT_CUDA(cudaMemset(ws->cand.cnt, 0, ws->cand.clear_bytes));
+  bt_cand& c = ws->cand;
+  c.rows_cap = rows;
+  c.stride = stride;
+  c.nseg = BT_CAND_MAXSEG;
+  c.seg = 128;
+  c.cols_cap = cols;
   BT_CHECK(cols <= BT_CAND_MAXSEG * 112, BT_ERR_CAPACITY, "max_dets %d exceeds %d", cols, BT_CAND_MAXSEG * 112);
-#define BT_LAP_ALLOC(field, type, count) BT_CUDA(cudaMalloc(&ws->field, sizeof(type) * (size_t)(count)))
+  // one "clear block" per video stream: cnt | total | segmask | rowdeg | indeg (one memset clears them all)
+  const size_t cnt_ints = (3 * (size_t)rows * c.nseg + 4 + 1) & ~size_t(1);   // keeps segmask 8 B aligned
+  c.clear_bytes = sizeof(int32_t) * cnt_ints + sizeof(unsigned long long) * 3 * rows +
+                  sizeof(int32_t) * 3 * ((size_t)rows + cols);
+  c.s_cnt = (c.clear_bytes + 255) & ~size_t(255);
+  c.s_rowcol = 3 * (size_t)rows;
+  c.s_deg = 3 * (size_t)rows;
+  c.s_edges = 3 * (size_t)rows * stride;
+  char* blk = nullptr;
+  BT_CUDA(cudaMalloc(&blk, c.s_cnt * S));
+  BT_CUDA(cudaMemset(blk, 0, c.s_cnt * S));
+  c.cnt = reinterpret_cast<int32_t*>(blk);
+  c.total = c.cnt + 3 * (size_t)rows * c.nseg;
+  c.segmask = reinterpret_cast<unsigned long long*>(c.cnt + cnt_ints);
+  c.rowdeg = reinterpret_cast<int32_t*>(c.segmask + 3 * (size_t)rows);
+  c.indeg = c.rowdeg + 3 * (size_t)rows;
+  BT_CUDA(cudaMalloc(&c.rowcol, sizeof(int32_t) * c.s_rowcol * S));
+  BT_CUDA(cudaMalloc(&c.deg, sizeof(int32_t) * c.s_deg * S));
+  BT_CUDA(cudaMalloc(&c.col, sizeof(int32_t) * c.s_edges * S));
+  BT_CUDA(cudaMalloc(&c.cost, sizeof(double) * c.s_edges * S));
+#define BT_LAP_ALLOC(field, type, count) BT_CUDA(cudaMalloc(&ws->field, sizeof(type) * (size_t)(count) * S))
   BT_LAP_ALLOC(label, int32_t, rows);
-  BT_LAP_ALLOC(collabel, int32_t, 3 * (size_t)cols);
-  BT_LAP_ALLOC(nvalid, int32_t, rows);
-  BT_LAP_ALLOC(onlycol, int32_t, rows);
+  BT_LAP_ALLOC(collabel, int32_t, cols);
   BT_LAP_ALLOC(clist, int32_t, rows);
   BT_LAP_ALLOC(compidx, int32_t, rows);
   BT_LAP_ALLOC(isroot, int32_t, rows);
@@ -877,18 +952,18 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
   BT_LAP_ALLOC(colcnt, int32_t, rows + 1);
   BT_LAP_ALLOC(fill, int32_t, rows + 1);
   BT_LAP_ALLOC(sorted_rows, int32_t, rows);
-  BT_LAP_ALLOC(counters, int32_t, 24);
-  BT_LAP_ALLOC(u, double, 3 * (size_t)rows);
-  BT_LAP_ALLOC(v, double, 3 * (size_t)cols);
+  BT_LAP_ALLOC(counters, int32_t, 8);
+  BT_LAP_ALLOC(u, double, rows);
+  BT_LAP_ALLOC(v, double, cols);
   BT_LAP_ALLOC(dist, double, cols);
   BT_LAP_ALLOC(pathrow, int32_t, cols);
-  BT_LAP_ALLOC(seen, int32_t, 3 * (size_t)cols);
-  BT_LAP_ALLOC(insc, int32_t, 3 * (size_t)cols);
+  BT_LAP_ALLOC(seen, int32_t, cols);
+  BT_LAP_ALLOC(insc, int32_t, cols);
   BT_LAP_ALLOC(touched, int32_t, cols);
   BT_LAP_ALLOC(treerows, int32_t, rows);
-  BT_LAP_ALLOC(x, int32_t, rows);
-  BT_LAP_ALLOC(y, int32_t, cols);
 #undef BT_LAP_ALLOC
+  BT_CUDA(cudaMalloc(&ws->x, sizeof(int32_t) * rows));
+  BT_CUDA(cudaMalloc(&ws->y, sizeof(int32_t) * cols));
   return BT_OK;
 }
 
@@ -896,7 +971,7 @@ void bt_lap_ws_destroy(bt_ctx* ctx) {
   bt_lap_ws* ws = ctx->lap;
   if (!ws) return;
   void* ptrs[] = {ws->cand.cnt, ws->cand.rowcol, ws->cand.deg, ws->cand.col, ws->cand.cost, ws->label, ws->collabel,
-                  ws->nvalid, ws->onlycol, ws->clist, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
+                  ws->clist, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
                   ws->sorted_rows, ws->counters, ws->u, ws->v, ws->dist, ws->pathrow, ws->seen, ws->insc,
                   ws->touched, ws->treerows, ws->x, ws->y};
   for (void* p : ptrs)
@@ -915,61 +990,53 @@ int32_t btk_lap_compact_dense(bt_ctx* ctx, const double* cost, int32_t n, int32_
   return BT_OK;
 }
 
-static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const LapParams& P) {
-  BT_CHECK(P.n <= ctx->lap->rows && P.m <= ctx->lap->cols, BT_ERR_CAPACITY,
-           "linear assignment %d x %d exceeds ctx capacity %d x %d", P.n, P.m, ctx->lap->rows, ctx->lap->cols);
-  if (P.n <= 0 && P.m <= 0) return BT_OK;
-  const int work = P.n > P.m ? P.n : P.m;
-  int nctas = (work + 255) / 256;          // ~256 rows per CTA keeps every thread busy in the row phases
-  if (nctas < 1) nctas = 1;
-  if (nctas > kLapMaxCtas) nctas = kLapMaxCtas;
+static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const LapParams& P, const bt_refine& rf) {
+  for (int k = 0; k < B.count; ++k)
+    BT_CHECK(B.n[k] <= ctx->lap->rows && B.m[k] <= ctx->lap->cols, BT_ERR_CAPACITY,
+             "linear assignment %d x %d exceeds ctx capacity %d x %d", B.n[k], B.m[k], ctx->lap->rows, ctx->lap->cols);
+  if (B.count <= 0) return BT_OK;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nctas);
+  cfg.gridDim = dim3(B.count);
   cfg.blockDim = dim3(kLapThreads);
   cfg.dynamicSmemBytes = sizeof(SmallSmem);
   cfg.stream = ctx->stream;
-  static bool attr_done = false;
-  if (!attr_done) {
-    BT_CUDA(cudaFuncSetAttribute(lap_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(SmallSmem)));
-    attr_done = true;
-  }
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = nctas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  static std::once_flag attr_once;
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] {
+    attr_err = cudaFuncSetAttribute(lap_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem));
+  });
+  BT_CUDA(attr_err);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->pdl ? 2 : 1;
-  BT_CUDA(cudaLaunchKernelEx(&cfg, lap_cluster_kernel, cand, *ctx->lap, P));
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  BT_CUDA(cudaLaunchKernelEx(&cfg, lap_stream_kernel, cand, *ctx->lap, B, P, rf));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
 int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n, int32_t m,
-                      double thresh, const int32_t* row_block, const int32_t* col_block, int32_t* x,
-                      int32_t* y) {
+                      double thresh, int32_t* x, int32_t* y) {
+  if (n <= 0 && m <= 0) return BT_OK;
   LapParams P = {};
   P.nstages = 1;
-  P.n = n;
-  P.m = m;
-  P.st[0] = LapStage{list, thresh, row_block, col_block, x, y};
-  return launch_lap(ctx, cand, P);
+  P.list0 = list;
+  P.thresh[0] = thresh;
+  bt_lap_batch B = {};
+  B.count = 1;
+  B.n[0] = n; B.m[0] = m;
+  B.x[0] = x; B.x_stride[0] = n; B.y[0] = y; B.y_stride = m;
+  bt_refine rf = {};
+  return launch_lap(ctx, cand, B, P, rf);
 }
 
-int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, int32_t n, int32_t m, const double thresh[3],
-                       int32_t* const x[3], int32_t* const y[3], int32_t* zero_word) {
+int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const double thresh[3],
+                       const bt_refine& rf) {
   LapParams P = {};
   P.clear_lists = 1;
-  P.zero_word = zero_word;
   P.nstages = 3;
-  P.n = n;
-  P.m = m;
-  P.st[0] = LapStage{0, thresh[0], nullptr, nullptr, x[0], y[0]};
-  P.st[1] = LapStage{1, thresh[1], x[0], nullptr, x[1], y[1]};   // stage 2: rows unmatched in stage 1
-  P.st[2] = LapStage{2, thresh[2], nullptr, y[0], x[2], y[2]};   // stage 3: columns unmatched in stage 1
+  for (int s = 0; s < 3; ++s) P.thresh[s] = thresh[s];
   P.debug = getenv("BT_LAP_DEBUG") != nullptr;
-  return launch_lap(ctx, cand, P);
+  return launch_lap(ctx, cand, B, P, rf);
 }

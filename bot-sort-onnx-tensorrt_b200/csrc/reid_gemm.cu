@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <math.h>
 #include <type_traits>
+#include <mutex>
+#include <string.h>
 #include <stdlib.h>
 
 namespace {
@@ -34,137 +36,175 @@ namespace {
 // epilogue element logic shared by the tensor-core and the CUDA-core kernels
 // ------------------------------------------------------------------------------------------------
 struct EpiParams {
+  // the batch (one entry per video stream / stand-alone problem)
+  int32_t count;
+  int32_t tile_start[BT_MAX_BATCH + 1];   // prefix sums of tiles per problem
+  int32_t n[BT_MAX_BATCH], m[BT_MAX_BATCH];
+  int32_t a_row0[BT_MAX_BATCH], b_row0[BT_MAX_BATCH];
+  int32_t row0[BT_MAX_BATCH], col0[BT_MAX_BATCH];
+  int32_t kind_off[BT_MAX_BATCH], pos_off[BT_MAX_BATCH];
+  int32_t cand_sid[BT_MAX_BATCH];
+  const float* face_sim[BT_MAX_BATCH];
+  // side inputs
   const double* row_tlbr;
   const float* row_tlbr_f32;
-  const uint8_t* row_kind;
+  const float* row_norm;
+  const char* row_kind_base;
   const double* col_tlbr;
   const uint8_t* col_kind;
   const uint2* col_pk;
-  const float* face_sim;
+  const float* col_norm;
   double match_thresh, second_thresh, unconf_thresh, proximity;
   float appearance;
   bt_cand cand;
   float* out_emb;
   double* out_dists;
   int dense_stage;
-  int n, m;
+  int operands_early;
   // BT_ASSOC_DEBUG bits (profiling / bisection aids of the tensor-core kernel, device printf):
   //   1 sampled CTA timestamps   2 similarity pass off   4 every CTA's timestamps   16 epilogue phase times
   //   32 no box pass (every pair evaluated by the similarity pass)   64 no early TMA prologue
   //   1024 globaltimer go/end of every epilogue warp
   int debug;
   float sim_gate;  // smallest similarity for which the appearance gate is open
+  float gate_band; // |sim - sim_gate| <= gate_band: the gate decision is within the tensor-core error (AMBIG)
   float iou_gate;  // a pair without open appearance gate needs IoU > 1 - max(stage thresholds); slightly lowered
 };
 
-__device__ __forceinline__ double iou_dist_f64(const double* __restrict__ a, const double* __restrict__ b) {
-  const double ixmin = fmax(a[0], b[0]), iymin = fmax(a[1], b[1]);
-  const double ixmax = fmin(a[2], b[2]), iymax = fmin(a[3], b[3]);
-  if (ixmax <= ixmin || iymax <= iymin) return 1.0;
-  const double inter = (ixmax - ixmin) * (iymax - iymin);
-  const double area1 = (a[2] - a[0]) * (a[3] - a[1]);
-  const double area2 = (b[2] - b[0]) * (b[3] - b[1]);
-  return 1.0 - inter / (area1 + area2 - inter);
+#define iou_dist_f64 bt_iou_dist_f64
+#define fuse_stage1 bt_fuse_stage1
+#define fuse_stage3 bt_fuse_stage3
+
+
+// ---- candidate-list addressing for video stream `sid` (all slices of the same allocations) --------
+__device__ __forceinline__ int32_t* c_cnt(const EpiParams& p, int sid) {
+  return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(p.cand.cnt) + (size_t)sid * p.cand.s_cnt);
+}
+__device__ __forceinline__ int32_t* c_total(const EpiParams& p, int sid) {
+  return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(p.cand.total) + (size_t)sid * p.cand.s_cnt);
+}
+__device__ __forceinline__ unsigned long long* c_segmask(const EpiParams& p, int sid) {
+  return reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p.cand.segmask) + (size_t)sid * p.cand.s_cnt);
+}
+__device__ __forceinline__ int32_t* c_rowdeg(const EpiParams& p, int sid) {
+  return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(p.cand.rowdeg) + (size_t)sid * p.cand.s_cnt);
+}
+__device__ __forceinline__ int32_t* c_indeg(const EpiParams& p, int sid) {
+  return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(p.cand.indeg) + (size_t)sid * p.cand.s_cnt);
+}
+__device__ __forceinline__ int32_t* c_rowcol(const EpiParams& p, int sid) { return p.cand.rowcol + (size_t)sid * p.cand.s_rowcol; }
+__device__ __forceinline__ int32_t* c_col(const EpiParams& p, int sid) { return p.cand.col + (size_t)sid * p.cand.s_edges; }
+__device__ __forceinline__ double* c_cost(const EpiParams& p, int sid) { return p.cand.cost + (size_t)sid * p.cand.s_edges; }
+
+// face similarity of (row, col) of problem k (0 when the stream has no face term)
+__device__ __forceinline__ float face_sim_of(const EpiParams& p, int k, int row, int col) {
+  const float* fs = p.face_sim[k];
+  if (!fs) return 0.0f;
+  int pr = row;
+  if (p.row_kind_base) pr = reinterpret_cast<const int32_t*>(p.row_kind_base + p.pos_off[k])[row];
+  return pr >= 0 ? fs[(size_t)pr * p.m[k] + col] : 0.0f;
 }
 
-__device__ __forceinline__ double fuse_stage1(double iou_d, float sim, float face, float appearance) {
-  float emb = 1.0f - sim;
-  const float face_emb = 1.0f - face;
-  if (fminf(emb, face_emb) > appearance) emb = 1.0f;
-  return fmin(iou_d, (double)emb);
-}
-
-__device__ __forceinline__ double fuse_stage3(double iou_d, float sim, float appearance, double proximity) {
-  float emb = 1.0f - fmaxf(0.0f, sim);
-  if (emb > appearance) emb = 1.0f;
-  if (iou_d > proximity) emb = 1.0f;
-  return fmin(iou_d, (double)emb);
-}
-
-// degree bookkeeping for the LAP's row classification (no return value needed: RED atomics)
-__device__ __forceinline__ void note_edge(const bt_cand& c, int list, int row, int col) {
-  atomicAdd(&c.rowdeg[(size_t)list * c.rows_cap + row], 1);
-  atomicAdd(&c.indeg[(size_t)list * c.cols_cap + col], 1);
-  c.rowcol[(size_t)list * c.rows_cap + row] = col;
-}
 // atomic append into the (row, column-segment) sub-list (CUDA-core kernel: several threads share a row)
-__device__ __forceinline__ void emit(const bt_cand& c, int list, int row, int col, double cost) {
+__device__ __forceinline__ void emit(const EpiParams& p, int sid, int list, int row, int col, double cost) {
+  const bt_cand& c = p.cand;
   const int seg = col / c.seg;
-  const int k = atomicAdd(c.cnt + ((size_t)list * c.rows_cap + row) * c.nseg + seg, 1);
-  const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * c.seg + k;
-  c.col[base] = col;
-  c.cost[base] = cost;
-  atomicAdd(&c.total[list], 1);
-  if (k == 0) atomicOr(&c.segmask[(size_t)list * c.rows_cap + row], 1ull << seg);
-  note_edge(c, list, row, col);
+  const size_t ri = (size_t)list * c.rows_cap + row;
+  const int k = atomicAdd(c_cnt(p, sid) + ri * c.nseg + seg, 1);
+  const size_t base = ri * (size_t)c.stride + (size_t)seg * c.seg + k;
+  c_col(p, sid)[base] = col;
+  c_cost(p, sid)[base] = cost;
+  atomicAdd(&c_total(p, sid)[list], 1);
+  if (k == 0) atomicOr(&c_segmask(p, sid)[ri], 1ull << seg);
+  atomicAdd(&c_rowdeg(p, sid)[ri], 1);
+  atomicAdd(&c_indeg(p, sid)[(size_t)list * c.cols_cap + col], 1);
+  c_rowcol(p, sid)[ri] = col;
 }
 // tensor-core kernel: the owner of (row, segment) adds the row degree once, at the end of its tile
-__device__ __forceinline__ void emit_owned_tc(const bt_cand& c, int list, int row, int seg, int k, int col, double cost) {
+__device__ __forceinline__ void emit_owned_tc(const EpiParams& p, int sid, int list, int row, int seg, int k, int col,
+                                              int flags, double cost) {
+  const bt_cand& c = p.cand;
   const size_t base = ((size_t)list * c.rows_cap + row) * (size_t)c.stride + (size_t)seg * c.seg + k;
-  c.col[base] = col;
-  c.cost[base] = cost;
-  atomicAdd(&c.indeg[(size_t)list * c.cols_cap + col], 1);
+  c_col(p, sid)[base] = col | flags;
+  c_cost(p, sid)[base] = cost;
+  atomicAdd(&c_indeg(p, sid)[(size_t)list * c.cols_cap + col], 1);
 }
 
-// exact path for one (row, col) pair that survived the cheap rejection test
-__device__ __noinline__ void assoc_exact(const EpiParams& p, int row, int col, float sim, int rkind,
-                                         int ckind) {
-  const double iou_d = iou_dist_f64(p.row_tlbr + (size_t)row * 4, p.col_tlbr + (size_t)col * 4);
-  const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
+// exact path of the CUDA-core kernel for one (row, col) pair that survived the cheap rejection test
+__device__ __noinline__ void assoc_exact(const EpiParams& p, int k, int row, int col, float sim, int rkind, int ckind) {
+  const int sid = p.cand_sid[k];
+  const double iou_d = iou_dist_f64(p.row_tlbr + ((size_t)p.row0[k] + row) * 4, p.col_tlbr + ((size_t)p.col0[k] + col) * 4);
   if (rkind == BT_ROW_UNCONFIRMED) {
     if (ckind == BT_COL_HIGH) {
       const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
-      if (c3 < p.unconf_thresh) emit(p.cand, 2, row, col, c3);
+      if (c3 < p.unconf_thresh) emit(p, sid, 2, row, col, c3);
     }
   } else {
     if (ckind == BT_COL_HIGH) {
-      const double c1 = fuse_stage1(iou_d, sim, face, p.appearance);
-      if (c1 < p.match_thresh) emit(p.cand, 0, row, col, c1);
+      const double c1 = fuse_stage1(iou_d, sim, face_sim_of(p, k, row, col), p.appearance);
+      if (c1 < p.match_thresh) emit(p, sid, 0, row, col, c1);
     } else if (ckind == BT_COL_LOW && rkind == BT_ROW_POOL_TRACKED) {
-      if (iou_d < p.second_thresh) emit(p.cand, 1, row, col, iou_d);
+      if (iou_d < p.second_thresh) emit(p, sid, 1, row, col, iou_d);
     }
   }
+}
+
+// Edge flags of a pair whose similarity has been looked at (tensor-core kernel).  SIM: the fused cost may be
+// the embedding distance, i.e. it carries the fp16 tensor-core error and is re-costed exactly by the LAP when
+// the row competes with others.  AMBIG: the appearance gate itself is within that error of flipping.
+__device__ __forceinline__ int sim_flags(const EpiParams& p, int list, float sim, float face) {
+  if (list == 1) return 0;
+  const bool face_open = (list == 0) && !((1.0f - face) > p.appearance);
+  const bool open = sim >= p.sim_gate;
+  int f = 0;
+  if (open || face_open) f |= BT_EDGE_SIM;
+  if (!face_open && fabsf(sim - p.sim_gate) <= p.gate_band) f |= BT_EDGE_AMBIG | BT_EDGE_SIM;
+  return f;
 }
 
 // Similarity pass of the tensor-core kernel for a pair that is not in the warp's shared-memory slots:
 // evaluates it from scratch; if the box pass spilled edges of this row straight to the list (more than
 // kPreSlots of them) the pair is looked up there first and re-costed in place.
-// Returns 1 when a new edge was appended at position `k_next` of the caller's (row, seg) sub-list.
-__device__ __noinline__ int open_pair_slow(const EpiParams& p, double r0, double r1, double r2, double r3,
+// Returns col | flags when a new edge was appended at position `k_next` of the caller's (row, seg) sub-list, else -1.
+__device__ __noinline__ int open_pair_slow(const EpiParams& p, int k, double r0, double r1, double r2, double r3,
                                            const double* __restrict__ cbox, int list, int row, int seg, int col,
                                            float sim, int k_next, int scan_from) {
+  const int sid = p.cand_sid[k];
   const double rb[4] = {r0, r1, r2, r3};
   const size_t eb = ((size_t)list * p.cand.rows_cap + row) * (size_t)p.cand.stride + (size_t)seg * p.cand.seg;
+  int32_t* ecol = c_col(p, sid);
+  double* ecost = c_cost(p, sid);
   int k_found = -1;
   if (scan_from >= 0)
     for (int j = scan_from; j < k_next; ++j)
-      if (p.cand.col[eb + j] == col) k_found = j;
+      if ((ecol[eb + j] & BT_EDGE_COLMASK) == col) k_found = j;
   const double iou_d = iou_dist_f64(rb, cbox);
   double cost = iou_d;
-  if (list == 0) {
-    const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
-    cost = fuse_stage1(iou_d, sim, face, p.appearance);
-  } else if (list == 2) {
-    cost = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
-  }
+  const float face = (list == 0) ? face_sim_of(p, k, row, col) : 0.0f;
+  if (list == 0) cost = fuse_stage1(iou_d, sim, face, p.appearance);
+  else if (list == 2) cost = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+  const int flags = sim_flags(p, list, sim, face);
   if (k_found >= 0) {
-    if (cost != iou_d) p.cand.cost[eb + k_found] = cost;
-    return 0;
+    if (cost != iou_d) ecost[eb + k_found] = cost;
+    if (flags) ecol[eb + k_found] = col | flags;
+    return -1;
   }
   const double thr = list == 0 ? p.match_thresh : (list == 1 ? p.second_thresh : p.unconf_thresh);
-  if (!(cost < thr)) return 0;
-  emit_owned_tc(p.cand, list, row, seg, k_next, col, cost);
-  return 1;
+  if (!(cost < thr) && !(flags & BT_EDGE_AMBIG)) return -1;
+  emit_owned_tc(p, sid, list, row, seg, k_next, col, flags, cost);
+  return col | flags;
 }
 
+// dense dumps (stand-alone entry points): problem 0
 __device__ __forceinline__ void assoc_dense(const EpiParams& p, int row, int col, float sim) {
-  if (p.out_emb) p.out_emb[(size_t)row * p.m + col] = 1.0f - fmaxf(0.0f, sim);
+  const int m = p.m[0];
+  if (p.out_emb) p.out_emb[(size_t)row * m + col] = 1.0f - fmaxf(0.0f, sim);
   if (p.out_dists) {
     const double iou_d = iou_dist_f64(p.row_tlbr + (size_t)row * 4, p.col_tlbr + (size_t)col * 4);
-    const float face = p.face_sim ? p.face_sim[(size_t)row * p.m + col] : 0.0f;
-    p.out_dists[(size_t)row * p.m + col] = (p.dense_stage == 3)
-                                               ? fuse_stage3(iou_d, sim, p.appearance, p.proximity)
-                                               : fuse_stage1(iou_d, sim, face, p.appearance);
+    const float face = p.face_sim[0] ? p.face_sim[0][(size_t)row * m + col] : 0.0f;
+    p.out_dists[(size_t)row * m + col] = (p.dense_stage == 3)
+                                             ? fuse_stage3(iou_d, sim, p.appearance, p.proximity)
+                                             : fuse_stage1(iou_d, sim, face, p.appearance);
   }
 }
 
@@ -203,32 +243,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
-}
-// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in cta_mask and
-// signals the mbarrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tmap, int x, int y,
-                                               uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y),
-        "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -316,9 +330,10 @@ struct TcSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kColPkOff = kStages * kStageBytes;             // uint2[BN]  packed integer det corners
   static constexpr int kColKindOff = kColPkOff + BN * 8;              // uint8[BN]
-  static constexpr int kColF64Off = kColKindOff + 256;                // double[BN][4] det box float64 (exact path)
+  static constexpr int kColInvOff = kColKindOff + 256;                // float[BN] 1 / detection feature norm (unconfirmed rows)
+  static constexpr int kColF64Off = kColInvOff + BN * 4;              // double[BN][4] det box float64 (exact path)
   static constexpr int kPreIouOff = kColF64Off + BN * 32;             // double[kEpiWarps][kPreSlots][32] IoU distance of box-pass edges
-  static constexpr int kPreKeyOff = kPreIouOff + 8 * 4 * 32 * 8;      // uint32[kEpiWarps][kPreSlots][32] their (column, position, list)
+  static constexpr int kPreKeyOff = kPreIouOff + 8 * 4 * 32 * 8;      // uint32[kEpiWarps][kPreSlots][32] their (column, list, flags)
   static constexpr int kBarOff = kPreKeyOff + 8 * 4 * 32 * 4;         // barriers (8B aligned)
   static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
@@ -326,20 +341,25 @@ struct TcSmem {
   static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024 B alignment
 };
 
-// Thread-block cluster of CM x CN CTAs (cluster rank = rm * CN + rn) covering CM x CN adjacent output
-// tiles.  The CN CTAs of a cluster row need the same A tile and the CM CTAs of a cluster column the
-// same B tile: every CTA loads a 1/CN slice of its A tile and a 1/CM slice of its B tile and TMA
-// multicasts them to its row / column mates, cutting the L2->SM operand traffic per CTA from
-// (BM + BN) to (BM/CN + BN/CM) rows per k-block (the v1 kernel was bound by exactly that traffic,
-// profiles/README.md).
-template <int BN, bool kDense, int CM, int CN>
+// tile t of the batch -> problem k and its tile coordinates
+__device__ __forceinline__ void tile_of(const EpiParams& p, int t, int bn, int& k, int& m0, int& n0) {
+  k = 0;
+  while (k + 1 < p.count && t >= p.tile_start[k + 1]) ++k;
+  const int local = t - p.tile_start[k];
+  const int tiles_n = (p.m[k] + bn - 1) / bn;
+  m0 = (local / tiles_n) * BM;
+  n0 = (local % tiles_n) * bn;
+}
+
+// One persistent CTA per SM walks the 128 x BN output tiles of every problem of the batch (video streams
+// are a leading dimension: tile -> (stream, tile row, tile column)); with more tiles than SMs the second
+// TMEM accumulator stage lets tile i's epilogue run under tile i+1's main loop.
+template <int BN, bool kDense>
+// 10 warps = 3 + 3 + 2 + 2 per SM sub-partition of 16 K registers: 168 registers per thread is the ceiling
 __global__ void __launch_bounds__(kTcThreads, 1)
 assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const __grid_constant__ EpiParams p, int d) {   // grid constant: &p (open_pair_slow) needs no local copy
   using L = TcSmem<BN>;
-  constexpr int CS = CM * CN;
-  constexpr int kASlice = BM / CN, kBSlice = BN / CM;  // rows each CTA loads itself
-  static_assert(kASlice % 8 == 0 && kBSlice % 8 == 0, "slices must keep the 8-row swizzle atoms whole");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -349,6 +369,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   uint2* s_colpk = reinterpret_cast<uint2*>(smem + L::kColPkOff);
   uint8_t* s_colkind = smem + L::kColKindOff;
+  float* s_colinv = reinterpret_cast<float*>(smem + L::kColInvOff);
   double* s_preiou = reinterpret_cast<double*>(smem + L::kPreIouOff);
   uint32_t* s_prekey = reinterpret_cast<uint32_t*>(smem + L::kPreKeyOff);
   double* s_col64 = reinterpret_cast<double*>(smem + L::kColF64Off);
@@ -357,21 +378,9 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const long long t_start = clock64();
   unsigned long long g_start = 0;
   if (p.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
-  const int tiles_m = (p.n + BM - 1) / BM, tiles_n = (p.m + BN - 1) / BN;
   const int num_kb = d / BK;
-  // cluster geometry: cluster `cid` walks "cluster tiles" of CM x CN output tiles; tiles past the
-  // matrix edge are still executed by their CTA (TMA zero-fills, the epilogue masks) so that every
-  // CTA of a cluster runs the same number of pipeline steps.
-  const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
-  const int rm = crank / CN, rn = crank % CN;
-  const int cid = blockIdx.x / CS, num_clusters = gridDim.x / CS;
-  const int ctiles_n = (tiles_n + CN - 1) / CN;
-  const int num_ctiles = ((tiles_m + CM - 1) / CM) * ctiles_n;
-  uint16_t row_mask = 0, col_mask = 0;   // my cluster-row mates (share A), my cluster-column mates (share B)
-#pragma unroll
-  for (int j = 0; j < CN; ++j) row_mask |= (uint16_t)(1u << (rm * CN + j));
-#pragma unroll
-  for (int i = 0; i < CM; ++i) col_mask |= (uint16_t)(1u << (i * CN + rn));
+  const int num_tiles = p.tile_start[p.count];
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as SMs free
   // up (it blocks in its own griddepcontrol.wait until this grid has completed and flushed).
@@ -380,21 +389,24 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
-    // a slot is free again when every CTA that receives my slices has consumed it
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CM + CN - 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (CS == 1 && cid < num_ctiles && !(p.debug & 64)) {
+    // The operands (feature bank, detection features) are complete before the previous kernel of the
+    // stream even starts when the host says so (operands_early): the main loop then runs under that
+    // kernel; only the epilogue (boxes, kinds, candidate lists) waits for it.
+    if (!p.operands_early) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (first_tile < num_tiles && !(p.debug & 64)) {
       // the pipeline's first kStages loads do not wait for anybody: request them before the TMEM
       // allocation and the CTA-wide sync so that their latency overlaps the rest of the ramp
-      asm volatile("griddepcontrol.wait;" ::: "memory");   // the operands come from the previous kernels
-      const int m0 = (cid / ctiles_n) * BM, n0 = (cid % ctiles_n) * BN;
+      int k, m0, n0;
+      tile_of(p, first_tile, BN, k, m0, n0);
       pro_kb = num_kb < kStages ? num_kb : kStages;
       for (int kb = 0; kb < pro_kb; ++kb) {
         mbar_expect_tx(&full_bar[kb], L::kStageBytes);
         uint8_t* sa = smem + kb * L::kStageBytes;
-        tma_load_2d(sa, &tmap_a, kb * BK, m0, &full_bar[kb]);
-        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, n0, &full_bar[kb]);
+        tma_load_2d(sa, &tmap_a, kb * BK, p.a_row0[k] + m0, &full_bar[kb]);
+        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, p.b_row0[k] + n0, &full_bar[kb]);
       }
     }
   }
@@ -411,8 +423,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  if (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast / remote arrive
-  else __syncthreads();
+  __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -421,18 +432,16 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (lane == 0) {
       int stage = pro_kb % kStages;
       uint32_t phase = pro_kb == kStages ? 1u : 0u;
-      if (CS > 1) asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
-        const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
-        for (int kb = (ct == cid) ? pro_kb : 0; kb < num_kb; ++kb) {
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        int k, m0, n0;
+        tile_of(p, t, BN, k, m0, n0);
+        const int ya = p.a_row0[k] + m0, yb = p.b_row0[k] + n0;
+        for (int kb = (t == first_tile) ? pro_kb : 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);   // the whole stage lands here (own + mates' slices)
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          if (CN > 1) tma_load_2d_mc(sa + rn * kASlice * 128, &tmap_a, kb * BK, m0 + rn * kASlice, &full_bar[stage], row_mask);
-          else tma_load_2d(sa, &tmap_a, kb * BK, m0, &full_bar[stage]);
-          if (CM > 1) tma_load_2d_mc(sb + rm * kBSlice * 128, &tmap_b, kb * BK, n0 + rm * kBSlice, &full_bar[stage], col_mask);
-          else tma_load_2d(sb, &tmap_b, kb * BK, n0, &full_bar[stage]);
+          tma_load_2d(sa, &tmap_a, kb * BK, ya, &full_bar[stage]);
+          tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, yb, &full_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -444,7 +453,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -455,14 +464,12 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
           const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::kABytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
             // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
-            tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                            (uint32_t)((kb | k) != 0));
+            tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                            (uint32_t)((kb | kk) != 0));
           }
-          // frees the smem slot (here and at every mate that multicasts into it) when these MMAs retire
-          if (CS > 1) tcgen05_commit_mc(&empty_bar[stage], (uint16_t)(row_mask | col_mask));
-          else tcgen05_commit(&empty_bar[stage]);
+          tcgen05_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
@@ -481,14 +488,19 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const long long t_go = clock64();
     unsigned long long g_go = 0;
     if (p.debug & 1024) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_go));
-    for (int ct = cid; ct < num_ctiles; ct += num_clusters) {
-      const int m0 = ((ct / ctiles_n) * CM + rm) * BM, n0 = ((ct % ctiles_n) * CN + rn) * BN;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      int k, m0, n0;
+      tile_of(p, t, BN, k, m0, n0);
+      const int pn = p.n[k], pm = p.m[k];
+      const int sid = p.cand_sid[k];
+      const size_t R0 = (size_t)p.row0[k], C0 = (size_t)p.col0[k];
       const int row = m0 + quarter * 32 + lane;
       int rkind = BT_ROW_NONE;
       double rbox[4] = {0.0, 0.0, 0.0, 0.0};
       uint32_t r2h = 0, r1p = 0;   // packed conservative integer row box (see pack16 below)
       int rix1 = 0, riy1 = 0, rix2 = 0, riy2 = 0;
       float r_area_lb = 0.f;
+      float rnorm = 1.0f;
       long long t_s1 = 0, t_s2 = 0, t_s3 = 0, t_rl = 0;
       if (!kDense) {
         // All global loads of the tile first, in one batch and without dependent chains: while the TMA
@@ -500,17 +512,20 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         float4 r32 = make_float4(0.f, 0.f, 0.f, 0.f);
         uint2 cpk = make_uint2(0u, 0u);
         uint8_t ck = BT_COL_NONE;
-        if (row < p.n) {
-          const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (size_t)row * 4);
-          rkind = p.row_kind[row];
+        float cn = 1.0f;
+        if (row < pn) {
+          const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (R0 + row) * 4);
+          rkind = reinterpret_cast<const uint8_t*>(p.row_kind_base + p.kind_off[k])[row];
           rlo = s[0]; rhi = s[1];
-          if (p.row_tlbr_f32) r32 = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
+          if (p.row_tlbr_f32) r32 = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (R0 + row) * 4);
+          if (p.row_norm) rnorm = p.row_norm[R0 + row];
         }
-        if (c < BN && col < p.m) {
-          const double2* s = reinterpret_cast<const double2*>(p.col_tlbr + (size_t)col * 4);
-          ck = p.col_kind[col];
+        if (c < BN && col < pm) {
+          const double2* s = reinterpret_cast<const double2*>(p.col_tlbr + (C0 + col) * 4);
+          ck = p.col_kind[C0 + col];
           clo = s[0]; chi = s[1];
-          if (p.col_pk) cpk = p.col_pk[col];
+          if (p.col_pk) cpk = p.col_pk[C0 + col];
+          if (p.col_norm) cn = p.col_norm[C0 + col];
         }
         // stage the detection boxes: packed 15-bit integer corners for the screen, float64 for the exact
         // path, and the score class
@@ -521,6 +536,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (ck != BT_COL_NONE) pk = p.col_pk ? cpk : pack16_box(clo.x, clo.y, chi.x, chi.y, true);
           s_colpk[c] = pk;
           s_colkind[c] = ck;
+          s_colinv[c] = cn > 0.f ? 1.0f / cn : 0.f;
           reinterpret_cast<double2*>(s_col64 + c * 4)[0] = clo;
           reinterpret_cast<double2*>(s_col64 + c * 4)[1] = chi;
         }
@@ -551,11 +567,15 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int cnt_a = 0, cnt_b = 0;   // edges appended so far: list 0 (or 2 for an unconfirmed row) | list 1
       my_prekey[lane] = 0u; my_prekey[32 + lane] = 0u;   // slots 0 / 1 are read unconditionally by the exact pass
       int npre = 0;               // box-pass candidates waiting in shared memory (<= kPreSlots)
-      int last_a = 0, last_b = 0; // column of the latest edge per list (the row's only column if its degree stays 1)
+      int last_a = 0, last_b = 0; // column (| flags) of the latest edge per list (the row's only column if its degree stays 1)
       int spill_a = -1, spill_b = -1;   // 0 once the box pass wrote edges of a crowded row straight to the list
       int dbg_open = 0;
-      const int la = (rkind == BT_ROW_UNCONFIRMED) ? 2 : 0;
-      const double thr_a = (rkind == BT_ROW_UNCONFIRMED) ? p.unconf_thresh : p.match_thresh;
+      const bool unc = rkind == BT_ROW_UNCONFIRMED;
+      const int la = unc ? 2 : 0;
+      const double thr_a = unc ? p.unconf_thresh : p.match_thresh;
+      // the raw accumulator of this row opens the appearance gate (or comes within the tensor-core error of
+      // it) at acc >= gate_lo: sim = acc / ||track feature|| (the bank holds raw rows)
+      const float gate_lo = (rnorm > 0.f) ? (p.sim_gate - p.gate_band) * rnorm : 3.0e38f;
       // candidate list a (row, detection class) pair belongs to: demo:1539-1556 (0), demo:1569-1571 (1), demo:1593-1604 (2)
       auto list_of = [&](const int ckind) -> int {
         if (ckind == BT_COL_HIGH) return la;
@@ -577,7 +597,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       //  3. exact float64 IoU distance against the stage threshold.
       // (With real face similarities the gate is not a function of the body similarity alone: everything
       // is left to the similarity pass.)
-      const bool all_open = p.face_sim != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
+      const bool all_open = p.face_sim[k] != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
       if (!kDense && !all_open && rkind != BT_ROW_NONE) {
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch) {
@@ -618,9 +638,9 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // crowded row (more than kPreSlots box candidates in this half tile): evaluate now, straight to the list
             const double iou_d = iou_dist_f64(rbox, s_col64 + lc * 4);
             if (!(iou_d < (list == 1 ? p.second_thresh : thr_a))) continue;
-            const int k = (list == 1) ? cnt_b++ : cnt_a++;
+            const int kk = (list == 1) ? cnt_b++ : cnt_a++;
             if (list == 1) { last_b = n0 + lc; spill_b = 0; } else { last_a = n0 + lc; spill_a = 0; }
-            emit_owned_tc(p.cand, list, row, seg, k, n0 + lc, iou_d);
+            emit_owned_tc(p, sid, list, row, seg, kk, n0 + lc, 0, iou_d);
           }
         }
       }
@@ -637,28 +657,34 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         else tmem_ld_32x32b_x16(taddr + c0, v);
       };
       // ---- Similarity pass.  A pair whose appearance gate is open (sim >= sim_gate, == !((1.0f - sim) >
-      // appearance), sim_gate_for()) gets the fused cost: an edge of the box pass is overwritten in place,
-      // otherwise the pair is evaluated from scratch.  Lane-local, no shuffles: the lane owns its row.
-      auto open_pair = [&](const int lc, const float sim) {
+      // appearance), sim_gate_for()) or within the tensor-core error of it gets the fused cost: an edge of
+      // the box pass is overwritten in place, otherwise the pair is evaluated from scratch.  Lane-local, no
+      // shuffles: the lane owns its row.
+      auto open_pair = [&](const int lc, const float accv) {
         const int list = list_of(s_colkind[lc]);
         if (list < 0) return;
+        float sim = accv;
+        if (p.row_norm) sim = (rnorm > 0.f) ? accv / rnorm : 0.f;       // curr feature = raw row / norm (demo:497-502)
+        if (unc && p.col_norm) sim *= s_colinv[lc];                     // stage 3 compares normalised detections (demo:1593-1599)
         const uint32_t want = (uint32_t)lc | ((uint32_t)(list == 1) << 16);
         bool found = false;
 #pragma unroll
         for (int j = 0; j < kPreSlots; ++j) {
-          if (j < npre && my_prekey[j * 32 + lane] == want) {
+          if (j < npre && (my_prekey[j * 32 + lane] & 0x1ffffu) == want) {
             // an edge of the box pass whose gate turned out open (slots exist only without a face term)
             const double iou_d = my_preiou[j * 32 + lane];
             if (list == 0) my_preiou[j * 32 + lane] = fuse_stage1(iou_d, sim, 0.0f, p.appearance);
             if (list == 2) my_preiou[j * 32 + lane] = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
+            const int fl = sim_flags(p, list, sim, 0.0f);
+            my_prekey[j * 32 + lane] = want | ((fl & BT_EDGE_SIM) ? (1u << 17) : 0u) | ((fl & BT_EDGE_AMBIG) ? (1u << 18) : 0u);
             found = true;
           }
         }
         if (found) return;
         const int cnt = (list == 1) ? cnt_b : cnt_a;
-        const int added = open_pair_slow(p, rbox[0], rbox[1], rbox[2], rbox[3], s_col64 + lc * 4, list, row, seg, n0 + lc, sim,
+        const int added = open_pair_slow(p, k, rbox[0], rbox[1], rbox[2], rbox[3], s_col64 + lc * 4, list, row, seg, n0 + lc, sim,
                                          cnt, (list == 1) ? spill_b : spill_a);
-        if (added) { if (list == 1) { ++cnt_b; last_b = n0 + lc; } else { ++cnt_a; last_a = n0 + lc; } }
+        if (added >= 0) { if (list == 1) { ++cnt_b; last_b = added; } else { ++cnt_a; last_a = added; } }
       };
       long long t_l0 = 0, t_l1 = 0;
       if (kDense) {
@@ -667,35 +693,53 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           issue(ch, va);
           tmem_ld_wait_dep(va);
           const int W = (ch < kFullChunks) ? 32 : kTailCols;
-          if (row < p.n) {
+          if (row < pn) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const int col = n0 + half * kHalfCols + ch * 32 + c;
-              if (c < W && col < p.m) assoc_dense(p, row, col, __uint_as_float(va[c]));
+              if (c < W && col < pm) assoc_dense(p, row, col, __uint_as_float(va[c]));
             }
           }
         }
       } else {
-        // phase A: chunk maxima, TMEM loads software-pipelined, no branches
+        // phase A: chunk maxima, TMEM loads software-pipelined, no branches.  Warps that hold an unconfirmed
+        // row while detection norms are in play (rare) scale every element by 1 / ||detection feature||.
         uint32_t gatebits = 0;
-        issue(0, va);
+        const bool scaled = __any_sync(0xffffffffu, unc && p.col_norm != nullptr);
+        if (!scaled) {
+          issue(0, va);
 #pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-          uint32_t (&cur)[32] = (ch & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
-          tmem_ld_wait_dep(cur);
-          if (p.debug & 16) { if (ch == 0) t_l0 = clock64(); if (ch == 1) t_l1 = clock64(); }
-          if (ch + 1 < kChunks) issue(ch + 1, nxt);
-          const int G = ((ch < kFullChunks) ? 32 : kTailCols) / 4;
-          float m4[8];
+          for (int ch = 0; ch < kChunks; ++ch) {
+            uint32_t (&cur)[32] = (ch & 1) ? vb : va;
+            uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
+            tmem_ld_wait_dep(cur);
+            if (p.debug & 16) { if (ch == 0) t_l0 = clock64(); if (ch == 1) t_l1 = clock64(); }
+            if (ch + 1 < kChunks) issue(ch + 1, nxt);
+            const int G = ((ch < kFullChunks) ? 32 : kTailCols) / 4;
+            float m4[8];
 #pragma unroll
-          for (int g = 0; g < G; ++g)
-            m4[g] = fmaxf(fmaxf(__uint_as_float(cur[4 * g]), __uint_as_float(cur[4 * g + 1])),
-                          fmaxf(__uint_as_float(cur[4 * g + 2]), __uint_as_float(cur[4 * g + 3])));
-          float mx = m4[0];
-          if (G == 8) mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
-          else mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          if (mx >= p.sim_gate) gatebits |= 1u << ch;
+            for (int g = 0; g < G; ++g)
+              m4[g] = fmaxf(fmaxf(__uint_as_float(cur[4 * g]), __uint_as_float(cur[4 * g + 1])),
+                            fmaxf(__uint_as_float(cur[4 * g + 2]), __uint_as_float(cur[4 * g + 3])));
+            float mx = m4[0];
+            if (G == 8) mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+            else mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            if (mx >= gate_lo) gatebits |= 1u << ch;
+          }
+        } else {
+#pragma unroll 1
+          for (int ch = 0; ch < kChunks; ++ch) {
+            tmem_ld_32x32b_x32(taddr + (uint32_t)(half * kHalfCols + ch * 32), va);
+            tmem_ld_wait_dep(va);
+            const int W = (ch < kFullChunks) ? 32 : kTailCols;
+            float mx = -3.0e38f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float f = unc ? s_colinv[half * kHalfCols + ch * 32 + (c < W ? c : 0)] : 1.0f;
+              if (c < W) mx = fmaxf(mx, __uint_as_float(va[c]) * f);
+            }
+            if (mx >= gate_lo) gatebits |= 1u << ch;
+          }
         }
         if (all_open) gatebits = (1u << kChunks) - 1u;
         // exact pass: float64 IoU distance of the remembered candidates, all lanes at once; slots 0 and 1
@@ -724,9 +768,15 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           tmem_ld_wait_dep(va);
           if ((gatebits >> ch) & 1u) {
             uint32_t hot = 0;
+            if (scaled && unc) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (__uint_as_float(va[c]) >= p.sim_gate) hot |= 1u << c;
+              for (int c = 0; c < 32; ++c)
+                if (__uint_as_float(va[c]) * s_colinv[half * kHalfCols + ch * 32 + ((ch < kFullChunks || c < kTailCols) ? c : 0)] >= gate_lo) hot |= 1u << c;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (__uint_as_float(va[c]) >= gate_lo) hot |= 1u << c;
+            }
             if (all_open) hot = 0xffffffffu;
             if (ch >= kFullChunks) hot &= (1u << kTailCols) - 1u;
             while (hot) {
@@ -742,8 +792,8 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               for (int i = 0; i < 4; ++i) s4[i] = (c & 4) ? s8[i + 4] : s8[i];
 #pragma unroll
               for (int i = 0; i < 2; ++i) s2[i] = (c & 2) ? s4[i + 2] : s4[i];
-              const float sim = __uint_as_float((c & 1) ? s2[1] : s2[0]);
-              open_pair(half * kHalfCols + ch * 32 + c, sim);
+              const float accv = __uint_as_float((c & 1) ? s2[1] : s2[0]);
+              open_pair(half * kHalfCols + ch * 32 + c, accv);
               ++dbg_open;
             }
           }
@@ -760,29 +810,30 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const uint32_t key = my_prekey[j * 32 + lane];
             const double cost = my_preiou[j * 32 + lane];
             const int col = n0 + (int)(key & 0xffu);
+            const int fl = ((key >> 17) & 1u ? BT_EDGE_SIM : 0) | ((key >> 18) & 1u ? BT_EDGE_AMBIG : 0);
             if ((key >> 16) & 1u) {
-              if (cost < p.second_thresh) { emit_owned_tc(p.cand, 1, row, seg, cnt_b++, col, cost); last_b = col; }
-            } else if (cost < thr_a) {
-              emit_owned_tc(p.cand, la, row, seg, cnt_a++, col, cost);
-              last_a = col;
+              if (cost < p.second_thresh) { emit_owned_tc(p, sid, 1, row, seg, cnt_b++, col, 0, cost); last_b = col; }
+            } else if (cost < thr_a || (fl & BT_EDGE_AMBIG)) {
+              emit_owned_tc(p, sid, la, row, seg, cnt_a++, col, fl, cost);
+              last_a = col | fl;
             }
           }
         }
         if (cnt_a) {
           const size_t ri = (size_t)la * p.cand.rows_cap + row;
-          p.cand.cnt[ri * p.cand.nseg + seg] = cnt_a;
-          atomicAdd(&p.cand.total[la], cnt_a);
-          atomicOr(&p.cand.segmask[ri], 1ull << seg);
-          atomicAdd(&p.cand.rowdeg[ri], cnt_a);
-          if (cnt_a == 1) p.cand.rowcol[ri] = last_a;
+          c_cnt(p, sid)[ri * p.cand.nseg + seg] = cnt_a;
+          atomicAdd(&c_total(p, sid)[la], cnt_a);
+          atomicOr(&c_segmask(p, sid)[ri], 1ull << seg);
+          atomicAdd(&c_rowdeg(p, sid)[ri], cnt_a);
+          if (cnt_a == 1) c_rowcol(p, sid)[ri] = last_a;
         }
         if (cnt_b) {
           const size_t ri = (size_t)1 * p.cand.rows_cap + row;
-          p.cand.cnt[ri * p.cand.nseg + seg] = cnt_b;
-          atomicAdd(&p.cand.total[1], cnt_b);
-          atomicOr(&p.cand.segmask[ri], 1ull << seg);
-          atomicAdd(&p.cand.rowdeg[ri], cnt_b);
-          if (cnt_b == 1) p.cand.rowcol[ri] = last_b;
+          c_cnt(p, sid)[ri * p.cand.nseg + seg] = cnt_b;
+          atomicAdd(&c_total(p, sid)[1], cnt_b);
+          atomicOr(&c_segmask(p, sid)[ri], 1ull << seg);
+          atomicAdd(&c_rowdeg(p, sid)[ri], cnt_b);
+          if (cnt_b == 1) c_rowcol(p, sid)[ri] = last_b;
         }
       }
       tcgen05_fence_before();
@@ -807,8 +858,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   tcgen05_fence_before();
   __syncwarp();
-  if (CS > 1) cluster_sync_all();   // no CTA leaves while a mate may still arrive on its barriers
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -822,17 +872,26 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// CUDA-core fp32 kernel (small problems, feature sizes that are not a multiple of 64, and the
-// on-device cross-check of the tensor path in the tests)
+// CUDA-core kernel (IoU-only association, small feature sizes, feature sizes that are not a multiple
+// of 64, and the exact cross-check of the tensor path in the tests): fp32 accumulation of fp32 or fp16
+// operands -- with fp16 ingest the operands ARE the reference's values, so this path is exact.
 // ------------------------------------------------------------------------------------------------
 constexpr int ST = 64, SK = 16;
 
-template <bool kDense>
+__device__ __forceinline__ float ld_feat(const float* p, size_t i) { return p[i]; }
+__device__ __forceinline__ float ld_feat(const __half* p, size_t i) { return __half2float(p[i]); }
+
+template <bool kDense, typename T>
 __global__ void __launch_bounds__(256)
-assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiParams p, int d) {
+assoc_simt_kernel(const T* __restrict__ a, const T* __restrict__ b, const __grid_constant__ EpiParams p, int d) {
   __shared__ float sa[SK][ST + 1];
   __shared__ float sb[SK][ST + 1];
+  const int k = blockIdx.z;
+  const int pn = p.n[k], pm = p.m[k];
   const int row0 = blockIdx.y * ST, col0 = blockIdx.x * ST;
+  if (row0 >= pn || col0 >= pm) return;
+  const size_t ar0 = (size_t)p.a_row0[k], br0 = (size_t)p.b_row0[k];
+  const size_t R0 = (size_t)p.row0[k], C0 = (size_t)p.col0[k];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -841,16 +900,16 @@ assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiP
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < d; k0 += SK) {
     for (int e = threadIdx.x; e < ST * SK; e += 256) {
-      const int r = e / SK, k = e % SK;
-      sa[k][r] = (row0 + r < p.n && k0 + k < d) ? a[(size_t)(row0 + r) * d + k0 + k] : 0.f;
-      sb[k][r] = (col0 + r < p.m && k0 + k < d) ? b[(size_t)(col0 + r) * d + k0 + k] : 0.f;
+      const int r = e / SK, kk = e % SK;
+      sa[kk][r] = (row0 + r < pn && k0 + kk < d) ? ld_feat(a, (ar0 + row0 + r) * d + k0 + kk) : 0.f;
+      sb[kk][r] = (col0 + r < pm && k0 + kk < d) ? ld_feat(b, (br0 + col0 + r) * d + k0 + kk) : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < SK; ++k) {
+    for (int kk = 0; kk < SK; ++kk) {
       float av[4], bv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { av[i] = sa[k][ty * 4 + i]; bv[i] = sb[k][tx * 4 + i]; }
+      for (int i = 0; i < 4; ++i) { av[i] = sa[kk][ty * 4 + i]; bv[i] = sb[kk][tx * 4 + i]; }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -863,44 +922,52 @@ assoc_simt_kernel(const float* __restrict__ a, const float* __restrict__ b, EpiP
   // float64 path
   uint2 cpk[4];
   int ckind[4];
+  float cinv[4];
   if (!kDense) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = col0 + tx * 4 + j;
       ckind[j] = BT_COL_NONE;
       cpk[j] = make_uint2(0x7fff7fffu, 0x80008000u);
-      if (col < p.m) {
-        ckind[j] = p.col_kind[col];
-        if (p.col_pk) cpk[j] = p.col_pk[col];
-        else { const double* c = p.col_tlbr + (size_t)col * 4; cpk[j] = pack16_box(c[0], c[1], c[2], c[3], true); }
+      cinv[j] = 1.0f;
+      if (col < pm) {
+        ckind[j] = p.col_kind[C0 + col];
+        if (p.col_pk) cpk[j] = p.col_pk[C0 + col];
+        else { const double* c = p.col_tlbr + (C0 + col) * 4; cpk[j] = pack16_box(c[0], c[1], c[2], c[3], true); }
+        if (p.col_norm) { const float cn = p.col_norm[C0 + col]; cinv[j] = cn > 0.f ? 1.0f / cn : 0.f; }
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = row0 + ty * 4 + i;
-    if (row >= p.n) continue;
-    const int rkind = (!kDense) ? p.row_kind[row] : 0;
+    if (row >= pn) continue;
+    const int rkind = (!kDense) ? reinterpret_cast<const uint8_t*>(p.row_kind_base + p.kind_off[k])[row] : 0;
     uint2 rpk = make_uint2(0u, 0u);
+    float rnorm = 1.0f;
     if (!kDense && rkind != BT_ROW_NONE) {
       if (p.row_tlbr_f32) {
-        const float4 r = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (size_t)row * 4);
+        const float4 r = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (R0 + row) * 4);
         rpk = bt_pack16_f32(r.x, r.y, r.z, r.w, false);
       } else {
-        const double* r = p.row_tlbr + (size_t)row * 4;
+        const double* r = p.row_tlbr + (R0 + row) * 4;
         rpk = pack16_box(r[0], r[1], r[2], r[3], false);
       }
+      if (p.row_norm) rnorm = p.row_norm[R0 + row];
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = col0 + tx * 4 + j;
-      if (col >= p.m) continue;
+      if (col >= pm) continue;
       if (kDense) {
         assoc_dense(p, row, col, acc[i][j]);
       } else {
         if (rkind == BT_ROW_NONE || ckind[j] == BT_COL_NONE) continue;
+        float sim = acc[i][j];
+        if (p.row_norm) sim = rnorm > 0.f ? sim / rnorm : 0.f;
+        if (rkind == BT_ROW_UNCONFIRMED) sim *= cinv[j];
         const bool overlap = ((rpk.y - cpk[j].x) & (cpk[j].y - rpk.x) & 0x80008000u) == 0x80008000u;
-        if (overlap || acc[i][j] >= p.sim_gate || p.face_sim != nullptr) assoc_exact(p, row, col, acc[i][j], rkind, ckind[j]);
+        if (overlap || sim >= p.sim_gate || p.face_sim[k] != nullptr) assoc_exact(p, k, row, col, sim, rkind, ckind[j]);
       }
     }
   }
@@ -946,7 +1013,7 @@ void bt_gemm_ws_destroy(bt_ctx* ctx) {
 }
 
 static int32_t make_tmap(bt_ctx* ctx, CUtensorMap* tm, const __half* base, int rows, int d, int box_rows) {
-  bt_gemm_ws* ws = ctx->gemm;
+  bt_gemm_ws* ws = ctx->gemm;      // per ctx (a ctx belongs to one host thread): no shared state between threads
   for (const auto& e : ws->cache)
     if (e.base == base && e.rows == rows && e.d == d && e.box_rows == box_rows) { *tm = e.map; return BT_OK; }
   const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
@@ -964,101 +1031,90 @@ static int32_t make_tmap(bt_ctx* ctx, CUtensorMap* tm, const __half* base, int r
   return BT_OK;
 }
 
-template <int BN, bool kDense, int CM, int CN>
-static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep) {
-  constexpr int CS = CM * CN;
+template <int BN, bool kDense>
+static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, EpiParams& ep) {
   CUtensorMap ta, tb;
-  BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.a_rows_alloc > 0 ? ap.a_rows_alloc : ap.n, ap.d, BM / CN));  // box = one CTA's slice
-  BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.b_rows_alloc > 0 ? ap.b_rows_alloc : ap.m, ap.d, BN / CM));
-  auto kern = assoc_tc_kernel<BN, kDense, CM, CN>;
-  static int cached_clusters = -1;   // per instantiation: attribute + occupancy query only once
-  if (cached_clusters < 0)
-    BT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn));
-  const int tiles_m = (ap.n + BM - 1) / BM, tiles_n = (ap.m + BN - 1) / BN;
-  const int ctiles = ((tiles_m + CM - 1) / CM) * ((tiles_n + CN - 1) / CN);
+  BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.a_rows_alloc, ap.d, BM));
+  BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.b_rows_alloc, ap.d, BN));
+  auto kern = assoc_tc_kernel<BN, kDense>;
+  static std::once_flag attr_once;     // per instantiation; safe with several host threads (one ctx each)
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn);
+  });
+  BT_CUDA(attr_err);
+  int tiles = 0;
+  for (int k = 0; k < ap.count; ++k) {
+    ep.tile_start[k] = tiles;
+    tiles += ((ap.n[k] + BM - 1) / BM) * ((ap.m[k] + BN - 1) / BN);
+  }
+  ep.tile_start[ap.count] = tiles;
+  for (int k = ap.count + 1; k <= BT_MAX_BATCH; ++k) ep.tile_start[k] = tiles;
+  if (tiles == 0) return BT_OK;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = TcSmem<BN>::kDyn;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(tiles < ctx->num_sms ? tiles : ctx->num_sms);
+  cudaLaunchAttribute attr[1];
+  // may start its ramp (and, with operands_early, its main loop) under the previous kernel (griddepcontrol.wait inside)
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (cached_clusters < 0) {
-    int q = ctx->num_sms / CS;
-    if (CS > 1) {
-      cfg.gridDim = dim3(CS);
-      BT_CUDA(cudaOccupancyMaxActiveClusters(&q, kern, &cfg));
-      BT_CHECK(q > 0, BT_ERR_CUDA, "cluster of %d CTAs cannot be scheduled", CS);
-    }
-    cached_clusters = q;
-  }
-  const int max_clusters = cached_clusters;
-  const int nclusters = ctiles < max_clusters ? ctiles : max_clusters;
-  cfg.gridDim = dim3(nclusters * CS);
-  if (CS == 1) {
-    // no cluster attribute; may start its ramp under the previous kernel's tail (griddepcontrol.wait inside)
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.numAttrs = ctx->pdl ? 1 : 0;
-  }
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
   BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
-// Cluster shape of the association GEMM.  BT_ASSOC_CLUSTER=CMxCN overrides (profiling sweeps).
-static void pick_cluster(int* cm, int* cn) {
-  *cm = 1; *cn = 1;   // measured: multicast clusters do not pay (the kernel is MMA/epilogue bound, profiles/README.md)
-  const char* e = getenv("BT_ASSOC_CLUSTER");
-  if (e && e[0] >= '1' && e[0] <= '4' && e[1] == 'x' && e[2] >= '1' && e[2] <= '4') { *cm = e[0] - '0'; *cn = e[2] - '0'; }
-}
-
-int32_t btk_assoc_pick_bn(const bt_ctx* ctx, int32_t n, int32_t m) {
+int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m, int32_t count) {
   const char* e = getenv("BT_ASSOC_BN");
   if (e) return atoi(e) == 224 ? 224 : 256;
-  const int tiles_m = (n + BM - 1) / BM;
   long best_cost = -1;
   int best = 256;
   for (int bn : {256, 224}) {
-    const long tiles = (long)tiles_m * ((m + bn - 1) / bn);
+    long tiles = 0;
+    for (int k = 0; k < count; ++k) tiles += (long)((n[k] + BM - 1) / BM) * ((m[k] + bn - 1) / bn);
     const long waves = (tiles + ctx->num_sms - 1) / ctx->num_sms;
-    const long cost = waves * bn;
+    const long cost = waves * bn;      // a tile's main loop costs the tensor pipe time proportional to its width
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
 
-template <bool kDense>
-static int32_t launch_tc_cluster(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep) {
-  int cm, cn;
-  pick_cluster(&cm, &cn);
-  if (ap.bn == 224) return launch_tc<224, kDense, 1, 1>(ctx, ap, ep);
-  if (cm == 1 && cn == 1) return launch_tc<256, kDense, 1, 1>(ctx, ap, ep);
-  if (cm == 1 && cn == 2) return launch_tc<256, kDense, 1, 2>(ctx, ap, ep);
-  if (cm == 2 && cn == 1) return launch_tc<256, kDense, 2, 1>(ctx, ap, ep);
-  if (cm == 2 && cn == 2) return launch_tc<256, kDense, 2, 2>(ctx, ap, ep);
-  if (cm == 4 && cn == 2) return launch_tc<256, kDense, 4, 2>(ctx, ap, ep);
-  if (cm == 2 && cn == 4) return launch_tc<256, kDense, 2, 4>(ctx, ap, ep);
-  if (cm == 4 && cn == 1) return launch_tc<256, kDense, 4, 1>(ctx, ap, ep);
-  if (cm == 1 && cn == 4) return launch_tc<256, kDense, 1, 4>(ctx, ap, ep);
-  return bt_fail(ctx, BT_ERR_INVALID, "unsupported BT_ASSOC_CLUSTER %dx%d", cm, cn);
-}
-
 int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
-  if (ap.n <= 0 || ap.m <= 0) return BT_OK;
+  BT_CHECK(ap.count >= 1 && ap.count <= BT_MAX_BATCH, BT_ERR_INVALID, "bad batch size %d", ap.count);
+  int any = 0, mx_n = 0, mx_m = 0;
+  for (int k = 0; k < ap.count; ++k) {
+    if (ap.n[k] > 0 && ap.m[k] > 0) any = 1;
+    mx_n = ap.n[k] > mx_n ? ap.n[k] : mx_n;
+    mx_m = ap.m[k] > mx_m ? ap.m[k] : mx_m;
+  }
+  if (!any) return BT_OK;
   EpiParams ep;
-  ep.row_tlbr = ap.row_tlbr; ep.row_tlbr_f32 = ap.row_tlbr_f32; ep.row_kind = ap.row_kind;
-  ep.col_tlbr = ap.col_tlbr; ep.col_kind = ap.col_kind; ep.col_pk = ap.col_pk; ep.face_sim = ap.face_sim;
+  memset(&ep, 0, sizeof(ep));
+  ep.count = ap.count;
+  for (int k = 0; k < ap.count; ++k) {
+    // an empty problem contributes no tiles: zero both sizes so that the tile arithmetic sees it
+    const bool empty = ap.n[k] <= 0 || ap.m[k] <= 0;
+    ep.n[k] = empty ? 0 : ap.n[k]; ep.m[k] = empty ? 0 : ap.m[k];
+    ep.a_row0[k] = ap.a_row0[k]; ep.b_row0[k] = ap.b_row0[k];
+    ep.row0[k] = ap.row0[k]; ep.col0[k] = ap.col0[k];
+    ep.kind_off[k] = ap.kind_off[k]; ep.pos_off[k] = ap.pos_off[k];
+    ep.cand_sid[k] = ap.cand_sid[k];
+    ep.face_sim[k] = ap.face_sim[k];
+  }
+  ep.row_tlbr = ap.row_tlbr; ep.row_tlbr_f32 = ap.row_tlbr_f32; ep.row_norm = ap.row_norm;
+  ep.row_kind_base = ap.row_kind_base;
+  ep.col_tlbr = ap.col_tlbr; ep.col_kind = ap.col_kind; ep.col_pk = ap.col_pk; ep.col_norm = ap.col_norm;
   ep.match_thresh = ap.match_thresh; ep.second_thresh = ap.second_thresh;
   ep.unconf_thresh = ap.unconf_thresh; ep.proximity = ap.proximity; ep.appearance = ap.appearance;
   ep.cand = ap.cand; ep.out_emb = ap.out_emb; ep.out_dists = ap.out_dists;
-  ep.dense_stage = ap.dense_stage; ep.n = ap.n; ep.m = ap.m;
+  ep.dense_stage = ap.dense_stage;
+  ep.operands_early = ap.operands_early;
   ep.debug = getenv("BT_ASSOC_DEBUG") ? atoi(getenv("BT_ASSOC_DEBUG")) : 0;
   ep.sim_gate = sim_gate_for(ap.appearance);
+  ep.gate_band = ap.gate_band;
   {
     double mx = ap.match_thresh > ap.second_thresh ? ap.match_thresh : ap.second_thresh;
     if (ap.unconf_thresh > mx) mx = ap.unconf_thresh;
@@ -1066,19 +1122,27 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
     ep.iou_gate = g > 0.0 ? (float)g : 0.0f;
   }
   const bool dense = (ap.out_emb != nullptr) || (ap.out_dists != nullptr);
+  BT_CHECK(!dense || ap.count == 1, BT_ERR_INVALID, "dense dumps take one problem");
   if (precision == 0) {
     BT_CHECK(ap.d % BK == 0 && ap.d >= BK, BT_ERR_INVALID,
              "tensor-core similarity needs feat_dim %% 64 == 0 (got %d)", ap.d);
     BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "fp16 operands missing");
     BT_CHECK(dense || ap.cand.seg * 2 == (ap.bn ? ap.bn : 256), BT_ERR_STATE,
              "candidate segment size %d does not match the tile width %d", ap.cand.seg, ap.bn ? ap.bn : 256);
-    if (dense) return launch_tc_cluster<true>(ctx, ap, ep);
-    return launch_tc_cluster<false>(ctx, ap, ep);
+    if (ap.bn == 224) return dense ? launch_tc<224, true>(ctx, ap, ep) : launch_tc<224, false>(ctx, ap, ep);
+    return dense ? launch_tc<256, true>(ctx, ap, ep) : launch_tc<256, false>(ctx, ap, ep);
   }
-  BT_CHECK(ap.a32 && ap.b32, BT_ERR_INVALID, "fp32 operands missing");
-  dim3 grid((ap.m + ST - 1) / ST, (ap.n + ST - 1) / ST);
-  if (dense) assoc_simt_kernel<true><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
-  else assoc_simt_kernel<false><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
+  ep.gate_band = 0.f;
+  dim3 grid((mx_m + ST - 1) / ST, (mx_n + ST - 1) / ST, ap.count);
+  if (ap.a32 != nullptr || ap.d == 0) {
+    BT_CHECK(ap.d == 0 || (ap.a32 && ap.b32), BT_ERR_INVALID, "fp32 operands missing");
+    if (dense) assoc_simt_kernel<true, float><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
+    else assoc_simt_kernel<false, float><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
+  } else {
+    BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "operands missing");
+    if (dense) assoc_simt_kernel<true, __half><<<grid, 256, 0, ctx->stream>>>(ap.a16, ap.b16, ep, ap.d);
+    else assoc_simt_kernel<false, __half><<<grid, 256, 0, ctx->stream>>>(ap.a16, ap.b16, ep, ap.d);
+  }
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BT_VERSION 100 /* 0.1.0 */
+#define BT_VERSION 200 /* 0.2.0: multi-stream contexts, fp16 feature ingest, submit/step split */
 
 typedef struct bt_ctx bt_ctx;
 
@@ -47,9 +47,20 @@ enum { BT_HOST = 0, BT_DEVICE = 1 };
 
 /* bt_create flags */
 enum {
-  BT_FLAG_SIMT_SIM = 1u << 0,     /* ReID similarity on the fp32 CUDA-core kernel instead of tcgen05 fp16 */
-  BT_FLAG_NO_F32_FEATURES = 1u << 1 /* do not keep the fp32 curr/smooth feature banks (A10 exposed state) */
+  BT_FLAG_SIMT_SIM = 1u << 0,     /* ReID similarity on the CUDA-core kernel instead of tcgen05 */
+  BT_FLAG_NO_F32_FEATURES = 1u << 1 /* do not keep the fp32 smooth (EMA) feature bank (A10 exposed state) */
 };
+
+/* dtype of the ReID feature rows handed to the tracker */
+enum {
+  BT_F32 = 0, /* float32 rows (what onnxruntime returns, demo:829-837) */
+  BT_F16 = 1  /* float16 rows (what the reference's fp16 TensorRT FastReID engine computes, demo:738, demo:35-49):
+                 half the bytes over PCIe / NVLink and no conversion pass; semantics = the reference fed with
+                 feats.astype(float32) */
+};
+
+/* most video streams one launch can serve (bt_update_streams batch size) */
+#define BT_MAX_BATCH 32
 
 /* Track states, demo:382-387 */
 enum { BT_STATE_NEW = 0, BT_STATE_TRACKED = 1, BT_STATE_LOST = 2, BT_STATE_LONGLOST = 3, BT_STATE_REMOVED = 4 };
@@ -57,30 +68,41 @@ enum { BT_STATE_NEW = 0, BT_STATE_TRACKED = 1, BT_STATE_LOST = 2, BT_STATE_LONGL
 /* Tracker hyper-parameters; defaults = the constants hard-coded at demo:1268-1277, demo:1571,
  * demo:1604, demo:1667, demo:473 (bt_default_config fills them). */
 typedef struct bt_config {
-  float track_high_thresh;  /* 0.40  demo:1268 */
-  float track_low_thresh;   /* 0.10  demo:1269 */
-  float new_track_thresh;   /* 0.90  demo:1270 */
+  /* score thresholds are Python floats (doubles) in the reference and are compared with float(score)
+   * (demo:1022, demo:1501, demo:1531, demo:1617): kept as doubles so that a score equal to float32(0.4)
+   * lands on the same side as in the reference */
+  double track_high_thresh; /* 0.40  demo:1268 */
+  double track_low_thresh;  /* 0.10  demo:1269 */
+  double new_track_thresh;  /* 0.90  demo:1270 */
   double match_thresh;      /* 0.80  demo:1271, first association */
   double second_thresh;     /* 0.50  demo:1571 */
   double unconfirmed_thresh;/* 0.70  demo:1604 */
   double proximity_thresh;  /* 0.50  demo:1274 */
-  float appearance_thresh;  /* 0.25  demo:1275 */
+  double appearance_thresh; /* 0.25  demo:1275 (compared with float32 distances: weak Python float -> float32) */
   double duplicate_iou_dist;/* 0.15  demo:1667 */
+  double ema_alpha;         /* 0.9   demo:473 (alpha and 1 - alpha are rounded to float32 separately, NEP 50) */
   int32_t track_buffer;     /* 300   demo:1272 */
   int32_t frame_rate;       /* 30    demo:1256 */
-  float ema_alpha;          /* 0.9   demo:473 */
   int32_t with_reid;        /* 1: features are given every frame; 0: IoU-only (similarities 0) */
+  int32_t reserved;
 } bt_config;
 
 int32_t bt_version(void);
 const char* bt_last_error(const bt_ctx* ctx);
 void bt_default_config(bt_config* cfg);
 
-/* One ctx = one CUDA device + one stream + workspaces + one tracker (video stream).
- * max_tracks bounds live track slots (tracked + lost + unconfirmed), max_dets the detections
- * per frame, feat_dim the ReID feature size (2048 for Fast-ReID, demo:1060). */
+/* One ctx = one CUDA device + one CUDA stream + workspaces + n_streams trackers (video streams).
+ * max_tracks bounds live track slots (tracked + lost + unconfirmed) PER video stream, max_dets the
+ * detections per frame and stream, feat_dim the ReID feature size (2048 for Fast-ReID, demo:1060).
+ * The video streams of one ctx are a leading batch dimension of every kernel: one
+ * bt_update_streams call steps any subset of them with ONE launch per kernel.  The reference runs one
+ * tracker per process (global id counter, demo:390, demo:1264); here ids are per video stream.
+ * bt_create == bt_create_streams with n_streams = 1. */
 int32_t bt_create(int32_t device, int32_t max_tracks, int32_t max_dets, int32_t feat_dim,
                   uint32_t flags, bt_ctx** out);
+int32_t bt_create_streams(int32_t device, int32_t n_streams, int32_t max_tracks, int32_t max_dets,
+                          int32_t feat_dim, uint32_t flags, bt_ctx** out);
+int32_t bt_num_streams(const bt_ctx* ctx);
 int32_t bt_destroy(bt_ctx* ctx);
 int32_t bt_sync(bt_ctx* ctx);
 /* cudaStream_t of the ctx as an opaque pointer (so callers can record CUDA events on it). */
@@ -199,7 +221,9 @@ int32_t bt_reid_crop_gather(bt_ctx* ctx, const uint8_t* frame, int32_t h, int32_
                             float* out, int32_t loc);
 
 /* ---- the tracker (replaces BoTSORT.update demo:1291-1639 driven by arrays) --------------- */
+/* Resets video stream 0 / one video stream / all of them (stream_id < 0). */
 int32_t bt_tracker_reset(bt_ctx* ctx, const bt_config* cfg /* NULL = defaults */);
+int32_t bt_tracker_reset_stream(bt_ctx* ctx, int32_t stream_id, const bt_config* cfg);
 
 typedef struct bt_frame_info {
   int32_t frame_id;
@@ -212,29 +236,69 @@ typedef struct bt_frame_info {
   int32_t n_unconfirmed;
   int32_t n_matches1, n_matches2, n_matches3;
   int32_t n_births;
+  int32_t n_births_skipped; /* births dropped because the track store of the stream was full (the reference
+                               has no bound; the frame stays consistent) */
+  int32_t reserved[3];
 } bt_frame_info;
 
-/* One BoTSORT.update on detector/encoder outputs: boxes int32[m,4] tlbr (as YOLOX._postprocess
- * emits them), scores float32[m], feats float32[m,feat_dim] (NULL when with_reid == 0).
+/* One BoTSORT.update on detector/encoder outputs of video stream 0: boxes int32[m,4] tlbr (as
+ * YOLOX._postprocess emits them), scores float32[m], feats float32[m,feat_dim] (NULL when with_reid == 0).
  * All class 0 (body).  info may be NULL. */
 int32_t bt_update_arrays(bt_ctx* ctx, const int32_t* boxes, const float* scores, const float* feats,
                          int32_t m, int32_t loc, bt_frame_info* info);
+
+/* The same for `count` video streams of the ctx at once (stream_ids[k] distinct, count <= BT_MAX_BATCH):
+ * boxes[k] / scores[k] / feats[k] / m[k] are stream stream_ids[k]'s detections; feats rows are
+ * feat_dtype (BT_F32 / BT_F16); face_sims is NULL or an array whose entries are NULL or the face
+ * similarity matrix float32[n_pool, m[k]] of that stream (demo:1465-1486: rows in pool order = activated
+ * tracked tracks in list order, then lost tracks in list order; the term `face_emb_dists` of demo:1541-1546).
+ * infos: NULL or bt_frame_info[count].  == bt_submit_streams + bt_step_streams. */
+int32_t bt_update_streams(bt_ctx* ctx, int32_t count, const int32_t* stream_ids, const int32_t* const* boxes,
+                          const float* const* scores, const void* const* feats, const int32_t* m,
+                          int32_t feat_dtype, const float* const* face_sims, int32_t loc, bt_frame_info* infos);
+
+/* Split form for pipelining: bt_submit_streams starts moving one frame of inputs into the ctx's
+ * (double-buffered) association buffers on a copy stream and returns; bt_step_streams runs the frame step
+ * of the OLDEST submitted frame of each listed stream and returns when the results are on the host.  A
+ * stream may have at most two submitted-but-not-stepped frames, so
+ *     submit(f0); loop { submit(f[k+1]); step() -> results of f[k]; }
+ * overlaps frame k+1's host->device copy with frame k's association and bookkeeping.
+ * Host input buffers must stay valid until the step of that frame returns (pinned memory makes the copy
+ * asynchronous). */
+int32_t bt_submit_streams(bt_ctx* ctx, int32_t count, const int32_t* stream_ids, const int32_t* const* boxes,
+                          const float* const* scores, const void* const* feats, const int32_t* m,
+                          int32_t feat_dtype, const float* const* face_sims, int32_t loc);
+int32_t bt_step_streams(bt_ctx* ctx, int32_t count, const int32_t* stream_ids, bt_frame_info* infos);
+
+/* Zero-copy ingest: device pointers of the buffers the NEXT bt_submit_streams of this
+ * video stream reads its inputs from when it is called with loc == BT_DEVICE and exactly these pointers --
+ * a detector / ReID engine that writes its outputs here (bt_yolox_postprocess + bt_reid_crop_gather ->
+ * encoder -> feats16) hands them over without any copy.  boxes int32[max_dets,4], scores
+ * float32[max_dets], feats16 float16[max_dets, feat_dim]. */
+int32_t bt_input_buffers(bt_ctx* ctx, int32_t stream_id, int32_t** boxes, float** scores, void** feats16);
 
 /* Read back a track list after a frame: which = 0 tracked_stracks (the list update() returns,
  * in the reference's order), 1 lost_stracks.  Any output pointer may be NULL.  Host pointers only.
  * ids/state/activated/frame_id/start_frame/tracklet_len/det_index: int32[n]; score float32[n];
  * tlbr float64[n,4]; mean float64[n,8]; cov float64[n,64].  Returns the list length in *n
- * (capacity `cap` rows; BT_ERR_CAPACITY if smaller). */
+ * (capacity `cap` rows; BT_ERR_CAPACITY if smaller).  bt_get_tracks == stream 0. */
 int32_t bt_get_tracks(bt_ctx* ctx, int32_t which, int32_t cap, int32_t* n, int32_t* ids,
                       int32_t* state, int32_t* activated, int32_t* frame_id, int32_t* start_frame,
                       int32_t* tracklet_len, int32_t* det_index, float* score, double* tlbr,
                       double* mean, double* cov);
-/* fp32 feature banks of a list (A10 exposed state): curr/smooth float32[n,feat_dim]. */
+int32_t bt_get_tracks_stream(bt_ctx* ctx, int32_t stream_id, int32_t which, int32_t cap, int32_t* n, int32_t* ids,
+                             int32_t* state, int32_t* activated, int32_t* frame_id, int32_t* start_frame,
+                             int32_t* tracklet_len, int32_t* det_index, float* score, double* tlbr,
+                             double* mean, double* cov);
+/* fp32 feature state of a list (A10 exposed state): curr/smooth float32[n,feat_dim]. */
 int32_t bt_get_track_features(bt_ctx* ctx, int32_t which, int32_t cap, float* curr, float* smooth);
-/* Per-frame intermediates of the last bt_update_arrays, for parity tests:
+int32_t bt_get_track_features_stream(bt_ctx* ctx, int32_t stream_id, int32_t which, int32_t cap, float* curr,
+                                     float* smooth);
+/* Per-frame intermediates of the last frame step, for parity tests:
  * stage 1/2/3 matches as (track list index, detection list index) pairs in the reference's
  * index spaces (demo:1556, demo:1571, demo:1604); pairs int32[cap,2]. */
 int32_t bt_get_matches(bt_ctx* ctx, int32_t stage, int32_t cap, int32_t* n, int32_t* pairs);
+int32_t bt_get_matches_stream(bt_ctx* ctx, int32_t stream_id, int32_t stage, int32_t cap, int32_t* n, int32_t* pairs);
 
 #ifdef __cplusplus
 }

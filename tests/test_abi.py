@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/botsort_b200.h but not exported"
     assert sorted(EXPORTS) == declared, "binding list and header disagree"
-    assert lib.bt_version() == 100
+    assert lib.bt_version() == 200
 
 
 def test_defaults_match_reference_constants():

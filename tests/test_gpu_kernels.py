@@ -150,9 +150,10 @@ def test_embedding_distance(ctx, n, m, d, precision):
     ref = O.embedding_distance(a, b)
     err = float(np.max(np.abs(got - ref)))
     assert got.shape == (n, m)
-    # fp16 operand rounding scales with the component size (~1/sqrt(d)): the 1e-4 budget is for the
-    # 2048-d (and 512-d) unit vectors of the path; the tiny d=64 plumbing case gets 5e-4
-    tol = (TOL if d >= 512 else 5e-4) if precision == 0 else 2e-5
+    # precision 0 = tcgen05 with fp16 operands for d >= 512 (3e-5 on unit rows); smaller feature sizes are
+    # routed to the fp32 CUDA-core kernel by the library (fp16 rounding of few large components would not
+    # hold 1e-4), so the north-star tolerance holds for every size
+    tol = TOL if precision == 0 else 2e-5
     assert err <= tol, err
 
 
@@ -161,8 +162,9 @@ def test_embedding_distance_simt_odd_dim(ctx):
     a, b = _unit_feats(rng, 33, 37), _unit_feats(rng, 65, 37)
     got = ctx.embedding_distance(a, b, precision=1)
     assert np.max(np.abs(got - O.embedding_distance(a, b))) <= 1e-5
-    with pytest.raises(ValueError):
-        ctx.embedding_distance(a, b, precision=0)
+    # a feature size the tensor-core kernel cannot take (d % 64 != 0) falls back to the exact kernel by itself
+    got0 = ctx.embedding_distance(a, b, precision=0)
+    np.testing.assert_array_equal(got0, got)
 
 
 @pytest.mark.parametrize("stage", [1, 3])
