@@ -182,7 +182,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import botsort_b200 as bs
-    from botsort_b200._lib import BT_DEVICE, BT_HOST
+    from botsort_b200._lib import BT_DEVICE, BT_F16, BT_F32, BT_HOST
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,6 +190,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
     if local_world > 1 and hasattr(os, "sched_setaffinity"):
         # one rank per GPU on one host: give every rank its own slice of the host cores so that the ranks'
@@ -203,22 +204,23 @@ def run_ours(args):
             pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
     n, D, reid = wl["n"], wl["feat_dim"], wl["reid"]
     K, W = args.steps, max(args.warmup, 3)
+    f16 = args.feat_dtype == "f16"
+    np_feat, th_feat, bt_feat = (np.float16, torch.float16, BT_F16) if f16 else (np.float32, torch.float32, BT_F32)
 
-    from concurrent.futures import ThreadPoolExecutor
-    from botsort_b200.sharding import shard_streams
+    from botsort_b200.sharding import aggregate_throughput, max_over_ranks, shard_streams
     S = int(wl.get("streams", 1))                       # independent video streams on THIS GPU
     my_streams = shard_streams(S * world, world, rank)  # global stream ids of this rank (no data-path collective)
     cap = (n + n // 8 + 255) // 128 * 128
-    ctxs = [bs.Context(max_tracks=cap, max_dets=cap, feat_dim=D, device=local) for _ in my_streams]
-    ctx = ctxs[0]
+    # ONE ctx per GPU: its S video streams are a leading batch dimension of every kernel
+    ctx = bs.Context(max_tracks=cap, max_dets=cap, feat_dim=D, device=local, n_streams=S)
+    sids = list(range(S))
     cfg = ctx.default_config()
     cfg.with_reid = 1 if reid else 0
-    cu_streams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)) for c in ctxs]
-    pool = ThreadPoolExecutor(max_workers=S) if S > 1 else None
+    cu_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     # every stream has its own synthetic scene (weak scaling: each GPU tracks its own video streams)
     n_frames = 1 + W + K
@@ -227,11 +229,12 @@ def run_ours(args):
         frames = make_frames(wl, n_frames, seed=1234 + sid)
         bh = [torch.from_numpy(f["boxes"]).pin_memory() for f in frames]
         sh = [torch.from_numpy(f["scores"]).pin_memory() for f in frames]
-        fh = [torch.from_numpy(f["feats"]).pin_memory() for f in frames] if reid else [None] * n_frames
-        data.append(dict(bh=bh, sh=sh, fh=fh, bd=[b.cuda(non_blocking=True) for b in bh],
-                         sd=[x.cuda(non_blocking=True) for x in sh],
-                         fd=[f.cuda(non_blocking=True) for f in fh] if reid else [None] * n_frames))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+        # the ReID encoder's output dtype: fp16 is what the reference's TensorRT FastReID engine computes in
+        # (demo:738, demo:35-49); --feat-dtype f32 feeds float32 rows (onnxruntime's output type)
+        fh = [torch.from_numpy(f["feats"].astype(np_feat)).pin_memory() for f in frames] if reid else [None] * n_frames
+        data.append(dict(bh=bh, sh=sh, fh=fh, bd=[b.to(dev) for b in bh], sd=[x.to(dev) for x in sh],
+                         fd=[f.to(dev) for f in fh] if reid else [None] * n_frames))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     torch.cuda.synchronize()
 
     def barrier():
@@ -240,89 +243,120 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_one(k, i, loc, read_back=False, events=None):
-        d, c = data[k], ctxs[k]
-        b, s, f = (d["bd"], d["sd"], d["fd"]) if loc == BT_DEVICE else (d["bh"], d["sh"], d["fh"])
-        if events is not None:
-            events[0].record(cu_streams[k])
-        c.update_arrays_raw(b[i].data_ptr(), s[i].data_ptr(), f[i].data_ptr() if reid else 0, b[i].shape[0], loc)
+    def ptrs(i, where):
+        b = [d["b" + where][i] for d in data]
+        s = [d["s" + where][i] for d in data]
+        f = [d["f" + where][i] for d in data]
+        return ([x.data_ptr() for x in b], [x.data_ptr() for x in s], [x.data_ptr() if reid else 0 for x in f],
+                [int(x.shape[0]) for x in b])
+
+    def place_inputs(i):
+        """Zero-copy ingest (bt_input_buffers): frame i is written into the ctx's own association
+        buffers -- what a detector / ReID engine bound to these addresses does -- OUTSIDE the timed region."""
+        out = []
+        for k, d in enumerate(data):
+            pb, ps, pf = ctx.input_buffers(k)
+            m = int(d["bd"][i].shape[0])
+            for src, ptr in ((d["bd"][i], pb), (d["sd"][i], ps)) + (((d["fd"][i], pf),) if (reid and f16) else ()):
+                bs_ = src.numel() * src.element_size()
+                torch.cuda.current_stream().synchronize()
+                _cudart().cudaMemcpy(ptr, src.data_ptr(), bs_, 3)          # device to device
+            out.append((pb, ps, (pf if f16 else d["fd"][i].data_ptr()) if reid else 0, m))
+        return ([o[0] for o in out], [o[1] for o in out], [o[2] for o in out], [o[3] for o in out])
+
+    def read_back():
         nbytes = 0
-        if read_back:
-            res = c.get_tracks(0)                       # ids + boxes of the returned list, on the host
-            nbytes = res["tlbr"].nbytes + res["ids"].nbytes
-        if events is not None:
-            events[1].record(cu_streams[k])
+        for k in range(S):
+            res = ctx.get_tracks(0, stream=k)               # ids + boxes of the returned list, on the host
+            nbytes += res["tlbr"].nbytes + res["ids"].nbytes
         return nbytes
 
-    def step(i, loc, read_back=False, events=None):
-        """One frame for every stream of this rank (threads: ctypes releases the GIL, the ctx streams overlap)."""
-        if pool is None:
-            return step_one(0, i, loc, read_back, None if events is None else events[0])
-        futs = [pool.submit(step_one, k, i, loc, read_back, None if events is None else events[k]) for k in range(S)]
-        return sum(f.result() for f in futs)
-
-    def run_pass(loc, read_back, profile=False, l2_flush=True):
-        """frame 0 = births (untimed), W warm-up frames, then K timed frames.  Returns per-step device
-        ms (CUDA events on the ctx stream), per-step wall ms, matched-track counts."""
-        for c in ctxs:
-            c.tracker_reset(cfg)
-        step(0, loc)
-        for i in range(1, 1 + W):
-            step(i, loc)
-        ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
-              for _ in range(K)]
-        wall = []
-        d2h = 0
+    def run_value_pass(profile=False, l2_flush=True):
+        """Device-resident inputs (already in the association buffers when the timed region starts): frame 0 =
+        births (untimed), W warm-up frames, then K timed frames; per-step CUDA events on the ctx stream."""
+        ctx.tracker_reset(cfg)
+        for i in range(0, 1 + W):
+            b, s_, f, m = place_inputs(i)
+            ctx.update_streams_raw(sids, b, s_, f, m, BT_DEVICE, bt_feat)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         barrier()
         if profile:
-            ctx.profile_enable(True)        # segment events only around the K timed steps (first stream)
-        launches0 = sum(c.launch_count for c in ctxs)
+            ctx.profile_enable(True)
+        launches0 = ctx.launch_count
         for k in range(K):
+            b, s_, f, m = place_inputs(1 + W + k)
             if l2_flush:
                 flush.zero_()                               # L2 flush between timed steps (untimed)
             torch.cuda.synchronize()
-            i = 1 + W + k
-            t0 = time.perf_counter()
-            d2h = step(i, loc, read_back, ev[k])
-            for c in ctxs:
-                c.sync()
-            wall.append(1e3 * (time.perf_counter() - t0))
-        launches = sum(c.launch_count for c in ctxs) - launches0
+            ev[k][0].record(cu_stream)
+            ctx.update_streams_raw(sids, b, s_, f, m, BT_DEVICE, bt_feat)
+            ev[k][1].record(cu_stream)
+        launches = ctx.launch_count - launches0
         barrier()
-        # a step ends when its slowest stream ends (the streams of a step start together)
-        dev = [max(a.elapsed_time(b) for a, b in evk) for evk in ev]
-        return dev, wall, launches, d2h
+        return [a.elapsed_time(b_) for a, b_ in ev], launches
+
+    def run_e2e_pass(pipelined):
+        """Pinned host inputs: every step's host->device copy and the read-back of its tracks are inside the
+        timed region.  pipelined: bt_submit_streams(frame k+1) is issued before bt_step_streams(frame k), so
+        the copy of the next frame runs under the current frame's step (both inside the timed region)."""
+        ctx.tracker_reset(cfg)
+        for i in range(0, 1 + W):
+            b, s_, f, m = ptrs(i, "h")
+            ctx.update_streams_raw(sids, b, s_, f, m, BT_HOST, bt_feat)
+        barrier()
+        d2h = 0
+        first = 1 + W
+        t_begin = time.perf_counter()
+        if pipelined:
+            b, s_, f, m = ptrs(first, "h")
+            ctx.submit_streams_raw(sids, b, s_, f, m, BT_HOST, bt_feat)
+        for k in range(K):
+            i = first + k
+            if pipelined:
+                if k + 1 < K:
+                    b, s_, f, m = ptrs(i + 1, "h")
+                    ctx.submit_streams_raw(sids, b, s_, f, m, BT_HOST, bt_feat)
+                ctx.step_streams_raw(sids)
+            else:
+                b, s_, f, m = ptrs(i, "h")
+                ctx.update_streams_raw(sids, b, s_, f, m, BT_HOST, bt_feat)
+            d2h = read_back()
+        ctx.sync()
+        total_ms = 1e3 * (time.perf_counter() - t_begin)
+        barrier()
+        return total_ms, d2h
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- device-resident pass (value) with segment profiling ----
-    run_pass(BT_DEVICE, read_back=False)                     # untimed: first-launch / module-load costs
-    dev_ms, _, launches, _ = run_pass(BT_DEVICE, read_back=False)   # `value`: no event bracketing inside
-    # the other admissible protocol: no flush, every step reads a detection frame it has never touched (the
-    # 1+W+K frames together exceed L2) while the tracker's own state stays as warm as it is in a running stream
-    dev_ms_warm, _, _, _ = run_pass(BT_DEVICE, read_back=False, l2_flush=False)
-    run_pass(BT_DEVICE, read_back=False, profile=True)       # same steps again with per-kernel CUDA events
+    run_value_pass()                                         # untimed: first-launch / module-load costs
+    dev_ms, launches = run_value_pass()                      # `value`
+    # the other admissible protocol: no flush, every step reads a detection frame it has never touched
+    dev_ms_warm, _ = run_value_pass(l2_flush=False)
+    run_value_pass(profile=True)                             # same steps again with per-kernel CUDA events
     prof = ctx.profile_read()
     ctx.profile_enable(False)
-    assoc_replay_ms = ctx.profile_replay_assoc(50)   # the frame's association kernel, 50 back-to-back launches
-    info_tracks = ctx.get_tracks(0)
-    n_live = int(len(info_tracks["ids"]))
-    # ---- end-to-end pass: pinned host inputs, H2D inside, result read back to the host ----
-    _, e2e_wall, _, d2h_bytes = run_pass(BT_HOST, read_back=True)
+    assoc_replay_ms = ctx.profile_replay_assoc(50) if (n > 0) else 0.0   # the frame's association kernel, 50 back-to-back launches
+    n_live = sum(int(len(ctx.get_tracks(0, stream=k)["ids"])) for k in range(S))
+    # ---- end-to-end passes ----
+    run_e2e_pass(True)
+    e2e_ms, d2h_bytes = run_e2e_pass(True)
+    e2e_plain_ms, _ = run_e2e_pass(False)
     # the timed regions are a few ms, shorter than nvidia-smi's sampling period: keep the same
     # device-resident step running for ~0.6 s so the clock record covers this exact load
     t_end = time.perf_counter() + 0.6
     while rank == 0 and time.perf_counter() < t_end:
         for i in range(1 + W, 1 + W + K):
-            step(i, BT_DEVICE)
+            b, s_, f, m = ptrs(i, "d")
+            ctx.update_streams_raw(sids, b, s_, f, m, BT_DEVICE, bt_feat)
     clocks = sampler.stop() if rank == 0 else None
 
-    from botsort_b200.sharding import aggregate_throughput, max_over_ranks
-    total_dev_ms, total_e2e_ms, total_warm_ms = max_over_ranks([sum(dev_ms), sum(e2e_wall), sum(dev_ms_warm)], device="cuda")
+    total_dev_ms, total_e2e_ms, total_warm_ms, total_plain_ms = max_over_ranks(
+        [sum(dev_ms), e2e_ms, sum(dev_ms_warm), e2e_plain_ms], device="cuda")
     value = aggregate_throughput(n * S, world, K, total_dev_ms)
     e2e_value = aggregate_throughput(n * S, world, K, total_e2e_ms)
-    h2d_bytes = S * (n * (16 + 4) + (n * D * 4 if reid else 0))
+    feat_bytes = 2 if f16 else 4
+    h2d_bytes = S * (n * (16 + 4) + (n * D * feat_bytes if reid else 0))
 
     if rank == 0:
         peaks = {}
@@ -330,13 +364,14 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        dev_sorted = sorted(dev_ms)
         assoc_ms, assoc_n = prof["assoc"]
         assoc_in_step_ms = assoc_ms / max(1, assoc_n)
         assoc_avg_ms = assoc_replay_ms
-        n_rows = n_live
-        if reid:
-            flops = 2.0 * n_rows * n * D
+        if reid and D >= 512:
+            flops = 2.0 * n_live * n * D
             peak = peaks.get("bf16_tflops", 1590.0)
+            traffic, traffic_src = ncu_traffic("assoc_tc_kernel", (n_live // max(1, S), n, D, S))
             roof = {"kernel": "assoc_tc_kernel (fused ReID GEMM + IoU + cost fusion + candidate emission)",
                     "bound": "tensor", "achieved": flops / (assoc_avg_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the same tensor rate)"
@@ -344,17 +379,17 @@ def run_ours(args):
                     "algorithmic_flops": flops, "avg_launch_ms": assoc_avg_ms,
                     "how": "one CUDA-event pair around 50 back-to-back launches of the last frame's kernel on the ctx "
                            "stream (bt_profile_replay_assoc), divided by 50; launched as in the step (programmatic "
-                           "dependent launch: a launch's ramp overlaps its predecessor's tail)",
+                           "dependent launch: a launch's main loop starts while its predecessor drains, only its epilogue "
+                           "waits for it)",
                     "in_step_event_ms": assoc_in_step_ms,
-                    "in_step_note": "events bracketing the same launch inside the step also count host enqueue gaps",
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
-                    # kernel on this workload (profiles/r01_ncu_assoc_tc_v3_details.csv); other workloads: not captured
-                    "traffic": (16927232.0 if (n_rows, n, D) == (2000, 2000, 2048) else None),
-                    "traffic_unit": "bytes/launch (algorithmic: the two fp16 operands once = %d)" % (2 * (n_rows + n) * D)}
+                    "in_step_note": "events bracketing the same launch inside the step also count host enqueue gaps and "
+                                    "the part of the prep kernel the launch overlaps",
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "traffic_unit": "bytes/launch (algorithmic: the two fp16 operands once = %d)" % (2 * (n_live + n * S) * D)}
         else:
-            nbytes = 32.0 * (n_rows + n) + 0.0      # boxes in, candidate edges out (sparse)
+            nbytes = 32.0 * (n_live + n * S) + 0.0      # boxes in, candidate edges out (sparse)
             peak = peaks.get("hbm_gbs", 6650.0)
-            roof = {"kernel": "assoc_simt_kernel (IoU-only candidate emission)", "bound": "hbm",
+            roof = {"kernel": "assoc_simt_kernel (IoU-only / small-feature candidate emission)", "bound": "hbm",
                     "achieved": nbytes / (assoc_avg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                     "algorithmic_bytes": nbytes, "avg_launch_ms": assoc_avg_ms, "in_step_event_ms": assoc_in_step_ms,
@@ -382,20 +417,23 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 Kalman/IoU/LAP, fp16-in/fp32-acc tcgen05 ReID similarity" if reid else "f64",
+            "dtype": ("f64 Kalman/IoU/LAP, fp16 tcgen05 ReID similarity (fp32 accumulate), exact fp32/f64 re-costing of contested edges"
+                      if reid else "f64"),
             "data": "synthetic",
             "config": config_of(wl, S),
+            "feat_dtype": args.feat_dtype,
             "live_tracks_end": n_live,
+            "step_ms": {"min": dev_sorted[0], "median": dev_sorted[len(dev_sorted) // 2], "max": dev_sorted[-1]},
             "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": total_e2e_ms / K,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                    "how": "bt_update_arrays on pinned host buffers + bt_get_tracks read-back, wall clock per step"},
+                    "how": "pinned host inputs: bt_submit_streams(frame k+1) then bt_step_streams(frame k) + bt_get_tracks; "
+                           "every step's H2D copy and result read-back are inside the timed region (wall clock over the K steps)",
+                    "unpipelined_ms_per_step": total_plain_ms / K,
+                    "unpipelined_how": "bt_update_streams on the same pinned buffers (copy, then step), wall clock"},
             "value_inputs_larger_than_l2": {
                 "value": aggregate_throughput(n * S, world, K, total_warm_ms), "unit": "tracks/s",
                 "ms_per_step": total_warm_ms / K,
-                "note": "same K steps without the L2 flush: each step's detection frame (%.1f MB) is one of %d distinct "
-                        "device-resident frames (%.0f MB in total, larger than L2) and has not been touched since its "
-                        "upload; the tracker's own state stays warm as in a running stream"
-                        % (h2d_bytes / S / 1e6, n_frames, n_frames * h2d_bytes / S / 1e6)},
+                "note": "same K steps without the L2 flush"},
             "gpu_launches": int(launches),
             "segments_ms": segs,
             "roofline": roof,
@@ -403,10 +441,50 @@ def run_ours(args):
             "clocks": clocks,
         }
         print(json.dumps(line))
-    for c in ctxs:
-        c.close()
+    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+_CUDART = None
+
+
+def _cudart():
+    """libcudart through ctypes (plumbing for placing synthetic inputs at raw device addresses)."""
+    global _CUDART
+    if _CUDART is None:
+        import ctypes
+        import torch
+        lib = None
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                lib = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            import glob
+            cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+                glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+            lib = ctypes.CDLL(cands[0])
+        lib.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        lib.cudaMemcpy.restype = ctypes.c_int
+        _CUDART = lib
+    return _CUDART
+
+
+def ncu_traffic(kernel, shape):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep), or (None, why)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        rec = json.load(open(path))
+        for e in rec.get("kernels", []):
+            if e["kernel"] == kernel and tuple(e["shape"]) == tuple(shape):
+                return float(e["dram_bytes_per_launch"]), f"profiles/r02_traffic.json ({e.get('capture', 'ncu --set full')})"
+        return None, "no ncu capture of this shape under profiles/"
+    except Exception:
+        return None, "profiles/r02_traffic.json absent"
 
 
 def main():
@@ -417,6 +495,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the cpu_baseline leg")
+    ap.add_argument("--feat-dtype", default="f16", choices=["f16", "f32"],
+                    help="dtype of the ReID feature rows fed to the tracker (fp16 = the reference's TensorRT engine precision)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

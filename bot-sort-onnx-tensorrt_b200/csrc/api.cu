@@ -172,7 +172,8 @@ int32_t bt_create_streams(int32_t device, int32_t n_streams, int32_t max_tracks,
     return code;
   };
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) {
     bt_fail(c, BT_ERR_CUDA, "cudaStreamCreate failed");
     return fail(BT_ERR_CUDA);
   }
@@ -189,6 +190,7 @@ int32_t bt_destroy(bt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->side_stream) cudaStreamSynchronize(ctx->side_stream);
   bt_tracker_destroy(ctx);
   bt_gemm_ws_destroy(ctx);
   bt_lap_ws_destroy(ctx);
@@ -196,6 +198,7 @@ int32_t bt_destroy(bt_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   delete ctx;
   return BT_OK;
 }

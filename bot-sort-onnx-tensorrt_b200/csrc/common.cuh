@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
 #include <vector>
 
 #include "../../include/botsort_b200.h"
@@ -19,11 +20,13 @@ struct bt_ctx {
   int max_tracks = 0, max_dets = 0, feat_dim = 0;
   int n_streams = 1;             // video streams (trackers) of this ctx: a leading batch dimension of every kernel
   cudaStream_t copy_stream = nullptr;   // input staging of bt_submit_streams (overlaps the frame step)
+  cudaStream_t side_stream = nullptr;   // work of a frame that is independent of its main chain (feature EMA)
   uint32_t flags = 0;
   int num_sms = 148;
   int pdl = 1;   // programmatic dependent launch between the frame step's kernels (BT_NO_PDL=1 turns it off)
   std::string err;
   int64_t launches = 0;
+  struct bt_launch_rec* rec = nullptr;  // != null: the frame launchers record their launch (CUDA-graph replay) instead of launching
   // bump arena for the stand-alone entry points (device) and a pinned mirror for small results
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
@@ -38,22 +41,56 @@ struct bt_ctx {
 
 int32_t bt_fail(bt_ctx* ctx, int32_t code, const char* fmt, ...);
 
+// A recorded kernel launch: what cudaGraphExecKernelNodeSetParams needs to retarget a captured kernel node
+// (function, geometry, argument values).  The frame step is captured into a CUDA graph once per launch shape;
+// afterwards a frame costs one graph launch plus one parameter update per kernel node instead of a dozen
+// driver calls on the critical path.
+struct bt_launch_rec {
+  const void* func = nullptr;
+  dim3 grid, block;
+  unsigned smem = 0;
+  int nargs = 0;
+  void* argp[8];
+  alignas(64) char store[3584];
+  size_t used = 0;
+};
+
 #ifdef __CUDACC__
-// Launch on ctx->stream, optionally as a programmatic dependent of the stream's previous kernel: the grid
+template <typename T>
+static inline void bt_rec_arg(bt_launch_rec* r, const T& v) {
+  size_t off = (r->used + alignof(T) - 1) & ~(alignof(T) - 1);
+  memcpy(r->store + off, &v, sizeof(T));
+  r->argp[r->nargs++] = r->store + off;
+  r->used = off + sizeof(T);
+}
+// Launch on `stream`, optionally as a programmatic dependent of the stream's previous kernel: the grid
 // may then be scheduled before that kernel has completed, and must execute griddepcontrol.wait
 // (bt_grid_dependency_wait) before it touches anything the earlier kernels of the stream produce -- and at
 // the latest before it exits, so that completion stays ordered for its own dependents.
+// With ctx->rec set the launch is only recorded.
 template <typename... KArgs, typename... Args>
-static inline cudaError_t bt_launch(bt_ctx* ctx, bool dependent, void (*kern)(KArgs...), dim3 grid, dim3 block,
-                                    size_t smem, Args... args) {
+static inline cudaError_t bt_launch_on(bt_ctx* ctx, cudaStream_t stream, bool dependent, void (*kern)(KArgs...), dim3 grid,
+                                       dim3 block, size_t smem, Args... args) {
+  if (ctx->rec) {
+    bt_launch_rec* r = ctx->rec;
+    r->func = reinterpret_cast<const void*>(kern);
+    r->grid = grid; r->block = block; r->smem = (unsigned)smem; r->nargs = 0; r->used = 0;
+    (bt_rec_arg<KArgs>(r, static_cast<KArgs>(args)), ...);
+    return cudaSuccess;
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = (dependent && ctx->pdl) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t bt_launch(bt_ctx* ctx, bool dependent, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                    size_t smem, Args... args) {
+  return bt_launch_on(ctx, ctx->stream, dependent, kern, grid, block, smem, args...);
 }
 __device__ __forceinline__ void bt_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bt_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -102,8 +139,10 @@ extern thread_local std::string g_bt_create_error;
 
 #define BT_LAUNCHED(ctx)                                                                           \
   do {                                                                                             \
-    (ctx)->launches++;                                                                             \
-    BT_CUDA(cudaGetLastError());                                                                   \
+    if (!(ctx)->rec) {                                                                             \
+      (ctx)->launches++;                                                                           \
+      BT_CUDA(cudaGetLastError());                                                                 \
+    }                                                                                              \
   } while (0)
 
 // ---- arena ----------------------------------------------------------------------------------
@@ -274,8 +313,10 @@ int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b);
 // detection prep (boxes -> tlbr / xywh / score class / packed corners) + batched Kalman predict of every
 // stream's pool + (optional) detection feature norms: one launch
 int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
-// Kalman update + feature EMA of every slot matched by one of the three stages: one launch
-int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, int32_t with_feat);
+// Kalman update of every slot matched by one of the three stages; feature EMA of the same slots (independent of
+// it: launched on `stream`, the ctx's side stream)
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
+int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, cudaStream_t stream);
 // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
 int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
 // births of one stream: Kalman initiate + feature adoption from the frame's detections

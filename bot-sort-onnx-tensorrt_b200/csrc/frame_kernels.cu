@@ -4,8 +4,8 @@
 //   frame_cast  (fp32 ingest only) float32 feature rows -> raw fp16 rows (GEMM B operand) + L2 norms
 //   frame_prep  detection prep (demo:1493-1532 boxes / score classes) + batched Kalman predict of every
 //               pool (demo:524-536, demo:265-302) + optional detection feature norms: ONE launch
-//   frame_post  Kalman update (demo:304-336) + feature EMA (demo:492-502) of every slot matched by one
-//               of the three association stages: ONE launch
+//   frame_post  Kalman update (demo:304-336) of every slot matched by one of the three association stages
+//   frame_ema   feature EMA (demo:492-502) of the same slots, on the ctx's side stream beside it
 //   frame_dup   remove_duplicate_stracks' IoU test (demo:1665-1668) over all live slots, sparse output
 //   births      Kalman initiate (demo:166-197) + feature adoption of the frame's new tracks
 // demo = /root/reference/demo_bottrack_onnx_tflite.py
@@ -246,10 +246,8 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
 }
 
 __global__ void __launch_bounds__(kThreads)
-frame_post_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_frame_cfg fc, int upd_blocks, int with_feat,
-                  bt_res_layout L) {
+frame_post_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_res_layout L) {
   bt_grid_launch_dependents();   // the duplicate test is queued behind this kernel and waits for its boxes
-  __shared__ float red[kThreads / 32];
   const int k = blockIdx.y;
   const int sid = b.sid[k];
   const int n_rows = b.n_rows[k];
@@ -257,35 +255,42 @@ frame_post_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_frame_cfg 
   const int32_t* x1 = res + L.o_x;
   const int32_t* x2 = x1 + st.cap;
   const int32_t* x3 = x2 + st.cap;
-  int bx = blockIdx.x;
-  if (bx < upd_blocks) {
-    if (bx * (kThreads / 8) >= n_rows) return;
-    const int g = (bx * kThreads + threadIdx.x) >> 3;
-    const int lane = threadIdx.x & 31, r = lane & 7, base = lane & ~7;
-    bool active = g < n_rows;
-    int zi = -1;
-    if (active) {
-      zi = x1[g];
-      if (zi < 0) zi = x2[g];
-      if (zi < 0) zi = x3[g];
-    }
-    const size_t t = (size_t)sid * st.cap + (active ? g : 0);
-    double* res_tlbr = reinterpret_cast<double*>(st.resB + (size_t)k * L.strideB + L.o_tlbr_bytes);
-    if (active && zi < 0 && r < 4) res_tlbr[(size_t)g * 4 + r] = st.tlbr[t * 4 + r];   // unchanged box
-    active = active && zi >= 0;
-    // the slot still holds initiate()'s float32 state: one lane reads the flag, the group shares it
-    int f32 = (active && r == 0) ? (int)st.slot_f32[t] : 0;
-    f32 = __shfl_sync(0xffffffffu, f32, base);
-    if (active && r == 0 && f32) st.slot_f32[t] = 0;
-    btd_update(st.mean, st.cov, st.tlbr, st.tlbr_f32, st.det_xywh, t, (size_t)sid * st.md + (active ? zi : 0), active,
-               f32 != 0, res_tlbr, (size_t)g, lane);
-    return;
+  const int bx = blockIdx.x;
+  if (bx * (kThreads / 8) >= n_rows) return;
+  const int g = (bx * kThreads + threadIdx.x) >> 3;
+  const int lane = threadIdx.x & 31, r = lane & 7, base = lane & ~7;
+  bool active = g < n_rows;
+  int zi = -1;
+  if (active) {
+    zi = x1[g];
+    if (zi < 0) zi = x2[g];
+    if (zi < 0) zi = x3[g];
   }
-  bx -= upd_blocks;
-  if (!with_feat || bx >= n_rows) return;
+  const size_t t = (size_t)sid * st.cap + (active ? g : 0);
+  double* res_tlbr = reinterpret_cast<double*>(st.resB + (size_t)k * L.strideB + L.o_tlbr_bytes);
+  if (active && zi < 0 && r < 4) res_tlbr[(size_t)g * 4 + r] = st.tlbr[t * 4 + r];   // unchanged box
+  active = active && zi >= 0;
+  // the slot still holds initiate()'s float32 state: one lane reads the flag, the group shares it
+  int f32 = (active && r == 0) ? (int)st.slot_f32[t] : 0;
+  f32 = __shfl_sync(0xffffffffu, f32, base);
+  if (active && r == 0 && f32) st.slot_f32[t] = 0;
+  btd_update(st.mean, st.cov, st.tlbr, st.tlbr_f32, st.det_xywh, t, (size_t)sid * st.md + (active ? zi : 0), active,
+             f32 != 0, res_tlbr, (size_t)g, lane);
+}
+
+// one CTA per slot: the matched ones adopt their detection's feature (independent of the Kalman update:
+// runs beside it on the ctx's side stream)
+__global__ void __launch_bounds__(kThreads)
+frame_ema_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_frame_cfg fc, bt_res_layout L) {
+  __shared__ float red[kThreads / 32];
+  const int k = blockIdx.y;
+  const int sid = b.sid[k];
+  const int bx = blockIdx.x;
+  if (bx >= b.n_rows[k]) return;
+  const int32_t* x1 = reinterpret_cast<const int32_t*>(st.res + (size_t)k * L.stride) + L.o_x;
   int z = x1[bx];
-  if (z < 0) z = x2[bx];
-  if (z < 0) z = x3[bx];
+  if (z < 0) z = x1[st.cap + bx];
+  if (z < 0) z = x1[2 * (size_t)st.cap + bx];
   if (z < 0) return;       // block-uniform
   const size_t gs = (size_t)sid * st.cap + bx;
   const size_t in_row = (size_t)b.parity[k] * st.S * st.md + (size_t)sid * st.md + z;
@@ -429,7 +434,7 @@ bt_res_layout bt_res_layout_for(int cap, int md, int prefetch_pairs) {
 int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b) {
   const int mx = bt_batch_max(b.m, b.count);
   if (mx <= 0) return BT_OK;
-  frame_cast_kernel<<<dim3(mx, b.count), kThreads, 0, ctx->stream>>>(st, b);
+  BT_CUDA(bt_launch(ctx, false, frame_cast_kernel, dim3(mx, b.count), dim3(kThreads), 0, st, b));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
@@ -444,18 +449,26 @@ int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const
   const int gx = pred_blocks + det_blocks + norm_blocks;
   if (gx <= 0) return BT_OK;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  frame_prep_kernel<<<dim3(gx, b.count), kThreads, 0, ctx->stream>>>(st, b, fc, pred_blocks, det_blocks, L);
+  BT_CUDA(bt_launch(ctx, false, frame_prep_kernel, dim3(gx, b.count), dim3(kThreads), 0, st, b, fc, pred_blocks, det_blocks, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
-int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, int32_t with_feat) {
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc) {
   const int mx_rows = bt_batch_max(b.n_rows, b.count);
   if (mx_rows <= 0) return BT_OK;
   const int upd_blocks = (mx_rows * 8 + kThreads - 1) / kThreads;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  frame_post_kernel<<<dim3(upd_blocks + (with_feat ? mx_rows : 0), b.count), kThreads, 0, ctx->stream>>>(
-      st, b, fc, upd_blocks, with_feat, L);
+  BT_CUDA(bt_launch(ctx, false, frame_post_kernel, dim3(upd_blocks, b.count), dim3(kThreads), 0, st, b, L));
+  BT_LAUNCHED(ctx);
+  return BT_OK;
+}
+
+int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, cudaStream_t stream) {
+  const int mx_rows = bt_batch_max(b.n_rows, b.count);
+  if (mx_rows <= 0) return BT_OK;
+  const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
+  BT_CUDA(bt_launch_on(ctx, stream, false, frame_ema_kernel, dim3(mx_rows, b.count), dim3(kThreads), 0, st, b, fc, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

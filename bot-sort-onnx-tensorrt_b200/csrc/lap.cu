@@ -419,11 +419,39 @@ __device__ void solve_component_enum(const SolveArrays& ws, int comp, double thr
 __device__ double refine_cost(const bt_refine& rf, const bt_lap_batch& B, int k, int list, int row, int col, int lane) {
   const size_t gs = (size_t)B.row0[k] + row, gd = (size_t)B.col0[k] + col, gi = (size_t)B.in0[k] + col;
   const int D = rf.d;
+  // everything that does not depend on the dot product first: the loads below are all in flight together
+  const float na = rf.f16 ? rf.a_norm[gs] : 1.0f;
+  const float nb = (list == 2 && rf.b_norm) ? rf.b_norm[gd] : 1.0f;
+  const double iou_d = bt_iou_dist_f64(rf.row_tlbr + gs * 4, rf.col_tlbr + gd * 4);
+  float face = 0.f;
+  if (list == 0 && B.face_sim[k]) {
+    const int pr = reinterpret_cast<const int32_t*>(rf.ctrl + B.pos_off[k])[row];
+    if (pr >= 0) face = B.face_sim[k][(size_t)pr * B.m[k] + col];
+  }
   double acc = 0.0;
   if (rf.f16) {
     const __half* a = rf.a16 + gs * D;
     const __half* b = rf.b16 + gi * D;
-    if ((D & 7) == 0) {
+    if ((D & 2047) == 0) {          // 2048-d Fast-ReID rows: 8 x 16 B per lane and operand, all issued at once
+      for (int base = 0; base < D; base += 2048) {
+        uint4 qa[8], qb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          qa[j] = *reinterpret_cast<const uint4*>(a + base + j * 256 + lane * 8);
+          qb[j] = *reinterpret_cast<const uint4*>(b + base + j * 256 + lane * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __half2* ha = reinterpret_cast<const __half2*>(&qa[j]);
+          const __half2* hb = reinterpret_cast<const __half2*>(&qb[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+            acc += (double)(fa.x * fb.x) + (double)(fa.y * fb.y);     // fp16 x fp16 is exact in fp32
+          }
+        }
+      }
+    } else if ((D & 7) == 0) {
       for (int i = lane * 8; i < D; i += 256) {
         const uint4 qa = *reinterpret_cast<const uint4*>(a + i), qb = *reinterpret_cast<const uint4*>(b + i);
         const __half2* ha = reinterpret_cast<const __half2*>(&qa);
@@ -431,7 +459,7 @@ __device__ double refine_cost(const bt_refine& rf, const bt_lap_batch& B, int k,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
-          acc += (double)(fa.x * fb.x) + (double)(fa.y * fb.y);     // fp16 x fp16 is exact in fp32
+          acc += (double)(fa.x * fb.x) + (double)(fa.y * fb.y);
         }
       }
     } else {
@@ -440,7 +468,19 @@ __device__ double refine_cost(const bt_refine& rf, const bt_lap_batch& B, int k,
   } else {
     const float* a = rf.a32 + gs * D;
     const float* b = rf.b32 + gi * D;
-    if ((D & 3) == 0) {
+    if ((D & 1023) == 0) {
+      for (int base = 0; base < D; base += 1024) {
+        float4 fa[8], fb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          fa[j] = *reinterpret_cast<const float4*>(a + base + j * 128 + lane * 4);
+          fb[j] = *reinterpret_cast<const float4*>(b + base + j * 128 + lane * 4);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          acc += (double)fa[j].x * fb[j].x + (double)fa[j].y * fb[j].y + (double)fa[j].z * fb[j].z + (double)fa[j].w * fb[j].w;
+      }
+    } else if ((D & 3) == 0) {
       for (int i = lane * 4; i < D; i += 128) {
         const float4 fa = *reinterpret_cast<const float4*>(a + i), fb = *reinterpret_cast<const float4*>(b + i);
         acc += (double)fa.x * fb.x + (double)fa.y * fb.y + (double)fa.z * fb.z + (double)fa.w * fb.w;
@@ -452,22 +492,11 @@ __device__ double refine_cost(const bt_refine& rf, const bt_lap_batch& B, int k,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   float sim;
-  if (rf.f16) {
-    const float na = rf.a_norm[gs];
-    sim = na > 0.f ? (float)(acc / (double)na) : 0.f;
-  } else {
-    sim = (float)acc;
-  }
-  if (list == 2 && rf.b_norm) {      // stage 3 compares the NORMALISED detection feature (demo:1593-1599)
-    const float nb = rf.b_norm[gd];
-    sim = nb > 0.f ? sim / nb : 0.f;
-  }
-  const double iou_d = bt_iou_dist_f64(rf.row_tlbr + gs * 4, rf.col_tlbr + gd * 4);
-  if (list == 2) return bt_fuse_stage3(iou_d, sim, rf.appearance, rf.proximity);
-  float face = 0.f;
-  if (B.face_sim[k]) {
-    const int pr = reinterpret_cast<const int32_t*>(rf.ctrl + B.pos_off[k])[row];
-    if (pr >= 0) face = B.face_sim[k][(size_t)pr * B.m[k] + col];
+  if (rf.f16) sim = na > 0.f ? (float)(acc / (double)na) : 0.f;
+  else sim = (float)acc;
+  if (list == 2) {      // stage 3 compares the NORMALISED detection feature (demo:1593-1599)
+    if (rf.b_norm) sim = nb > 0.f ? sim / nb : 0.f;
+    return bt_fuse_stage3(iou_d, sim, rf.appearance, rf.proximity);
   }
   return bt_fuse_stage1(iou_d, sim, face, rf.appearance);
 }
@@ -480,7 +509,8 @@ __device__ double refine_cost(const bt_refine& rf, const bt_lap_batch& B, int k,
 constexpr int kSmallRows = 512;
 constexpr int kSmallEdges = 4096;
 constexpr int kSmallCols = 2560;
-constexpr int kOneWarpRows = 16;
+constexpr int kOneWarpRows = 4;
+constexpr double kTieGap = 1.0e-3;         // two costs closer than this may swap order within the tensor-core error
 constexpr double kBlockedCost = 1.0e300;   // an edge whose column an earlier stage took: never beats staying unmatched
 
 struct SmallSmem {
@@ -556,38 +586,54 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ 
     // ---- P1: classify every row from the emitters' degree bookkeeping (no edge traversal for the bulk):
     //      isolated edges (row degree 1, column in-degree 1, gate decision not in doubt) are final; rows
     //      with several candidates, a contested column or an ambiguous gate are "complex" ----
-    for (int r = tid; r < n; r += GT) {
-      const size_t ri = (size_t)list * cand.rows_cap + r;
-      const int deg = cand.rowdeg[ri];
-      if (deg == 0) continue;                      // nothing was emitted for this row
-      const int rc = cand.rowcol[ri];
-      const int col1 = rc & BT_EDGE_COLMASK;
-      const unsigned long long mask = cand.segmask[ri];
-      if (P.clear_lists) { cand.rowdeg[ri] = 0; cand.segmask[ri] = 0ull; }
-      const bool row_on = row_block == nullptr || row_block[r] < 0;
-      bool complex_row = row_on;
-      if (row_on && deg == 1) {
-        const bool col_ok = edge_ok(col_block, col1);
-        if (!col_ok) complex_row = false;            // its only column is taken already
-        else if (indeg[col1] == 1 && !(rc & BT_EDGE_AMBIG)) {
-          x[r] = col1; y[col1] = r;                  // isolated edge
-          complex_row = false;
+    for (int r0 = tid; r0 < n; r0 += 2 * GT) {
+      // two rows per thread and pass, all their loads in flight before the first dependent one: the phase is a
+      // chain of L2 round trips (degree -> the row's column -> that column's in-degree)
+      int rr[2] = {r0, r0 + GT}, degs[2], rcs[2], inds[2];
+      unsigned long long masks[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        degs[q] = 0; rcs[q] = 0; masks[q] = 0ull;
+        if (rr[q] < n) {
+          const size_t ri = (size_t)list * cand.rows_cap + rr[q];
+          degs[q] = cand.rowdeg[ri]; rcs[q] = cand.rowcol[ri]; masks[q] = cand.segmask[ri];
         }
       }
-      if (!complex_row) {
-        if (P.clear_lists) {                          // leave the segment counters zeroed
-          unsigned long long mm = mask;
-          while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) inds[q] = (degs[q] == 1) ? indeg[rcs[q] & BT_EDGE_COLMASK] : 0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int r = rr[q], deg = degs[q], rc = rcs[q];
+        if (deg == 0) continue;                      // nothing was emitted for this row
+        const size_t ri = (size_t)list * cand.rows_cap + r;
+        const int col1 = rc & BT_EDGE_COLMASK;
+        const unsigned long long mask = masks[q];
+        if (P.clear_lists) { cand.rowdeg[ri] = 0; cand.segmask[ri] = 0ull; }
+        const bool row_on = row_block == nullptr || row_block[r] < 0;
+        bool complex_row = row_on;
+        if (row_on && deg == 1) {
+          const bool col_ok = edge_ok(col_block, col1);
+          if (!col_ok) complex_row = false;            // its only column is taken already
+          else if (inds[q] == 1 && !(rc & BT_EDGE_AMBIG)) {
+            x[r] = col1; y[col1] = r;                  // isolated edge
+            complex_row = false;
+          }
         }
-        continue;
-      }
-      const int kc = atomicAdd(&sm.nC, 1);
-      const int e0 = atomicAdd(&sm.nE, deg);
-      W.clist[kc] = r;
-      if (kc < kSmallRows && e0 + deg <= kSmallEdges) {
-        sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0; sm.rmask[kc] = mask;
-      } else {
-        sm.big = 1;
+        if (!complex_row) {
+          if (P.clear_lists) {                          // leave the segment counters zeroed
+            unsigned long long mm = mask;
+            while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
+          }
+          continue;
+        }
+        const int kc = atomicAdd(&sm.nC, 1);
+        const int e0 = atomicAdd(&sm.nE, deg);
+        W.clist[kc] = r;
+        if (kc < kSmallRows && e0 + deg <= kSmallEdges) {
+          sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0; sm.rmask[kc] = mask;
+        } else {
+          sm.big = 1;
+        }
       }
     }
     __syncthreads();
@@ -634,17 +680,65 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ 
         const int e0 = sm.rstart[i];
         const int32_t* rc = ecol + (size_t)r * cand.stride;
         const double* rv = ecost + (size_t)r * cand.stride;
+        // while gathering: the row's cheapest and second cheapest usable edge (provisional costs)
+        double b1 = kBlockedCost, b2 = kBlockedCost;
+        int bc = kInf, amb = 0;
         for (int half = 0; half < 2; ++half) {
           const int kk = half ? k1 : k0, dst0 = e0 + (half ? p1 : p0), src0 = (half ? g1 : g0) * cand.seg;
           for (int j = 0; j < kk; ++j) {
             const int colf = rc[src0 + j];
             const int col = colf & BT_EDGE_COLMASK;
             const bool ok = edge_ok(col_block, col);
+            const double cst = ok ? rv[src0 + j] : kBlockedCost;
             sm.ecol[dst0 + j] = col;
-            sm.ecst[dst0 + j] = ok ? rv[src0 + j] : kBlockedCost;
+            sm.ecst[dst0 + j] = cst;
             if (ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG))) sm.rlist[atomicAdd(&sm.nR, 1)] = (i << 12) | (dst0 + j);
+            if (ok) {
+              if (colf & BT_EDGE_AMBIG) amb = 1;
+              if (cst < b1 || (cst == b1 && col < bc)) { b2 = b1; b1 = cst; bc = col; }
+              else if (cst < b2) b2 = cst;
+            }
           }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
+          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+          amb |= __shfl_xor_sync(0xffffffffu, amb, o);
+          if (ob1 < b1 || (ob1 == b1 && oc < bc)) { b2 = fmin(b1, ob2); b1 = ob1; bc = oc; }
+          else b2 = fmin(b2, ob1);
+        }
+        if (lane == 0) {
+          // decided without looking at anybody else: no gate in doubt, and the row's choice cannot change within
+          // the error of a tensor-core similarity (its runner-up is out of reach or clearly worse)
+          const bool decided = !amb && (b1 >= thresh || b2 >= thresh || b2 - b1 > kTieGap);
+          sm.xl[i] = (b1 < thresh) ? bc : -1;
+          sm.isroot[i] = decided ? 1 : 0;
+        }
+      }
+      if (tid == 0) sm.changed = 0;
+      __syncthreads();
+      // ---- S2b: every complex row takes its cheapest edge -- if those choices are decided and pairwise
+      //      distinct they are the optimum (each row at its own lower bound), which is the usual frame ----
+      for (int i = tid; i < nC; i += GT) {
+        const int c = sm.xl[i];
+        bool clash = sm.isroot[i] == 0;
+        if (c >= 0 && atomicCAS(&sm.yl[c], -1, i) != -1) clash = true;
+        if (clash) sm.changed = 1;
+      }
+      __syncthreads();
+      const bool greedy_ok = sm.changed == 0;
+      __syncthreads();
+      if (greedy_ok) {
+        for (int i = tid; i < nC; i += GT) {
+          const int c = sm.xl[i];
+          if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
+        }
+        dbg_ncomp = -1;
+      } else {
+      for (int i = tid; i < nC; i += GT) {
+        const int c = sm.xl[i];
+        if (c >= 0) sm.yl[c] = -1;
       }
       __syncthreads();
       // ---- S3: exact re-costing of the flagged edges, one warp each ----
@@ -737,6 +831,7 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ 
         const int c = sm.xl[i];
         if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
       }
+      }   // general (non-greedy) path
     } else if (nC > 0) {
       // ---- large complex part (a crowded scene, a dense cost matrix, more detections than the on-chip
       //      arrays hold): same algorithm over global scratch ----
@@ -995,23 +1090,13 @@ static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& 
     BT_CHECK(B.n[k] <= ctx->lap->rows && B.m[k] <= ctx->lap->cols, BT_ERR_CAPACITY,
              "linear assignment %d x %d exceeds ctx capacity %d x %d", B.n[k], B.m[k], ctx->lap->rows, ctx->lap->cols);
   if (B.count <= 0) return BT_OK;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(B.count);
-  cfg.blockDim = dim3(kLapThreads);
-  cfg.dynamicSmemBytes = sizeof(SmallSmem);
-  cfg.stream = ctx->stream;
   static std::once_flag attr_once;
   cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [&] {
     attr_err = cudaFuncSetAttribute(lap_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem));
   });
   BT_CUDA(attr_err);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = ctx->pdl ? 1 : 0;
-  BT_CUDA(cudaLaunchKernelEx(&cfg, lap_stream_kernel, cand, *ctx->lap, B, P, rf));
+  BT_CUDA(bt_launch(ctx, true, lap_stream_kernel, dim3(B.count), dim3(kLapThreads), sizeof(SmallSmem), cand, *ctx->lap, B, P, rf));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

@@ -1051,18 +1051,9 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, EpiParams& ep) 
   ep.tile_start[ap.count] = tiles;
   for (int k = ap.count + 1; k <= BT_MAX_BATCH; ++k) ep.tile_start[k] = tiles;
   if (tiles == 0) return BT_OK;
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kTcThreads);
-  cfg.dynamicSmemBytes = TcSmem<BN>::kDyn;
-  cfg.stream = ctx->stream;
-  cfg.gridDim = dim3(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  cudaLaunchAttribute attr[1];
   // may start its ramp (and, with operands_early, its main loop) under the previous kernel (griddepcontrol.wait inside)
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = ctx->pdl ? 1 : 0;
-  BT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, ep, ap.d));
+  BT_CUDA(bt_launch(ctx, true, kern, dim3(tiles < ctx->num_sms ? tiles : ctx->num_sms), dim3(kTcThreads), TcSmem<BN>::kDyn,
+                    ta, tb, ep, ap.d));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
@@ -1136,12 +1127,12 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   dim3 grid((mx_m + ST - 1) / ST, (mx_n + ST - 1) / ST, ap.count);
   if (ap.a32 != nullptr || ap.d == 0) {
     BT_CHECK(ap.d == 0 || (ap.a32 && ap.b32), BT_ERR_INVALID, "fp32 operands missing");
-    if (dense) assoc_simt_kernel<true, float><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
-    else assoc_simt_kernel<false, float><<<grid, 256, 0, ctx->stream>>>(ap.a32, ap.b32, ep, ap.d);
+    if (dense) BT_CUDA(bt_launch(ctx, false, assoc_simt_kernel<true, float>, grid, dim3(256), 0, ap.a32, ap.b32, ep, ap.d));
+    else BT_CUDA(bt_launch(ctx, false, assoc_simt_kernel<false, float>, grid, dim3(256), 0, ap.a32, ap.b32, ep, ap.d));
   } else {
     BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "operands missing");
-    if (dense) assoc_simt_kernel<true, __half><<<grid, 256, 0, ctx->stream>>>(ap.a16, ap.b16, ep, ap.d);
-    else assoc_simt_kernel<false, __half><<<grid, 256, 0, ctx->stream>>>(ap.a16, ap.b16, ep, ap.d);
+    if (dense) BT_CUDA(bt_launch(ctx, false, assoc_simt_kernel<true, __half>, grid, dim3(256), 0, ap.a16, ap.b16, ep, ap.d));
+    else BT_CUDA(bt_launch(ctx, false, assoc_simt_kernel<false, __half>, grid, dim3(256), 0, ap.a16, ap.b16, ep, ap.d));
   }
   BT_LAUNCHED(ctx);
   return BT_OK;

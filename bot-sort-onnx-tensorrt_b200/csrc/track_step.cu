@@ -80,14 +80,40 @@ struct StreamState {
       v_removed_now, v_r_tracked, v_u_det_pos, v_new_tracked, v_new_lost, v_tmp, v_birth_slot, v_birth_det;
   std::vector<uint8_t> v_det_taken, v_pool_matched, scratch_a, scratch_b;
   std::vector<int> scratch_pos_t, scratch_pos_l;
-  std::vector<double> tlbr_cache;   // tlbr of `tracked` after the frame
+  const double* tlbr_src = nullptr; // boxes of all slots after the last step (host copy of result part B)
+  int tlbr_n_rows = 0;
+  int tlbr_region = 0;              // result region the copy lives in, and that region's generation at the time
+  uint64_t tlbr_gen = 0;
+  bool boxes_valid = false;         // host_boxes (this frame's detections) has not been overwritten since the step
   bool tlbr_cache_valid = false;
 };
 
 }  // namespace
 
+// the kernel launches of a steady-state frame, in the order they are issued
+enum { R_CAST = 0, R_PREP, R_ASSOC, R_LAP, R_EMA, R_POST, R_DUP, R_COUNT };
+struct GraphKey {
+  int count, f32, reid, dev, bn, precision, f16;
+  bool operator==(const GraphKey& o) const {
+    return count == o.count && f32 == o.f32 && reid == o.reid && dev == o.dev && bn == o.bn && precision == o.precision && f16 == o.f16;
+  }
+};
+struct FrameGraph {
+  GraphKey key;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t node[R_COUNT] = {};
+  bool has[R_COUNT] = {};
+  int n_kernels = 0;
+};
+
 struct bt_tracker {
   int S = 1, cap = 0, md = 0, D = 0;
+  // the frame step as a CUDA graph, one per launch shape (BT_NO_GRAPH=1: plain enqueue every frame)
+  bool use_graph = true;
+  std::vector<GraphKey> seen_keys;      // shapes that ran once the plain way (module loading, function attributes)
+  std::vector<FrameGraph> graphs;
+  bt_launch_rec recs[R_COUNT];
   bt_store st = {};
   bt_res_layout L = {};
   std::vector<StreamState> streams;
@@ -96,6 +122,8 @@ struct bt_tracker {
   char* h_ctrl = nullptr;
   char* h_res = nullptr;            // part A regions
   char* h_resB = nullptr;           // part B regions
+  int32_t* h_in_boxes = nullptr;    // [2][S*md][4] pinned copies of the submitted boxes / scores of host inputs: the
+  float* h_in_scores = nullptr;     // [2][S*md]     list bookkeeping reads them at step time (the caller's may be gone)
   int32_t* h_birth = nullptr;       // [S][2*md + cap] birth slot / det lists + lost list
   int32_t* d_birth = nullptr;
   int32_t* h_pairs = nullptr;       // [2*kPairCap] overflow fetch (one stream at a time)
@@ -104,12 +132,15 @@ struct bt_tracker {
   int32_t* h_list = nullptr; int32_t* d_list = nullptr;   // list read-backs
   double* d_gather = nullptr;       // [cap*64]
   float* d_gather32 = nullptr;      // [cap*D] (allocated on first use)
+  uint64_t region_gen[BT_MAX_BATCH] = {};   // bumped whenever a step overwrites result region k
   cudaEvent_t ev_x = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // side stream (feature EMA) fork / join
   cudaEvent_t ev_tail = nullptr;    // end of the work a step left running on the main stream (births)
   bool tail_pending = false;
   std::vector<cudaEvent_t> in_events;
   int in_seq = 0;
   bool host_debug = false;
+  bool no_refine = false;           // BT_NO_REFINE=1: tests show what the exact re-costing buys
   bt_assoc_params last_assoc;       // for bt_profile_replay_assoc
   int last_assoc_precision = 0;
   bool last_assoc_valid = false;
@@ -255,6 +286,8 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_CUDA(cudaMallocHost(&t->h_ctrl, t->ctrl_stride * S));
   BT_CUDA(cudaMallocHost(&t->h_res, t->L.stride * S));
   BT_CUDA(cudaMallocHost(&t->h_resB, t->L.strideB * S));
+  BT_CUDA(cudaMallocHost(&t->h_in_boxes, sizeof(int32_t) * 2 * ND * 4));
+  BT_CUDA(cudaMallocHost(&t->h_in_scores, sizeof(float) * 2 * ND));
   BT_CUDA(cudaMallocHost(&t->h_birth, sizeof(int32_t) * (size_t)S * (2 * md + cap)));
   BT_CUDA(cudaMallocHost(&t->h_pairs, sizeof(int32_t) * 2 * (size_t)kPairCap));
   BT_CUDA(cudaMallocHost(&t->h_bpairs, sizeof(int32_t) * 2 * (size_t)t->bpair_cap));
@@ -264,9 +297,13 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   for (auto& s : t->streams) reset_stream(t, s, nullptr);
   BT_CUDA(cudaEventCreateWithFlags(&t->ev_x, cudaEventDisableTiming));
   BT_CUDA(cudaEventCreateWithFlags(&t->ev_tail, cudaEventDisableTiming));
+  BT_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+  BT_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
   t->in_events.resize(2 * (size_t)S + 2);
   for (auto& e : t->in_events) BT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   t->host_debug = getenv("BT_HOST_DEBUG") != nullptr;
+  t->no_refine = getenv("BT_NO_REFINE") != nullptr;
+  t->use_graph = getenv("BT_NO_GRAPH") == nullptr;
   return BT_OK;
 }
 
@@ -282,16 +319,22 @@ void bt_tracker_destroy(bt_ctx* ctx) {
     if (p) cudaFree(p);
   for (auto& s : t->streams)
     if (s.face_dev) cudaFree(s.face_dev);
-  void* hptrs[] = {t->h_ctrl, t->h_res, t->h_resB, t->h_birth, t->h_pairs, t->h_bpairs, t->h_bpair_count, t->h_list};
+  void* hptrs[] = {t->h_ctrl, t->h_res, t->h_resB, t->h_in_boxes, t->h_in_scores, t->h_birth, t->h_pairs, t->h_bpairs, t->h_bpair_count, t->h_list};
   for (void* p : hptrs)
     if (p) cudaFreeHost(p);
   if (t->ev_x) cudaEventDestroy(t->ev_x);
   if (t->ev_tail) cudaEventDestroy(t->ev_tail);
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_join) cudaEventDestroy(t->ev_join);
   for (auto& e : t->in_events)
     if (e) cudaEventDestroy(e);
   for (int s = 0; s < BT_SEG_HOST_ENQUEUE1; ++s)
     for (cudaEvent_t e : t->ev[s])
       if (e) cudaEventDestroy(e);
+  for (auto& g : t->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
   delete t;
   ctx->trk = nullptr;
 }
@@ -356,6 +399,7 @@ static int32_t submit_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, con
     const int m = m_arr[k];
     const int parity = s.next_parity;
     s.next_parity ^= 1;
+    if (parity == s.parity) s.boxes_valid = false;   // the half the last stepped frame came from is being refilled
     FrameIn& in = s.in[parity];
     in = FrameIn();
     in.m = m; in.dtype = dtype; in.loc = loc;
@@ -365,8 +409,16 @@ static int32_t submit_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, con
     if (m > 0) {
       int32_t* db = st.det_boxes + g0 * 4;
       float* ds = st.det_scores + g0;
-      if (boxes[k] != db) { BT_CUDA(cudaMemcpyAsync(db, boxes[k], sizeof(int32_t) * 4 * m, kind, cs)); copied = true; }
-      if (scores[k] != ds) { BT_CUDA(cudaMemcpyAsync(ds, scores[k], sizeof(float) * m, kind, cs)); copied = true; }
+      const int32_t* src_b = boxes[k];
+      const float* src_s = scores[k];
+      if (loc == BT_HOST) {   // pinned copies: truly asynchronous H2D, and the host-side bookkeeping owns what it reads
+        memcpy(t->h_in_boxes + g0 * 4, boxes[k], sizeof(int32_t) * 4 * m);
+        memcpy(t->h_in_scores + g0, scores[k], sizeof(float) * m);
+        src_b = t->h_in_boxes + g0 * 4;
+        src_s = t->h_in_scores + g0;
+      }
+      if (src_b != db) { BT_CUDA(cudaMemcpyAsync(db, src_b, sizeof(int32_t) * 4 * m, kind, cs)); copied = true; }
+      if (src_s != ds) { BT_CUDA(cudaMemcpyAsync(ds, src_s, sizeof(float) * m, kind, cs)); copied = true; }
       if (reid) {
         if (dtype == BT_F16) {
           __half* d16 = st.det16 + g0 * D;
@@ -376,7 +428,7 @@ static int32_t submit_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, con
           copied = true;
         }
       }
-      if (loc == BT_HOST) { in.host_boxes = boxes[k]; in.host_scores = scores[k]; }
+      if (loc == BT_HOST) { in.host_boxes = t->h_in_boxes + g0 * 4; in.host_scores = t->h_in_scores + g0; }
     }
     if (face_sims && face_sims[k] && m > 0) {
       // rows in pool order: activated tracked tracks then lost tracks (the pool of THIS step; no frame of
@@ -412,6 +464,92 @@ static int32_t submit_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// A steady-state frame issues ~14 driver calls (copies, 6-7 kernel launches, events); on the host that is
+// 60-90 us -- longer than the GPU needs for the work.  The same sequence is therefore captured ONCE per
+// launch shape into a CUDA graph (programmatic-dependent-launch edges included); every later frame records
+// its kernels' geometry + arguments (bt_launch_rec), patches the instantiated graph's kernel nodes with them
+// and launches the graph: one launch + one cheap update per kernel.
+// ------------------------------------------------------------------------------------------------
+template <typename Enqueue>
+static int32_t run_enqueue(bt_ctx* ctx, bt_tracker* t, Enqueue& enqueue, const GraphKey& key, bool eligible) {
+  cudaStream_t st = ctx->stream;
+  if (!eligible) return enqueue(0);
+  FrameGraph* g = nullptr;
+  for (auto& cand : t->graphs)
+    if (cand.key == key) g = &cand;
+  if (!g) {
+    bool seen = false;
+    for (const auto& k : t->seen_keys) seen = seen || k == key;
+    if (!seen) {       // first frame of this shape: the plain way (first-launch work must not happen under capture)
+      t->seen_keys.push_back(key);
+      return enqueue(0);
+    }
+    FrameGraph fg;
+    fg.key = key;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int32_t rc = BT_OK;
+    if (e == cudaSuccess) {
+      rc = enqueue(1);
+      cudaError_t e2 = cudaStreamEndCapture(st, &fg.graph);
+      if (rc == BT_OK && e2 != cudaSuccess) e = e2;
+    }
+    if (e == cudaSuccess && rc == BT_OK) e = cudaGraphInstantiate(&fg.exec, fg.graph, 0);
+    if (e != cudaSuccess || rc != BT_OK) {
+      // graphs are an optimisation: fall back to the plain enqueue for good
+      (void)cudaGetLastError();
+      if (fg.exec) cudaGraphExecDestroy(fg.exec);
+      if (fg.graph) cudaGraphDestroy(fg.graph);
+      t->use_graph = false;
+      if (getenv("BT_HOST_DEBUG")) fprintf(stderr, "botsort_b200: frame graph capture failed (%s), using plain launches\n", cudaGetErrorString(e));
+      return enqueue(0);
+    }
+    // which captured kernel node is which launch: match by function
+    for (auto& r : t->recs) r.func = nullptr;
+    rc = enqueue(2);
+    ctx->rec = nullptr;
+    BT_TRY(rc);
+    size_t nn = 0;
+    BT_CUDA(cudaGraphGetNodes(fg.graph, nullptr, &nn));
+    std::vector<cudaGraphNode_t> nodes(nn);
+    BT_CUDA(cudaGraphGetNodes(fg.graph, nodes.data(), &nn));
+    for (size_t i = 0; i < nn; ++i) {
+      cudaGraphNodeType ty;
+      BT_CUDA(cudaGraphNodeGetType(nodes[i], &ty));
+      if (ty != cudaGraphNodeTypeKernel) continue;
+      cudaKernelNodeParams kp;
+      BT_CUDA(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+      for (int q = 0; q < R_COUNT; ++q)
+        if (t->recs[q].func && t->recs[q].func == kp.func) { fg.node[q] = nodes[i]; fg.has[q] = true; }
+      fg.n_kernels += 1;
+    }
+    for (int q = 0; q < R_COUNT; ++q)
+      BT_CHECK((t->recs[q].func != nullptr) == fg.has[q], BT_ERR_STATE, "frame graph: kernel node %d not found", q);
+    t->graphs.push_back(fg);
+    g = &t->graphs.back();
+    BT_CUDA(cudaGraphLaunch(g->exec, st));     // the capture executed nothing: this runs the frame
+    ctx->launches += g->n_kernels;
+    return BT_OK;
+  }
+  for (auto& r : t->recs) r.func = nullptr;
+  int32_t rc = enqueue(2);
+  ctx->rec = nullptr;
+  BT_TRY(rc);
+  for (int q = 0; q < R_COUNT; ++q) {
+    BT_CHECK((t->recs[q].func != nullptr) == g->has[q], BT_ERR_STATE, "frame graph: launch %d does not match the captured shape", q);
+    if (!g->has[q]) continue;
+    bt_launch_rec& r = t->recs[q];
+    cudaKernelNodeParams kp = {};
+    kp.func = const_cast<void*>(r.func);
+    kp.gridDim = r.grid; kp.blockDim = r.block; kp.sharedMemBytes = r.smem;
+    kp.kernelParams = r.argp; kp.extra = nullptr;
+    BT_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->node[q], &kp));
+  }
+  BT_CUDA(cudaGraphLaunch(g->exec, st));
+  ctx->launches += g->n_kernels;
+  return BT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // the frame step of a batch of video streams
 // ------------------------------------------------------------------------------------------------
 static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_frame_info* infos) {
@@ -425,6 +563,9 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   const int D = t->D;
   double t_host = now_ms();
   double hphase[5] = {0, 0, 0, 0, 0};
+  const char* fm_name[24]; double fm_t[24]; int fm_n = 0;
+  auto fmark = [&](const char* nm) { if (t->host_debug && fm_n < 24) { fm_name[fm_n] = nm; fm_t[fm_n++] = now_ms(); } };
+  fmark("start");
 
   // ---- per-stream set-up: pop the oldest frame, split lists (demo:1415-1423), control segments ----
   bt_batch B;
@@ -446,6 +587,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     s.device_inputs = in.loc == BT_DEVICE;
     s.frame_id += 1;  // demo:1292
     s.tlbr_cache_valid = false;
+    t->region_gen[k] += 1;
     const bool reid = s.cfg.with_reid != 0;
     if (reid && in.m > 0) {
       s.feat_dtype = in.dtype;
@@ -521,18 +663,29 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   fc.prefetch_pairs = kPairPrefetch;
 
   const int mx_rows = bt_batch_max(B.n_rows, count), mx_m = bt_batch_max(B.m, count);
+  fmark("setup");
+  const int assoc_bn = (any_reid && tensor_path) ? btk_assoc_pick_bn(ctx, B.n_rows, B.m, count) : 256;
+  const int assoc_precision = (any_reid && tensor_path) ? 0 : 1;
+  bool part_a_sent = false, ema_pending = false;
+  // mode 0: plain enqueue; 1: the same calls under stream capture (fixed copy sizes, the side stream rejoins);
+  // 2: kernel launches are only RECORDED (ctx->rec) for the parameter update of an instantiated graph
+  auto enqueue = [&](const int mode) -> int32_t {
   // ---- enqueue: control block, cast, prep + predict, association, LAP ----
-  if (ctrl_off > 0) BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_off, cudaMemcpyHostToDevice, st));
+  // (graph capture: fixed sizes -- the tail of the copy is padding)
+  const size_t ctrl_bytes_now = mode == 1 ? t->ctrl_stride * (size_t)count : ctrl_off;
+  if (ctrl_bytes_now > 0 && mode != 2) BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_bytes_now, cudaMemcpyHostToDevice, st));
+  fmark("ctrl_h2d");
   SEG_BEGIN(BT_SEG_PREP);
+  if (mode == 2) ctx->rec = &t->recs[R_CAST];
   if (any_f32) BT_TRY(btk_frame_cast(ctx, dst, B));
   SEG_END(BT_SEG_PREP);
   SEG_BEGIN(BT_SEG_PREDICT);
+  if (mode == 2) ctx->rec = &t->recs[R_PREP];
   BT_TRY(btk_frame_prep(ctx, dst, B, fc));
   SEG_END(BT_SEG_PREDICT);
+  fmark("prep");
 
-  bool part_a_sent = false;
   bt_cand cand = *bt_lap_own_cand(ctx);
-  const int assoc_bn = (any_reid && tensor_path) ? btk_assoc_pick_bn(ctx, B.n_rows, B.m, count) : 256;
   cand.seg = assoc_bn / 2;    // one epilogue thread owns one (row, segment) pair; the LAP gather follows
   const size_t ND = (size_t)t->S * t->md;
   if (mx_rows > 0) {
@@ -569,7 +722,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       LB.zero_word[k] = reinterpret_cast<int32_t*>(dst.resB + (size_t)k * L.strideB) + L.o_hdr;
     }
     if (mx_m > 0) {
-      const int precision = (any_reid && tensor_path) ? 0 : 1;
+      const int precision = assoc_precision;
       p.d = any_reid ? D : 0;
       p.a_rows_alloc = t->S * t->cap; p.b_rows_alloc = (int32_t)(2 * ND);
       p.bn = assoc_bn;
@@ -598,14 +751,17 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       t->last_assoc = p;
       t->last_assoc_precision = precision;
       t->last_assoc_valid = true;
+      fmark("assoc_params");
+      if (mode == 2) ctx->rec = &t->recs[R_ASSOC];
       BT_TRY(btk_assoc(ctx, p, precision));
+      fmark("assoc");
     }
     SEG_END(BT_SEG_ASSOC);
     SEG_BEGIN(BT_SEG_LAP);
     const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
     bt_refine rf;
     memset(&rf, 0, sizeof(rf));
-    if (any_reid && tensor_path && mx_m > 0) {
+    if (any_reid && tensor_path && mx_m > 0 && !t->no_refine) {
       rf.enabled = 1; rf.d = D; rf.f16 = f16 ? 1 : 0;
       rf.a16 = dst.feat16; rf.a_norm = dst.norm; rf.a32 = dst.curr32;
       rf.b16 = dst.det16; rf.b32 = dst.det32;
@@ -613,33 +769,71 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       rf.row_tlbr = dst.tlbr; rf.col_tlbr = dst.det_tlbr; rf.ctrl = dst.ctrl;
       rf.proximity = cfg.proximity_thresh; rf.appearance = (float)cfg.appearance_thresh;
     }
+    if (mode == 2) ctx->rec = &t->recs[R_LAP];
     BT_TRY(btk_lap_solve3(ctx, cand, LB, th, rf));   // also zeroes the pair counters
     SEG_END(BT_SEG_LAP);
+    fmark("lap");
   }
   // part A of the result regions: the assignment vectors (+ echoed scores / boxes of device inputs)
   const size_t widthA = sizeof(int32_t) * (any_dev_inputs ? L.o_endA : L.o_sc);
   if (mx_rows > 0 || (any_dev_inputs && mx_m > 0)) {
-    if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_res, dst.res, widthA, cudaMemcpyDeviceToHost, st));
-    else BT_CUDA(cudaMemcpy2DAsync(t->h_res, L.stride, dst.res, L.stride, widthA, count, cudaMemcpyDeviceToHost, st));
-    BT_CUDA(cudaEventRecord(t->ev_x, st));
+    if (mode != 2) {
+      if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_res, dst.res, widthA, cudaMemcpyDeviceToHost, st));
+      else BT_CUDA(cudaMemcpy2DAsync(t->h_res, L.stride, dst.res, L.stride, widthA, count, cudaMemcpyDeviceToHost, st));
+      // under capture: an event RECORD NODE the host can wait on (a plain record would only order captured work)
+      if (mode == 1) BT_CUDA(cudaEventRecordWithFlags(t->ev_x, st, cudaEventRecordExternal));
+      else BT_CUDA(cudaEventRecord(t->ev_x, st));
+    }
     part_a_sent = true;
+    fmark("copyA+ev");
   }
   if (mx_rows > 0) {
     // The matched tracks' Kalman update and feature EMA are a pure function of the three assignment
     // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
     // demo:570-610) while the host is still waiting for / digesting the assignments.
     SEG_BEGIN(BT_SEG_UPDATE);
-    BT_TRY(btk_frame_post(ctx, dst, B, fc, (any_reid && mx_m > 0) ? 1 : 0));
+    if (any_reid && mx_m > 0) {
+      // the feature EMA only needs the assignment vectors: side stream, next to update + duplicate test
+      // (profiling keeps it on the main stream so that its time shows up in the segment)
+      cudaStream_t es = t->prof ? st : ctx->side_stream;
+      if (!t->prof && mode != 2) {
+        BT_CUDA(cudaEventRecord(t->ev_fork, st));
+        BT_CUDA(cudaStreamWaitEvent(es, t->ev_fork, 0));
+      }
+      if (mode == 2) ctx->rec = &t->recs[R_EMA];
+      BT_TRY(btk_frame_ema(ctx, dst, B, fc, es));
+      if (!t->prof && mode != 2) { BT_CUDA(cudaEventRecord(t->ev_join, es)); ema_pending = true; }
+    }
+    fmark("ema(fork/join)");
+    if (mode == 2) ctx->rec = &t->recs[R_POST];
+    BT_TRY(btk_frame_post(ctx, dst, B, fc));
     SEG_END(BT_SEG_UPDATE);
+    fmark("post");
     // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
     SEG_BEGIN(BT_SEG_DUP);
+    if (mode == 2) ctx->rec = &t->recs[R_DUP];
     BT_TRY(btk_frame_dup(ctx, dst, B, fc));
     SEG_END(BT_SEG_DUP);
+    fmark("dup");
     // part B: pair count + first pairs, boxes of all slots
-    const size_t widthB = L.o_tlbr_bytes + sizeof(double) * 4 * (size_t)mx_rows;
-    if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_resB, dst.resB, widthB, cudaMemcpyDeviceToHost, st));
-    else BT_CUDA(cudaMemcpy2DAsync(t->h_resB, L.strideB, dst.resB, L.strideB, widthB, count, cudaMemcpyDeviceToHost, st));
+    const size_t widthB = L.o_tlbr_bytes + sizeof(double) * 4 * (size_t)(mode == 1 ? t->cap : mx_rows);
+    if (mode != 2) {
+      if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_resB, dst.resB, widthB, cudaMemcpyDeviceToHost, st));
+      else BT_CUDA(cudaMemcpy2DAsync(t->h_resB, L.strideB, dst.resB, L.strideB, widthB, count, cudaMemcpyDeviceToHost, st));
+    }
+    if (mode == 1 && ema_pending) {     // a captured fork must rejoin its origin stream
+      BT_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));
+      ema_pending = false;
+    }
   }
+    return BT_OK;
+  };
+  {
+    GraphKey key = {count, any_f32 ? 1 : 0, any_reid ? 1 : 0, any_dev_inputs ? 1 : 0, assoc_bn, assoc_precision, f16 ? 1 : 0};
+    const bool eligible = t->use_graph && !t->prof && mx_rows > 0 && mx_m > 0;
+    BT_TRY(run_enqueue(ctx, t, enqueue, key, eligible));
+  }
+  fmark("copyB");
   HOST_MARK(BT_SEG_HOST_ENQUEUE1);
   // wait only for the assignments (+ scores / boxes): the list bookkeeping below overlaps the GPU's
   // update / EMA / duplicate-test tail
@@ -800,6 +994,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   }
   HOST_MARK(BT_SEG_HOST_LISTS);
   BT_CUDA(cudaStreamSynchronize(st));    // the frame's device work is complete, part B is on the host
+  if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join));   // the side stream's EMA (usually done already)
   HOST_MARK(BT_SEG_HOST_WAIT2);
   BT_TRY(prof_collect(ctx, t));
 
@@ -909,16 +1104,17 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     }
     s.tracked.clear();
     s.lost.clear();
-    s.tlbr_cache.resize(4 * (size_t)nt);
-    size_t n_out = 0;
-    for (int i = 0; i < nt; ++i) {
-      if (dupa[i]) continue;
-      s.tracked.push_back(new_tracked[i]);
-      box_of(new_tracked[i], s.tlbr_cache.data() + 4 * n_out++);
-    }
-    s.tlbr_cache.resize(4 * n_out);
+    for (int i = 0; i < nt; ++i)
+      if (!dupa[i]) s.tracked.push_back(new_tracked[i]);
     for (int i = 0; i < nl; ++i)
       if (!dupb[i]) s.lost.push_back(new_lost[i]);
+    // the boxes of the returned list are on the host already (result part B / this frame's detections): bt_get_tracks
+    // assembles them on demand from there (valid until this stream's next step)
+    s.tlbr_src = hres_tlbr;
+    s.tlbr_n_rows = s.n_rows;
+    s.tlbr_region = k;
+    s.tlbr_gen = t->region_gen[k];
+    s.boxes_valid = true;
     s.tlbr_cache_valid = true;
     // ---- recycle slots that left both lists ----
     for (int slot : s.tracked) meta[slot].mark = 1;
@@ -957,6 +1153,11 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     if (any_births) { BT_CUDA(cudaEventRecord(t->ev_tail, st)); t->tail_pending = true; }
   }
   HOST_MARK(BT_SEG_HOST_FINAL);
+  if (t->host_debug) {
+    fprintf(stderr, "  enqueue detail (us):");
+    for (int i = 1; i < fm_n; ++i) fprintf(stderr, " %s %.1f", fm_name[i], 1e3 * (fm_t[i] - fm_t[i - 1]));
+    fprintf(stderr, "\n");
+  }
   if (t->host_debug)
     fprintf(stderr, "step of %d stream(s), host phases (us): enqueue %.1f wait_x %.1f lists %.1f wait_end %.1f final %.1f\n", count,
             1e3 * hphase[0], 1e3 * hphase[1], 1e3 * hphase[2], 1e3 * hphase[3], 1e3 * hphase[4]);
@@ -1128,8 +1329,17 @@ int32_t bt_get_tracks_stream(bt_ctx* ctx, int32_t stream_id, int32_t which, int3
     if (score) score[i] = tm.score;
   }
   if (cnt == 0) return BT_OK;
-  if (tlbr && which == 0 && s.tlbr_cache_valid) {
-    memcpy(tlbr, s.tlbr_cache.data(), sizeof(double) * 4 * cnt);
+  if (tlbr && which == 0 && s.tlbr_cache_valid && s.boxes_valid && t->region_gen[s.tlbr_region] == s.tlbr_gen) {
+    for (int i = 0; i < cnt; ++i) {
+      const int slot = lst[i];
+      const SlotMeta& tm = s.meta[slot];
+      const bool born_now = tm.f32_state && tm.start_frame == s.frame_id;   // its box is the detection's (demo:624-648 on initiate's mean)
+      if (!born_now && slot < s.tlbr_n_rows) memcpy(tlbr + 4 * (size_t)i, s.tlbr_src + 4 * (size_t)slot, 4 * sizeof(double));
+      else {
+        const int32_t* bx = s.host_boxes + 4 * (size_t)tm.det_index;
+        for (int q = 0; q < 4; ++q) tlbr[4 * (size_t)i + q] = (double)bx[q];
+      }
+    }
     tlbr = nullptr;
   }
   if (tlbr || mean || cov) {

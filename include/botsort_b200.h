@@ -263,8 +263,8 @@ int32_t bt_update_streams(bt_ctx* ctx, int32_t count, const int32_t* stream_ids,
  * stream may have at most two submitted-but-not-stepped frames, so
  *     submit(f0); loop { submit(f[k+1]); step() -> results of f[k]; }
  * overlaps frame k+1's host->device copy with frame k's association and bookkeeping.
- * Host input buffers must stay valid until the step of that frame returns (pinned memory makes the copy
- * asynchronous). */
+ * Host feature buffers must stay valid until the step of that frame returns (pinned memory makes the copy
+ * asynchronous); boxes and scores are copied at once. */
 int32_t bt_submit_streams(bt_ctx* ctx, int32_t count, const int32_t* stream_ids, const int32_t* const* boxes,
                           const float* const* scores, const void* const* feats, const int32_t* m,
                           int32_t feat_dtype, const float* const* face_sims, int32_t loc);

@@ -489,8 +489,11 @@ class OracleBoTSORT:
             trk.det_index = det.det_index
 
     # -- the frame step ------------------------------------------------------------
-    def update_arrays(self, boxes: np.ndarray, scores: np.ndarray, feats: Optional[np.ndarray]):
-        """boxes int [M,4] tlbr, scores float32 [M], feats float32 [M,D] (or None)."""
+    def update_arrays(self, boxes: np.ndarray, scores: np.ndarray, feats: Optional[np.ndarray],
+                      face_sims: Optional[np.ndarray] = None):
+        """boxes int [M,4] tlbr, scores float32 [M], feats float32 [M,D] (or None).
+        face_sims: optional float32 [n_pool, M] face similarities in pool order (what the face encoder returns
+        at demo:1473-1486, transposed like demo:1480; default 0 = the face encoder is out of scope)."""
         self.frame_id += 1
         activated: List[OTrack] = []
         refind: List[OTrack] = []
@@ -512,17 +515,25 @@ class OracleBoTSORT:
         else:
             sims_all = np.zeros((len(pool), m_all), dtype=np.float32)
 
-        hi_idx = [i for i in range(m_all) if scores[i] > TRACK_HIGH_THRESH]    # demo:1501
+        # body.score is a Python float (float(score), demo:1022): float32(0.4) > 0.4 is True
+        fs = [float(v) for v in scores]
+        hi_idx = [i for i in range(m_all) if fs[i] > TRACK_HIGH_THRESH]    # demo:1501
         lo_idx = [i for i in range(m_all)
-                  if scores[i] <= TRACK_HIGH_THRESH and scores[i] >= TRACK_LOW_THRESH]   # demo:1531
+                  if fs[i] <= TRACK_HIGH_THRESH and fs[i] >= TRACK_LOW_THRESH]   # demo:1531
         dets_hi = [OTrack(boxes[i], float(scores[i]), None if feats is None else feats[i], i) for i in hi_idx]
         dets_lo = [OTrack(boxes[i], float(scores[i]), None if feats is None else feats[i], i) for i in lo_idx]
         body_sim = sims_all[:, hi_idx] if len(hi_idx) else np.zeros((len(pool), 0), np.float32)
+        face_sim = None
+        if face_sims is not None and len(pool) > 0 and m_all > 0:
+            face_sim = np.asarray(face_sims, dtype=np.float32).reshape(len(pool), m_all)[:, hi_idx]   # demo:1509-1514
 
         # first association (demo:1538-1566)
         ious_d = self._iou_dist(pool, dets_hi)
-        dists = fuse_stage1(ious_d, body_sim, None)
+        dists = fuse_stage1(ious_d, body_sim, face_sim)
         self.last["dists1"] = dists
+        self.last["iou1"] = ious_d
+        self.last["emb1"] = 1.0 - np.asarray(body_sim, dtype=np.float32)
+        self.last["scores"] = np.asarray(scores, dtype=np.float32)
         matches, u_track, u_det = linear_assignment(dists, MATCH_THRESH, self.lap_solver)
         self.last["matches1"] = np.asarray(matches).reshape(-1, 2)
         self._apply_matches(pool, dets_hi, matches, activated, refind)
@@ -530,6 +541,7 @@ class OracleBoTSORT:
         # second association (demo:1568-1586)
         r_tracked = [pool[i] for i in u_track if pool[i].state == ST_TRACKED]
         dists2 = self._iou_dist(r_tracked, dets_lo)
+        self.last["dists2"] = dists2
         matches2, u_track2, _u_det2 = linear_assignment(dists2, SECOND_THRESH, self.lap_solver)
         self.last["matches2"] = np.asarray(matches2).reshape(-1, 2)
         self._apply_matches(r_tracked, dets_lo, matches2, activated, refind)
@@ -549,6 +561,9 @@ class OracleBoTSORT:
               if len(u_boxes) > 0 and feats is not None else np.zeros((len(u_boxes), d_feat), np.float32))
         emb3 = embedding_distance(uf, bf)
         dists3 = fuse_stage3(ious_d3, emb3)
+        self.last["dists3"] = dists3
+        self.last["iou3"] = ious_d3
+        self.last["emb3"] = emb3
         matches3, u_unconf, u_det3 = linear_assignment(dists3, UNCONF_THRESH, self.lap_solver)
         self.last["matches3"] = np.asarray(matches3).reshape(-1, 2)
         self._apply_matches(unconfirmed, u_boxes, matches3, activated, refind)
@@ -593,6 +608,7 @@ class OracleBoTSORT:
     def _remove_duplicates(self, sa: List[OTrack], sb: List[OTrack]):
         """demo:1665-1680."""
         pdist = self._iou_dist(sa, sb)
+        self.last["dup_dist"] = pdist
         pairs = np.where(pdist < DUP_IOU_DIST)
         dupa, dupb = set(), set()
         for p, q in zip(*pairs):

@@ -15,10 +15,10 @@ TOL = 1e-4
 INT_FIELDS = ("ids", "state", "activated", "frame_id", "start_frame", "tracklet_len", "det_index")
 
 
-def _compare_frame(ctx, oracle, frame_no):
+def _compare_frame(ctx, oracle, frame_no, stream=0):
     snap = oracle.snapshot()
     for which, name in ((0, "tracked"), (1, "lost")):
-        got = ctx.get_tracks(which, with_state=True)
+        got = ctx.get_tracks(which, with_state=True, stream=stream)
         ref = snap[name]
         for f in INT_FIELDS:
             np.testing.assert_array_equal(got[f], ref[f].astype(np.int32), err_msg=f"frame {frame_no} {name}.{f}")
@@ -28,8 +28,8 @@ def _compare_frame(ctx, oracle, frame_no):
             assert np.max(np.abs(got["mean"] - ref["mean"])) <= TOL, f"frame {frame_no} {name}.mean"
             assert np.max(np.abs(got["cov"] - ref["cov"])) <= TOL, f"frame {frame_no} {name}.cov"
     for stage in (1, 2, 3):
-        np.testing.assert_array_equal(ctx.get_matches(stage), oracle.last[f"matches{stage}"].astype(np.int32),
-                                      err_msg=f"frame {frame_no} matches{stage}")
+        np.testing.assert_array_equal(ctx.get_matches(stage, stream=stream), oracle.last[f"matches{stage}"].astype(np.int32),
+                                      err_msg=f"frame {frame_no} stream {stream} matches{stage}")
 
 
 def _run(ctx, scene_cfg, frames, with_reid=True):
