@@ -177,6 +177,10 @@ int32_t bt_create_streams(int32_t device, int32_t n_streams, int32_t max_tracks,
     bt_fail(c, BT_ERR_CUDA, "cudaStreamCreate failed");
     return fail(BT_ERR_CUDA);
   }
+  if (cudaMalloc(&c->d_desc, 16384) != cudaSuccess) {
+    bt_fail(c, BT_ERR_CUDA, "cudaMalloc failed");
+    return fail(BT_ERR_CUDA);
+  }
   if ((s = bt_arena_reserve(c, 1 << 20)) != BT_OK) return fail(s);
   if ((s = bt_lap_ws_create(c)) != BT_OK) return fail(s);
   if ((s = bt_gemm_ws_create(c)) != BT_OK) return fail(s);
@@ -195,6 +199,7 @@ int32_t bt_destroy(bt_ctx* ctx) {
   bt_gemm_ws_destroy(ctx);
   bt_lap_ws_destroy(ctx);
   if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->d_desc) cudaFree(ctx->d_desc);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -26,7 +26,7 @@ struct bt_ctx {
   int pdl = 1;   // programmatic dependent launch between the frame step's kernels (BT_NO_PDL=1 turns it off)
   std::string err;
   int64_t launches = 0;
-  struct bt_launch_rec* rec = nullptr;  // != null: the frame launchers record their launch (CUDA-graph replay) instead of launching
+  char* d_desc = nullptr;   // device scratch for the launch descriptors of the stand-alone entry points (16 KB)
   // bump arena for the stand-alone entry points (device) and a pinned mirror for small results
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;
@@ -41,43 +41,14 @@ struct bt_ctx {
 
 int32_t bt_fail(bt_ctx* ctx, int32_t code, const char* fmt, ...);
 
-// A recorded kernel launch: what cudaGraphExecKernelNodeSetParams needs to retarget a captured kernel node
-// (function, geometry, argument values).  The frame step is captured into a CUDA graph once per launch shape;
-// afterwards a frame costs one graph launch plus one parameter update per kernel node instead of a dozen
-// driver calls on the critical path.
-struct bt_launch_rec {
-  const void* func = nullptr;
-  dim3 grid, block;
-  unsigned smem = 0;
-  int nargs = 0;
-  void* argp[8];
-  alignas(64) char store[3584];
-  size_t used = 0;
-};
-
 #ifdef __CUDACC__
-template <typename T>
-static inline void bt_rec_arg(bt_launch_rec* r, const T& v) {
-  size_t off = (r->used + alignof(T) - 1) & ~(alignof(T) - 1);
-  memcpy(r->store + off, &v, sizeof(T));
-  r->argp[r->nargs++] = r->store + off;
-  r->used = off + sizeof(T);
-}
 // Launch on `stream`, optionally as a programmatic dependent of the stream's previous kernel: the grid
 // may then be scheduled before that kernel has completed, and must execute griddepcontrol.wait
 // (bt_grid_dependency_wait) before it touches anything the earlier kernels of the stream produce -- and at
 // the latest before it exits, so that completion stays ordered for its own dependents.
-// With ctx->rec set the launch is only recorded.
 template <typename... KArgs, typename... Args>
 static inline cudaError_t bt_launch_on(bt_ctx* ctx, cudaStream_t stream, bool dependent, void (*kern)(KArgs...), dim3 grid,
                                        dim3 block, size_t smem, Args... args) {
-  if (ctx->rec) {
-    bt_launch_rec* r = ctx->rec;
-    r->func = reinterpret_cast<const void*>(kern);
-    r->grid = grid; r->block = block; r->smem = (unsigned)smem; r->nargs = 0; r->used = 0;
-    (bt_rec_arg<KArgs>(r, static_cast<KArgs>(args)), ...);
-    return cudaSuccess;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -139,10 +110,8 @@ extern thread_local std::string g_bt_create_error;
 
 #define BT_LAUNCHED(ctx)                                                                           \
   do {                                                                                             \
-    if (!(ctx)->rec) {                                                                             \
-      (ctx)->launches++;                                                                           \
-      BT_CUDA(cudaGetLastError());                                                                 \
-    }                                                                                              \
+    (ctx)->launches++;                                                                             \
+    BT_CUDA(cudaGetLastError());                                                                   \
   } while (0)
 
 // ---- arena ----------------------------------------------------------------------------------
@@ -307,18 +276,24 @@ struct bt_frame_cfg {
   int32_t f16_inputs;          // the frame's features came as fp16 (det16 holds them as they are)
   int32_t keep_smooth;
   int32_t prefetch_pairs;      // duplicate pairs kept in the result block
+  int32_t with_reid;           // feature rows are part of the frame
 };
+// The per-frame kernels read the batch description (`db`: bt_batch in DEVICE memory, uploaded with the frame's
+// control block) themselves, so their kernel arguments never change from frame to frame and the whole frame can
+// be replayed as a CUDA graph; `b` is the host copy, used for the launch geometry only.  fixed != 0: geometry
+// from the ctx capacities instead (what a captured graph needs; surplus blocks exit at once).
 // fp32 ingest: det32 rows -> det16 (raw, round to nearest) + L2 norms
-int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b);
+int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, int fixed);
 // detection prep (boxes -> tlbr / xywh / score class / packed corners) + batched Kalman predict of every
 // stream's pool + (optional) detection feature norms: one launch
-int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
+int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed);
 // Kalman update of every slot matched by one of the three stages; feature EMA of the same slots (independent of
 // it: launched on `stream`, the ctx's side stream)
-int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
-int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, cudaStream_t stream);
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed);
+int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc,
+                      cudaStream_t stream, int fixed);
 // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
-int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc);
+int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed);
 // births of one stream: Kalman initiate + feature adoption from the frame's detections
 int32_t btk_frame_births(bt_ctx* ctx, const bt_store& st, int32_t sid, int32_t parity, const int32_t* d_slot,
                          const int32_t* d_det, int32_t n_births, const bt_frame_cfg& fc, int32_t with_feat);
@@ -426,7 +401,25 @@ struct bt_assoc_params {
   double* out_dists;        // [n,m] fused cost      (dense dump of problem 0, null => off)
   int32_t dense_stage;      // 1 or 3: which fusion rule the dense dump uses
 };
+// the per-frame part of an association launch, as the kernels read it from DEVICE memory
+struct bt_assoc_frame {
+  int32_t count;
+  int32_t tile_start[BT_MAX_BATCH + 1];   // prefix sums of the problems' tile counts (tensor-core kernel)
+  int32_t n[BT_MAX_BATCH], m[BT_MAX_BATCH];
+  int32_t a_row0[BT_MAX_BATCH], b_row0[BT_MAX_BATCH];
+  int32_t row0[BT_MAX_BATCH], col0[BT_MAX_BATCH];
+  int32_t kind_off[BT_MAX_BATCH], pos_off[BT_MAX_BATCH];
+  int32_t cand_sid[BT_MAX_BATCH];
+  const float* face_sim[BT_MAX_BATCH];
+};
+// stand-alone: fills a frame description from p, uploads it to the ctx's scratch and launches
 int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& p, int32_t precision);
+// tracker: fill the host copy (goes up with the control block) ...
+void btk_assoc_fill(const bt_assoc_params& p, int32_t precision, bt_assoc_frame* out);
+// ... and launch against its device copy.  fixed != 0: grid from (max_rows x max_cols) per problem instead of the
+// frame's sizes (captured graphs).
+int32_t btk_assoc_launch(bt_ctx* ctx, const bt_assoc_params& p, int32_t precision, const bt_assoc_frame& hf,
+                         const bt_assoc_frame* df, int fixed, int max_rows, int max_cols);
 // tile width that minimises (waves x MMA time per tile) for a batch of n[k] x m[k] problems on this GPU
 int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m, int32_t count);
 int32_t bt_gemm_ws_create(bt_ctx* ctx);
@@ -468,8 +461,8 @@ struct bt_lap_batch {
   int32_t y_stride;
   int32_t* zero_word[BT_MAX_BATCH]; // device word to clear (the frame's duplicate-pair counter)
 };
-int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& b, const double thresh[3],
-                       const bt_refine& rf);
+int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& b, const bt_lap_batch* db,
+                       const double thresh[3], const bt_refine& rf);
 
 // ---- detector side ------------------------------------------------------------------------------
 int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_config& cfg,

@@ -33,7 +33,8 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
 // encoder output to the first association's similarity, demo:1453-1460; rows are normalised only
 // when a track adopts them, demo:497-502), det_norm = ||row||_2 in float32.
 __global__ void __launch_bounds__(kThreads)
-frame_cast_kernel(bt_store st, const __grid_constant__ bt_batch b) {
+frame_cast_kernel(bt_store st, const bt_batch* __restrict__ bp) {
+  const bt_batch& b = *bp;
   __shared__ float red[kThreads / 32];
   const int k = blockIdx.y, j = blockIdx.x;
   if (j >= b.m[k]) return;
@@ -70,8 +71,9 @@ frame_cast_kernel(bt_store st, const __grid_constant__ bt_batch b) {
 // (demo:1501: high = score > 0.40; demo:1531: low = 0.1 <= score <= 0.40; float(score) against Python
 // doubles), packed integer corners for the association kernel's overlap screen.
 __global__ void __launch_bounds__(kThreads)
-frame_prep_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_frame_cfg fc, int pred_blocks,
+frame_prep_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, int pred_blocks,
                   int det_blocks, bt_res_layout L) {
+  const bt_batch& b = *bp;
   bt_grid_launch_dependents();   // the association kernel behind this one loads its operands meanwhile
   __shared__ float red[kThreads / 32];
   const int k = blockIdx.y;
@@ -157,14 +159,19 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
   float* smooth = (fc.keep_smooth && st.smooth32) ? st.smooth32 + gs * D : nullptr;
   float* curr = (!kF16 && st.curr32) ? st.curr32 + gs * D : nullptr;
   if (held) {
-    float4 xv[kHold];
+    // all loads of the row first (the detection's raw row AND the track's old smooth row: two independent DRAM
+    // round trips in flight together), then the two norms
+    float4 xv[kHold], ov[kHold];
     float ss = 0.f;
+    const bool blend = mode == 0 && smooth != nullptr;
 #pragma unroll
     for (int t = 0; t < kHold; ++t) {
       const int i = (threadIdx.x + t * kThreads) * 4;
       xv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ov[t] = xv[t];
       if (i < D) {
         const uint2 q = __ldg(reinterpret_cast<const uint2*>(raw16 + i));
+        if (blend) ov[t] = *reinterpret_cast<const float4*>(smooth + i);
         *reinterpret_cast<uint2*>(bank + i) = q;     // the track adopts the raw fp16 row
         if (kF16) {
           const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -174,8 +181,9 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
           xv[t] = __ldg(reinterpret_cast<const float4*>(raw32 + i));
         }
       }
-      ss += xv[t].x * xv[t].x + xv[t].y * xv[t].y + xv[t].z * xv[t].z + xv[t].w * xv[t].w;
     }
+#pragma unroll
+    for (int t = 0; t < kHold; ++t) ss += xv[t].x * xv[t].x + xv[t].y * xv[t].y + xv[t].z * xv[t].z + xv[t].w * xv[t].w;
     const float norm = sqrtf(block_sum256(ss, red));
     if (threadIdx.x == 0) st.norm[gs] = norm;
     if (!smooth && !curr) return;
@@ -183,20 +191,18 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
     float ss2 = 0.f;
 #pragma unroll
     for (int t = 0; t < kHold; ++t) {
-      const int i = (threadIdx.x + t * kThreads) * 4;
       if (norm > 0.f) { xv[t].x /= norm; xv[t].y /= norm; xv[t].z /= norm; xv[t].w /= norm; }
       sv[t] = xv[t];
-      if (mode == 0 && smooth && i < D) {
-        const float4 o = *reinterpret_cast<const float4*>(smooth + i);
-        sv[t].x = __fadd_rn(__fmul_rn(fc.alpha, o.x), __fmul_rn(fc.one_minus_alpha, xv[t].x));
-        sv[t].y = __fadd_rn(__fmul_rn(fc.alpha, o.y), __fmul_rn(fc.one_minus_alpha, xv[t].y));
-        sv[t].z = __fadd_rn(__fmul_rn(fc.alpha, o.z), __fmul_rn(fc.one_minus_alpha, xv[t].z));
-        sv[t].w = __fadd_rn(__fmul_rn(fc.alpha, o.w), __fmul_rn(fc.one_minus_alpha, xv[t].w));
+      if (blend) {
+        sv[t].x = __fadd_rn(__fmul_rn(fc.alpha, ov[t].x), __fmul_rn(fc.one_minus_alpha, xv[t].x));
+        sv[t].y = __fadd_rn(__fmul_rn(fc.alpha, ov[t].y), __fmul_rn(fc.one_minus_alpha, xv[t].y));
+        sv[t].z = __fadd_rn(__fmul_rn(fc.alpha, ov[t].z), __fmul_rn(fc.one_minus_alpha, xv[t].z));
+        sv[t].w = __fadd_rn(__fmul_rn(fc.alpha, ov[t].w), __fmul_rn(fc.one_minus_alpha, xv[t].w));
       }
       ss2 += sv[t].x * sv[t].x + sv[t].y * sv[t].y + sv[t].z * sv[t].z + sv[t].w * sv[t].w;
     }
     float n2 = 1.f;
-    if (mode == 0 && smooth) n2 = sqrtf(block_sum256(ss2, red));   // block-uniform condition
+    if (blend) n2 = sqrtf(block_sum256(ss2, red));   // block-uniform condition
 #pragma unroll
     for (int t = 0; t < kHold; ++t) {
       const int i = (threadIdx.x + t * kThreads) * 4;
@@ -204,7 +210,7 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
       if (curr) *reinterpret_cast<float4*>(curr + i) = xv[t];
       if (smooth) {
         float4 o = sv[t];
-        if (mode == 0 && n2 > 0.f) { o.x /= n2; o.y /= n2; o.z /= n2; o.w /= n2; }
+        if (blend && n2 > 0.f) { o.x /= n2; o.y /= n2; o.z /= n2; o.w /= n2; }
         *reinterpret_cast<float4*>(smooth + i) = o;
       }
     }
@@ -246,7 +252,8 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
 }
 
 __global__ void __launch_bounds__(kThreads)
-frame_post_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_res_layout L) {
+frame_post_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_res_layout L) {
+  const bt_batch& b = *bp;
   bt_grid_launch_dependents();   // the duplicate test is queued behind this kernel and waits for its boxes
   const int k = blockIdx.y;
   const int sid = b.sid[k];
@@ -281,7 +288,8 @@ frame_post_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_res_layout
 // one CTA per slot: the matched ones adopt their detection's feature (independent of the Kalman update:
 // runs beside it on the ctx's side stream)
 __global__ void __launch_bounds__(kThreads)
-frame_ema_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_frame_cfg fc, bt_res_layout L) {
+frame_ema_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, bt_res_layout L) {
+  const bt_batch& b = *bp;
   __shared__ float red[kThreads / 32];
   const int k = blockIdx.y;
   const int sid = b.sid[k];
@@ -338,7 +346,8 @@ __device__ __forceinline__ double iou_of(const Box& a, const Box& b) {
 // host filters this (tiny) superset by list membership without a second round trip.
 // grid (j tile of 64, i tile of 256, batch entry), only tiles that can hold a pair j > i.
 __global__ void __launch_bounds__(256)
-frame_dup_kernel(bt_store st, const __grid_constant__ bt_batch b, bt_frame_cfg fc, bt_res_layout L) {
+frame_dup_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, bt_res_layout L) {
+  const bt_batch& b = *bp;
   constexpr int JT = 64;
   bt_grid_dependency_wait();   // programmatic dependent of the Kalman update that writes the boxes
   const int k = blockIdx.z;
@@ -431,53 +440,56 @@ bt_res_layout bt_res_layout_for(int cap, int md, int prefetch_pairs) {
   return L;
 }
 
-int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b) {
-  const int mx = bt_batch_max(b.m, b.count);
+int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, int fixed) {
+  const int mx = fixed ? st.md : bt_batch_max(b.m, b.count);
   if (mx <= 0) return BT_OK;
-  BT_CUDA(bt_launch(ctx, false, frame_cast_kernel, dim3(mx, b.count), dim3(kThreads), 0, st, b));
+  BT_CUDA(bt_launch(ctx, false, frame_cast_kernel, dim3(mx, b.count), dim3(kThreads), 0, st, db));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
-int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc) {
-  const int mx_m = bt_batch_max(b.m, b.count), mx_pool = bt_batch_max(b.n_pool, b.count);
+int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed) {
+  const int mx_m = fixed ? st.md : bt_batch_max(b.m, b.count), mx_pool = fixed ? st.cap : bt_batch_max(b.n_pool, b.count);
   const int pred_blocks = (mx_pool * 8 + kThreads - 1) / kThreads;
   const int det_blocks = (mx_m + kThreads - 1) / kThreads;
   int norm_blocks = 0;
-  for (int k = 0; k < b.count; ++k)
-    if (b.want_norm[k] && b.m[k] > norm_blocks) norm_blocks = b.m[k];
+  if (fixed) norm_blocks = (fc.f16_inputs && fc.with_reid) ? st.md : 0;
+  else
+    for (int k = 0; k < b.count; ++k)
+      if (b.want_norm[k] && b.m[k] > norm_blocks) norm_blocks = b.m[k];
   const int gx = pred_blocks + det_blocks + norm_blocks;
   if (gx <= 0) return BT_OK;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch(ctx, false, frame_prep_kernel, dim3(gx, b.count), dim3(kThreads), 0, st, b, fc, pred_blocks, det_blocks, L));
+  BT_CUDA(bt_launch(ctx, false, frame_prep_kernel, dim3(gx, b.count), dim3(kThreads), 0, st, db, fc, pred_blocks, det_blocks, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
-int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc) {
-  const int mx_rows = bt_batch_max(b.n_rows, b.count);
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed) {
+  const int mx_rows = fixed ? st.cap : bt_batch_max(b.n_rows, b.count);
   if (mx_rows <= 0) return BT_OK;
   const int upd_blocks = (mx_rows * 8 + kThreads - 1) / kThreads;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch(ctx, false, frame_post_kernel, dim3(upd_blocks, b.count), dim3(kThreads), 0, st, b, L));
+  BT_CUDA(bt_launch(ctx, false, frame_post_kernel, dim3(upd_blocks, b.count), dim3(kThreads), 0, st, db, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
-int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc, cudaStream_t stream) {
-  const int mx_rows = bt_batch_max(b.n_rows, b.count);
+int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc,
+                      cudaStream_t stream, int fixed) {
+  const int mx_rows = fixed ? st.cap : bt_batch_max(b.n_rows, b.count);
   if (mx_rows <= 0) return BT_OK;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch_on(ctx, stream, false, frame_ema_kernel, dim3(mx_rows, b.count), dim3(kThreads), 0, st, b, fc, L));
+  BT_CUDA(bt_launch_on(ctx, stream, false, frame_ema_kernel, dim3(mx_rows, b.count), dim3(kThreads), 0, st, db, fc, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
 
-int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_frame_cfg& fc) {
-  const int n = bt_batch_max(b.n_rows, b.count);
+int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed) {
+  const int n = fixed ? st.cap : bt_batch_max(b.n_rows, b.count);
   if (n <= 1) return BT_OK;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch(ctx, true, frame_dup_kernel, dim3((n + 63) / 64, (n + 255) / 256, b.count), dim3(256), 0, st, b, fc, L));
+  BT_CUDA(bt_launch(ctx, true, frame_dup_kernel, dim3((n + 63) / 64, (n + 255) / 256, b.count), dim3(256), 0, st, db, fc, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

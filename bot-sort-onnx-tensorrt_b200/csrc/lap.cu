@@ -531,8 +531,9 @@ struct SmallSmem {
 
 // One CTA per video stream solves the (up to three chained) association stages of its frame.
 __global__ void __launch_bounds__(kLapThreads, 1)
-lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ bt_lap_batch B, LapParams P,
+lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __restrict__ Bp, LapParams P,
                   const __grid_constant__ bt_refine rf) {
+  const bt_lap_batch& B = *Bp;     // the frame's batch description, in device memory (same kernel arguments every frame)
   extern __shared__ __align__(16) unsigned char lap_dyn_smem[];
   SmallSmem& sm = *reinterpret_cast<SmallSmem*>(lap_dyn_smem);
   const int kb = blockIdx.x;
@@ -718,6 +719,7 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ 
       }
       if (tid == 0) sm.changed = 0;
       __syncthreads();
+      LAP_T(5);
       // ---- S2b: every complex row takes its cheapest edge -- if those choices are decided and pairwise
       //      distinct they are the optimum (each row at its own lower bound), which is the usual frame ----
       for (int i = tid; i < nC; i += GT) {
@@ -735,6 +737,7 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ 
           if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
         }
         dbg_ncomp = -1;
+        LAP_T(3);
       } else {
       for (int i = tid; i < nC; i += GT) {
         const int c = sm.xl[i];
@@ -953,8 +956,8 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const __grid_constant__ 
     if (P.clear_lists && tid == 0) cand.total[list] = 0;
     LAP_T(4);
     if (P.debug && tid == 0)
-      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d comps=%d big=%d | init %llu classify %llu gather+recost %llu solve %llu ns\n",
-             sid, stage, n, m, nC, sm.nE, sm.nR, dbg_ncomp, (int)big, tq[1] - tq[0], tq[2] - tq[1], tq[3] - tq[2], tq[4] - tq[3]);
+      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d comps=%d big=%d | init %llu classify %llu gather %llu (to recost/greedy end %llu) solve %llu ns\n",
+             sid, stage, n, m, nC, sm.nE, sm.nR, dbg_ncomp, (int)big, tq[1] - tq[0], tq[2] - tq[1], tq[5] - tq[2], tq[3] - tq[2], tq[4] - tq[3]);
     LAP_T(1);
   }
 }
@@ -1085,7 +1088,8 @@ int32_t btk_lap_compact_dense(bt_ctx* ctx, const double* cost, int32_t n, int32_
   return BT_OK;
 }
 
-static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const LapParams& P, const bt_refine& rf) {
+static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const bt_lap_batch* dB,
+                          const LapParams& P, const bt_refine& rf) {
   for (int k = 0; k < B.count; ++k)
     BT_CHECK(B.n[k] <= ctx->lap->rows && B.m[k] <= ctx->lap->cols, BT_ERR_CAPACITY,
              "linear assignment %d x %d exceeds ctx capacity %d x %d", B.n[k], B.m[k], ctx->lap->rows, ctx->lap->cols);
@@ -1096,7 +1100,7 @@ static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& 
     attr_err = cudaFuncSetAttribute(lap_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem));
   });
   BT_CUDA(attr_err);
-  BT_CUDA(bt_launch(ctx, true, lap_stream_kernel, dim3(B.count), dim3(kLapThreads), sizeof(SmallSmem), cand, *ctx->lap, B, P, rf));
+  BT_CUDA(bt_launch(ctx, true, lap_stream_kernel, dim3(B.count), dim3(kLapThreads), sizeof(SmallSmem), cand, *ctx->lap, dB, P, rf));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
@@ -1113,15 +1117,18 @@ int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n,
   B.n[0] = n; B.m[0] = m;
   B.x[0] = x; B.x_stride[0] = n; B.y[0] = y; B.y_stride = m;
   bt_refine rf = {};
-  return launch_lap(ctx, cand, B, P, rf);
+  // stand-alone: the batch description goes up through the ctx's descriptor scratch (second half)
+  bt_lap_batch* dB = reinterpret_cast<bt_lap_batch*>(ctx->d_desc + 8192);
+  BT_CUDA(cudaMemcpyAsync(dB, &B, sizeof(B), cudaMemcpyHostToDevice, ctx->stream));
+  return launch_lap(ctx, cand, B, dB, P, rf);
 }
 
-int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const double thresh[3],
-                       const bt_refine& rf) {
+int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const bt_lap_batch* dB,
+                       const double thresh[3], const bt_refine& rf) {
   LapParams P = {};
   P.clear_lists = 1;
   P.nstages = 3;
   for (int s = 0; s < 3; ++s) P.thresh[s] = thresh[s];
   P.debug = getenv("BT_LAP_DEBUG") != nullptr;
-  return launch_lap(ctx, cand, B, P, rf);
+  return launch_lap(ctx, cand, B, dB, P, rf);
 }

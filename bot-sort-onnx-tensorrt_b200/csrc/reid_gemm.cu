@@ -36,15 +36,9 @@ namespace {
 // epilogue element logic shared by the tensor-core and the CUDA-core kernels
 // ------------------------------------------------------------------------------------------------
 struct EpiParams {
-  // the batch (one entry per video stream / stand-alone problem)
-  int32_t count;
-  int32_t tile_start[BT_MAX_BATCH + 1];   // prefix sums of tiles per problem
-  int32_t n[BT_MAX_BATCH], m[BT_MAX_BATCH];
-  int32_t a_row0[BT_MAX_BATCH], b_row0[BT_MAX_BATCH];
-  int32_t row0[BT_MAX_BATCH], col0[BT_MAX_BATCH];
-  int32_t kind_off[BT_MAX_BATCH], pos_off[BT_MAX_BATCH];
-  int32_t cand_sid[BT_MAX_BATCH];
-  const float* face_sim[BT_MAX_BATCH];
+  // the batch (one entry per video stream / stand-alone problem): sizes, operand / side-array offsets, tile
+  // prefix sums -- read from DEVICE memory, so that the kernel arguments are the same every frame
+  const bt_assoc_frame* F;
   // side inputs
   const double* row_tlbr;
   const float* row_tlbr_f32;
@@ -98,11 +92,11 @@ __device__ __forceinline__ double* c_cost(const EpiParams& p, int sid) { return 
 
 // face similarity of (row, col) of problem k (0 when the stream has no face term)
 __device__ __forceinline__ float face_sim_of(const EpiParams& p, int k, int row, int col) {
-  const float* fs = p.face_sim[k];
+  const float* fs = p.F->face_sim[k];
   if (!fs) return 0.0f;
   int pr = row;
-  if (p.row_kind_base) pr = reinterpret_cast<const int32_t*>(p.row_kind_base + p.pos_off[k])[row];
-  return pr >= 0 ? fs[(size_t)pr * p.m[k] + col] : 0.0f;
+  if (p.row_kind_base) pr = reinterpret_cast<const int32_t*>(p.row_kind_base + p.F->pos_off[k])[row];
+  return pr >= 0 ? fs[(size_t)pr * p.F->m[k] + col] : 0.0f;
 }
 
 // atomic append into the (row, column-segment) sub-list (CUDA-core kernel: several threads share a row)
@@ -132,8 +126,8 @@ __device__ __forceinline__ void emit_owned_tc(const EpiParams& p, int sid, int l
 
 // exact path of the CUDA-core kernel for one (row, col) pair that survived the cheap rejection test
 __device__ __noinline__ void assoc_exact(const EpiParams& p, int k, int row, int col, float sim, int rkind, int ckind) {
-  const int sid = p.cand_sid[k];
-  const double iou_d = iou_dist_f64(p.row_tlbr + ((size_t)p.row0[k] + row) * 4, p.col_tlbr + ((size_t)p.col0[k] + col) * 4);
+  const int sid = p.F->cand_sid[k];
+  const double iou_d = iou_dist_f64(p.row_tlbr + ((size_t)p.F->row0[k] + row) * 4, p.col_tlbr + ((size_t)p.F->col0[k] + col) * 4);
   if (rkind == BT_ROW_UNCONFIRMED) {
     if (ckind == BT_COL_HIGH) {
       const double c3 = fuse_stage3(iou_d, sim, p.appearance, p.proximity);
@@ -169,7 +163,7 @@ __device__ __forceinline__ int sim_flags(const EpiParams& p, int list, float sim
 __device__ __noinline__ int open_pair_slow(const EpiParams& p, int k, double r0, double r1, double r2, double r3,
                                            const double* __restrict__ cbox, int list, int row, int seg, int col,
                                            float sim, int k_next, int scan_from) {
-  const int sid = p.cand_sid[k];
+  const int sid = p.F->cand_sid[k];
   const double rb[4] = {r0, r1, r2, r3};
   const size_t eb = ((size_t)list * p.cand.rows_cap + row) * (size_t)p.cand.stride + (size_t)seg * p.cand.seg;
   int32_t* ecol = c_col(p, sid);
@@ -197,11 +191,11 @@ __device__ __noinline__ int open_pair_slow(const EpiParams& p, int k, double r0,
 
 // dense dumps (stand-alone entry points): problem 0
 __device__ __forceinline__ void assoc_dense(const EpiParams& p, int row, int col, float sim) {
-  const int m = p.m[0];
+  const int m = p.F->m[0];
   if (p.out_emb) p.out_emb[(size_t)row * m + col] = 1.0f - fmaxf(0.0f, sim);
   if (p.out_dists) {
     const double iou_d = iou_dist_f64(p.row_tlbr + (size_t)row * 4, p.col_tlbr + (size_t)col * 4);
-    const float face = p.face_sim[0] ? p.face_sim[0][(size_t)row * m + col] : 0.0f;
+    const float face = p.F->face_sim[0] ? p.F->face_sim[0][(size_t)row * m + col] : 0.0f;
     p.out_dists[(size_t)row * m + col] = (p.dense_stage == 3)
                                              ? fuse_stage3(iou_d, sim, p.appearance, p.proximity)
                                              : fuse_stage1(iou_d, sim, face, p.appearance);
@@ -344,9 +338,9 @@ struct TcSmem {
 // tile t of the batch -> problem k and its tile coordinates
 __device__ __forceinline__ void tile_of(const EpiParams& p, int t, int bn, int& k, int& m0, int& n0) {
   k = 0;
-  while (k + 1 < p.count && t >= p.tile_start[k + 1]) ++k;
-  const int local = t - p.tile_start[k];
-  const int tiles_n = (p.m[k] + bn - 1) / bn;
+  while (k + 1 < p.F->count && t >= p.F->tile_start[k + 1]) ++k;
+  const int local = t - p.F->tile_start[k];
+  const int tiles_n = (p.F->m[k] + bn - 1) / bn;
   m0 = (local / tiles_n) * BM;
   n0 = (local % tiles_n) * bn;
 }
@@ -379,7 +373,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   unsigned long long g_start = 0;
   if (p.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
   const int num_kb = d / BK;
-  const int num_tiles = p.tile_start[p.count];
+  const int num_tiles = p.F->tile_start[p.F->count];
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as SMs free
@@ -405,8 +399,8 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int kb = 0; kb < pro_kb; ++kb) {
         mbar_expect_tx(&full_bar[kb], L::kStageBytes);
         uint8_t* sa = smem + kb * L::kStageBytes;
-        tma_load_2d(sa, &tmap_a, kb * BK, p.a_row0[k] + m0, &full_bar[kb]);
-        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, p.b_row0[k] + n0, &full_bar[kb]);
+        tma_load_2d(sa, &tmap_a, kb * BK, p.F->a_row0[k] + m0, &full_bar[kb]);
+        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, p.F->b_row0[k] + n0, &full_bar[kb]);
       }
     }
   }
@@ -435,7 +429,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         int k, m0, n0;
         tile_of(p, t, BN, k, m0, n0);
-        const int ya = p.a_row0[k] + m0, yb = p.b_row0[k] + n0;
+        const int ya = p.F->a_row0[k] + m0, yb = p.F->b_row0[k] + n0;
         for (int kb = (t == first_tile) ? pro_kb : 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -491,9 +485,9 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       int k, m0, n0;
       tile_of(p, t, BN, k, m0, n0);
-      const int pn = p.n[k], pm = p.m[k];
-      const int sid = p.cand_sid[k];
-      const size_t R0 = (size_t)p.row0[k], C0 = (size_t)p.col0[k];
+      const int pn = p.F->n[k], pm = p.F->m[k];
+      const int sid = p.F->cand_sid[k];
+      const size_t R0 = (size_t)p.F->row0[k], C0 = (size_t)p.F->col0[k];
       const int row = m0 + quarter * 32 + lane;
       int rkind = BT_ROW_NONE;
       double rbox[4] = {0.0, 0.0, 0.0, 0.0};
@@ -515,7 +509,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         float cn = 1.0f;
         if (row < pn) {
           const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (R0 + row) * 4);
-          rkind = reinterpret_cast<const uint8_t*>(p.row_kind_base + p.kind_off[k])[row];
+          rkind = reinterpret_cast<const uint8_t*>(p.row_kind_base + p.F->kind_off[k])[row];
           rlo = s[0]; rhi = s[1];
           if (p.row_tlbr_f32) r32 = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (R0 + row) * 4);
           if (p.row_norm) rnorm = p.row_norm[R0 + row];
@@ -597,7 +591,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       //  3. exact float64 IoU distance against the stage threshold.
       // (With real face similarities the gate is not a function of the body similarity alone: everything
       // is left to the similarity pass.)
-      const bool all_open = p.face_sim[k] != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
+      const bool all_open = p.F->face_sim[k] != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
       if (!kDense && !all_open && rkind != BT_ROW_NONE) {
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch) {
@@ -887,11 +881,11 @@ assoc_simt_kernel(const T* __restrict__ a, const T* __restrict__ b, const __grid
   __shared__ float sa[SK][ST + 1];
   __shared__ float sb[SK][ST + 1];
   const int k = blockIdx.z;
-  const int pn = p.n[k], pm = p.m[k];
+  const int pn = p.F->n[k], pm = p.F->m[k];
   const int row0 = blockIdx.y * ST, col0 = blockIdx.x * ST;
   if (row0 >= pn || col0 >= pm) return;
-  const size_t ar0 = (size_t)p.a_row0[k], br0 = (size_t)p.b_row0[k];
-  const size_t R0 = (size_t)p.row0[k], C0 = (size_t)p.col0[k];
+  const size_t ar0 = (size_t)p.F->a_row0[k], br0 = (size_t)p.F->b_row0[k];
+  const size_t R0 = (size_t)p.F->row0[k], C0 = (size_t)p.F->col0[k];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
@@ -942,7 +936,7 @@ assoc_simt_kernel(const T* __restrict__ a, const T* __restrict__ b, const __grid
   for (int i = 0; i < 4; ++i) {
     const int row = row0 + ty * 4 + i;
     if (row >= pn) continue;
-    const int rkind = (!kDense) ? reinterpret_cast<const uint8_t*>(p.row_kind_base + p.kind_off[k])[row] : 0;
+    const int rkind = (!kDense) ? reinterpret_cast<const uint8_t*>(p.row_kind_base + p.F->kind_off[k])[row] : 0;
     uint2 rpk = make_uint2(0u, 0u);
     float rnorm = 1.0f;
     if (!kDense && rkind != BT_ROW_NONE) {
@@ -967,7 +961,7 @@ assoc_simt_kernel(const T* __restrict__ a, const T* __restrict__ b, const __grid
         if (p.row_norm) sim = rnorm > 0.f ? sim / rnorm : 0.f;
         if (rkind == BT_ROW_UNCONFIRMED) sim *= cinv[j];
         const bool overlap = ((rpk.y - cpk[j].x) & (cpk[j].y - rpk.x) & 0x80008000u) == 0x80008000u;
-        if (overlap || sim >= p.sim_gate || p.face_sim[k] != nullptr) assoc_exact(p, k, row, col, sim, rkind, ckind[j]);
+        if (overlap || sim >= p.sim_gate || p.F->face_sim[k] != nullptr) assoc_exact(p, k, row, col, sim, rkind, ckind[j]);
       }
     }
   }
@@ -1032,7 +1026,7 @@ static int32_t make_tmap(bt_ctx* ctx, CUtensorMap* tm, const __half* base, int r
 }
 
 template <int BN, bool kDense>
-static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, EpiParams& ep) {
+static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams& ep, int tiles) {
   CUtensorMap ta, tb;
   BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.a_rows_alloc, ap.d, BM));
   BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.b_rows_alloc, ap.d, BN));
@@ -1043,14 +1037,7 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, EpiParams& ep) 
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn);
   });
   BT_CUDA(attr_err);
-  int tiles = 0;
-  for (int k = 0; k < ap.count; ++k) {
-    ep.tile_start[k] = tiles;
-    tiles += ((ap.n[k] + BM - 1) / BM) * ((ap.m[k] + BN - 1) / BN);
-  }
-  ep.tile_start[ap.count] = tiles;
-  for (int k = ap.count + 1; k <= BT_MAX_BATCH; ++k) ep.tile_start[k] = tiles;
-  if (tiles == 0) return BT_OK;
+  if (tiles <= 0) return BT_OK;
   // may start its ramp (and, with operands_early, its main loop) under the previous kernel (griddepcontrol.wait inside)
   BT_CUDA(bt_launch(ctx, true, kern, dim3(tiles < ctx->num_sms ? tiles : ctx->num_sms), dim3(kTcThreads), TcSmem<BN>::kDyn,
                     ta, tb, ep, ap.d));
@@ -1073,28 +1060,40 @@ int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m,
   return best;
 }
 
-int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
-  BT_CHECK(ap.count >= 1 && ap.count <= BT_MAX_BATCH, BT_ERR_INVALID, "bad batch size %d", ap.count);
-  int any = 0, mx_n = 0, mx_m = 0;
-  for (int k = 0; k < ap.count; ++k) {
-    if (ap.n[k] > 0 && ap.m[k] > 0) any = 1;
-    mx_n = ap.n[k] > mx_n ? ap.n[k] : mx_n;
-    mx_m = ap.m[k] > mx_m ? ap.m[k] : mx_m;
-  }
-  if (!any) return BT_OK;
-  EpiParams ep;
-  memset(&ep, 0, sizeof(ep));
-  ep.count = ap.count;
+void btk_assoc_fill(const bt_assoc_params& ap, int32_t precision, bt_assoc_frame* f) {
+  memset(f, 0, sizeof(*f));
+  f->count = ap.count;
+  const int bn = ap.bn ? ap.bn : 256;
+  int tiles = 0;
   for (int k = 0; k < ap.count; ++k) {
     // an empty problem contributes no tiles: zero both sizes so that the tile arithmetic sees it
     const bool empty = ap.n[k] <= 0 || ap.m[k] <= 0;
-    ep.n[k] = empty ? 0 : ap.n[k]; ep.m[k] = empty ? 0 : ap.m[k];
-    ep.a_row0[k] = ap.a_row0[k]; ep.b_row0[k] = ap.b_row0[k];
-    ep.row0[k] = ap.row0[k]; ep.col0[k] = ap.col0[k];
-    ep.kind_off[k] = ap.kind_off[k]; ep.pos_off[k] = ap.pos_off[k];
-    ep.cand_sid[k] = ap.cand_sid[k];
-    ep.face_sim[k] = ap.face_sim[k];
+    f->n[k] = empty ? 0 : ap.n[k]; f->m[k] = empty ? 0 : ap.m[k];
+    f->a_row0[k] = ap.a_row0[k]; f->b_row0[k] = ap.b_row0[k];
+    f->row0[k] = ap.row0[k]; f->col0[k] = ap.col0[k];
+    f->kind_off[k] = ap.kind_off[k]; f->pos_off[k] = ap.pos_off[k];
+    f->cand_sid[k] = ap.cand_sid[k];
+    f->face_sim[k] = ap.face_sim[k];
+    f->tile_start[k] = tiles;
+    if (precision == 0) tiles += ((f->n[k] + BM - 1) / BM) * ((f->m[k] + bn - 1) / bn);
   }
+  for (int k = ap.count; k <= BT_MAX_BATCH; ++k) f->tile_start[k] = tiles;
+}
+
+int32_t btk_assoc_launch(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision, const bt_assoc_frame& hf,
+                         const bt_assoc_frame* df, int fixed, int max_rows, int max_cols) {
+  BT_CHECK(ap.count >= 1 && ap.count <= BT_MAX_BATCH, BT_ERR_INVALID, "bad batch size %d", ap.count);
+  int any = 0, mx_n = 0, mx_m = 0;
+  for (int k = 0; k < ap.count; ++k) {
+    if (hf.n[k] > 0 && hf.m[k] > 0) any = 1;
+    mx_n = hf.n[k] > mx_n ? hf.n[k] : mx_n;
+    mx_m = hf.m[k] > mx_m ? hf.m[k] : mx_m;
+  }
+  if (!any && !fixed) return BT_OK;
+  if (fixed) { mx_n = max_rows; mx_m = max_cols; }
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.F = df;
   ep.row_tlbr = ap.row_tlbr; ep.row_tlbr_f32 = ap.row_tlbr_f32; ep.row_norm = ap.row_norm;
   ep.row_kind_base = ap.row_kind_base;
   ep.col_tlbr = ap.col_tlbr; ep.col_kind = ap.col_kind; ep.col_pk = ap.col_pk; ep.col_norm = ap.col_norm;
@@ -1118,10 +1117,12 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
     BT_CHECK(ap.d % BK == 0 && ap.d >= BK, BT_ERR_INVALID,
              "tensor-core similarity needs feat_dim %% 64 == 0 (got %d)", ap.d);
     BT_CHECK(ap.a16 && ap.b16, BT_ERR_INVALID, "fp16 operands missing");
-    BT_CHECK(dense || ap.cand.seg * 2 == (ap.bn ? ap.bn : 256), BT_ERR_STATE,
-             "candidate segment size %d does not match the tile width %d", ap.cand.seg, ap.bn ? ap.bn : 256);
-    if (ap.bn == 224) return dense ? launch_tc<224, true>(ctx, ap, ep) : launch_tc<224, false>(ctx, ap, ep);
-    return dense ? launch_tc<256, true>(ctx, ap, ep) : launch_tc<256, false>(ctx, ap, ep);
+    const int bn = ap.bn ? ap.bn : 256;
+    BT_CHECK(dense || ap.cand.seg * 2 == bn, BT_ERR_STATE,
+             "candidate segment size %d does not match the tile width %d", ap.cand.seg, bn);
+    const int tiles = fixed ? ap.count * ((max_rows + BM - 1) / BM) * ((max_cols + bn - 1) / bn) : hf.tile_start[ap.count];
+    if (bn == 224) return dense ? launch_tc<224, true>(ctx, ap, ep, tiles) : launch_tc<224, false>(ctx, ap, ep, tiles);
+    return dense ? launch_tc<256, true>(ctx, ap, ep, tiles) : launch_tc<256, false>(ctx, ap, ep, tiles);
   }
   ep.gate_band = 0.f;
   dim3 grid((mx_m + ST - 1) / ST, (mx_n + ST - 1) / ST, ap.count);
@@ -1136,4 +1137,14 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   }
   BT_LAUNCHED(ctx);
   return BT_OK;
+}
+
+// stand-alone entry points: the frame description goes up through the ctx's descriptor scratch (a pageable
+// source is staged by the runtime before cudaMemcpyAsync returns, so the local may die)
+int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
+  bt_assoc_frame hf;
+  btk_assoc_fill(ap, precision, &hf);
+  bt_assoc_frame* df = reinterpret_cast<bt_assoc_frame*>(ctx->d_desc);
+  BT_CUDA(cudaMemcpyAsync(df, &hf, sizeof(hf), cudaMemcpyHostToDevice, ctx->stream));
+  return btk_assoc_launch(ctx, ap, precision, hf, df, 0, 0, 0);
 }

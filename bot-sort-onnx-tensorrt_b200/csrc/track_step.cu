@@ -76,6 +76,9 @@ struct StreamState {
   const float* sc = nullptr;            // this frame's scores on the host
   const int32_t* host_boxes = nullptr;  // this frame's boxes on the host
   const int32_t* hx[3] = {nullptr, nullptr, nullptr};
+  const int32_t* pool = nullptr;        // this step's pool (slots, pool order) inside the pinned control block
+  int n_high = 0, n_low = 0, n_m1 = 0, n_m2 = 0, n_m3 = 0;
+  bool matches_valid = false;
   std::vector<int> v_unconfirmed, v_pool, v_hi_pos, v_lo_pos, v_hi_list, v_lo_list, v_activated, v_refind, v_lost_now,
       v_removed_now, v_r_tracked, v_u_det_pos, v_new_tracked, v_new_lost, v_tmp, v_birth_slot, v_birth_det;
   std::vector<uint8_t> v_det_taken, v_pool_matched, scratch_a, scratch_b;
@@ -90,8 +93,17 @@ struct StreamState {
 
 }  // namespace
 
-// the kernel launches of a steady-state frame, in the order they are issued
-enum { R_CAST = 0, R_PREP, R_ASSOC, R_LAP, R_EMA, R_POST, R_DUP, R_COUNT };
+// Per-frame launch description, first thing in the control block (pinned host copy -> device copy with ONE H2D
+// that also carries the per-stream control segments): everything a frame's kernels need to know that changes
+// from frame to frame.  Their kernel ARGUMENTS therefore never change, and a captured CUDA graph of the frame
+// can be replayed with no per-launch patching.
+struct FrameDesc {
+  bt_batch B;
+  bt_assoc_frame AF;
+  bt_lap_batch LB;
+};
+constexpr size_t kDescBytes = (sizeof(FrameDesc) + 255) & ~size_t(255);
+
 struct GraphKey {
   int count, f32, reid, dev, bn, precision, f16;
   bool operator==(const GraphKey& o) const {
@@ -102,8 +114,6 @@ struct FrameGraph {
   GraphKey key;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  cudaGraphNode_t node[R_COUNT] = {};
-  bool has[R_COUNT] = {};
   int n_kernels = 0;
 };
 
@@ -113,7 +123,6 @@ struct bt_tracker {
   bool use_graph = true;
   std::vector<GraphKey> seen_keys;      // shapes that ran once the plain way (module loading, function attributes)
   std::vector<FrameGraph> graphs;
-  bt_launch_rec recs[R_COUNT];
   bt_store st = {};
   bt_res_layout L = {};
   std::vector<StreamState> streams;
@@ -142,6 +151,7 @@ struct bt_tracker {
   bool host_debug = false;
   bool no_refine = false;           // BT_NO_REFINE=1: tests show what the exact re-costing buys
   bt_assoc_params last_assoc;       // for bt_profile_replay_assoc
+  bt_assoc_frame last_AF;
   int last_assoc_precision = 0;
   bool last_assoc_valid = false;
   // ---- optional segment timing (bt_profile_*) ----
@@ -220,6 +230,7 @@ void reset_stream(bt_tracker* t, StreamState& s, const bt_config* cfg) {
   s.feat_dtype = -1;
   for (auto& mm : s.matches) mm.clear();
   s.tlbr_cache_valid = false;
+  s.matches_valid = false;
   s.n_pending = 0;
   s.next_parity = 0;
 }
@@ -272,7 +283,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &st.col_kind, ND));
   BT_TRY(dev_alloc(ctx, &st.col_pk, ND));
   t->ctrl_stride = (ctrl_bytes(t->cap, t->cap, true) + 255) & ~size_t(255);
-  BT_TRY(dev_alloc(ctx, &st.ctrl, t->ctrl_stride * S));
+  BT_TRY(dev_alloc(ctx, &st.ctrl, kDescBytes + t->ctrl_stride * S));
   BT_TRY(dev_alloc(ctx, &st.res, t->L.stride * S));
   BT_TRY(dev_alloc(ctx, &st.resB, t->L.strideB * S));
   BT_TRY(dev_alloc(ctx, &st.y, (size_t)S * 3 * md));
@@ -283,7 +294,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_TRY(dev_alloc(ctx, &t->d_list, cap > md ? cap : md));
   BT_TRY(dev_alloc(ctx, &t->d_gather, cap * 64));
 
-  BT_CUDA(cudaMallocHost(&t->h_ctrl, t->ctrl_stride * S));
+  BT_CUDA(cudaMallocHost(&t->h_ctrl, kDescBytes + t->ctrl_stride * S));
   BT_CUDA(cudaMallocHost(&t->h_res, t->L.stride * S));
   BT_CUDA(cudaMallocHost(&t->h_resB, t->L.strideB * S));
   BT_CUDA(cudaMallocHost(&t->h_in_boxes, sizeof(int32_t) * 2 * ND * 4));
@@ -471,7 +482,8 @@ static int32_t submit_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, con
 // and launches the graph: one launch + one cheap update per kernel.
 // ------------------------------------------------------------------------------------------------
 template <typename Enqueue>
-static int32_t run_enqueue(bt_ctx* ctx, bt_tracker* t, Enqueue& enqueue, const GraphKey& key, bool eligible) {
+static int32_t run_enqueue(bt_ctx* ctx, bt_tracker* t, Enqueue& enqueue, const GraphKey& key, bool eligible,
+                           bool& part_a_sent, bool& ema_pending) {
   cudaStream_t st = ctx->stream;
   if (!eligible) return enqueue(0);
   FrameGraph* g = nullptr;
@@ -486,6 +498,7 @@ static int32_t run_enqueue(bt_ctx* ctx, bt_tracker* t, Enqueue& enqueue, const G
     }
     FrameGraph fg;
     fg.key = key;
+    const int64_t launches0 = ctx->launches;
     cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
     int32_t rc = BT_OK;
     if (e == cudaSuccess) {
@@ -493,6 +506,8 @@ static int32_t run_enqueue(bt_ctx* ctx, bt_tracker* t, Enqueue& enqueue, const G
       cudaError_t e2 = cudaStreamEndCapture(st, &fg.graph);
       if (rc == BT_OK && e2 != cudaSuccess) e = e2;
     }
+    fg.n_kernels = (int)(ctx->launches - launches0);
+    ctx->launches = launches0;
     if (e == cudaSuccess && rc == BT_OK) e = cudaGraphInstantiate(&fg.exec, fg.graph, 0);
     if (e != cudaSuccess || rc != BT_OK) {
       // graphs are an optimisation: fall back to the plain enqueue for good
@@ -501,51 +516,18 @@ static int32_t run_enqueue(bt_ctx* ctx, bt_tracker* t, Enqueue& enqueue, const G
       if (fg.graph) cudaGraphDestroy(fg.graph);
       t->use_graph = false;
       if (getenv("BT_HOST_DEBUG")) fprintf(stderr, "botsort_b200: frame graph capture failed (%s), using plain launches\n", cudaGetErrorString(e));
+      part_a_sent = false; ema_pending = false;
       return enqueue(0);
     }
-    // which captured kernel node is which launch: match by function
-    for (auto& r : t->recs) r.func = nullptr;
-    rc = enqueue(2);
-    ctx->rec = nullptr;
-    BT_TRY(rc);
-    size_t nn = 0;
-    BT_CUDA(cudaGraphGetNodes(fg.graph, nullptr, &nn));
-    std::vector<cudaGraphNode_t> nodes(nn);
-    BT_CUDA(cudaGraphGetNodes(fg.graph, nodes.data(), &nn));
-    for (size_t i = 0; i < nn; ++i) {
-      cudaGraphNodeType ty;
-      BT_CUDA(cudaGraphNodeGetType(nodes[i], &ty));
-      if (ty != cudaGraphNodeTypeKernel) continue;
-      cudaKernelNodeParams kp;
-      BT_CUDA(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-      for (int q = 0; q < R_COUNT; ++q)
-        if (t->recs[q].func && t->recs[q].func == kp.func) { fg.node[q] = nodes[i]; fg.has[q] = true; }
-      fg.n_kernels += 1;
-    }
-    for (int q = 0; q < R_COUNT; ++q)
-      BT_CHECK((t->recs[q].func != nullptr) == fg.has[q], BT_ERR_STATE, "frame graph: kernel node %d not found", q);
     t->graphs.push_back(fg);
     g = &t->graphs.back();
-    BT_CUDA(cudaGraphLaunch(g->exec, st));     // the capture executed nothing: this runs the frame
-    ctx->launches += g->n_kernels;
-    return BT_OK;
   }
-  for (auto& r : t->recs) r.func = nullptr;
-  int32_t rc = enqueue(2);
-  ctx->rec = nullptr;
-  BT_TRY(rc);
-  for (int q = 0; q < R_COUNT; ++q) {
-    BT_CHECK((t->recs[q].func != nullptr) == g->has[q], BT_ERR_STATE, "frame graph: launch %d does not match the captured shape", q);
-    if (!g->has[q]) continue;
-    bt_launch_rec& r = t->recs[q];
-    cudaKernelNodeParams kp = {};
-    kp.func = const_cast<void*>(r.func);
-    kp.gridDim = r.grid; kp.blockDim = r.block; kp.sharedMemBytes = r.smem;
-    kp.kernelParams = r.argp; kp.extra = nullptr;
-    BT_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->node[q], &kp));
-  }
+  // the kernels read this frame's sizes / offsets from the launch description that the graph's first node copies
+  // up: nothing to patch
   BT_CUDA(cudaGraphLaunch(g->exec, st));
   ctx->launches += g->n_kernels;
+  part_a_sent = true;
+  ema_pending = false;
   return BT_OK;
 }
 
@@ -563,18 +545,20 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   const int D = t->D;
   double t_host = now_ms();
   double hphase[5] = {0, 0, 0, 0, 0};
-  const char* fm_name[24]; double fm_t[24]; int fm_n = 0;
-  auto fmark = [&](const char* nm) { if (t->host_debug && fm_n < 24) { fm_name[fm_n] = nm; fm_t[fm_n++] = now_ms(); } };
+  const char* fm_name[40]; double fm_t[40]; int fm_n = 0;
+  auto fmark = [&](const char* nm) { if (t->host_debug && fm_n < 40) { fm_name[fm_n] = nm; fm_t[fm_n++] = now_ms(); } };
   fmark("start");
 
   // ---- per-stream set-up: pop the oldest frame, split lists (demo:1415-1423), control segments ----
-  bt_batch B;
+  FrameDesc* hd = reinterpret_cast<FrameDesc*>(t->h_ctrl);
+  const FrameDesc* dd = reinterpret_cast<const FrameDesc*>(dst.ctrl);
+  bt_batch& B = hd->B;
   memset(&B, 0, sizeof(B));
   B.count = count;
   bool any_reid = false, any_dev_inputs = false, any_f32 = false, any_f16 = false, any_face = false;
   int waited[BT_MAX_BATCH];
   int n_waited = 0;
-  size_t ctrl_off = 0;
+  size_t ctrl_off = kDescBytes;
   for (int k = 0; k < count; ++k) {
     const int sid = sids[k];
     StreamState& s = t->streams[sid];
@@ -602,18 +586,14 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     }
     std::vector<SlotMeta>& meta = s.meta;
     std::vector<int>& unconfirmed = s.v_unconfirmed; unconfirmed.clear();
-    std::vector<int>& pool = s.v_pool; pool.clear();
-    for (int slot : s.tracked) {
-      if (!meta[slot].activated) unconfirmed.push_back(slot);
-      else pool.push_back(slot);
-    }
-    for (int slot : s.lost) pool.push_back(slot);  // joint_stracks: ids are unique per slot, no overlap
-    s.n_pool = (int)pool.size();
-    s.n_unc = (int)unconfirmed.size();
+    // pool = activated tracked tracks (list order) then lost tracks (joint_stracks, demo:1423: ids are unique per
+    // slot, no overlap): written straight into the control segment, which the list bookkeeping reads back later
+    int n_act = 0;
+    for (int slot : s.tracked) n_act += meta[slot].activated ? 1 : 0;
+    s.n_pool = n_act + (int)s.lost.size();
     s.n_rows = s.high_water;
     const bool face = in.face_sim != nullptr && s.n_pool > 0;
     any_face = any_face || face;
-    // control segment
     char* seg = t->h_ctrl + ctrl_off;
     int32_t* h_idx = reinterpret_cast<int32_t*>(seg);
     int32_t* h_state = h_idx + s.n_pool;
@@ -622,16 +602,24 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     memset(h_kind, BT_ROW_NONE, ((size_t)s.n_rows + 3) & ~size_t(3));
     if (face) for (int r = 0; r < s.n_rows; ++r) h_pos[r] = -1;
     bool all_f32 = s.n_pool > 0;
-    for (int i = 0; i < s.n_pool; ++i) {
-      const int slot = pool[i];
-      h_idx[i] = slot;
-      h_state[i] = meta[slot].state;
-      h_kind[slot] = (meta[slot].state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
-      if (face) h_pos[slot] = i;
-      all_f32 = all_f32 && meta[slot].f32_state;
-      meta[slot].f32_state = 0;     // predicted below: float64 from now on
+    int np = 0;
+    auto add_pool = [&](int slot) {
+      SlotMeta& tm = meta[slot];
+      h_idx[np] = slot;
+      h_state[np] = tm.state;
+      h_kind[slot] = (tm.state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
+      if (face) h_pos[slot] = np;
+      all_f32 = all_f32 && tm.f32_state;
+      tm.f32_state = 0;     // predicted below: float64 from now on
+      ++np;
+    };
+    for (int slot : s.tracked) {
+      if (!meta[slot].activated) { unconfirmed.push_back(slot); h_kind[slot] = BT_ROW_UNCONFIRMED; }
+      else add_pool(slot);
     }
-    for (int slot : unconfirmed) h_kind[slot] = BT_ROW_UNCONFIRMED;
+    for (int slot : s.lost) add_pool(slot);
+    s.pool = h_idx;
+    s.n_unc = (int)unconfirmed.size();
     B.sid[k] = sid;
     B.m[k] = s.m;
     B.n_rows[k] = s.n_rows;
@@ -647,6 +635,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     s.sc = s.device_inputs ? reinterpret_cast<const float*>(hresA + L.o_sc) : in.host_scores;
     s.host_boxes = s.device_inputs ? hresA + L.o_bx : in.host_boxes;
   }
+  fmark("streams_setup");
   BT_CHECK(!(any_f32 && any_f16), BT_ERR_INVALID, "one batch cannot mix fp16 and fp32 feature streams");
   const bool f16 = any_f16;
   const uint32_t flags = ctx->flags;
@@ -661,219 +650,200 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   fc.f16_inputs = f16 ? 1 : 0;
   fc.keep_smooth = dst.smooth32 != nullptr;
   fc.prefetch_pairs = kPairPrefetch;
+  fc.with_reid = any_reid ? 1 : 0;
 
   const int mx_rows = bt_batch_max(B.n_rows, count), mx_m = bt_batch_max(B.m, count);
-  fmark("setup");
   const int assoc_bn = (any_reid && tensor_path) ? btk_assoc_pick_bn(ctx, B.n_rows, B.m, count) : 256;
   const int assoc_precision = (any_reid && tensor_path) ? 0 : 1;
-  bool part_a_sent = false, ema_pending = false;
-  // mode 0: plain enqueue; 1: the same calls under stream capture (fixed copy sizes, the side stream rejoins);
-  // 2: kernel launches are only RECORDED (ctx->rec) for the parameter update of an instantiated graph
-  auto enqueue = [&](const int mode) -> int32_t {
-  // ---- enqueue: control block, cast, prep + predict, association, LAP ----
-  // (graph capture: fixed sizes -- the tail of the copy is padding)
-  const size_t ctrl_bytes_now = mode == 1 ? t->ctrl_stride * (size_t)count : ctrl_off;
-  if (ctrl_bytes_now > 0 && mode != 2) BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_bytes_now, cudaMemcpyHostToDevice, st));
-  fmark("ctrl_h2d");
-  SEG_BEGIN(BT_SEG_PREP);
-  if (mode == 2) ctx->rec = &t->recs[R_CAST];
-  if (any_f32) BT_TRY(btk_frame_cast(ctx, dst, B));
-  SEG_END(BT_SEG_PREP);
-  SEG_BEGIN(BT_SEG_PREDICT);
-  if (mode == 2) ctx->rec = &t->recs[R_PREP];
-  BT_TRY(btk_frame_prep(ctx, dst, B, fc));
-  SEG_END(BT_SEG_PREDICT);
-  fmark("prep");
-
+  const size_t ND = (size_t)t->S * t->md;
   bt_cand cand = *bt_lap_own_cand(ctx);
   cand.seg = assoc_bn / 2;    // one epilogue thread owns one (row, segment) pair; the LAP gather follows
-  const size_t ND = (size_t)t->S * t->md;
-  if (mx_rows > 0) {
-    // the candidate counters are left zeroed by the previous frame's LAP kernel (no memset here)
-    SEG_BEGIN(BT_SEG_ASSOC);
-    bt_lap_batch LB;
-    memset(&LB, 0, sizeof(LB));
-    LB.count = count;
-    LB.y_stride = t->md;
-    bt_assoc_params p;
-    memset(&p, 0, sizeof(p));
-    p.count = count;
-    for (int k = 0; k < count; ++k) {
-      const int sid = sids[k];
-      const StreamState& s = t->streams[sid];
-      const FrameIn& in = s.in[s.parity];
-      const bool face = in.face_sim != nullptr && s.n_pool > 0;
-      const int pos_off = B.ctrl_off[k] + 8 * s.n_pool + (int)(((size_t)s.n_rows + 3) & ~size_t(3));
-      p.n[k] = s.n_rows; p.m[k] = s.m;
-      p.a_row0[k] = sid * t->cap;
-      p.b_row0[k] = (int32_t)((size_t)s.parity * ND + (size_t)sid * t->md);
-      p.row0[k] = sid * t->cap; p.col0[k] = sid * t->md;
-      p.kind_off[k] = B.ctrl_off[k] + 8 * s.n_pool;
-      p.pos_off[k] = pos_off;
-      p.cand_sid[k] = sid;
-      p.face_sim[k] = face ? in.face_sim : nullptr;
-      LB.sid[k] = sid; LB.n[k] = s.n_rows; LB.m[k] = s.m;
-      LB.row0[k] = p.row0[k]; LB.col0[k] = p.col0[k]; LB.in0[k] = p.b_row0[k];
-      LB.pos_off[k] = pos_off;
-      LB.face_sim[k] = p.face_sim[k];
-      int32_t* dresA = reinterpret_cast<int32_t*>(dst.res + (size_t)k * L.stride);
-      LB.x[k] = dresA + L.o_x; LB.x_stride[k] = t->cap;
-      LB.y[k] = dst.y + (size_t)k * 3 * t->md;
-      LB.zero_word[k] = reinterpret_cast<int32_t*>(dst.resB + (size_t)k * L.strideB) + L.o_hdr;
-    }
-    if (mx_m > 0) {
-      const int precision = assoc_precision;
-      p.d = any_reid ? D : 0;
-      p.a_rows_alloc = t->S * t->cap; p.b_rows_alloc = (int32_t)(2 * ND);
-      p.bn = assoc_bn;
-      // both operands are complete before the prep kernel starts (the bank since the last frame, the
-      // detection features since the copy / cast ahead of it): the main loop may run under it
-      p.operands_early = 1;
-      if (precision == 0) {
-        p.a16 = dst.feat16; p.b16 = dst.det16; p.row_norm = dst.norm;
-      } else if (any_reid && f16) {
-        p.a16 = dst.feat16; p.b16 = dst.det16; p.row_norm = dst.norm;
-      } else if (any_reid) {
-        p.a32 = dst.curr32; p.b32 = dst.det32;      // normalised fp32 current features x raw fp32 detections
-      }
-      p.row_tlbr = dst.tlbr; p.row_tlbr_f32 = dst.tlbr_f32; p.row_kind_base = dst.ctrl;
-      p.col_tlbr = dst.det_tlbr; p.col_kind = dst.col_kind; p.col_pk = dst.col_pk;
-      bool any_norm = any_f32;
-      for (int k = 0; k < count; ++k) any_norm = any_norm || B.want_norm[k];
-      p.col_norm = (any_reid && any_norm) ? dst.det_norm : nullptr;
-      p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
-      p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
-      p.appearance = (float)cfg.appearance_thresh;
-      // fp32 ingest rounds the operands to fp16 (3e-5 on unit 2048-d rows, SURVEY hard part 2); fp16 ingest
-      // multiplies the reference's own values exactly and only the accumulation order differs
-      p.gate_band = f16 ? 1.0e-4f : 5.0e-4f;
-      p.cand = cand;
-      t->last_assoc = p;
-      t->last_assoc_precision = precision;
-      t->last_assoc_valid = true;
-      fmark("assoc_params");
-      if (mode == 2) ctx->rec = &t->recs[R_ASSOC];
-      BT_TRY(btk_assoc(ctx, p, precision));
-      fmark("assoc");
-    }
-    SEG_END(BT_SEG_ASSOC);
-    SEG_BEGIN(BT_SEG_LAP);
-    const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
-    bt_refine rf;
-    memset(&rf, 0, sizeof(rf));
-    if (any_reid && tensor_path && mx_m > 0 && !t->no_refine) {
-      rf.enabled = 1; rf.d = D; rf.f16 = f16 ? 1 : 0;
-      rf.a16 = dst.feat16; rf.a_norm = dst.norm; rf.a32 = dst.curr32;
-      rf.b16 = dst.det16; rf.b32 = dst.det32;
-      rf.b_norm = t->last_assoc.col_norm;
-      rf.row_tlbr = dst.tlbr; rf.col_tlbr = dst.det_tlbr; rf.ctrl = dst.ctrl;
-      rf.proximity = cfg.proximity_thresh; rf.appearance = (float)cfg.appearance_thresh;
-    }
-    if (mode == 2) ctx->rec = &t->recs[R_LAP];
-    BT_TRY(btk_lap_solve3(ctx, cand, LB, th, rf));   // also zeroes the pair counters
-    SEG_END(BT_SEG_LAP);
-    fmark("lap");
+
+  // ---- the frame's launch description: association problems + LAP batch (host copy; goes up with the control block) ----
+  bt_lap_batch& LB = hd->LB;
+  memset(&LB, 0, sizeof(LB));
+  LB.count = count;
+  LB.y_stride = t->md;
+  bt_assoc_params p;
+  memset(&p, 0, sizeof(p));
+  p.count = count;
+  for (int k = 0; k < count; ++k) {
+    const int sid = sids[k];
+    const StreamState& s = t->streams[sid];
+    const FrameIn& in = s.in[s.parity];
+    const bool face = in.face_sim != nullptr && s.n_pool > 0;
+    const int pos_off = B.ctrl_off[k] + 8 * s.n_pool + (int)(((size_t)s.n_rows + 3) & ~size_t(3));
+    p.n[k] = s.n_rows; p.m[k] = s.m;
+    p.a_row0[k] = sid * t->cap;
+    p.b_row0[k] = (int32_t)((size_t)s.parity * ND + (size_t)sid * t->md);
+    p.row0[k] = sid * t->cap; p.col0[k] = sid * t->md;
+    p.kind_off[k] = B.ctrl_off[k] + 8 * s.n_pool;
+    p.pos_off[k] = pos_off;
+    p.cand_sid[k] = sid;
+    p.face_sim[k] = face ? in.face_sim : nullptr;
+    LB.sid[k] = sid; LB.n[k] = s.n_rows; LB.m[k] = s.m;
+    LB.row0[k] = p.row0[k]; LB.col0[k] = p.col0[k]; LB.in0[k] = p.b_row0[k];
+    LB.pos_off[k] = pos_off;
+    LB.face_sim[k] = p.face_sim[k];
+    int32_t* dresA = reinterpret_cast<int32_t*>(dst.res + (size_t)k * L.stride);
+    LB.x[k] = dresA + L.o_x; LB.x_stride[k] = t->cap;
+    LB.y[k] = dst.y + (size_t)k * 3 * t->md;
+    LB.zero_word[k] = reinterpret_cast<int32_t*>(dst.resB + (size_t)k * L.strideB) + L.o_hdr;
   }
-  // part A of the result regions: the assignment vectors (+ echoed scores / boxes of device inputs)
-  const size_t widthA = sizeof(int32_t) * (any_dev_inputs ? L.o_endA : L.o_sc);
-  if (mx_rows > 0 || (any_dev_inputs && mx_m > 0)) {
-    if (mode != 2) {
+  p.d = any_reid ? D : 0;
+  p.a_rows_alloc = t->S * t->cap; p.b_rows_alloc = (int32_t)(2 * ND);
+  p.bn = assoc_bn;
+  // both operands are complete before the prep kernel starts (the bank since the last frame, the
+  // detection features since the copy / cast ahead of it): the main loop may run under it
+  p.operands_early = 1;
+  if (assoc_precision == 0 || (any_reid && f16)) {
+    p.a16 = dst.feat16; p.b16 = dst.det16; p.row_norm = dst.norm;
+  } else if (any_reid) {
+    p.a32 = dst.curr32; p.b32 = dst.det32;      // normalised fp32 current features x raw fp32 detections
+  }
+  p.row_tlbr = dst.tlbr; p.row_tlbr_f32 = dst.tlbr_f32; p.row_kind_base = dst.ctrl;
+  p.col_tlbr = dst.det_tlbr; p.col_kind = dst.col_kind; p.col_pk = dst.col_pk;
+  // detection feature norms (stage 3 compares normalised detections): always there with fp32 ingest, computed on
+  // demand (streams with unconfirmed rows) with fp16 ingest; nobody else looks at them
+  p.col_norm = any_reid ? dst.det_norm : nullptr;
+  p.match_thresh = cfg.match_thresh; p.second_thresh = cfg.second_thresh;
+  p.unconf_thresh = cfg.unconfirmed_thresh; p.proximity = cfg.proximity_thresh;
+  p.appearance = (float)cfg.appearance_thresh;
+  // fp32 ingest rounds the operands to fp16 (3e-5 on unit 2048-d rows, SURVEY hard part 2); fp16 ingest
+  // multiplies the reference's own values exactly and only the accumulation order differs
+  p.gate_band = f16 ? 1.0e-4f : 5.0e-4f;
+  p.cand = cand;
+  btk_assoc_fill(p, assoc_precision, &hd->AF);
+  bt_refine rf;
+  memset(&rf, 0, sizeof(rf));
+  if (any_reid && tensor_path && !t->no_refine) {
+    rf.enabled = 1; rf.d = D; rf.f16 = f16 ? 1 : 0;
+    rf.a16 = dst.feat16; rf.a_norm = dst.norm; rf.a32 = dst.curr32;
+    rf.b16 = dst.det16; rf.b32 = dst.det32;
+    rf.b_norm = p.col_norm;
+    rf.row_tlbr = dst.tlbr; rf.col_tlbr = dst.det_tlbr; rf.ctrl = dst.ctrl;
+    rf.proximity = cfg.proximity_thresh; rf.appearance = (float)cfg.appearance_thresh;
+  }
+  if (mx_rows > 0 && mx_m > 0) {
+    t->last_assoc = p;
+    t->last_AF = hd->AF;
+    t->last_assoc_precision = assoc_precision;
+    t->last_assoc_valid = true;
+  }
+  fmark("setup");
+
+  bool part_a_sent = false, ema_pending = false;
+  // fixed == 0: plain enqueue with the frame's own launch geometry; fixed == 1: the same calls under stream
+  // capture, with capacity-sized geometry and copies (what a graph that is replayed for every frame needs) and the
+  // side stream joined back
+  auto enqueue = [&](const int fixed) -> int32_t {
+    const size_t ctrl_bytes_now = fixed ? kDescBytes + t->ctrl_stride * (size_t)count : ctrl_off;
+    BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_bytes_now, cudaMemcpyHostToDevice, st));
+    fmark("ctrl_h2d");
+    SEG_BEGIN(BT_SEG_PREP);
+    if (any_f32) BT_TRY(btk_frame_cast(ctx, dst, B, &dd->B, fixed));
+    SEG_END(BT_SEG_PREP);
+    SEG_BEGIN(BT_SEG_PREDICT);
+    BT_TRY(btk_frame_prep(ctx, dst, B, &dd->B, fc, fixed));
+    SEG_END(BT_SEG_PREDICT);
+    fmark("prep");
+    if (mx_rows > 0 || fixed) {
+      // the candidate counters are left zeroed by the previous frame's LAP kernel (no memset here)
+      SEG_BEGIN(BT_SEG_ASSOC);
+      if (mx_m > 0 || fixed) BT_TRY(btk_assoc_launch(ctx, p, assoc_precision, hd->AF, &dd->AF, fixed, t->cap, t->md));
+      SEG_END(BT_SEG_ASSOC);
+      fmark("assoc");
+      SEG_BEGIN(BT_SEG_LAP);
+      const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
+      BT_TRY(btk_lap_solve3(ctx, cand, LB, &dd->LB, th, rf));   // also zeroes the pair counters
+      SEG_END(BT_SEG_LAP);
+      fmark("lap");
+    }
+    // part A of the result regions: the assignment vectors (+ echoed scores / boxes of device inputs)
+    const size_t widthA = sizeof(int32_t) * (any_dev_inputs ? L.o_endA : L.o_sc);
+    if (mx_rows > 0 || (any_dev_inputs && mx_m > 0) || fixed) {
       if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_res, dst.res, widthA, cudaMemcpyDeviceToHost, st));
       else BT_CUDA(cudaMemcpy2DAsync(t->h_res, L.stride, dst.res, L.stride, widthA, count, cudaMemcpyDeviceToHost, st));
       // under capture: an event RECORD NODE the host can wait on (a plain record would only order captured work)
-      if (mode == 1) BT_CUDA(cudaEventRecordWithFlags(t->ev_x, st, cudaEventRecordExternal));
+      if (fixed) BT_CUDA(cudaEventRecordWithFlags(t->ev_x, st, cudaEventRecordExternal));
       else BT_CUDA(cudaEventRecord(t->ev_x, st));
+      part_a_sent = true;
+      fmark("copyA+ev");
     }
-    part_a_sent = true;
-    fmark("copyA+ev");
-  }
-  if (mx_rows > 0) {
-    // The matched tracks' Kalman update and feature EMA are a pure function of the three assignment
-    // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
-    // demo:570-610) while the host is still waiting for / digesting the assignments.
-    SEG_BEGIN(BT_SEG_UPDATE);
-    if (any_reid && mx_m > 0) {
-      // the feature EMA only needs the assignment vectors: side stream, next to update + duplicate test
-      // (profiling keeps it on the main stream so that its time shows up in the segment)
-      cudaStream_t es = t->prof ? st : ctx->side_stream;
-      if (!t->prof && mode != 2) {
-        BT_CUDA(cudaEventRecord(t->ev_fork, st));
-        BT_CUDA(cudaStreamWaitEvent(es, t->ev_fork, 0));
+    if (mx_rows > 0 || fixed) {
+      // The matched tracks' Kalman update and feature EMA are a pure function of the three assignment
+      // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
+      // demo:570-610) while the host is still waiting for / digesting the assignments.
+      SEG_BEGIN(BT_SEG_UPDATE);
+      if (any_reid && (mx_m > 0 || fixed)) {
+        // the feature EMA only needs the assignment vectors: side stream, next to update + duplicate test
+        // (profiling keeps it on the main stream so that its time shows up in the segment)
+        cudaStream_t es = t->prof ? st : ctx->side_stream;
+        if (!t->prof) {
+          BT_CUDA(cudaEventRecord(t->ev_fork, st));
+          BT_CUDA(cudaStreamWaitEvent(es, t->ev_fork, 0));
+        }
+        BT_TRY(btk_frame_ema(ctx, dst, B, &dd->B, fc, es, fixed));
+        if (!t->prof) { BT_CUDA(cudaEventRecord(t->ev_join, es)); ema_pending = true; }
       }
-      if (mode == 2) ctx->rec = &t->recs[R_EMA];
-      BT_TRY(btk_frame_ema(ctx, dst, B, fc, es));
-      if (!t->prof && mode != 2) { BT_CUDA(cudaEventRecord(t->ev_join, es)); ema_pending = true; }
-    }
-    fmark("ema(fork/join)");
-    if (mode == 2) ctx->rec = &t->recs[R_POST];
-    BT_TRY(btk_frame_post(ctx, dst, B, fc));
-    SEG_END(BT_SEG_UPDATE);
-    fmark("post");
-    // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
-    SEG_BEGIN(BT_SEG_DUP);
-    if (mode == 2) ctx->rec = &t->recs[R_DUP];
-    BT_TRY(btk_frame_dup(ctx, dst, B, fc));
-    SEG_END(BT_SEG_DUP);
-    fmark("dup");
-    // part B: pair count + first pairs, boxes of all slots
-    const size_t widthB = L.o_tlbr_bytes + sizeof(double) * 4 * (size_t)(mode == 1 ? t->cap : mx_rows);
-    if (mode != 2) {
+      fmark("ema(fork/join)");
+      BT_TRY(btk_frame_post(ctx, dst, B, &dd->B, fc, fixed));
+      SEG_END(BT_SEG_UPDATE);
+      fmark("post");
+      // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
+      SEG_BEGIN(BT_SEG_DUP);
+      BT_TRY(btk_frame_dup(ctx, dst, B, &dd->B, fc, fixed));
+      SEG_END(BT_SEG_DUP);
+      fmark("dup");
+      // part B: pair count + first pairs, boxes of all slots
+      const size_t widthB = L.o_tlbr_bytes + sizeof(double) * 4 * (size_t)(fixed ? t->cap : mx_rows);
       if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_resB, dst.resB, widthB, cudaMemcpyDeviceToHost, st));
       else BT_CUDA(cudaMemcpy2DAsync(t->h_resB, L.strideB, dst.resB, L.strideB, widthB, count, cudaMemcpyDeviceToHost, st));
+      if (fixed && ema_pending) {     // a captured fork must rejoin its origin stream
+        BT_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));
+        ema_pending = false;
+      }
     }
-    if (mode == 1 && ema_pending) {     // a captured fork must rejoin its origin stream
-      BT_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));
-      ema_pending = false;
-    }
-  }
     return BT_OK;
   };
   {
     GraphKey key = {count, any_f32 ? 1 : 0, any_reid ? 1 : 0, any_dev_inputs ? 1 : 0, assoc_bn, assoc_precision, f16 ? 1 : 0};
     const bool eligible = t->use_graph && !t->prof && mx_rows > 0 && mx_m > 0;
-    BT_TRY(run_enqueue(ctx, t, enqueue, key, eligible));
+    BT_TRY(run_enqueue(ctx, t, enqueue, key, eligible, part_a_sent, ema_pending));
   }
   fmark("copyB");
   HOST_MARK(BT_SEG_HOST_ENQUEUE1);
   // wait only for the assignments (+ scores / boxes): the list bookkeeping below overlaps the GPU's
   // update / EMA / duplicate-test tail
+  fmark("launch");
   if (part_a_sent) BT_CUDA(cudaEventSynchronize(t->ev_x));
   HOST_MARK(BT_SEG_HOST_WAIT1);
+  fmark("wait_x");
 
   // ---- per-stream list bookkeeping (demo:1493-1636) -------------------------------------------------
   for (int k = 0; k < count; ++k) {
     StreamState& s = t->streams[sids[k]];
-    std::vector<SlotMeta>& meta = s.meta;
+    SlotMeta* meta = s.meta.data();
     const bt_config& c = s.cfg;
     const int m = s.m, n_pool = s.n_pool, n_unc = s.n_unc, n_rows = s.n_rows, frame_id = s.frame_id;
     const float* sc = s.sc;
-    const std::vector<int>& pool = s.v_pool;
+    const int32_t* pool = s.pool;
     const std::vector<int>& unconfirmed = s.v_unconfirmed;
-    // detection lists (demo:1493-1532): float(score) against the Python-double thresholds
-    std::vector<int>& hi_pos = s.v_hi_pos; hi_pos.assign(m, -1);
-    std::vector<int>& lo_pos = s.v_lo_pos; lo_pos.assign(m, -1);
-    std::vector<int>& hi_list = s.v_hi_list; hi_list.clear();
-    std::vector<int>& lo_list = s.v_lo_list; lo_list.clear();
-    for (int j = 0; j < m; ++j) {
-      const double sd = (double)sc[j];
-      if (sd > c.track_high_thresh) { hi_pos[j] = (int)hi_list.size(); hi_list.push_back(j); }
-      else if (sd >= c.track_low_thresh) { lo_pos[j] = (int)lo_list.size(); lo_list.push_back(j); }
-    }
     std::vector<uint8_t>& det_taken = s.v_det_taken; det_taken.assign(m, 0);
-    std::vector<int>& activated = s.v_activated; activated.clear();
     std::vector<int>& refind = s.v_refind; refind.clear();
     std::vector<int>& lost_now = s.v_lost_now; lost_now.clear();
     std::vector<int>& removed_now = s.v_removed_now; removed_now.clear();
+    std::vector<int>& r_tracked = s.v_r_tracked; r_tracked.clear();
+    const int32_t* hx0 = s.hx[0]; const int32_t* hx1 = s.hx[1]; const int32_t* hx2 = s.hx[2];
+    s.n_m1 = s.n_m2 = s.n_m3 = 0;
+    // STrack.update (demo:586-610) / STrack.re_activate (demo:570-584) bookkeeping of a matched slot.  The order
+    // of the reference's activated / refind lists only matters for tracks that are not in tracked_stracks yet:
+    // re-found lost tracks (first association only: ascending pool index) and births.
     auto apply_match = [&](int slot, int det) {
       SlotMeta& tm = meta[slot];
       tm.f32_state = 0;
-      if (tm.state == BT_STATE_TRACKED) {  // STrack.update, demo:586-610
-        tm.tracklet_len += 1;
-        activated.push_back(slot);
-      } else {                             // STrack.re_activate, demo:570-584
-        tm.tracklet_len = 0;
-        refind.push_back(slot);
-      }
+      if (tm.state == BT_STATE_TRACKED) tm.tracklet_len += 1;
+      else { tm.tracklet_len = 0; refind.push_back(slot); }
       tm.frame_id = frame_id;
       tm.state = BT_STATE_TRACKED;
       tm.activated = 1;
@@ -881,92 +851,63 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       tm.det_index = det;
       det_taken[det] = 1;
     };
-    for (auto& mm : s.matches) mm.clear();
-    const int32_t* hx0 = s.hx[0]; const int32_t* hx1 = s.hx[1]; const int32_t* hx2 = s.hx[2];
-    // first association (demo:1556-1566): matches in ascending pool order
-    std::vector<uint8_t>& pool_matched = s.v_pool_matched; pool_matched.assign(n_pool, 0);
-    for (int i = 0; i < n_pool; ++i) {
-      const int slot = pool[i];
-      const int j = (n_rows > 0) ? hx0[slot] : -1;
-      if (j >= 0) {
-        s.matches[0].push_back(i);
-        s.matches[0].push_back(hi_pos[j]);
-        pool_matched[i] = 1;
+    // first association (demo:1556-1566).  Stage 2's candidates (demo:1569: unmatched pool tracks in state Tracked)
+    // are collected in the same pass: a stage-1 update never touches an unmatched track.
+    if (n_rows > 0) {
+      for (int i = 0; i < n_pool; ++i) {
+        const int slot = pool[i];
+        const int j = hx0[slot];
+        if (j >= 0) { apply_match(slot, j); s.n_m1 += 1; }
+        else if (meta[slot].state == BT_STATE_TRACKED) r_tracked.push_back(slot);
       }
     }
-    // the state test of stage 2 (demo:1569) reads the state BEFORE stage-1 updates touch the
-    // unmatched tracks, which they never do; build r_tracked first, then apply stage 1.
-    std::vector<int>& r_tracked = s.v_r_tracked; r_tracked.clear();
-    for (int i = 0; i < n_pool; ++i)
-      if (!pool_matched[i] && meta[pool[i]].state == BT_STATE_TRACKED) r_tracked.push_back(pool[i]);
-    for (int i = 0; i < n_pool; ++i)
-      if (pool_matched[i]) apply_match(pool[i], hx0[pool[i]]);
+    if (k == 0) fmark("L:stage1");
     // second association (demo:1568-1586)
-    for (int i = 0; i < (int)r_tracked.size(); ++i) {
-      const int slot = r_tracked[i];
-      const int j = hx1[slot];
-      if (j >= 0) {
-        s.matches[1].push_back(i);
-        s.matches[1].push_back(lo_pos[j]);
-        apply_match(slot, j);
-      }
-    }
     for (int slot : r_tracked) {
-      if (hx1[slot] < 0 && meta[slot].state != BT_STATE_LOST) {
-        meta[slot].state = BT_STATE_LOST;  // mark_lost
-        lost_now.push_back(slot);
-      }
+      const int j = hx1[slot];
+      if (j >= 0) { apply_match(slot, j); s.n_m2 += 1; }
+      else { meta[slot].state = BT_STATE_LOST; lost_now.push_back(slot); }   // mark_lost
     }
-    // unconfirmed (demo:1588-1612): detections = unmatched high detections, in order
-    std::vector<int>& u_det_pos = s.v_u_det_pos; u_det_pos.assign(m, -1);
-    {
-      int q = 0;
-      for (int j : hi_list)
-        if (!det_taken[j]) u_det_pos[j] = q++;
-    }
-    for (int i = 0; i < n_unc; ++i) {
-      const int j = hx2[unconfirmed[i]];
-      if (j >= 0) {
-        s.matches[2].push_back(i);
-        s.matches[2].push_back(u_det_pos[j]);
-      }
-    }
-    for (int i = 0; i < n_unc; ++i) {
-      const int j = hx2[unconfirmed[i]];
-      if (j >= 0) apply_match(unconfirmed[i], j);
-    }
+    // unconfirmed (demo:1588-1612)
     for (int slot : unconfirmed) {
-      if (hx2[slot] < 0) {
-        meta[slot].state = BT_STATE_REMOVED;  // mark_removed, demo:1609-1612
-        removed_now.push_back(slot);
-      }
+      const int j = hx2[slot];
+      if (j >= 0) { apply_match(slot, j); s.n_m3 += 1; }
+      else { meta[slot].state = BT_STATE_REMOVED; removed_now.push_back(slot); }   // mark_removed, demo:1609-1612
     }
-    // births (demo:1614-1621, STrack.activate demo:556-568).  The reference's track store is unbounded;
-    // here a full store drops the birth (the detection stays unmatched, as if its score were below
+    if (k == 0) fmark("L:stage23");
+    // births (demo:1614-1621, STrack.activate demo:556-568): unmatched high detections (demo:1501: float(score) >
+    // 0.40 as Python doubles) with score >= new_track_thresh, in detection order.  The reference's track store is
+    // unbounded; here a full store drops the birth (the detection stays unmatched, as if its score were below
     // new_track_thresh) and the frame stays consistent: nothing else depends on it.
     s.v_birth_slot.clear(); s.v_birth_det.clear();
     s.n_births_skipped = 0;
-    for (int j : hi_list) {
-      if (det_taken[j]) continue;
-      if ((double)sc[j] < c.new_track_thresh) continue;
-      const int slot = alloc_slot(s, t->cap);
-      if (slot < 0) { s.n_births_skipped += 1; continue; }
-      SlotMeta& tm = meta[slot];
-      tm = SlotMeta();
-      tm.used = 1;
-      tm.track_id = ++s.id_count;
-      tm.state = BT_STATE_TRACKED;
-      tm.activated = (frame_id == 1) ? 1 : 0;
-      tm.frame_id = frame_id;
-      tm.start_frame = frame_id;
-      tm.tracklet_len = 0;
-      tm.score = sc[j];
-      tm.det_index = j;
-      tm.f32_state = 1;
-      s.v_birth_slot.push_back(slot);
-      s.v_birth_det.push_back(j);
-      activated.push_back(slot);
+    int n_high = 0, n_low = 0;
+    for (int j = 0; j < m; ++j) {
+      const double sd = (double)sc[j];
+      if (sd > c.track_high_thresh) {
+        n_high += 1;
+        if (det_taken[j] || sd < c.new_track_thresh) continue;
+        const int slot = alloc_slot(s, t->cap);
+        if (slot < 0) { s.n_births_skipped += 1; continue; }
+        SlotMeta& tm = meta[slot];
+        tm = SlotMeta();
+        tm.used = 1;
+        tm.track_id = ++s.id_count;
+        tm.state = BT_STATE_TRACKED;
+        tm.activated = (frame_id == 1) ? 1 : 0;
+        tm.frame_id = frame_id;
+        tm.start_frame = frame_id;
+        tm.tracklet_len = 0;
+        tm.score = sc[j];
+        tm.det_index = j;
+        tm.f32_state = 1;
+        s.v_birth_slot.push_back(slot);
+        s.v_birth_det.push_back(j);
+      } else if (sd >= c.track_low_thresh) {
+        n_low += 1;
+      }
     }
+    s.n_high = n_high; s.n_low = n_low;
     s.n_births = (int)s.v_birth_slot.size();
     // expiry (demo:1623-1627)
     for (int slot : s.lost) {
@@ -975,23 +916,26 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
         removed_now.push_back(slot);
       }
     }
-    // merge lists (demo:1629-1636)
+    if (k == 0) fmark("L:births");
+    // merge lists (demo:1629-1636): tracked tracks that are still Tracked keep their positions, then births
+    // (detection order), then re-found tracks (pool order)
     std::vector<int>& new_tracked = s.v_new_tracked; new_tracked.clear();
     for (int slot : s.tracked)
-      if (meta[slot].state == BT_STATE_TRACKED) { new_tracked.push_back(slot); meta[slot].mark = 1; }
-    for (int slot : activated)
-      if (!meta[slot].mark) { new_tracked.push_back(slot); meta[slot].mark = 1; }
-    for (int slot : refind)
-      if (!meta[slot].mark) { new_tracked.push_back(slot); meta[slot].mark = 1; }
+      if (meta[slot].state == BT_STATE_TRACKED) new_tracked.push_back(slot);
+    for (int slot : s.v_birth_slot) new_tracked.push_back(slot);
+    for (int slot : refind) { new_tracked.push_back(slot); meta[slot].mark = 1; }
     std::vector<int>& new_lost = s.v_new_lost; new_lost.clear();
     for (int slot : s.lost)
       if (!meta[slot].mark && !meta[slot].in_removed) new_lost.push_back(slot);   // sub_stracks(lost, tracked), then sub_stracks(lost, removed) BEFORE this frame's removals
     for (int slot : lost_now)
       if (!meta[slot].in_removed) new_lost.push_back(slot);                        // extend(lost_stracks)
-    for (int slot : new_tracked) meta[slot].mark = 0;
+    for (int slot : refind) meta[slot].mark = 0;
     for (int slot : removed_now) meta[slot].in_removed = 1; // removed_stracks.extend
     s.n_removed_total += (int)removed_now.size();
+    s.v_pool.assign(pool, pool + n_pool);   // the control block is rewritten by the next step; diagnostics may ask later
+    s.matches_valid = true;
   }
+  fmark("L:merge");
   HOST_MARK(BT_SEG_HOST_LISTS);
   BT_CUDA(cudaStreamSynchronize(st));    // the frame's device work is complete, part B is on the host
   if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join));   // the side stream's EMA (usually done already)
@@ -1137,12 +1081,12 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       info.n_lost = (int)s.lost.size();
       info.n_removed_total = s.n_removed_total;
       info.n_pool = s.n_pool;
-      info.n_high = (int)s.v_hi_list.size();
-      info.n_low = (int)s.v_lo_list.size();
+      info.n_high = s.n_high;
+      info.n_low = s.n_low;
       info.n_unconfirmed = s.n_unc;
-      info.n_matches1 = (int)s.matches[0].size() / 2;
-      info.n_matches2 = (int)s.matches[1].size() / 2;
-      info.n_matches3 = (int)s.matches[2].size() / 2;
+      info.n_matches1 = s.n_m1;
+      info.n_matches2 = s.n_m2;
+      info.n_matches3 = s.n_m3;
       info.n_births = n_births;
       info.n_births_skipped = s.n_births_skipped;
     }
@@ -1175,6 +1119,12 @@ int32_t bt_tracker_reset_stream(bt_ctx* ctx, int32_t stream_id, const bt_config*
   BT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   const bt_cand& cand = *bt_lap_own_cand(ctx);
   const size_t D = t->D;
+  // captured frame graphs carry the thresholds of the configuration they were captured under
+  for (auto& g : t->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  t->graphs.clear();
   for (int sid = (stream_id < 0 ? 0 : stream_id); sid < (stream_id < 0 ? t->S : stream_id + 1); ++sid) {
     reset_stream(t, t->streams[sid], cfg);
     BT_CUDA(cudaMemsetAsync(t->st.feat16 + (size_t)sid * t->cap * D, 0, sizeof(__half) * (size_t)t->cap * D, ctx->stream));
@@ -1265,9 +1215,11 @@ int32_t bt_profile_replay_assoc(bt_ctx* ctx, int32_t iters, double* total_ms) {
   };
   double sum = 0.0;
   if (idempotent) {
-    BT_TRY(btk_assoc(ctx, t->last_assoc, t->last_assoc_precision));   // warm
+    // the frame description of the last step is still in the device control block
+    const bt_assoc_frame* dAF = &reinterpret_cast<const FrameDesc*>(t->st.ctrl)->AF;
+    BT_TRY(btk_assoc_launch(ctx, t->last_assoc, 0, t->last_AF, dAF, 0, 0, 0));   // warm
     BT_CUDA(cudaEventRecord(e0, st));
-    for (int i = 0; i < iters; ++i) BT_TRY(btk_assoc(ctx, t->last_assoc, t->last_assoc_precision));
+    for (int i = 0; i < iters; ++i) BT_TRY(btk_assoc_launch(ctx, t->last_assoc, 0, t->last_AF, dAF, 0, 0, 0));
     BT_CUDA(cudaEventRecord(e1, st));
     BT_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -1402,12 +1354,54 @@ int32_t bt_get_track_features(bt_ctx* ctx, int32_t which, int32_t cap, float* cu
   return bt_get_track_features_stream(ctx, 0, which, cap, curr, smooth);
 }
 
+// The matches of the last step in the reference's index spaces (demo:1556, demo:1571, demo:1604), assembled on
+// demand from what the step left on the host (assignment vectors, pool order, scores) -- the hot path does not pay
+// for a diagnostic read-back.
+static int32_t build_matches(bt_ctx* ctx, bt_tracker* t, StreamState& s) {
+  BT_CHECK(s.matches_valid && s.boxes_valid && t->region_gen[s.tlbr_region] == s.tlbr_gen, BT_ERR_STATE,
+           "the matches of the last step are no longer available (another step or submit has reused its buffers)");
+  for (auto& mm : s.matches) mm.clear();
+  const int m = s.m;
+  const float* sc = s.sc;
+  const bt_config& c = s.cfg;
+  std::vector<int>& hi_pos = s.v_hi_pos; hi_pos.assign(m, -1);
+  std::vector<int>& lo_pos = s.v_lo_pos; lo_pos.assign(m, -1);
+  int nh = 0, nl = 0;
+  for (int j = 0; j < m; ++j) {
+    const double sd = (double)sc[j];
+    if (sd > c.track_high_thresh) hi_pos[j] = nh++;
+    else if (sd >= c.track_low_thresh) lo_pos[j] = nl++;
+  }
+  std::vector<uint8_t>& taken = s.scratch_a; taken.assign(m, 0);
+  if (s.n_rows > 0) {
+    for (int i = 0; i < s.n_pool; ++i) {
+      const int j = s.hx[0][s.v_pool[i]];
+      if (j >= 0) { s.matches[0].push_back(i); s.matches[0].push_back(hi_pos[j]); taken[j] = 1; }
+    }
+    for (int i = 0; i < (int)s.v_r_tracked.size(); ++i) {
+      const int j = s.hx[1][s.v_r_tracked[i]];
+      if (j >= 0) { s.matches[1].push_back(i); s.matches[1].push_back(lo_pos[j]); taken[j] = 1; }
+    }
+    std::vector<int>& u_det_pos = s.v_u_det_pos; u_det_pos.assign(m, -1);
+    int q = 0;
+    for (int j = 0; j < m; ++j)
+      if (hi_pos[j] >= 0 && !taken[j]) u_det_pos[j] = q++;
+    for (int i = 0; i < s.n_unc; ++i) {
+      const int j = s.hx[2][s.v_unconfirmed[i]];
+      if (j >= 0) { s.matches[2].push_back(i); s.matches[2].push_back(u_det_pos[j]); }
+    }
+  }
+  return BT_OK;
+}
+
 int32_t bt_get_matches_stream(bt_ctx* ctx, int32_t stream_id, int32_t stage, int32_t cap, int32_t* n, int32_t* pairs) {
   if (!ctx) return BT_ERR_INVALID;
   bt_tracker* t = ctx->trk;
   BT_CHECK(stream_id >= 0 && stream_id < t->S, BT_ERR_INVALID, "stream id %d out of range (ctx has %d)", stream_id, t->S);
   BT_CHECK(stage >= 1 && stage <= 3, BT_ERR_INVALID, "stage must be 1, 2 or 3");
-  const std::vector<int32_t>& mm = t->streams[stream_id].matches[stage - 1];
+  StreamState& s = t->streams[stream_id];
+  if (s.frame_id > 0) BT_TRY(build_matches(ctx, t, s));
+  const std::vector<int32_t>& mm = s.matches[stage - 1];
   const int cnt = (int)mm.size() / 2;
   if (n) *n = cnt;
   if (pairs) {
