@@ -31,6 +31,7 @@
 #include <float.h>
 #include <stdlib.h>
 #include <mutex>
+#include <vector>
 
 struct bt_lap_ws {
   bt_cand cand;            // ctx-wide candidate lists (3 lists per video stream)
@@ -57,11 +58,15 @@ struct bt_lap_ws {
   int32_t* y = nullptr;            // [cols]
   int rows = 0, cols = 0;
   int rows_stride = 0, cols_stride = 0;
+  // a two-row dummy problem (never cleared) + its outputs: the kernel's instruction-cache warm-up run
+  bt_cand warm = {};
+  int32_t* warm_xy = nullptr;      // [streams][8]
+  char* warm_blk = nullptr;
 };
 
 namespace {
 
-constexpr int kLapThreads = 1024;
+constexpr int kLapThreads = 512;   // 128 registers per thread: the phases are latency chains, spills to local memory cost L2 round trips
 constexpr int kInf = 0x7fffffff;
 
 struct LapParams {
@@ -93,7 +98,7 @@ __device__ int block_exclusive_scan(int32_t* data, int n, int32_t* s_warp, int32
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-      int w = s_warp[lane];
+      int w = (lane < kLapThreads / 32) ? s_warp[lane] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, w, o);
@@ -106,7 +111,7 @@ __device__ int block_exclusive_scan(int32_t* data, int n, int32_t* s_warp, int32
     const int warp_off = (warp == 0) ? 0 : s_warp[warp - 1];
     if (i < n) data[i] = carry + warp_off + incl - val;
     __syncthreads();
-    if (tid == kLapThreads - 1) *s_carry = carry + s_warp[31];
+    if (tid == kLapThreads - 1) *s_carry = carry + s_warp[kLapThreads / 32 - 1];
     __syncthreads();
   }
   return *s_carry;
@@ -513,7 +518,21 @@ constexpr int kOneWarpRows = 4;
 constexpr double kTieGap = 1.0e-3;         // two costs closer than this may swap order within the tensor-core error
 constexpr double kBlockedCost = 1.0e300;   // an edge whose column an earlier stage took: never beats staying unmatched
 
+// a stage's arguments, in shared memory: by-reference arguments of a real function call would live in the
+// caller's LOCAL memory (1024 threads x ~0.5 KB: every field access an L2 round trip)
+struct StageArgs {
+  bt_cand cand;
+  bt_lap_ws W;
+  int kb, list, n, m, clear, debug;
+  double thresh;
+  int32_t* x; int32_t* y;
+  const int32_t* row_block; const int32_t* col_block;
+  unsigned long long* tq;
+};
+
 struct SmallSmem {
+  StageArgs sa;
+  unsigned long long tq[8];
   int32_t rg[kSmallRows], rdeg[kSmallRows], rstart[kSmallRows + 1], rlabel[kSmallRows], xl[kSmallRows];
   int32_t sorted_rows[kSmallRows], treerows[kSmallRows], compidx[kSmallRows], isroot[kSmallRows];
   int32_t rowcnt[kSmallRows + 1], colcnt[kSmallRows + 1], fill[kSmallRows + 1];
@@ -528,6 +547,398 @@ struct SmallSmem {
   int32_t s_carry;
   int nC, nE, nR, changed, big;
 };
+
+// One association stage of one video stream.  A real (noinline) function on purpose: the kernel calls it once on
+// a two-row dummy problem BEFORE griddepcontrol.wait -- every phase of this latency-bound kernel runs exactly once
+// per launch, so its time used to be dominated by cold instruction fetches; the dry run pulls the hot path's
+// instructions into the SM's instruction cache while the association kernel is still running.
+__device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& rf, SmallSmem& sm) {
+  const StageArgs& a = sm.sa;
+  const bt_cand& cand = a.cand;
+  const bt_lap_ws& W = a.W;
+  const int kb = a.kb, list = a.list, n = a.n, m = a.m;
+  const double thresh = a.thresh;
+  int32_t* x = a.x; int32_t* y = a.y;
+  const int32_t* row_block = a.row_block; const int32_t* col_block = a.col_block;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int GT = kLapThreads, NW = kLapThreads / 32;
+#undef LAP_T
+#define LAP_T(i) do { if (a.debug && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sm.tq[i])); } while (0)
+    int32_t* segcnt_all = cand.cnt + (size_t)list * cand.rows_cap * cand.nseg;
+  int32_t* ecol = cand.col + (size_t)list * cand.rows_cap * cand.stride;
+  double* ecost = cand.cost + (size_t)list * cand.rows_cap * cand.stride;
+  int32_t* indeg = cand.indeg + (size_t)list * cand.cols_cap;
+  // ---- P1: classify every row from the emitters' degree bookkeeping (no edge traversal for the bulk):
+  //      isolated edges (row degree 1, column in-degree 1, gate decision not in doubt) are final; rows
+  //      with several candidates, a contested column or an ambiguous gate are "complex" ----
+  for (int r0 = tid; r0 < n; r0 += 2 * GT) {
+    // two rows per thread and pass, all their loads in flight before the first dependent one: the phase is a
+    // chain of L2 round trips (degree -> the row's column -> that column's in-degree)
+    int rr[2] = {r0, r0 + GT}, degs[2], rcs[2], inds[2];
+    unsigned long long masks[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      degs[q] = 0; rcs[q] = 0; masks[q] = 0ull;
+      if (rr[q] < n) {
+        const size_t ri = (size_t)list * cand.rows_cap + rr[q];
+        degs[q] = cand.rowdeg[ri]; rcs[q] = cand.rowcol[ri]; masks[q] = cand.segmask[ri];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) inds[q] = (degs[q] == 1) ? indeg[rcs[q] & BT_EDGE_COLMASK] : 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int r = rr[q], deg = degs[q], rc = rcs[q];
+      if (deg == 0) continue;                      // nothing was emitted for this row
+      const size_t ri = (size_t)list * cand.rows_cap + r;
+      const int col1 = rc & BT_EDGE_COLMASK;
+      const unsigned long long mask = masks[q];
+      if (a.clear) { cand.rowdeg[ri] = 0; cand.segmask[ri] = 0ull; }
+      const bool row_on = row_block == nullptr || row_block[r] < 0;
+      bool complex_row = row_on;
+      if (row_on && deg == 1) {
+        const bool col_ok = edge_ok(col_block, col1);
+        if (!col_ok) complex_row = false;            // its only column is taken already
+        else if (inds[q] == 1 && !(rc & BT_EDGE_AMBIG)) {
+          x[r] = col1; y[col1] = r;                  // isolated edge
+          complex_row = false;
+        }
+      }
+      if (!complex_row) {
+        if (a.clear) {                          // leave the segment counters zeroed
+          unsigned long long mm = mask;
+          while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
+        }
+        continue;
+      }
+      const int kc = atomicAdd(&sm.nC, 1);
+      const int e0 = atomicAdd(&sm.nE, deg);
+      W.clist[kc] = r;
+      if (kc < kSmallRows && e0 + deg <= kSmallEdges) {
+        sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0; sm.rmask[kc] = mask;
+      } else {
+        sm.big = 1;
+      }
+    }
+  }
+  __syncthreads();
+  LAP_T(2);
+  const int nC = sm.nC;
+  if (a.clear)                              // every read of the in-degrees is behind us
+    for (int c = tid; c < cand.cols_cap; c += GT) indeg[c] = 0;
+  const bool big = sm.big != 0 || m > kSmallCols;
+  int dbg_ncomp = 0;
+  (void)dbg_ncomp;
+
+  if (nC > 0 && !big) {
+    // ---- S1: ascending row order (deterministic tie-breaking), by rank ----
+    {
+      int my_r = 0, my_deg = 0, my_start = 0, rank = 0;
+      unsigned long long my_mask = 0;
+      if (tid < nC) {
+        my_r = sm.rg[tid]; my_deg = sm.rdeg[tid]; my_start = sm.rstart[tid]; my_mask = sm.rmask[tid];
+        for (int j = 0; j < nC; ++j) rank += (sm.rg[j] < my_r) ? 1 : 0;
+      }
+      __syncthreads();
+      if (tid < nC) { sm.rg[rank] = my_r; sm.rdeg[rank] = my_deg; sm.rstart[rank] = my_start; sm.rmask[rank] = my_mask; }
+    }
+    // per-column solver state (global column ids)
+    for (int c = tid; c < m; c += GT) { sm.v[c] = 0.0; sm.seen[c] = 0; sm.insc[c] = 0; sm.yl[c] = -1; sm.clabel[c] = kInf; }
+    __syncthreads();
+    // ---- S2: gather the rows' segments into the shared-memory CSR: one warp per row, lanes over segments ----
+    for (int i = warp; i < nC; i += NW) {
+      const int r = sm.rg[i];
+      const size_t ri = (size_t)list * cand.rows_cap + r;
+      const unsigned long long mask = sm.rmask[i];
+      int32_t* segcnt = cand.cnt + ri * cand.nseg;
+      const int g0 = lane, g1 = lane + 32;
+      int k0 = ((mask >> g0) & 1ull) ? segcnt[g0] : 0;
+      int k1 = ((mask >> g1) & 1ull) ? segcnt[g1] : 0;
+      if (a.clear) { if ((mask >> g0) & 1ull) segcnt[g0] = 0; if ((mask >> g1) & 1ull) segcnt[g1] = 0; }
+      int p0 = k0, p1 = k1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, p0, o), t1 = __shfl_up_sync(0xffffffffu, p1, o);
+        if (lane >= o) { p0 += t0; p1 += t1; }
+      }
+      const int tot0 = __shfl_sync(0xffffffffu, p0, 31);
+      p0 -= k0; p1 += tot0 - k1;
+      const int e0 = sm.rstart[i];
+      const int32_t* rc = ecol + (size_t)r * cand.stride;
+      const double* rv = ecost + (size_t)r * cand.stride;
+      // while gathering: the row's cheapest and second cheapest usable edge (provisional costs)
+      double b1 = kBlockedCost, b2 = kBlockedCost;
+      int bc = kInf, amb = 0;
+      for (int half = 0; half < 2; ++half) {
+        const int kk = half ? k1 : k0, dst0 = e0 + (half ? p1 : p0), src0 = (half ? g1 : g0) * cand.seg;
+        for (int j = 0; j < kk; ++j) {
+          const int colf = rc[src0 + j];
+          const int col = colf & BT_EDGE_COLMASK;
+          const bool ok = edge_ok(col_block, col);
+          const double cst = ok ? rv[src0 + j] : kBlockedCost;
+          sm.ecol[dst0 + j] = col;
+          sm.ecst[dst0 + j] = cst;
+          if (ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG))) sm.rlist[atomicAdd(&sm.nR, 1)] = (i << 12) | (dst0 + j);
+          if (ok) {
+            if (colf & BT_EDGE_AMBIG) amb = 1;
+            if (cst < b1 || (cst == b1 && col < bc)) { b2 = b1; b1 = cst; bc = col; }
+            else if (cst < b2) b2 = cst;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        amb |= __shfl_xor_sync(0xffffffffu, amb, o);
+        if (ob1 < b1 || (ob1 == b1 && oc < bc)) { b2 = fmin(b1, ob2); b1 = ob1; bc = oc; }
+        else b2 = fmin(b2, ob1);
+      }
+      if (lane == 0) {
+        // decided without looking at anybody else: no gate in doubt, and the row's choice cannot change within
+        // the error of a tensor-core similarity (its runner-up is out of reach or clearly worse)
+        const bool decided = !amb && (b1 >= thresh || b2 >= thresh || b2 - b1 > kTieGap);
+        sm.xl[i] = (b1 < thresh) ? bc : -1;
+        sm.isroot[i] = decided ? 1 : 0;
+      }
+    }
+    if (tid == 0) sm.changed = 0;
+    __syncthreads();
+    LAP_T(5);
+    // ---- S2b: every complex row takes its cheapest edge -- if those choices are decided and pairwise
+    //      distinct they are the optimum (each row at its own lower bound), which is the usual frame ----
+    for (int i = tid; i < nC; i += GT) {
+      const int c = sm.xl[i];
+      bool clash = sm.isroot[i] == 0;
+      if (c >= 0 && atomicCAS(&sm.yl[c], -1, i) != -1) clash = true;
+      if (clash) sm.changed = 1;
+    }
+    __syncthreads();
+    const bool greedy_ok = sm.changed == 0;
+    __syncthreads();
+    if (greedy_ok) {
+      for (int i = tid; i < nC; i += GT) {
+        const int c = sm.xl[i];
+        if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
+      }
+      dbg_ncomp = -1;
+      LAP_T(3);
+    } else {
+    for (int i = tid; i < nC; i += GT) {
+      const int c = sm.xl[i];
+      if (c >= 0) sm.yl[c] = -1;
+    }
+    __syncthreads();
+    // ---- S3: exact re-costing of the flagged edges, one warp each ----
+    {
+      const int nR = sm.nR;
+      for (int q = warp; q < nR; q += NW) {
+        const int i = sm.rlist[q] >> 12, e = sm.rlist[q] & 4095;
+        const double c = refine_cost(rf, B, kb, list, sm.rg[i], sm.ecol[e], lane);
+        if (lane == 0) sm.ecst[e] = c;
+      }
+    }
+    for (int i = tid; i < nC; i += GT) { sm.xl[i] = -1; sm.u[i] = 0.0; sm.rlabel[i] = i; }
+    __syncthreads();
+    LAP_T(3);
+    const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
+                        sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
+    if (nC <= kOneWarpRows) {
+      // ---- a handful of rows: one warp runs the shortest-augmenting-path solver over all of them ----
+      if (warp == 0) {
+        if (lane < nC) sm.sorted_rows[lane] = lane;
+        if (lane == 0) { sm.rowcnt[0] = 0; sm.rowcnt[1] = nC; sm.colcnt[0] = 0; sm.colcnt[1] = 0; }
+        __syncwarp();
+        solve_component(A, 0, thresh, nullptr, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl, lane);
+      }
+      dbg_ncomp = 1;
+    } else {
+      // ---- S4: components by min-label propagation + pointer jumping (shared memory) ----
+      while (true) {
+        if (tid == 0) sm.changed = 0;
+        __syncthreads();
+        bool changed = false;
+        for (int i = tid; i < nC; i += GT) {
+          int lr = sm.rlabel[i];
+          const int l0 = lr;
+          for (int q = sm.rstart[i]; q < sm.rstart[i] + sm.rdeg[i]; ++q) {
+            const int c = sm.ecol[q];
+            const int lc = sm.clabel[c];
+            if (lc < lr) lr = lc;
+            else if (lc > lr) { atomicMin(&sm.clabel[c], lr); changed = true; }
+          }
+          if (lr < l0) { atomicMin(&sm.rlabel[i], lr); changed = true; }
+        }
+        __syncthreads();
+        for (int i = tid; i < nC; i += GT) {
+          const int l = sm.rlabel[i];
+          const int ll = sm.rlabel[l];
+          if (ll < l) { atomicMin(&sm.rlabel[i], ll); changed = true; }
+        }
+        if (changed) sm.changed = 1;
+        __syncthreads();
+        const int any = sm.changed;
+        __syncthreads();
+        if (!any) break;
+      }
+      // ---- S5: grouping ----
+      for (int i = tid; i < nC; i += GT) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
+      for (int i = tid; i <= nC; i += GT) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
+      __syncthreads();
+      const int ncomp = block_exclusive_scan(sm.isroot, nC, sm.s_warp, &sm.s_carry);
+      for (int i = tid; i < nC; i += GT)
+        if (sm.rlabel[i] == i) sm.compidx[i] = sm.isroot[i];
+      __syncthreads();
+      for (int i = tid; i < nC; i += GT) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
+      for (int c = tid; c < m; c += GT)
+        if (sm.clabel[c] != kInf) atomicAdd(&sm.colcnt[sm.compidx[sm.clabel[c]]], 1);
+      __syncthreads();
+      block_exclusive_scan(sm.rowcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+      block_exclusive_scan(sm.colcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+      for (int i = tid; i < nC; i += GT) {
+        const int q = sm.compidx[sm.rlabel[i]];
+        sm.sorted_rows[sm.rowcnt[q] + atomicAdd(&sm.fill[q], 1)] = i;
+      }
+      __syncthreads();
+      // ---- S6: tiny components one thread each, the others one warp each ----
+      constexpr int kSerialRows = 6;
+      for (int comp = tid; comp < ncomp; comp += GT) {
+        const int nr = sm.rowcnt[comp + 1] - sm.rowcnt[comp];
+        if (nr <= 3) solve_component_enum(A, comp, thresh, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl);
+        else if (nr <= kSerialRows) solve_component_serial(A, comp, thresh, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl);
+      }
+      __syncwarp();
+      for (int comp = warp; comp < ncomp; comp += NW)
+        if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] > kSerialRows)
+          solve_component(A, comp, thresh, nullptr, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl, lane);
+      dbg_ncomp = ncomp;
+    }
+    __syncthreads();
+    // ---- S7: write back ----
+    for (int i = tid; i < nC; i += GT) {
+      const int c = sm.xl[i];
+      if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
+    }
+    }   // general (non-greedy) path
+  } else if (nC > 0) {
+    // ---- large complex part (a crowded scene, a dense cost matrix, more detections than the on-chip
+    //      arrays hold): same algorithm over global scratch ----
+    int32_t* cnt = cand.deg + (size_t)list * cand.rows_cap;
+    for (int c = tid; c < m; c += GT) { W.collabel[c] = kInf; W.v[c] = 0.0; W.seen[c] = 0; W.insc[c] = 0; }
+    for (int r = tid; r < n; r += GT) { W.u[r] = 0.0; W.label[r] = kInf; }
+    if (tid < 8) W.counters[tid] = 0;
+    __syncthreads();
+    // compact the complex rows' segments in place (ascending copy), one thread per row
+    for (int i = tid; i < nC; i += GT) {
+      const int r = W.clist[i];
+      const size_t ri = (size_t)list * cand.rows_cap + r;
+      // rows that made it into the on-chip arrays still have their segment mask in shared memory; the
+      // others lost it with the clearing above -- walk all segments of those
+      unsigned long long mask = ~0ull;
+      int32_t* segcnt = cand.cnt + ri * cand.nseg;
+      int32_t* rc = ecol + (size_t)r * cand.stride;
+      double* rv = ecost + (size_t)r * cand.stride;
+      int total = 0;
+      for (int g = 0; g < cand.nseg; ++g) {
+        if (!((mask >> g) & 1ull)) continue;
+        const int kk = segcnt[g];
+        if (kk == 0) continue;
+        if (a.clear) segcnt[g] = 0;
+        const int src = g * cand.seg;
+        for (int e = 0; e < kk; ++e) {
+          if (src + e != total) { rc[total] = rc[src + e]; rv[total] = rv[src + e]; }
+          ++total;
+        }
+      }
+      cnt[r] = total;
+      W.label[r] = r;
+    }
+    __syncthreads();
+    // exact re-costing of the flagged edges: one warp per row, flagged edges one after the other
+    for (int i = warp; i < nC; i += NW) {
+      const int r = W.clist[i];
+      const int deg = cnt[r];
+      int32_t* rc = ecol + (size_t)r * cand.stride;
+      double* rv = ecost + (size_t)r * cand.stride;
+      for (int q0 = 0; q0 < deg; q0 += 32) {
+        const int q = q0 + lane;
+        const int colf = q < deg ? rc[q] : 0;
+        const bool ok = q < deg && edge_ok(col_block, colf & BT_EDGE_COLMASK);
+        unsigned todo = __ballot_sync(0xffffffffu, ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG)));
+        while (todo) {
+          const int bsrc = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int col = __shfl_sync(0xffffffffu, colf, bsrc) & BT_EDGE_COLMASK;
+          const double c = refine_cost(rf, B, kb, list, r, col, lane);
+          if (lane == bsrc) rv[q] = c;
+        }
+        if (q < deg) rc[q] = colf & BT_EDGE_COLMASK;
+      }
+    }
+    __syncthreads();
+    // components of the complex part
+    for (int iter = 0;; ++iter) {
+      int32_t* flag = &W.counters[2 + (iter & 1)];
+      bool changed = false;
+      for (int i = tid; i < nC; i += GT) {
+        const int r = W.clist[i];
+        int lr = W.label[r];
+        const int l0 = lr;
+        const int deg = cnt[r];
+        const int32_t* e = ecol + (size_t)r * cand.stride;
+        for (int q = 0; q < deg; ++q) {
+          const int c = e[q];
+          if (!edge_ok(col_block, c)) continue;
+          const int lc = W.collabel[c];
+          if (lc < lr) lr = lc;
+          else if (lc > lr) { atomicMin(&W.collabel[c], lr); changed = true; }
+        }
+        if (lr < l0) { atomicMin(&W.label[r], lr); changed = true; }
+      }
+      __syncthreads();
+      for (int i = tid; i < nC; i += GT) {
+        const int r = W.clist[i];
+        const int l = W.label[r];
+        const int ll = W.label[l];
+        if (ll < l) { atomicMin(&W.label[r], ll); changed = true; }
+      }
+      if (changed) *flag = 1;
+      if (tid == 0) W.counters[2 + ((iter + 1) & 1)] = 0;   // the other flag, for the next round
+      __syncthreads();
+      if (*flag == 0) break;
+    }
+    // component bookkeeping
+    for (int i = tid; i < nC; i += GT) W.isroot[i] = (W.label[W.clist[i]] == W.clist[i]) ? 1 : 0;
+    for (int i = tid; i <= nC; i += GT) { W.rowcnt[i] = 0; W.colcnt[i] = 0; W.fill[i] = 0; }
+    __syncthreads();
+    const int ncomp = block_exclusive_scan(W.isroot, nC, sm.s_warp, &sm.s_carry);
+    for (int i = tid; i < nC; i += GT) {
+      const int r = W.clist[i];
+      if (W.label[r] == r) W.compidx[r] = W.isroot[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < nC; i += GT) atomicAdd(&W.rowcnt[W.compidx[W.label[W.clist[i]]]], 1);
+    for (int c = tid; c < m; c += GT) {
+      const int l = W.collabel[c];
+      if (l != kInf) atomicAdd(&W.colcnt[W.compidx[l]], 1);
+    }
+    __syncthreads();
+    block_exclusive_scan(W.rowcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+    block_exclusive_scan(W.colcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
+    for (int i = tid; i < nC; i += GT) {
+      const int r = W.clist[i];
+      const int q = W.compidx[W.label[r]];
+      W.sorted_rows[W.rowcnt[q] + atomicAdd(&W.fill[q], 1)] = r;
+    }
+    __syncthreads();
+    const SolveArrays GA{W.rowcnt, W.colcnt, W.sorted_rows, W.touched, W.treerows, W.u, W.v, W.dist,
+                         W.pathrow, W.seen, W.insc, nullptr, (size_t)cand.stride};
+    for (int comp = warp; comp < ncomp; comp += NW)
+      solve_component(GA, comp, thresh, col_block, cnt, ecol, ecost, x, y, lane);
+    dbg_ncomp = ncomp;
+  }
+  (void)kb;
+}
 
 // One CTA per video stream solves the (up to three chained) association stages of its frame.
 __global__ void __launch_bounds__(kLapThreads, 1)
@@ -550,7 +961,8 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
     W.collabel += co; W.v += co; W.dist += co; W.pathrow += co; W.seen += co; W.insc += co; W.touched += co;
     W.counters += (size_t)sid * 8;
   }
-  unsigned long long tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long* tq = sm.tq;
+#undef LAP_T
 #define LAP_T(i) do { if (P.debug && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tq[i])); } while (0)
   LAP_T(0);
 
@@ -564,6 +976,18 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
   if (tid == 0 && B.zero_word[kb]) *B.zero_word[kb] = 0;
   // Everything above touches only this kernel's own outputs, so under programmatic dependent launch it
   // runs while the emitting kernel drains; the candidate lists are read below.
+  // ---- dry run on the ctx's two-row dummy lists (see lap_stage): instruction-cache warm-up under the wait ----
+  if (P.nstages == 3) {
+    StageArgs& wa = sm.sa;
+    if (tid == 0) {
+    wa.cand = ws_base.warm; wa.W = W; wa.kb = kb; wa.list = 0; wa.n = 2; wa.m = 3; wa.clear = 0; wa.debug = 0;
+    wa.thresh = 0.8; wa.x = ws_base.warm_xy + (size_t)sid * 8; wa.y = wa.x + 4; wa.row_block = nullptr; wa.col_block = nullptr; wa.tq = nullptr;
+    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.big = 0;
+    }
+    __syncthreads();
+    lap_stage(B, rf, sm);
+    __syncthreads();
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   LAP_T(1);
@@ -571,393 +995,26 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
   for (int stage = 0; stage < P.nstages; ++stage) {
     const int list = P.nstages == 1 ? P.list0 : stage;
     if (cand.total[list] == 0) continue;   // nothing was emitted for this stage (CTA-uniform)
-    const double thresh = P.thresh[stage];
-    int32_t* x = B.x[kb] + (size_t)stage * B.x_stride[kb];
-    int32_t* y = B.y[kb] + (size_t)stage * B.y_stride;
+    StageArgs& sa = sm.sa;
+    if (tid == 0) {
+    sa.cand = cand; sa.W = W; sa.kb = kb; sa.list = list; sa.n = n; sa.m = m; sa.clear = P.clear_lists; sa.debug = P.debug;
+    sa.thresh = P.thresh[stage];
+    sa.x = B.x[kb] + (size_t)stage * B.x_stride[kb];
+    sa.y = B.y[kb] + (size_t)stage * B.y_stride;
     // stage 2 (demo:1568-1571): rows unmatched in stage 1; stage 3 (demo:1588-1604): columns unmatched in stage 1
-    const int32_t* row_block = (P.nstages == 3 && stage == 1) ? B.x[kb] : nullptr;
-    const int32_t* col_block = (P.nstages == 3 && stage == 2) ? B.y[kb] : nullptr;
-    int32_t* segcnt_all = cand.cnt + (size_t)list * cand.rows_cap * cand.nseg;
-    int32_t* ecol = cand.col + (size_t)list * cand.rows_cap * cand.stride;
-    double* ecost = cand.cost + (size_t)list * cand.rows_cap * cand.stride;
-    int32_t* indeg = cand.indeg + (size_t)list * cand.cols_cap;
-    if (tid == 0) { sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.big = 0; }
-    __syncthreads();
-
-    // ---- P1: classify every row from the emitters' degree bookkeeping (no edge traversal for the bulk):
-    //      isolated edges (row degree 1, column in-degree 1, gate decision not in doubt) are final; rows
-    //      with several candidates, a contested column or an ambiguous gate are "complex" ----
-    for (int r0 = tid; r0 < n; r0 += 2 * GT) {
-      // two rows per thread and pass, all their loads in flight before the first dependent one: the phase is a
-      // chain of L2 round trips (degree -> the row's column -> that column's in-degree)
-      int rr[2] = {r0, r0 + GT}, degs[2], rcs[2], inds[2];
-      unsigned long long masks[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        degs[q] = 0; rcs[q] = 0; masks[q] = 0ull;
-        if (rr[q] < n) {
-          const size_t ri = (size_t)list * cand.rows_cap + rr[q];
-          degs[q] = cand.rowdeg[ri]; rcs[q] = cand.rowcol[ri]; masks[q] = cand.segmask[ri];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) inds[q] = (degs[q] == 1) ? indeg[rcs[q] & BT_EDGE_COLMASK] : 0;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int r = rr[q], deg = degs[q], rc = rcs[q];
-        if (deg == 0) continue;                      // nothing was emitted for this row
-        const size_t ri = (size_t)list * cand.rows_cap + r;
-        const int col1 = rc & BT_EDGE_COLMASK;
-        const unsigned long long mask = masks[q];
-        if (P.clear_lists) { cand.rowdeg[ri] = 0; cand.segmask[ri] = 0ull; }
-        const bool row_on = row_block == nullptr || row_block[r] < 0;
-        bool complex_row = row_on;
-        if (row_on && deg == 1) {
-          const bool col_ok = edge_ok(col_block, col1);
-          if (!col_ok) complex_row = false;            // its only column is taken already
-          else if (inds[q] == 1 && !(rc & BT_EDGE_AMBIG)) {
-            x[r] = col1; y[col1] = r;                  // isolated edge
-            complex_row = false;
-          }
-        }
-        if (!complex_row) {
-          if (P.clear_lists) {                          // leave the segment counters zeroed
-            unsigned long long mm = mask;
-            while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
-          }
-          continue;
-        }
-        const int kc = atomicAdd(&sm.nC, 1);
-        const int e0 = atomicAdd(&sm.nE, deg);
-        W.clist[kc] = r;
-        if (kc < kSmallRows && e0 + deg <= kSmallEdges) {
-          sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0; sm.rmask[kc] = mask;
-        } else {
-          sm.big = 1;
-        }
-      }
+    sa.row_block = (P.nstages == 3 && stage == 1) ? B.x[kb] : nullptr;
+    sa.col_block = (P.nstages == 3 && stage == 2) ? B.y[kb] : nullptr;
+    sa.tq = nullptr;
+    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.big = 0;
     }
     __syncthreads();
-    LAP_T(2);
-    const int nC = sm.nC;
-    if (P.clear_lists)                              // every read of the in-degrees is behind us
-      for (int c = tid; c < cand.cols_cap; c += GT) indeg[c] = 0;
-    const bool big = sm.big != 0 || m > kSmallCols;
-    int dbg_ncomp = 0;
-
-    if (nC > 0 && !big) {
-      // ---- S1: ascending row order (deterministic tie-breaking), by rank ----
-      {
-        int my_r = 0, my_deg = 0, my_start = 0, rank = 0;
-        unsigned long long my_mask = 0;
-        if (tid < nC) {
-          my_r = sm.rg[tid]; my_deg = sm.rdeg[tid]; my_start = sm.rstart[tid]; my_mask = sm.rmask[tid];
-          for (int j = 0; j < nC; ++j) rank += (sm.rg[j] < my_r) ? 1 : 0;
-        }
-        __syncthreads();
-        if (tid < nC) { sm.rg[rank] = my_r; sm.rdeg[rank] = my_deg; sm.rstart[rank] = my_start; sm.rmask[rank] = my_mask; }
-      }
-      // per-column solver state (global column ids)
-      for (int c = tid; c < m; c += GT) { sm.v[c] = 0.0; sm.seen[c] = 0; sm.insc[c] = 0; sm.yl[c] = -1; sm.clabel[c] = kInf; }
-      __syncthreads();
-      // ---- S2: gather the rows' segments into the shared-memory CSR: one warp per row, lanes over segments ----
-      for (int i = warp; i < nC; i += NW) {
-        const int r = sm.rg[i];
-        const size_t ri = (size_t)list * cand.rows_cap + r;
-        const unsigned long long mask = sm.rmask[i];
-        int32_t* segcnt = cand.cnt + ri * cand.nseg;
-        const int g0 = lane, g1 = lane + 32;
-        int k0 = ((mask >> g0) & 1ull) ? segcnt[g0] : 0;
-        int k1 = ((mask >> g1) & 1ull) ? segcnt[g1] : 0;
-        if (P.clear_lists) { if ((mask >> g0) & 1ull) segcnt[g0] = 0; if ((mask >> g1) & 1ull) segcnt[g1] = 0; }
-        int p0 = k0, p1 = k1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t0 = __shfl_up_sync(0xffffffffu, p0, o), t1 = __shfl_up_sync(0xffffffffu, p1, o);
-          if (lane >= o) { p0 += t0; p1 += t1; }
-        }
-        const int tot0 = __shfl_sync(0xffffffffu, p0, 31);
-        p0 -= k0; p1 += tot0 - k1;
-        const int e0 = sm.rstart[i];
-        const int32_t* rc = ecol + (size_t)r * cand.stride;
-        const double* rv = ecost + (size_t)r * cand.stride;
-        // while gathering: the row's cheapest and second cheapest usable edge (provisional costs)
-        double b1 = kBlockedCost, b2 = kBlockedCost;
-        int bc = kInf, amb = 0;
-        for (int half = 0; half < 2; ++half) {
-          const int kk = half ? k1 : k0, dst0 = e0 + (half ? p1 : p0), src0 = (half ? g1 : g0) * cand.seg;
-          for (int j = 0; j < kk; ++j) {
-            const int colf = rc[src0 + j];
-            const int col = colf & BT_EDGE_COLMASK;
-            const bool ok = edge_ok(col_block, col);
-            const double cst = ok ? rv[src0 + j] : kBlockedCost;
-            sm.ecol[dst0 + j] = col;
-            sm.ecst[dst0 + j] = cst;
-            if (ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG))) sm.rlist[atomicAdd(&sm.nR, 1)] = (i << 12) | (dst0 + j);
-            if (ok) {
-              if (colf & BT_EDGE_AMBIG) amb = 1;
-              if (cst < b1 || (cst == b1 && col < bc)) { b2 = b1; b1 = cst; bc = col; }
-              else if (cst < b2) b2 = cst;
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
-          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-          amb |= __shfl_xor_sync(0xffffffffu, amb, o);
-          if (ob1 < b1 || (ob1 == b1 && oc < bc)) { b2 = fmin(b1, ob2); b1 = ob1; bc = oc; }
-          else b2 = fmin(b2, ob1);
-        }
-        if (lane == 0) {
-          // decided without looking at anybody else: no gate in doubt, and the row's choice cannot change within
-          // the error of a tensor-core similarity (its runner-up is out of reach or clearly worse)
-          const bool decided = !amb && (b1 >= thresh || b2 >= thresh || b2 - b1 > kTieGap);
-          sm.xl[i] = (b1 < thresh) ? bc : -1;
-          sm.isroot[i] = decided ? 1 : 0;
-        }
-      }
-      if (tid == 0) sm.changed = 0;
-      __syncthreads();
-      LAP_T(5);
-      // ---- S2b: every complex row takes its cheapest edge -- if those choices are decided and pairwise
-      //      distinct they are the optimum (each row at its own lower bound), which is the usual frame ----
-      for (int i = tid; i < nC; i += GT) {
-        const int c = sm.xl[i];
-        bool clash = sm.isroot[i] == 0;
-        if (c >= 0 && atomicCAS(&sm.yl[c], -1, i) != -1) clash = true;
-        if (clash) sm.changed = 1;
-      }
-      __syncthreads();
-      const bool greedy_ok = sm.changed == 0;
-      __syncthreads();
-      if (greedy_ok) {
-        for (int i = tid; i < nC; i += GT) {
-          const int c = sm.xl[i];
-          if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
-        }
-        dbg_ncomp = -1;
-        LAP_T(3);
-      } else {
-      for (int i = tid; i < nC; i += GT) {
-        const int c = sm.xl[i];
-        if (c >= 0) sm.yl[c] = -1;
-      }
-      __syncthreads();
-      // ---- S3: exact re-costing of the flagged edges, one warp each ----
-      {
-        const int nR = sm.nR;
-        for (int q = warp; q < nR; q += NW) {
-          const int i = sm.rlist[q] >> 12, e = sm.rlist[q] & 4095;
-          const double c = refine_cost(rf, B, kb, list, sm.rg[i], sm.ecol[e], lane);
-          if (lane == 0) sm.ecst[e] = c;
-        }
-      }
-      for (int i = tid; i < nC; i += GT) { sm.xl[i] = -1; sm.u[i] = 0.0; sm.rlabel[i] = i; }
-      __syncthreads();
-      LAP_T(3);
-      const SolveArrays A{sm.rowcnt, sm.colcnt, sm.sorted_rows, sm.touched, sm.treerows, sm.u, sm.v, sm.dist,
-                          sm.pathrow, sm.seen, sm.insc, sm.rstart, 0};
-      if (nC <= kOneWarpRows) {
-        // ---- a handful of rows: one warp runs the shortest-augmenting-path solver over all of them ----
-        if (warp == 0) {
-          if (lane < nC) sm.sorted_rows[lane] = lane;
-          if (lane == 0) { sm.rowcnt[0] = 0; sm.rowcnt[1] = nC; sm.colcnt[0] = 0; sm.colcnt[1] = 0; }
-          __syncwarp();
-          solve_component(A, 0, thresh, nullptr, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl, lane);
-        }
-        dbg_ncomp = 1;
-      } else {
-        // ---- S4: components by min-label propagation + pointer jumping (shared memory) ----
-        while (true) {
-          if (tid == 0) sm.changed = 0;
-          __syncthreads();
-          bool changed = false;
-          for (int i = tid; i < nC; i += GT) {
-            int lr = sm.rlabel[i];
-            const int l0 = lr;
-            for (int q = sm.rstart[i]; q < sm.rstart[i] + sm.rdeg[i]; ++q) {
-              const int c = sm.ecol[q];
-              const int lc = sm.clabel[c];
-              if (lc < lr) lr = lc;
-              else if (lc > lr) { atomicMin(&sm.clabel[c], lr); changed = true; }
-            }
-            if (lr < l0) { atomicMin(&sm.rlabel[i], lr); changed = true; }
-          }
-          __syncthreads();
-          for (int i = tid; i < nC; i += GT) {
-            const int l = sm.rlabel[i];
-            const int ll = sm.rlabel[l];
-            if (ll < l) { atomicMin(&sm.rlabel[i], ll); changed = true; }
-          }
-          if (changed) sm.changed = 1;
-          __syncthreads();
-          const int any = sm.changed;
-          __syncthreads();
-          if (!any) break;
-        }
-        // ---- S5: grouping ----
-        for (int i = tid; i < nC; i += GT) sm.isroot[i] = (sm.rlabel[i] == i) ? 1 : 0;
-        for (int i = tid; i <= nC; i += GT) { sm.rowcnt[i] = 0; sm.colcnt[i] = 0; sm.fill[i] = 0; }
-        __syncthreads();
-        const int ncomp = block_exclusive_scan(sm.isroot, nC, sm.s_warp, &sm.s_carry);
-        for (int i = tid; i < nC; i += GT)
-          if (sm.rlabel[i] == i) sm.compidx[i] = sm.isroot[i];
-        __syncthreads();
-        for (int i = tid; i < nC; i += GT) atomicAdd(&sm.rowcnt[sm.compidx[sm.rlabel[i]]], 1);
-        for (int c = tid; c < m; c += GT)
-          if (sm.clabel[c] != kInf) atomicAdd(&sm.colcnt[sm.compidx[sm.clabel[c]]], 1);
-        __syncthreads();
-        block_exclusive_scan(sm.rowcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
-        block_exclusive_scan(sm.colcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
-        for (int i = tid; i < nC; i += GT) {
-          const int q = sm.compidx[sm.rlabel[i]];
-          sm.sorted_rows[sm.rowcnt[q] + atomicAdd(&sm.fill[q], 1)] = i;
-        }
-        __syncthreads();
-        // ---- S6: tiny components one thread each, the others one warp each ----
-        constexpr int kSerialRows = 6;
-        for (int comp = tid; comp < ncomp; comp += GT) {
-          const int nr = sm.rowcnt[comp + 1] - sm.rowcnt[comp];
-          if (nr <= 3) solve_component_enum(A, comp, thresh, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl);
-          else if (nr <= kSerialRows) solve_component_serial(A, comp, thresh, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl);
-        }
-        __syncwarp();
-        for (int comp = warp; comp < ncomp; comp += NW)
-          if (sm.rowcnt[comp + 1] - sm.rowcnt[comp] > kSerialRows)
-            solve_component(A, comp, thresh, nullptr, sm.rdeg, sm.ecol, sm.ecst, sm.xl, sm.yl, lane);
-        dbg_ncomp = ncomp;
-      }
-      __syncthreads();
-      // ---- S7: write back ----
-      for (int i = tid; i < nC; i += GT) {
-        const int c = sm.xl[i];
-        if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
-      }
-      }   // general (non-greedy) path
-    } else if (nC > 0) {
-      // ---- large complex part (a crowded scene, a dense cost matrix, more detections than the on-chip
-      //      arrays hold): same algorithm over global scratch ----
-      int32_t* cnt = cand.deg + (size_t)list * cand.rows_cap;
-      for (int c = tid; c < m; c += GT) { W.collabel[c] = kInf; W.v[c] = 0.0; W.seen[c] = 0; W.insc[c] = 0; }
-      for (int r = tid; r < n; r += GT) { W.u[r] = 0.0; W.label[r] = kInf; }
-      if (tid < 8) W.counters[tid] = 0;
-      __syncthreads();
-      // compact the complex rows' segments in place (ascending copy), one thread per row
-      for (int i = tid; i < nC; i += GT) {
-        const int r = W.clist[i];
-        const size_t ri = (size_t)list * cand.rows_cap + r;
-        // rows that made it into the on-chip arrays still have their segment mask in shared memory; the
-        // others lost it with the clearing above -- walk all segments of those
-        unsigned long long mask = ~0ull;
-        int32_t* segcnt = cand.cnt + ri * cand.nseg;
-        int32_t* rc = ecol + (size_t)r * cand.stride;
-        double* rv = ecost + (size_t)r * cand.stride;
-        int total = 0;
-        for (int g = 0; g < cand.nseg; ++g) {
-          if (!((mask >> g) & 1ull)) continue;
-          const int kk = segcnt[g];
-          if (kk == 0) continue;
-          if (P.clear_lists) segcnt[g] = 0;
-          const int src = g * cand.seg;
-          for (int e = 0; e < kk; ++e) {
-            if (src + e != total) { rc[total] = rc[src + e]; rv[total] = rv[src + e]; }
-            ++total;
-          }
-        }
-        cnt[r] = total;
-        W.label[r] = r;
-      }
-      __syncthreads();
-      // exact re-costing of the flagged edges: one warp per row, flagged edges one after the other
-      for (int i = warp; i < nC; i += NW) {
-        const int r = W.clist[i];
-        const int deg = cnt[r];
-        int32_t* rc = ecol + (size_t)r * cand.stride;
-        double* rv = ecost + (size_t)r * cand.stride;
-        for (int q0 = 0; q0 < deg; q0 += 32) {
-          const int q = q0 + lane;
-          const int colf = q < deg ? rc[q] : 0;
-          const bool ok = q < deg && edge_ok(col_block, colf & BT_EDGE_COLMASK);
-          unsigned todo = __ballot_sync(0xffffffffu, ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG)));
-          while (todo) {
-            const int bsrc = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int col = __shfl_sync(0xffffffffu, colf, bsrc) & BT_EDGE_COLMASK;
-            const double c = refine_cost(rf, B, kb, list, r, col, lane);
-            if (lane == bsrc) rv[q] = c;
-          }
-          if (q < deg) rc[q] = colf & BT_EDGE_COLMASK;
-        }
-      }
-      __syncthreads();
-      // components of the complex part
-      for (int iter = 0;; ++iter) {
-        int32_t* flag = &W.counters[2 + (iter & 1)];
-        bool changed = false;
-        for (int i = tid; i < nC; i += GT) {
-          const int r = W.clist[i];
-          int lr = W.label[r];
-          const int l0 = lr;
-          const int deg = cnt[r];
-          const int32_t* e = ecol + (size_t)r * cand.stride;
-          for (int q = 0; q < deg; ++q) {
-            const int c = e[q];
-            if (!edge_ok(col_block, c)) continue;
-            const int lc = W.collabel[c];
-            if (lc < lr) lr = lc;
-            else if (lc > lr) { atomicMin(&W.collabel[c], lr); changed = true; }
-          }
-          if (lr < l0) { atomicMin(&W.label[r], lr); changed = true; }
-        }
-        __syncthreads();
-        for (int i = tid; i < nC; i += GT) {
-          const int r = W.clist[i];
-          const int l = W.label[r];
-          const int ll = W.label[l];
-          if (ll < l) { atomicMin(&W.label[r], ll); changed = true; }
-        }
-        if (changed) *flag = 1;
-        if (tid == 0) W.counters[2 + ((iter + 1) & 1)] = 0;   // the other flag, for the next round
-        __syncthreads();
-        if (*flag == 0) break;
-      }
-      // component bookkeeping
-      for (int i = tid; i < nC; i += GT) W.isroot[i] = (W.label[W.clist[i]] == W.clist[i]) ? 1 : 0;
-      for (int i = tid; i <= nC; i += GT) { W.rowcnt[i] = 0; W.colcnt[i] = 0; W.fill[i] = 0; }
-      __syncthreads();
-      const int ncomp = block_exclusive_scan(W.isroot, nC, sm.s_warp, &sm.s_carry);
-      for (int i = tid; i < nC; i += GT) {
-        const int r = W.clist[i];
-        if (W.label[r] == r) W.compidx[r] = W.isroot[i];
-      }
-      __syncthreads();
-      for (int i = tid; i < nC; i += GT) atomicAdd(&W.rowcnt[W.compidx[W.label[W.clist[i]]]], 1);
-      for (int c = tid; c < m; c += GT) {
-        const int l = W.collabel[c];
-        if (l != kInf) atomicAdd(&W.colcnt[W.compidx[l]], 1);
-      }
-      __syncthreads();
-      block_exclusive_scan(W.rowcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
-      block_exclusive_scan(W.colcnt, ncomp + 1, sm.s_warp, &sm.s_carry);
-      for (int i = tid; i < nC; i += GT) {
-        const int r = W.clist[i];
-        const int q = W.compidx[W.label[r]];
-        W.sorted_rows[W.rowcnt[q] + atomicAdd(&W.fill[q], 1)] = r;
-      }
-      __syncthreads();
-      const SolveArrays GA{W.rowcnt, W.colcnt, W.sorted_rows, W.touched, W.treerows, W.u, W.v, W.dist,
-                           W.pathrow, W.seen, W.insc, nullptr, (size_t)cand.stride};
-      for (int comp = warp; comp < ncomp; comp += NW)
-        solve_component(GA, comp, thresh, col_block, cnt, ecol, ecost, x, y, lane);
-      dbg_ncomp = ncomp;
-    }
+    lap_stage(B, rf, sm);
     __syncthreads();                                  // x / y of this stage gate the next one
     if (P.clear_lists && tid == 0) cand.total[list] = 0;
     LAP_T(4);
     if (P.debug && tid == 0)
-      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d comps=%d big=%d | init %llu classify %llu gather %llu (to recost/greedy end %llu) solve %llu ns\n",
-             sid, stage, n, m, nC, sm.nE, sm.nR, dbg_ncomp, (int)big, tq[1] - tq[0], tq[2] - tq[1], tq[5] - tq[2], tq[3] - tq[2], tq[4] - tq[3]);
+      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d | init %llu classify %llu gather %llu (to recost/greedy end %llu) solve %llu ns\n",
+             sid, stage, n, m, sm.nC, sm.nE, sm.nR, tq[1] - tq[0], tq[2] - tq[1], tq[5] - tq[2], tq[3] - tq[2], tq[4] - tq[3]);
     LAP_T(1);
   }
 }
@@ -1062,6 +1119,46 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
 #undef BT_LAP_ALLOC
   BT_CUDA(cudaMalloc(&ws->x, sizeof(int32_t) * rows));
   BT_CUDA(cudaMalloc(&ws->y, sizeof(int32_t) * cols));
+  {
+    // dummy lists: rows 0 and 1 with two candidates each (row 0: columns 0, 1; row 1: columns 1, 2), so both are
+    // "complex" rows whose cheapest edges are distinct: classification, gather and the greedy check all run
+    bt_cand& w = ws->warm;
+    w.rows_cap = 4; w.cols_cap = 4; w.nseg = BT_CAND_MAXSEG; w.seg = 128; w.stride = 256;
+    const size_t n_cnt = 3 * 4 * BT_CAND_MAXSEG, n_edges = 3 * 4 * 256;
+    const size_t bytes = sizeof(int32_t) * (n_cnt + 4 + 12 + 12 + 12 + 12) + sizeof(unsigned long long) * 12 +
+                         sizeof(int32_t) * n_edges + sizeof(double) * n_edges + 64;
+    std::vector<char> h(bytes, 0);
+    BT_CUDA(cudaMalloc(&ws->warm_blk, bytes));
+    size_t off = 0;
+    auto carve = [&](size_t nbytes, size_t align) { off = (off + align - 1) & ~(align - 1); const size_t o = off; off += nbytes; return o; };
+    const size_t o_cost = carve(sizeof(double) * n_edges, 8), o_mask = carve(sizeof(unsigned long long) * 12, 8);
+    const size_t o_cnt = carve(sizeof(int32_t) * n_cnt, 4), o_total = carve(16, 4), o_rowdeg = carve(48, 4), o_indeg = carve(48, 4),
+                 o_rowcol = carve(48, 4), o_deg = carve(48, 4), o_col = carve(sizeof(int32_t) * n_edges, 4);
+    double* hc = reinterpret_cast<double*>(h.data() + o_cost);
+    int32_t* hcol = reinterpret_cast<int32_t*>(h.data() + o_col);
+    int32_t* hcnt = reinterpret_cast<int32_t*>(h.data() + o_cnt);
+    hcol[0 * 256 + 0] = 0; hc[0 * 256 + 0] = 0.1; hcol[0 * 256 + 1] = 1; hc[0 * 256 + 1] = 0.5;
+    hcol[1 * 256 + 0] = 1; hc[1 * 256 + 0] = 0.1; hcol[1 * 256 + 1] = 2; hc[1 * 256 + 1] = 0.6;
+    hcnt[0 * BT_CAND_MAXSEG] = 2; hcnt[1 * BT_CAND_MAXSEG] = 2;
+    reinterpret_cast<unsigned long long*>(h.data() + o_mask)[0] = 1ull;
+    reinterpret_cast<unsigned long long*>(h.data() + o_mask)[1] = 1ull;
+    reinterpret_cast<int32_t*>(h.data() + o_total)[0] = 4;
+    reinterpret_cast<int32_t*>(h.data() + o_rowdeg)[0] = 2; reinterpret_cast<int32_t*>(h.data() + o_rowdeg)[1] = 2;
+    int32_t* hin = reinterpret_cast<int32_t*>(h.data() + o_indeg);
+    hin[0] = 1; hin[1] = 2; hin[2] = 1;
+    BT_CUDA(cudaMemcpy(ws->warm_blk, h.data(), bytes, cudaMemcpyHostToDevice));
+    char* d = ws->warm_blk;
+    w.cost = reinterpret_cast<double*>(d + o_cost);
+    w.segmask = reinterpret_cast<unsigned long long*>(d + o_mask);
+    w.cnt = reinterpret_cast<int32_t*>(d + o_cnt);
+    w.total = reinterpret_cast<int32_t*>(d + o_total);
+    w.rowdeg = reinterpret_cast<int32_t*>(d + o_rowdeg);
+    w.indeg = reinterpret_cast<int32_t*>(d + o_indeg);
+    w.rowcol = reinterpret_cast<int32_t*>(d + o_rowcol);
+    w.deg = reinterpret_cast<int32_t*>(d + o_deg);
+    w.col = reinterpret_cast<int32_t*>(d + o_col);
+    BT_CUDA(cudaMalloc(&ws->warm_xy, sizeof(int32_t) * 8 * (size_t)S));
+  }
   return BT_OK;
 }
 
@@ -1071,7 +1168,7 @@ void bt_lap_ws_destroy(bt_ctx* ctx) {
   void* ptrs[] = {ws->cand.cnt, ws->cand.rowcol, ws->cand.deg, ws->cand.col, ws->cand.cost, ws->label, ws->collabel,
                   ws->clist, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
                   ws->sorted_rows, ws->counters, ws->u, ws->v, ws->dist, ws->pathrow, ws->seen, ws->insc,
-                  ws->touched, ws->treerows, ws->x, ws->y};
+                  ws->touched, ws->treerows, ws->x, ws->y, ws->warm_blk, ws->warm_xy};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   delete ws;

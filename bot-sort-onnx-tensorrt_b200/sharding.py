@@ -1,6 +1,9 @@
 """Multi-GPU plumbing: video streams are independent, so the path shards by
-stream with NO data-path collective.  One process per GPU (torchrun); torch.distributed is used only
-for the barrier around the timed region and the max-over-ranks of the per-rank timings."""
+stream and no collective exists INSIDE the algorithm.  One process per GPU (torchrun, NCCL); the only
+communication is the per-stream scatter of a frame's detector outputs from the producer rank to the ranks that
+own the streams and the gather of their results (BASELINE config 5: "NCCL only for the trivial per-stream
+scatter"), plus the barrier / max-over-ranks of the timings.  Everything here works on whatever backend the
+default process group uses (NCCL + device tensors on the GPUs, gloo + CPU tensors in the tests)."""
 from __future__ import annotations
 
 from typing import List, Sequence
@@ -30,3 +33,131 @@ def max_over_ranks(values: Sequence[float], device="cpu") -> List[float]:
 def aggregate_throughput(units_per_rank: int, world: int, steps: int, max_total_ms: float) -> float:
     """Whole-job units/s: all ranks' units over the slowest rank's time."""
     return units_per_rank * world * steps / (max_total_ms / 1e3)
+
+
+# ---- per-stream scatter / gather (BASELINE config 5) -------------------------------------------------------
+# One frame of one video stream travels as a fixed-size int32 slot (so that a rank's streams are one contiguous
+# message and `dist.scatter` needs no size negotiation):
+#     [m | boxes int32[4*cap] | scores float32 bits [cap] | gt int32[cap]]
+# and its result as
+#     [n | ids int32[cap] | tlbr float64 bits [8*cap]]
+def frame_slot_ints(cap: int) -> int:
+    return 1 + 6 * cap
+
+
+def result_slot_ints(cap: int) -> int:
+    return 1 + 9 * cap
+
+
+def pack_frame(boxes, scores, gt, cap: int):
+    """boxes int32[m,4], scores float32[m], gt int[m] -> int32[frame_slot_ints(cap)] (NumPy)."""
+    import numpy as np
+    m = int(len(boxes))
+    if m > cap:
+        raise ValueError(f"{m} detections exceed the slot capacity {cap}")
+    out = np.zeros(frame_slot_ints(cap), np.int32)
+    out[0] = m
+    out[1:1 + 4 * m] = np.asarray(boxes, np.int32).reshape(-1)
+    out[1 + 4 * cap:1 + 4 * cap + m] = np.asarray(scores, np.float32).view(np.int32)
+    out[1 + 5 * cap:1 + 5 * cap + m] = np.asarray(gt).astype(np.int32)
+    return out
+
+
+def unpack_frame(slot, cap: int):
+    """Inverse of pack_frame on a torch or NumPy int32 vector: (m, boxes[m,4], scores[m] float32, gt[m])."""
+    m = int(slot[0])
+    boxes = slot[1:1 + 4 * m].reshape(m, 4)
+    sc_bits = slot[1 + 4 * cap:1 + 4 * cap + m]
+    scores = None
+    try:
+        import torch
+        if isinstance(slot, torch.Tensor):
+            scores = sc_bits.view(torch.float32)
+    except ImportError:      # pragma: no cover
+        pass
+    if scores is None:
+        import numpy as np
+        scores = np.asarray(sc_bits).view(np.float32)
+    gt = slot[1 + 5 * cap:1 + 5 * cap + m]
+    return m, boxes, scores, gt
+
+
+def pack_result(ids, tlbr, cap: int):
+    import numpy as np
+    n = int(len(ids))
+    out = np.zeros(result_slot_ints(cap), np.int32)
+    out[0] = n
+    out[1:1 + n] = np.asarray(ids, np.int32)
+    out[1 + cap:1 + cap + 8 * n] = np.ascontiguousarray(tlbr, np.float64).reshape(-1).view(np.int32)
+    return out
+
+
+def unpack_result(slot, cap: int):
+    import numpy as np
+    slot = np.asarray(slot)
+    n = int(slot[0])
+    ids = slot[1:1 + n].copy()
+    tlbr = slot[1 + cap:1 + cap + 8 * n].copy().view(np.float64).reshape(n, 4)
+    return ids, tlbr
+
+
+def scatter_streams(packed_all, n_streams: int, slot_ints: int, src: int = 0, device="cpu"):
+    """Per-stream scatter: `packed_all` (rank `src` only; int32 tensor [n_streams, slot_ints] on `device`) is cut
+    into the contiguous stream blocks of shard_streams() and scattered; returns this rank's [my_streams, slot_ints]."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    mine = shard_streams(n_streams, world, rank)
+    if world == 1:
+        return packed_all
+    recv = torch.empty((len(mine), slot_ints), dtype=torch.int32, device=device)
+    if rank == src:
+        parts = []
+        for r in range(world):
+            ids = shard_streams(n_streams, world, r)
+            parts.append(packed_all[ids[0]:ids[-1] + 1].contiguous() if ids else torch.empty((0, slot_ints), dtype=torch.int32, device=device))
+        sizes = {p.shape[0] for p in parts}
+        if len(sizes) == 1:
+            dist.scatter(recv, parts, src=src)
+        else:                     # ragged partition: point-to-point
+            reqs = [dist.isend(parts[r], dst=r) for r in range(world) if r != src and parts[r].numel()]
+            recv.copy_(parts[src])
+            for q in reqs:
+                q.wait()
+    else:
+        sizes_equal = n_streams % world == 0
+        if sizes_equal:
+            dist.scatter(recv, None, src=src)
+        elif recv.numel():
+            dist.recv(recv, src=src)
+    return recv
+
+
+def gather_streams(mine_packed, n_streams: int, slot_ints: int, dst: int = 0, device="cpu"):
+    """Inverse: every rank's [my_streams, slot_ints] results are gathered to rank `dst` as [n_streams, slot_ints]
+    (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        return mine_packed
+    if n_streams % world == 0:
+        outs = [torch.empty_like(mine_packed) for _ in range(world)] if rank == dst else None
+        dist.gather(mine_packed, outs, dst=dst)
+        return torch.cat(outs, 0) if rank == dst else None
+    if rank == dst:
+        outs = []
+        for r in range(world):
+            ids = shard_streams(n_streams, world, r)
+            buf = torch.empty((len(ids), slot_ints), dtype=torch.int32, device=device)
+            if r == dst:
+                buf.copy_(mine_packed)
+            elif buf.numel():
+                dist.recv(buf, src=r)
+            outs.append(buf)
+        return torch.cat(outs, 0)
+    if mine_packed.numel():
+        dist.send(mine_packed, dst=dst)
+    return None

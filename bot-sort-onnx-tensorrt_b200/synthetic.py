@@ -36,6 +36,8 @@ class SceneConfig:
     feat_noise: float = 0.005       # sigma of the per-frame feature noise (per component)
     newcomer_every: int = 0         # every k frames one hidden identity starts to appear (0 = off)
     with_features: bool = True      # False => IoU-only (features all-zero rows)
+    emit_features: bool = True      # False => next_frame() returns feats=None (the features of a frame are produced
+                                    # elsewhere from `gt` and `identity`, e.g. on the GPU that owns the stream)
 
 
 class SyntheticScene:
@@ -103,7 +105,9 @@ class SyntheticScene:
             mid = (~low) & (r < cfg.low_frac + cfg.mid_frac)
             scores[low] = rng.uniform(0.15, 0.35, int(low.sum())).astype(np.float32)
             scores[mid] = rng.uniform(0.50, 0.85, int(mid.sum())).astype(np.float32)
-        if cfg.with_features:
+        if not cfg.emit_features:
+            feats = None
+        elif cfg.with_features:
             f = self.identity[ids] + cfg.feat_noise * rng.standard_normal((m, cfg.feat_dim)).astype(np.float32)
             f /= np.linalg.norm(f, axis=1, keepdims=True)
             feats = np.ascontiguousarray(f, dtype=np.float32)
