@@ -461,8 +461,10 @@ struct bt_lap_batch {
   int32_t y_stride;
   int32_t* zero_word[BT_MAX_BATCH]; // device word to clear (the frame's duplicate-pair counter)
 };
+// atomic_emitter != 0: the lists were filled by the CUDA-core kernel (atomic appends: its segment counters must be
+// left zeroed for the next frame)
 int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& b, const bt_lap_batch* db,
-                       const double thresh[3], const bt_refine& rf);
+                       const double thresh[3], const bt_refine& rf, int atomic_emitter);
 
 // ---- detector side ------------------------------------------------------------------------------
 int32_t btk_yolox_postprocess(bt_ctx* ctx, const float* raw, const bt_yolox_config& cfg,

@@ -39,6 +39,7 @@ struct bt_lap_ws {
   int32_t* label = nullptr;     // [rows]
   int32_t* collabel = nullptr;  // [cols]
   int32_t* clist = nullptr;     // [rows]  complex rows
+  unsigned long long* rmaskg = nullptr;  // [rows] their segment masks
   int32_t* compidx = nullptr;   // [rows]  component index of a root row (indexed by row)
   int32_t* isroot = nullptr;    // [rows]  scan scratch (indexed by clist position)
   int32_t* rowcnt = nullptr;    // [rows+1] per component -> exclusive scan = row_start
@@ -73,7 +74,9 @@ struct LapParams {
   int nstages;          // 1 (stand-alone: list `list0`) or 3 (the frame's chained stages: lists 0, 1, 2)
   int list0;
   double thresh[3];
-  int clear_lists;      // tracker mode: leave cnt / segmask / rowdeg / indeg / total zeroed for the next frame
+  int clear_lists;      // tracker mode: leave segmask / rowdeg / indeg / total zeroed for the next frame
+  int clear_cnt;        // ... and the segment counters too (only the CUDA-core emitter, which appends with atomics, needs
+                        // them zeroed; the tensor-core epilogue overwrites the counters of the segments it flags)
   int debug;            // BT_LAP_DEBUG=1: phase timestamps (ns) by device printf
 };
 
@@ -515,6 +518,7 @@ constexpr int kSmallRows = 512;
 constexpr int kSmallEdges = 4096;
 constexpr int kSmallCols = 2560;
 constexpr int kOneWarpRows = 4;
+constexpr int kSmallPairs = 2048;  // non-empty (row, segment) pairs of the complex rows
 constexpr double kTieGap = 1.0e-3;         // two costs closer than this may swap order within the tensor-core error
 constexpr double kBlockedCost = 1.0e300;   // an edge whose column an earlier stage took: never beats staying unmatched
 
@@ -523,7 +527,7 @@ constexpr double kBlockedCost = 1.0e300;   // an edge whose column an earlier st
 struct StageArgs {
   bt_cand cand;
   bt_lap_ws W;
-  int kb, list, n, m, clear, debug;
+  int kb, list, n, m, clear, clear_cnt, need_y, debug;
   double thresh;
   int32_t* x; int32_t* y;
   const int32_t* row_block; const int32_t* col_block;
@@ -536,17 +540,19 @@ struct SmallSmem {
   int32_t rg[kSmallRows], rdeg[kSmallRows], rstart[kSmallRows + 1], rlabel[kSmallRows], xl[kSmallRows];
   int32_t sorted_rows[kSmallRows], treerows[kSmallRows], compidx[kSmallRows], isroot[kSmallRows];
   int32_t rowcnt[kSmallRows + 1], colcnt[kSmallRows + 1], fill[kSmallRows + 1];
-  unsigned long long rmask[kSmallRows];
   double u[kSmallRows];
   int32_t ecol[kSmallEdges];
   double ecst[kSmallEdges];
   int32_t rlist[kSmallEdges];
+  int32_t pairs[kSmallPairs];
   double v[kSmallCols], dist[kSmallCols];
   int32_t pathrow[kSmallCols], seen[kSmallCols], insc[kSmallCols], yl[kSmallCols], clabel[kSmallCols], touched[kSmallCols];
   int32_t s_warp[32];
   int32_t s_carry;
-  int nC, nE, nR, changed, big;
+  int nC, nE, nR, nP, changed, big;
 };
+
+static_assert(sizeof(SmallSmem) <= 227 * 1024, "the LAP's on-chip state must fit the SM's shared memory");
 
 // One association stage of one video stream.  A real (noinline) function on purpose: the kernel calls it once on
 // a two-row dummy problem BEFORE griddepcontrol.wait -- every phase of this latency-bound kernel runs exactly once
@@ -570,57 +576,84 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
   int32_t* indeg = cand.indeg + (size_t)list * cand.cols_cap;
   // ---- P1: classify every row from the emitters' degree bookkeeping (no edge traversal for the bulk):
   //      isolated edges (row degree 1, column in-degree 1, gate decision not in doubt) are final; rows
-  //      with several candidates, a contested column or an ambiguous gate are "complex" ----
-  for (int r0 = tid; r0 < n; r0 += 2 * GT) {
-    // two rows per thread and pass, all their loads in flight before the first dependent one: the phase is a
-    // chain of L2 round trips (degree -> the row's column -> that column's in-degree)
-    int rr[2] = {r0, r0 + GT}, degs[2], rcs[2], inds[2];
-    unsigned long long masks[2];
+  //      with several candidates, a contested column or an ambiguous gate are "complex".  The phase is a chain
+  //      of dependent global round trips (degree -> the row's column -> that column's in-degree), so every
+  //      thread keeps four rows in flight and issues each level's loads for all of them together. ----
+  // One SM classifies the whole stream, and the loop is bound by instruction issue: it only does what every row
+  // needs (two loads, one dependent load, a few coalesced stores); complex rows are merely noted here and set
+  // up by the pass below.
+  constexpr int kP1 = 4;
+  LAP_T(6);
+  const size_t rbase = (size_t)list * cand.rows_cap;
+  for (int r0 = tid; r0 < n; r0 += kP1 * GT) {
+    int degs[kP1], rcs[kP1], inds[kP1], rbl[kP1];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      degs[q] = 0; rcs[q] = 0; masks[q] = 0ull;
-      if (rr[q] < n) {
-        const size_t ri = (size_t)list * cand.rows_cap + rr[q];
-        degs[q] = cand.rowdeg[ri]; rcs[q] = cand.rowcol[ri]; masks[q] = cand.segmask[ri];
+    for (int q = 0; q < kP1; ++q) {
+      const int r = r0 + q * GT;
+      degs[q] = 0; rcs[q] = 0; rbl[q] = -1;
+      if (r < n) {
+        degs[q] = cand.rowdeg[rbase + r]; rcs[q] = cand.rowcol[rbase + r];
+        if (row_block) rbl[q] = row_block[r];
       }
     }
+    if (a.debug && tid == 0) { asm volatile("" :: "r"(degs[0]), "r"(rcs[0]) : "memory"); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sm.tq[7])); }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) inds[q] = (degs[q] == 1) ? indeg[rcs[q] & BT_EDGE_COLMASK] : 0;
+    for (int q = 0; q < kP1; ++q) {
+      const int c1 = rcs[q] & BT_EDGE_COLMASK;
+      inds[q] = (degs[q] == 1) ? indeg[c1] : 0;
+      if (degs[q] == 1 && col_block && col_block[c1] >= 0) inds[q] = -1;     // its only column is taken already
+    }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int r = rr[q], deg = degs[q], rc = rcs[q];
+    for (int q = 0; q < kP1; ++q) {
+      const int r = r0 + q * GT, deg = degs[q], rc = rcs[q];
       if (deg == 0) continue;                      // nothing was emitted for this row
-      const size_t ri = (size_t)list * cand.rows_cap + r;
-      const int col1 = rc & BT_EDGE_COLMASK;
-      const unsigned long long mask = masks[q];
-      if (a.clear) { cand.rowdeg[ri] = 0; cand.segmask[ri] = 0ull; }
-      const bool row_on = row_block == nullptr || row_block[r] < 0;
-      bool complex_row = row_on;
-      if (row_on && deg == 1) {
-        const bool col_ok = edge_ok(col_block, col1);
-        if (!col_ok) complex_row = false;            // its only column is taken already
-        else if (inds[q] == 1 && !(rc & BT_EDGE_AMBIG)) {
-          x[r] = col1; y[col1] = r;                  // isolated edge
-          complex_row = false;
+      if (a.clear) cand.rowdeg[rbase + r] = 0;
+      const bool dead = rbl[q] >= 0 || (deg == 1 && inds[q] < 0);             // row matched by stage 1 / its only column taken
+      const bool simple = deg == 1 && inds[q] == 1 && !(rc & BT_EDGE_AMBIG);   // isolated edge
+      if (dead || simple) {
+        if (simple && !dead) {
+          const int col1 = rc & BT_EDGE_COLMASK;
+          x[r] = col1;
+          if (a.need_y) y[col1] = r;               // (a scattered store per row: only when somebody reads y)
         }
-      }
-      if (!complex_row) {
-        if (a.clear) {                          // leave the segment counters zeroed
-          unsigned long long mm = mask;
+        if (a.clear_cnt) {                         // atomic emitter: leave the segment counters zeroed
+          unsigned long long mm = cand.segmask[rbase + r];
           while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
         }
-        continue;
+        if (a.clear) cand.segmask[rbase + r] = 0ull;
+      } else {
+        const int kc = atomicAdd(&sm.nC, 1);
+        W.clist[kc] = r;
+        W.isroot[kc] = deg;
       }
-      const int kc = atomicAdd(&sm.nC, 1);
+    }
+  }
+  __syncthreads();
+  // ---- P1b: set up the complex rows: their segment masks, their slice of the on-chip edge arrays, one
+  //      (row, segment) work item per non-empty segment for the gather ----
+  {
+    const int nNoted = sm.nC;
+    for (int kc = tid; kc < nNoted; kc += GT) {
+      const int r = W.clist[kc], deg = W.isroot[kc];
+      const unsigned long long mask = cand.segmask[rbase + r];
+      if (a.clear) cand.segmask[rbase + r] = 0ull;
+      W.rmaskg[r] = mask;                       // (the large-problem path walks the row's segments from here)
       const int e0 = atomicAdd(&sm.nE, deg);
-      W.clist[kc] = r;
-      if (kc < kSmallRows && e0 + deg <= kSmallEdges) {
-        sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0; sm.rmask[kc] = mask;
+      if (kc < kSmallRows && e0 + deg <= kSmallEdges && r < 4096) {
+        sm.rg[kc] = r; sm.rdeg[kc] = deg; sm.rstart[kc] = e0;
+        sm.fill[kc] = 0; sm.compidx[kc] = 0;
+        unsigned long long mm = mask;
+        while (mm) {
+          const int g = __ffsll((long long)mm) - 1; mm &= mm - 1;
+          const int pi = atomicAdd(&sm.nP, 1);
+          if (pi < kSmallPairs) sm.pairs[pi] = (kc << 6) | g; else sm.big = 1;
+        }
       } else {
         sm.big = 1;
       }
     }
   }
+  if (a.debug && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(sm.tq[0]));
   __syncthreads();
   LAP_T(2);
   const int nC = sm.nC;
@@ -631,95 +664,63 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
   (void)dbg_ncomp;
 
   if (nC > 0 && !big) {
-    // ---- S1: ascending row order (deterministic tie-breaking), by rank ----
-    {
-      int my_r = 0, my_deg = 0, my_start = 0, rank = 0;
-      unsigned long long my_mask = 0;
-      if (tid < nC) {
-        my_r = sm.rg[tid]; my_deg = sm.rdeg[tid]; my_start = sm.rstart[tid]; my_mask = sm.rmask[tid];
-        for (int j = 0; j < nC; ++j) rank += (sm.rg[j] < my_r) ? 1 : 0;
-      }
-      __syncthreads();
-      if (tid < nC) { sm.rg[rank] = my_r; sm.rdeg[rank] = my_deg; sm.rstart[rank] = my_start; sm.rmask[rank] = my_mask; }
-    }
     // per-column solver state (global column ids)
     for (int c = tid; c < m; c += GT) { sm.v[c] = 0.0; sm.seen[c] = 0; sm.insc[c] = 0; sm.yl[c] = -1; sm.clabel[c] = kInf; }
-    __syncthreads();
-    // ---- S2: gather the rows' segments into the shared-memory CSR: one warp per row, lanes over segments ----
-    for (int i = warp; i < nC; i += NW) {
+    // ---- S2: gather: one thread per non-empty (row, segment) pair -- two dependent round trips for the whole
+    //      complex part (segment count -> its edges), whatever the number of rows ----
+    const int nP = sm.nP;
+    for (int q = tid; q < nP; q += GT) {
+      const int i = sm.pairs[q] >> 6, g = sm.pairs[q] & 63;
       const int r = sm.rg[i];
       const size_t ri = (size_t)list * cand.rows_cap + r;
-      const unsigned long long mask = sm.rmask[i];
       int32_t* segcnt = cand.cnt + ri * cand.nseg;
-      const int g0 = lane, g1 = lane + 32;
-      int k0 = ((mask >> g0) & 1ull) ? segcnt[g0] : 0;
-      int k1 = ((mask >> g1) & 1ull) ? segcnt[g1] : 0;
-      if (a.clear) { if ((mask >> g0) & 1ull) segcnt[g0] = 0; if ((mask >> g1) & 1ull) segcnt[g1] = 0; }
-      int p0 = k0, p1 = k1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t0 = __shfl_up_sync(0xffffffffu, p0, o), t1 = __shfl_up_sync(0xffffffffu, p1, o);
-        if (lane >= o) { p0 += t0; p1 += t1; }
-      }
-      const int tot0 = __shfl_sync(0xffffffffu, p0, 31);
-      p0 -= k0; p1 += tot0 - k1;
-      const int e0 = sm.rstart[i];
-      const int32_t* rc = ecol + (size_t)r * cand.stride;
-      const double* rv = ecost + (size_t)r * cand.stride;
-      // while gathering: the row's cheapest and second cheapest usable edge (provisional costs)
-      double b1 = kBlockedCost, b2 = kBlockedCost;
-      int bc = kInf, amb = 0;
-      for (int half = 0; half < 2; ++half) {
-        const int kk = half ? k1 : k0, dst0 = e0 + (half ? p1 : p0), src0 = (half ? g1 : g0) * cand.seg;
-        for (int j = 0; j < kk; ++j) {
-          const int colf = rc[src0 + j];
-          const int col = colf & BT_EDGE_COLMASK;
-          const bool ok = edge_ok(col_block, col);
-          const double cst = ok ? rv[src0 + j] : kBlockedCost;
-          sm.ecol[dst0 + j] = col;
-          sm.ecst[dst0 + j] = cst;
-          if (ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG))) sm.rlist[atomicAdd(&sm.nR, 1)] = (i << 12) | (dst0 + j);
-          if (ok) {
-            if (colf & BT_EDGE_AMBIG) amb = 1;
-            if (cst < b1 || (cst == b1 && col < bc)) { b2 = b1; b1 = cst; bc = col; }
-            else if (cst < b2) b2 = cst;
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob1 = __shfl_xor_sync(0xffffffffu, b1, o), ob2 = __shfl_xor_sync(0xffffffffu, b2, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-        amb |= __shfl_xor_sync(0xffffffffu, amb, o);
-        if (ob1 < b1 || (ob1 == b1 && oc < bc)) { b2 = fmin(b1, ob2); b1 = ob1; bc = oc; }
-        else b2 = fmin(b2, ob1);
-      }
-      if (lane == 0) {
-        // decided without looking at anybody else: no gate in doubt, and the row's choice cannot change within
-        // the error of a tensor-core similarity (its runner-up is out of reach or clearly worse)
-        const bool decided = !amb && (b1 >= thresh || b2 >= thresh || b2 - b1 > kTieGap);
-        sm.xl[i] = (b1 < thresh) ? bc : -1;
-        sm.isroot[i] = decided ? 1 : 0;
+      const int kk = segcnt[g];
+      if (a.clear_cnt) segcnt[g] = 0;
+      const int32_t* rc = ecol + (size_t)r * cand.stride + (size_t)g * cand.seg;
+      const double* rv = ecost + (size_t)r * cand.stride + (size_t)g * cand.seg;
+      const int dst0 = sm.rstart[i] + atomicAdd(&sm.fill[i], kk);
+      for (int j = 0; j < kk; ++j) {
+        const int colf = rc[j];
+        const int col = colf & BT_EDGE_COLMASK;
+        const bool ok = edge_ok(col_block, col);
+        sm.ecol[dst0 + j] = col;
+        sm.ecst[dst0 + j] = ok ? rv[j] : kBlockedCost;
+        if (ok && (colf & BT_EDGE_AMBIG)) sm.compidx[i] = 1;       // the row's gate decision is in doubt
+        if (ok && rf.enabled && (colf & (BT_EDGE_SIM | BT_EDGE_AMBIG))) sm.rlist[atomicAdd(&sm.nR, 1)] = (r << 12) | (dst0 + j);
       }
     }
     if (tid == 0) sm.changed = 0;
     __syncthreads();
-    LAP_T(5);
-    // ---- S2b: every complex row takes its cheapest edge -- if those choices are decided and pairwise
-    //      distinct they are the optimum (each row at its own lower bound), which is the usual frame ----
+    // the row's cheapest and second cheapest usable edge (provisional costs)
     for (int i = tid; i < nC; i += GT) {
-      const int c = sm.xl[i];
-      bool clash = sm.isroot[i] == 0;
+      double b1 = kBlockedCost, b2 = kBlockedCost;
+      int bc = kInf;
+      const int e0 = sm.rstart[i], deg = sm.rdeg[i];
+      for (int j = 0; j < deg; ++j) {
+        const double cst = sm.ecst[e0 + j];
+        const int col = sm.ecol[e0 + j];
+        if (cst < b1 || (cst == b1 && col < bc)) { b2 = b1; b1 = cst; bc = col; }
+        else if (cst < b2) b2 = cst;
+      }
+      // decided without looking at anybody else: no gate in doubt, and the row's choice cannot change within
+      // the error of a tensor-core similarity (its runner-up is out of reach or clearly worse)
+      const bool decided = sm.compidx[i] == 0 && (b1 >= thresh || b2 >= thresh || b2 - b1 > kTieGap);
+      const int c = (b1 < thresh) ? bc : -1;
+      sm.xl[i] = c;
+      // ---- S2b: every complex row takes its cheapest edge -- if those choices are decided and pairwise
+      //      distinct they are the optimum (each row at its own lower bound), which is the usual frame ----
+      bool clash = !decided;
       if (c >= 0 && atomicCAS(&sm.yl[c], -1, i) != -1) clash = true;
       if (clash) sm.changed = 1;
     }
     __syncthreads();
+    LAP_T(5);
     const bool greedy_ok = sm.changed == 0;
     __syncthreads();
     if (greedy_ok) {
       for (int i = tid; i < nC; i += GT) {
         const int c = sm.xl[i];
-        if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
+        if (c >= 0) { x[sm.rg[i]] = c; if (a.need_y) y[c] = sm.rg[i]; }
       }
       dbg_ncomp = -1;
       LAP_T(3);
@@ -729,12 +730,23 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
       if (c >= 0) sm.yl[c] = -1;
     }
     __syncthreads();
+    // ---- S1: ascending row order (deterministic tie-breaking of the general solver), by rank ----
+    {
+      int my_r = 0, my_deg = 0, my_start = 0, rank = 0;
+      if (tid < nC) {
+        my_r = sm.rg[tid]; my_deg = sm.rdeg[tid]; my_start = sm.rstart[tid];
+        for (int j = 0; j < nC; ++j) rank += (sm.rg[j] < my_r) ? 1 : 0;
+      }
+      __syncthreads();
+      if (tid < nC) { sm.rg[rank] = my_r; sm.rdeg[rank] = my_deg; sm.rstart[rank] = my_start; }
+      __syncthreads();
+    }
     // ---- S3: exact re-costing of the flagged edges, one warp each ----
     {
       const int nR = sm.nR;
       for (int q = warp; q < nR; q += NW) {
-        const int i = sm.rlist[q] >> 12, e = sm.rlist[q] & 4095;
-        const double c = refine_cost(rf, B, kb, list, sm.rg[i], sm.ecol[e], lane);
+        const int r = sm.rlist[q] >> 12, e = sm.rlist[q] & 4095;
+        const double c = refine_cost(rf, B, kb, list, r, sm.ecol[e], lane);
         if (lane == 0) sm.ecst[e] = c;
       }
     }
@@ -817,7 +829,7 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
     // ---- S7: write back ----
     for (int i = tid; i < nC; i += GT) {
       const int c = sm.xl[i];
-      if (c >= 0) { x[sm.rg[i]] = c; y[c] = sm.rg[i]; }
+      if (c >= 0) { x[sm.rg[i]] = c; if (a.need_y) y[c] = sm.rg[i]; }
     }
     }   // general (non-greedy) path
   } else if (nC > 0) {
@@ -832,9 +844,7 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
     for (int i = tid; i < nC; i += GT) {
       const int r = W.clist[i];
       const size_t ri = (size_t)list * cand.rows_cap + r;
-      // rows that made it into the on-chip arrays still have their segment mask in shared memory; the
-      // others lost it with the clearing above -- walk all segments of those
-      unsigned long long mask = ~0ull;
+      const unsigned long long mask = W.rmaskg[r];
       int32_t* segcnt = cand.cnt + ri * cand.nseg;
       int32_t* rc = ecol + (size_t)r * cand.stride;
       double* rv = ecost + (size_t)r * cand.stride;
@@ -843,7 +853,7 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
         if (!((mask >> g) & 1ull)) continue;
         const int kk = segcnt[g];
         if (kk == 0) continue;
-        if (a.clear) segcnt[g] = 0;
+        if (a.clear_cnt) segcnt[g] = 0;
         const int src = g * cand.seg;
         for (int e = 0; e < kk; ++e) {
           if (src + e != total) { rc[total] = rc[src + e]; rv[total] = rv[src + e]; }
@@ -956,7 +966,7 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
   bt_lap_ws W = ws_base;
   {
     const size_t ro = (size_t)sid * ws_base.rows_stride, co = (size_t)sid * ws_base.cols_stride;
-    W.label += ro; W.clist += ro; W.compidx += ro; W.isroot += ro; W.rowcnt += ro + sid; W.colcnt += ro + sid;
+    W.label += ro; W.clist += ro; W.rmaskg += ro; W.compidx += ro; W.isroot += ro; W.rowcnt += ro + sid; W.colcnt += ro + sid;
     W.fill += ro + sid; W.sorted_rows += ro; W.u += ro; W.treerows += ro;
     W.collabel += co; W.v += co; W.dist += co; W.pathrow += co; W.seen += co; W.insc += co; W.touched += co;
     W.counters += (size_t)sid * 8;
@@ -980,9 +990,9 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
   if (P.nstages == 3) {
     StageArgs& wa = sm.sa;
     if (tid == 0) {
-    wa.cand = ws_base.warm; wa.W = W; wa.kb = kb; wa.list = 0; wa.n = 2; wa.m = 3; wa.clear = 0; wa.debug = 0;
+    wa.cand = ws_base.warm; wa.W = W; wa.kb = kb; wa.list = 0; wa.n = 2; wa.m = 3; wa.clear = 0; wa.clear_cnt = 0; wa.need_y = 1; wa.debug = 0;
     wa.thresh = 0.8; wa.x = ws_base.warm_xy + (size_t)sid * 8; wa.y = wa.x + 4; wa.row_block = nullptr; wa.col_block = nullptr; wa.tq = nullptr;
-    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.big = 0;
+    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.nP = 0; sm.big = 0;
     }
     __syncthreads();
     lap_stage(B, rf, sm);
@@ -992,12 +1002,18 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
   __syncthreads();
   LAP_T(1);
 
+  // which stages have any candidates at all: one round trip for the three counters
+  const int tot0 = cand.total[0], tot1 = cand.total[1], tot2 = cand.total[2];
   for (int stage = 0; stage < P.nstages; ++stage) {
     const int list = P.nstages == 1 ? P.list0 : stage;
-    if (cand.total[list] == 0) continue;   // nothing was emitted for this stage (CTA-uniform)
+    if ((list == 0 ? tot0 : (list == 1 ? tot1 : tot2)) == 0) continue;   // nothing was emitted for this stage (CTA-uniform)
     StageArgs& sa = sm.sa;
     if (tid == 0) {
     sa.cand = cand; sa.W = W; sa.kb = kb; sa.list = list; sa.n = n; sa.m = m; sa.clear = P.clear_lists; sa.debug = P.debug;
+    sa.clear_cnt = P.clear_lists && P.clear_cnt;
+    // y (column -> row) of a stage is read by the caller of the stand-alone solver and, for the frame's first
+    // stage, by stage 3 (columns stage 1 took are blocked) -- when stage 3 has any candidates at all
+    sa.need_y = (P.nstages == 1) || (stage == 0 && tot2 != 0);
     sa.thresh = P.thresh[stage];
     sa.x = B.x[kb] + (size_t)stage * B.x_stride[kb];
     sa.y = B.y[kb] + (size_t)stage * B.y_stride;
@@ -1005,7 +1021,7 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
     sa.row_block = (P.nstages == 3 && stage == 1) ? B.x[kb] : nullptr;
     sa.col_block = (P.nstages == 3 && stage == 2) ? B.y[kb] : nullptr;
     sa.tq = nullptr;
-    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.big = 0;
+    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.nP = 0; sm.big = 0;
     }
     __syncthreads();
     lap_stage(B, rf, sm);
@@ -1013,8 +1029,8 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
     if (P.clear_lists && tid == 0) cand.total[list] = 0;
     LAP_T(4);
     if (P.debug && tid == 0)
-      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d | init %llu classify %llu gather %llu (to recost/greedy end %llu) solve %llu ns\n",
-             sid, stage, n, m, sm.nC, sm.nE, sm.nR, tq[1] - tq[0], tq[2] - tq[1], tq[5] - tq[2], tq[3] - tq[2], tq[4] - tq[3]);
+      printf("lap stream %d stage %d: n=%d m=%d complex=%d edges=%d flagged=%d | classify %llu [entry +%llu, level-1 loads +%llu, thread 0 done +%llu] gather %llu (to recost/greedy end %llu) solve %llu ns\n",
+             sid, stage, n, m, sm.nC, sm.nE, sm.nR, tq[2] - tq[1], tq[6] - tq[1], tq[7] - tq[1], tq[0] - tq[1], tq[5] - tq[2], tq[3] - tq[2], tq[4] - tq[3]);
     LAP_T(1);
   }
 }
@@ -1101,6 +1117,7 @@ int32_t bt_lap_ws_create(bt_ctx* ctx) {
   BT_LAP_ALLOC(label, int32_t, rows);
   BT_LAP_ALLOC(collabel, int32_t, cols);
   BT_LAP_ALLOC(clist, int32_t, rows);
+  BT_LAP_ALLOC(rmaskg, unsigned long long, rows);
   BT_LAP_ALLOC(compidx, int32_t, rows);
   BT_LAP_ALLOC(isroot, int32_t, rows);
   BT_LAP_ALLOC(rowcnt, int32_t, rows + 1);
@@ -1166,7 +1183,7 @@ void bt_lap_ws_destroy(bt_ctx* ctx) {
   bt_lap_ws* ws = ctx->lap;
   if (!ws) return;
   void* ptrs[] = {ws->cand.cnt, ws->cand.rowcol, ws->cand.deg, ws->cand.col, ws->cand.cost, ws->label, ws->collabel,
-                  ws->clist, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
+                  ws->clist, ws->rmaskg, ws->compidx, ws->isroot, ws->rowcnt, ws->colcnt, ws->fill,
                   ws->sorted_rows, ws->counters, ws->u, ws->v, ws->dist, ws->pathrow, ws->seen, ws->insc,
                   ws->touched, ws->treerows, ws->x, ws->y, ws->warm_blk, ws->warm_xy};
   for (void* p : ptrs)
@@ -1221,9 +1238,10 @@ int32_t btk_lap_solve(bt_ctx* ctx, const bt_cand& cand, int32_t list, int32_t n,
 }
 
 int32_t btk_lap_solve3(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& B, const bt_lap_batch* dB,
-                       const double thresh[3], const bt_refine& rf) {
+                       const double thresh[3], const bt_refine& rf, int atomic_emitter) {
   LapParams P = {};
   P.clear_lists = 1;
+  P.clear_cnt = atomic_emitter;
   P.nstages = 3;
   for (int s = 0; s < 3; ++s) P.thresh[s] = thresh[s];
   P.debug = getenv("BT_LAP_DEBUG") != nullptr;

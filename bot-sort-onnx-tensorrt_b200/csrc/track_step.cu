@@ -119,8 +119,8 @@ struct FrameGraph {
 
 struct bt_tracker {
   int S = 1, cap = 0, md = 0, D = 0;
-  // the frame step as a CUDA graph, one per launch shape (BT_NO_GRAPH=1: plain enqueue every frame)
-  bool use_graph = true;
+  // the frame step as a CUDA graph, one per launch shape (opt-in: BT_GRAPH=1)
+  bool use_graph = false;
   std::vector<GraphKey> seen_keys;      // shapes that ran once the plain way (module loading, function attributes)
   std::vector<FrameGraph> graphs;
   bt_store st = {};
@@ -314,7 +314,11 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   for (auto& e : t->in_events) BT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   t->host_debug = getenv("BT_HOST_DEBUG") != nullptr;
   t->no_refine = getenv("BT_NO_REFINE") != nullptr;
-  t->use_graph = getenv("BT_NO_GRAPH") == nullptr;
+  // measured at C3 (profiles/README.md): replaying the captured frame costs one ~23 us cudaGraphLaunch before the GPU
+  // starts, the plain enqueue ~70 us of driver calls of which only the first ~25 us delay the GPU -- the plain
+  // enqueue wins on this driver, and clearly so when a copy stream is busy next to it (pipelined ingest).  The graph
+  // path stays available (BT_GRAPH=1) for hosts with slower launches.
+  t->use_graph = getenv("BT_GRAPH") != nullptr && getenv("BT_NO_GRAPH") == nullptr;
   return BT_OK;
 }
 
@@ -755,7 +759,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       fmark("assoc");
       SEG_BEGIN(BT_SEG_LAP);
       const double th[3] = {cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh};
-      BT_TRY(btk_lap_solve3(ctx, cand, LB, &dd->LB, th, rf));   // also zeroes the pair counters
+      BT_TRY(btk_lap_solve3(ctx, cand, LB, &dd->LB, th, rf, assoc_precision != 0));   // also zeroes the pair counters
       SEG_END(BT_SEG_LAP);
       fmark("lap");
     }
