@@ -440,10 +440,168 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
     ctx.close()
+    c5 = None
+    if not args.no_c5 and args.workload == "c3":
+        del data, flush
+        torch.cuda.empty_cache()
+        c5 = run_c5(args, rank, world, local, dev, K, W)
+    if rank == 0:
+        line["c5"] = c5
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 5: 32 independent video streams x 1000 tracks, block-partitioned over the ranks,
+# per-stream NCCL scatter of the detector outputs from rank 0 and gather of ids + boxes back
+# ------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """A device buffer owned by the tracker ctx, exposed to torch without a copy."""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def run_c5(args, rank, world, local, dev, K, W):
+    import torch
+    import torch.distributed as dist
+    import botsort_b200 as bs
+    from botsort_b200._lib import BT_DEVICE, BT_F16
+    from botsort_b200.sharding import (frame_slot_ints, gather_streams, max_over_ranks, pack_frame, pack_result,
+                                       result_slot_ints, scatter_streams, shard_streams, unpack_frame, unpack_result)
+    from botsort_b200.synthetic import SceneConfig, SyntheticScene
+    n_streams, n, D = 32, 1000, 2048
+    mine = shard_streams(n_streams, world, rank)
+    S = len(mine)
+    cap = 1152
+    K5, W5 = min(K, 10), 3
+    n_frames = 1 + W5 + K5
+    ctx = bs.Context(max_tracks=cap, max_dets=cap, feat_dim=D, device=local, n_streams=S)
+    cfg = ctx.default_config()
+    ctx.tracker_reset(cfg)
+    sids = list(range(S))
+    # identity banks of the streams this GPU owns ("features produced on the owning GPU": the stand-in for its
+    # own TensorRT ReID engine, which writes fp16 rows straight into the association buffers)
+    scene_cfg = lambda sid: SceneConfig(n_ids=n, feat_dim=D, seed=5000 + sid, emit_features=False)
+    ident = [torch.from_numpy(SyntheticScene(scene_cfg(sid)).identity).to(dev) for sid in mine]
+    all_scenes = [SyntheticScene(scene_cfg(sid)) for sid in range(n_streams)] if rank == 0 else None
+    all_ident16 = None
+    if rank == 0 and args.c5_full_scatter:
+        all_ident16 = [torch.from_numpy(sc.identity).to(dev) for sc in all_scenes]
+    slot_f, slot_r = frame_slot_ints(cap), result_slot_ints(cap)
+    # rank 0 is the producer: every stream's detector outputs of every frame, packed into per-stream slots up front
+    # (scene generation is not part of the scatter)
+    stage_h = None
+    if rank == 0:
+        stage_h = torch.empty((n_frames, n_streams, slot_f), dtype=torch.int32).pin_memory()
+        for i in range(n_frames):
+            for sid, sc in enumerate(all_scenes):
+                fr = sc.next_frame()
+                stage_h[i, sid].copy_(torch.from_numpy(pack_frame(fr["boxes"], fr["scores"], fr["gt"], cap)))
+    res_h = torch.empty((S, slot_r), dtype=torch.int32).pin_memory()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77 + rank)
+    views = {}
+
+    def in_views(k):
+        pb, ps, pf = ctx.input_buffers(k)
+        key = (k, pb)
+        if key not in views:
+            views[key] = (pb, ps, pf,
+                          torch.as_tensor(_RawCuda(pb, (cap, 4), "<i4"), device=dev),
+                          torch.as_tensor(_RawCuda(ps, (cap,), "<f4"), device=dev),
+                          torch.as_tensor(_RawCuda(pf, (cap, D), "<f2"), device=dev))
+        return views[key]
+
+    t_scatter = t_step = t_gather = t_feat = t_full = 0.0
+    checked = 0
+    for i in range(n_frames):
+        timed = i >= 1 + W5
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        # ---- scatter: rank 0 packs every stream's detector output, one NCCL scatter of per-stream slots ----
+        packed = None
+        if rank == 0:
+            packed = stage_h[i].to(dev, non_blocking=True)
+        recv = scatter_streams(packed, n_streams, slot_f, src=0, device=dev)
+        ms = recv[:, 0].cpu().tolist()
+        bufs = []
+        gts = []
+        for k in range(S):
+            pb, ps, pf, vb, vs, vf = in_views(k)
+            m, boxes, scores, gt = unpack_frame(recv[k], cap)
+            vb[:m].copy_(boxes)
+            vs[:m].copy_(scores)
+            bufs.append((pb, ps, pf, m, vf))
+            gts.append(gt.long())
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        # ---- features on the owning GPU (ReID stand-in, not part of the tracker's time) ----
+        for k in range(S):
+            m, vf = bufs[k][3], bufs[k][4]
+            f = ident[k][gts[k]] + 0.005 * torch.randn((m, D), device=dev, generator=gen)
+            f = f / f.norm(dim=1, keepdim=True)
+            vf[:m].copy_(f.half())
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        # ---- the tracker: all local streams in ONE batched frame step ----
+        ctx.update_streams_raw(sids, [b[0] for b in bufs], [b[1] for b in bufs], [b[2] for b in bufs],
+                               [b[3] for b in bufs], BT_DEVICE, BT_F16)
+        t3 = time.perf_counter()
+        # ---- gather: ids + boxes of every stream back to rank 0 ----
+        for k in range(S):
+            tr = ctx.get_tracks(0, stream=k)
+            res_h[k].copy_(torch.from_numpy(pack_result(tr["ids"], tr["tlbr"], cap)))
+        allres = gather_streams(res_h.to(dev, non_blocking=True), n_streams, slot_r, dst=0, device=dev)
+        if rank == 0:
+            host = allres.cpu().numpy()
+            if i == n_frames - 1:
+                for sid in range(n_streams):
+                    ids, tlbr = unpack_result(host[sid], cap)
+                    checked += int(len(ids))
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        if timed:
+            t_scatter += t1 - t0; t_feat += t2 - t1; t_step += t3 - t2; t_gather += t4 - t3
+        # ---- mode 2: what scattering the FEATURES from one rank would cost (NVLink), timed on its own ----
+        if timed and args.c5_full_scatter and world > 1:
+            parts = None
+            if rank == 0:
+                parts = [torch.empty((len(shard_streams(n_streams, world, r)), cap, D), dtype=torch.float16, device=dev) for r in range(world)]
+            mine_f = torch.empty((S, cap, D), dtype=torch.float16, device=dev)
+            dist.barrier(); torch.cuda.synchronize()
+            tf0 = time.perf_counter()
+            dist.scatter(mine_f, parts, src=0)
+            torch.cuda.synchronize()
+            t_full += time.perf_counter() - tf0
+    totals = max_over_ranks([t_scatter, t_step, t_gather, t_feat, t_full], device="cuda")
+    live = sum(int(len(ctx.get_tracks(0, stream=k)["ids"])) for k in range(S))
+    ctx.close()
+    if rank != 0:
+        return None
+    sc_ms, st_ms, ga_ms, fe_ms, fu_ms = (1e3 * v / K5 for v in totals)
+    return {
+        "workload": "32 independent synthetic video streams x 1000 tracks x 1000 dets x 2048-d, block-partitioned over the GPUs "
+                    f"({n_streams // world} streams per GPU, ONE batched frame step per GPU and frame)",
+        "n_gpus": world, "streams": n_streams, "streams_per_gpu": n_streams // world, "steps": K5, "warmup": W5,
+        "value": n_streams * n / (st_ms / 1e3), "unit": "tracks/s",
+        "step_ms": st_ms,
+        "value_incl_scatter_gather": n_streams * n / ((sc_ms + st_ms + ga_ms) / 1e3),
+        "scatter_ms": sc_ms, "gather_ms": ga_ms,
+        "scatter_bytes_per_frame": n_streams * slot_f * 4, "gather_bytes_per_frame": n_streams * slot_r * 4,
+        "feature_production_ms_excluded": fe_ms,
+        "full_feature_scatter_ms": (fu_ms if (args.c5_full_scatter and world > 1) else None),
+        "full_feature_scatter_bytes_per_frame": n_streams * cap * D * 2,
+        "mode": "features produced on the owning GPU (fp16 rows written into the association buffers in place); NCCL carries "
+                "boxes / scores / identities out and ids / boxes back; full_feature_scatter_ms = the NVLink cost of scattering "
+                "the feature rows from rank 0 instead (SURVEY 8(e) mode 2), timed separately",
+        "how": "wall clock per phase with device synchronisation on both sides, max over ranks; frame step = bt_update_streams "
+               "(device-resident inputs, results on the host when it returns)",
+        "tracks_gathered_last_frame": checked, "live_tracks_rank0": live,
+    }
 
 
 _CUDART = None
@@ -498,6 +656,9 @@ def main():
     ap.add_argument("--feat-dtype", default="f16", choices=["f16", "f32"],
                     help="dtype of the ReID feature rows fed to the tracker (fp16 = the reference's TensorRT engine precision)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE config-5 sub-record (32 streams, NCCL scatter / gather)")
+    ap.add_argument("--no-c5-full-scatter", dest="c5_full_scatter", action="store_false",
+                    help="skip timing the NVLink scatter of the feature rows (config 5, mode 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
