@@ -27,7 +27,7 @@ EXPORTS = [
     "bt_destroy", "bt_sync", "bt_stream",
     "bt_launch_count", "bt_kalman_initiate", "bt_kalman_multi_predict", "bt_kalman_update", "bt_kalman_project",
     "bt_iou_distance", "bt_embedding_distance", "bt_fused_cost", "bt_fuse_score", "bt_linear_assignment",
-    "bt_feature_ema", "bt_default_yolox_config", "bt_yolox_postprocess", "bt_reid_crop_gather",
+    "bt_feature_ema", "bt_default_yolox_config", "bt_yolox_postprocess", "bt_reid_crop_gather", "bt_detect_stage",
     "bt_tracker_reset", "bt_tracker_reset_stream", "bt_update_arrays", "bt_update_streams", "bt_submit_streams",
     "bt_step_streams", "bt_input_buffers", "bt_get_tracks", "bt_get_tracks_stream", "bt_get_track_features",
     "bt_get_track_features_stream", "bt_get_matches", "bt_get_matches_stream",
@@ -113,6 +113,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
         "bt_feature_ema": [vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_float, i32],
         "bt_yolox_postprocess": [vp, vp, C.POINTER(BtYoloxConfig), vp, i32, vp, i32],
         "bt_reid_crop_gather": [vp, vp, i32, i32, vp, i32, i32, i32, vp, i32],
+        "bt_detect_stage": [vp, i32, vp, C.POINTER(BtYoloxConfig), vp, i32, i32, i32, i32, vp, vp, i32, vp],
         "bt_tracker_reset": [vp, C.POINTER(BtConfig)],
         "bt_tracker_reset_stream": [vp, i32, C.POINTER(BtConfig)],
         "bt_update_arrays": [vp, vp, vp, vp, i32, i32, C.POINTER(BtFrameInfo)],
@@ -332,6 +333,20 @@ class Context:
         self._check(self.lib.bt_reid_crop_gather(self.h, _ptr(f), h, w, _ptr(b), b.shape[0], out_h, out_w, _ptr(out),
                                                  BT_HOST))
         return out
+
+    def detect_stage(self, raw_head_ptr: int, frame_ptr: int, h: int, w: int, crops_ptr: int,
+                     cfg: Optional[BtYoloxConfig] = None, out_h: int = 256, out_w: int = 128, stream: int = 0,
+                     det_out_ptr: int = 0, max_out: int = 0, det_count_ptr: int = 0):
+        """Device-chained detector side (all device pointers, asynchronous): raw YOLOX head -> body detections in the
+        stream's next input buffers + their ReID crops in `crops_ptr`."""
+        if cfg is None:
+            cfg = BtYoloxConfig()
+            self.lib.bt_default_yolox_config(C.byref(cfg))
+        self._check(self.lib.bt_detect_stage(self.h, stream, C.c_void_p(raw_head_ptr), C.byref(cfg), C.c_void_p(frame_ptr),
+                                             h, w, out_h, out_w, C.c_void_p(crops_ptr),
+                                             C.c_void_p(det_out_ptr) if det_out_ptr else None, max_out,
+                                             C.c_void_p(det_count_ptr) if det_count_ptr else None))
+        return cfg
 
     # ---- tracker ----
     def default_config(self) -> BtConfig:

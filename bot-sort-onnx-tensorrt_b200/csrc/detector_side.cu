@@ -233,8 +233,9 @@ __device__ __forceinline__ void resize_coord(int d, int src, int dst, bool is_x,
 
 __global__ void __launch_bounds__(256)
 reid_crop_kernel(const uint8_t* __restrict__ frame, int h, int w, const int32_t* __restrict__ boxes, int out_h,
-                 int out_w, float* __restrict__ out) {
+                 int out_w, float* __restrict__ out, const int32_t* __restrict__ n_dev) {
   const int det = blockIdx.y;
+  if (n_dev && det >= *n_dev) return;       // device-chained use: the number of bodies never visits the host
   const int pix = blockIdx.x * 256 + threadIdx.x;
   if (pix >= out_h * out_w) return;
   const int dy = pix / out_w, dx = pix % out_w;
@@ -298,10 +299,36 @@ int32_t btk_reid_crop_gather(bt_ctx* ctx, const uint8_t* frame, int32_t h, int32
                              int32_t n, int32_t out_h, int32_t out_w, float* out) {
   if (n <= 0) return BT_OK;
   dim3 grid((out_h * out_w + 255) / 256, n);
-  reid_crop_kernel<<<grid, 256, 0, ctx->stream>>>(frame, h, w, boxes, out_h, out_w, out);
+  reid_crop_kernel<<<grid, 256, 0, ctx->stream>>>(frame, h, w, boxes, out_h, out_w, out, nullptr);
   BT_LAUNCHED(ctx);
   return BT_OK;
 }
+
+namespace {
+// The decoded list is ordered by class, then by descending score: the class-0 (body) rows are its head.  They
+// become the tracker's detections of the frame, written where the next bt_submit_streams of the stream expects
+// them; rows past the last body get score 0 (below track_low_thresh: ignored by every association stage and never
+// born), so the tracker can be stepped with m = max_bodies without the count ever reaching the host.
+__global__ void stage_bodies_kernel(const double* __restrict__ det, const int32_t* __restrict__ det_count, int max_bodies,
+                                    int32_t* __restrict__ boxes, float* __restrict__ scores, int32_t* __restrict__ n_bodies) {
+  const int j = threadIdx.x;
+  const int cnt = *det_count;
+  const bool body = j < max_bodies && j < cnt && det[(size_t)j * 6] == 0.0;
+  if (j < max_bodies) {
+    int4 b = make_int4(0, 0, 0, 0);
+    float sc = 0.f;
+    if (body) {
+      const double* r = det + (size_t)j * 6;
+      b = make_int4((int)r[2], (int)r[3], (int)r[4], (int)r[5]);
+      sc = (float)r[1];
+    }
+    *reinterpret_cast<int4*>(boxes + (size_t)j * 4) = b;
+    scores[j] = sc;
+  }
+  const int nb = __syncthreads_count(body ? 1 : 0);
+  if (j == 0) *n_bodies = nb;
+}
+}  // namespace
 
 
 extern "C" {
@@ -328,6 +355,41 @@ int32_t bt_yolox_postprocess(bt_ctx* ctx, const float* raw_head, const bt_yolox_
   BT_TRY(bt_unstage_out(ctx, out_boxes, d_out, sizeof(double) * 6 * max_out, loc));
   BT_TRY(bt_unstage_out(ctx, out_count, d_cnt, sizeof(int32_t), loc));
   return bt_finish(ctx, loc);
+}
+
+int32_t bt_detect_stage(bt_ctx* ctx, int32_t stream_id, const float* raw_head, const bt_yolox_config* cfg,
+                        const uint8_t* frame, int32_t h, int32_t w, int32_t out_h, int32_t out_w, float* crops,
+                        double* det_out, int32_t max_out, int32_t* det_count) {
+  if (!ctx) return BT_ERR_INVALID;
+  BT_CUDA(cudaSetDevice(ctx->device));
+  BT_CHECK(raw_head && cfg && frame && crops, BT_ERR_INVALID, "NULL buffer");
+  BT_CHECK(h > 0 && w > 0 && out_h > 0 && out_w > 0, BT_ERR_INVALID, "bad size");
+  BT_CHECK(cfg->in_h % 32 == 0 && cfg->in_w % 32 == 0 && cfg->in_h > 0 && cfg->in_w > 0, BT_ERR_INVALID,
+           "input size must be a positive multiple of 32");
+  BT_CHECK(cfg->max_per_class >= 1 && cfg->max_per_class <= ctx->max_dets && cfg->max_per_class <= 1024, BT_ERR_CAPACITY,
+           "max_per_class %d exceeds the ctx's max_dets %d", cfg->max_per_class, ctx->max_dets);
+  const int max_bodies = cfg->max_per_class;
+  const int list_cap = det_out ? max_out : cfg->num_classes * cfg->max_per_class;
+  BT_CHECK(list_cap >= max_bodies, BT_ERR_INVALID, "max_out %d is smaller than max_per_class %d", list_cap, max_bodies);
+  int32_t* in_boxes = nullptr; float* in_scores = nullptr;
+  BT_TRY(bt_input_buffers(ctx, stream_id, &in_boxes, &in_scores, nullptr));
+  const int anchors = (cfg->in_h / 8) * (cfg->in_w / 8) + (cfg->in_h / 16) * (cfg->in_w / 16) +
+                      (cfg->in_h / 32) * (cfg->in_w / 32);
+  // scratch from the ctx arena (grown on the first call only: no synchronisation in steady state)
+  BT_TRY(bt_arena_reserve(ctx, (size_t)anchors * (16 + 16 * kMaxClasses) + 4096 + (size_t)list_cap * 48 + 1024));
+  double* d_det = det_out;
+  int32_t* d_cnt = det_count;
+  if (!d_det) BT_TRY(bt_arena(ctx, (size_t)list_cap * 6, &d_det));
+  if (!d_cnt) BT_TRY(bt_arena(ctx, (size_t)4, &d_cnt));
+  int32_t* d_nb = nullptr;
+  BT_TRY(bt_arena(ctx, (size_t)4, &d_nb));
+  BT_TRY(btk_yolox_postprocess(ctx, raw_head, *cfg, d_det, list_cap, d_cnt));
+  stage_bodies_kernel<<<1, 1024, 0, ctx->stream>>>(d_det, d_cnt, max_bodies, in_boxes, in_scores, d_nb);
+  BT_LAUNCHED(ctx);
+  dim3 grid((out_h * out_w + 255) / 256, max_bodies);
+  reid_crop_kernel<<<grid, 256, 0, ctx->stream>>>(frame, h, w, in_boxes, out_h, out_w, crops, d_nb);
+  BT_LAUNCHED(ctx);
+  return BT_OK;
 }
 
 int32_t bt_reid_crop_gather(bt_ctx* ctx, const uint8_t* frame, int32_t h, int32_t w, const int32_t* boxes,

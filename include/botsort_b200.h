@@ -220,6 +220,23 @@ int32_t bt_reid_crop_gather(bt_ctx* ctx, const uint8_t* frame, int32_t h, int32_
                             const int32_t* boxes, int32_t n, int32_t out_h, int32_t out_w,
                             float* out, int32_t loc);
 
+/* Device-chained detector side (the reference bounces every model output through host NumPy,
+ * demo:829-837, demo:916-918, demo:1096-1098).  All pointers are DEVICE pointers, everything is enqueued on the ctx
+ * stream, nothing is synchronised:
+ *   raw YOLOX head -> decode + NMS + _postprocess (as bt_yolox_postprocess)
+ *     -> the class-0 (body) detections land in the input buffers of the NEXT bt_submit_streams of `stream_id`
+ *        (bt_input_buffers: boxes, scores); rows past the last body get score 0, which every association stage
+ *        ignores, so the tracker can be stepped with m = cfg->max_per_class and no count visits the host
+ *     -> their ReID crops (as bt_reid_crop_gather) in `crops` float32[max_per_class, 3, out_h, out_w] -- the input
+ *        binding of the ReID engine, whose fp16 output binding is the feats16 buffer of bt_input_buffers.
+ * det_out / det_count: optional device float64[max_out,6] + int32 with the whole decoded list (all classes), e.g. for
+ * the host-side body-part grouping (demo:1372-1411).  Then:
+ *   bt_update_streams(ctx, 1, &stream_id, &boxes, &scores, &feats16, &max_per_class, BT_F16, NULL, BT_DEVICE, info)
+ * with the bt_input_buffers pointers. */
+int32_t bt_detect_stage(bt_ctx* ctx, int32_t stream_id, const float* raw_head, const bt_yolox_config* cfg,
+                        const uint8_t* frame, int32_t h, int32_t w, int32_t out_h, int32_t out_w, float* crops,
+                        double* det_out, int32_t max_out, int32_t* det_count);
+
 /* ---- the tracker (replaces BoTSORT.update demo:1291-1639 driven by arrays) --------------- */
 /* Resets video stream 0 / one video stream / all of them (stream_id < 0). */
 int32_t bt_tracker_reset(bt_ctx* ctx, const bt_config* cfg /* NULL = defaults */);
