@@ -34,6 +34,10 @@ WORKLOADS = {
     # BASELINE.json configs[0] (CPU-runnable case)
     "c1": dict(n=64, feat_dim=2048, reid=True, desc="64 tracks x 64 dets, 2048-d ReID features, 1 stream/GPU"),
     # per-stream shape of BASELINE.json configs[4]
+    # BASELINE.json configs[3]: detector side chained on the device into the tracker
+    "c4": dict(n=40, feat_dim=2048, reid=True, persons=40, img_h=480, img_w=640,
+               desc="480x640 synthetic frames + raw YOLOX head (6300 anchors x 4 classes) -> decode+NMS+crop gather -> "
+                    "stub ReID encoder (256x128 crops -> 2048-d fp16) -> BoTSORT.update, all chained on the device, 1 stream/GPU"),
     "c5": dict(n=1000, feat_dim=2048, reid=True, streams=4,
                desc="1000 tracks x 1000 dets per stream, 4 independent streams per GPU (BASELINE config 5: 32 streams over 8 GPUs)"),
 }
@@ -604,6 +608,287 @@ def run_c5(args, rank, world, local, dev, K, W):
     }
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 4: raw YOLOX head + camera frame -> bt_detect_stage -> stub encoder -> bt_update_streams
+# ------------------------------------------------------------------------------------------------
+C4_POOL = 16          # the stub encoder: 16x16 average pooling of the crop tensor, then a fixed random projection
+
+
+def c4_projection(D):
+    return (np.random.default_rng(7).standard_normal((3 * (256 // C4_POOL) * (128 // C4_POOL), D)) / 8.0).astype(np.float32)
+
+
+def c4_frames(wl, count, seed):
+    from botsort_b200.synthetic import DetectorScene
+    sc = DetectorScene(k=wl["persons"], h=wl["img_h"], w=wl["img_w"], seed=seed)
+    return [sc.next_frame() for _ in range(count)]
+
+
+def c4_cpu_times(wl, frames):
+    """The same chain on the host cores: oracle decode + NMS + _postprocess, cv2-exact crop + normalise, the stub
+    encoder in NumPy, the oracle tracker in the reference's loop structure.  First frame untimed (births)."""
+    from oracle import detector_np as Dn
+    from oracle import oracle_np as O
+    proj = c4_projection(wl["feat_dim"])
+    trk = O.OracleBoTSORT(mode="faithful", lap_solver="jv", use_features=True)
+    times, parts, n_live = [], [], 0
+    for k, (frame, raw) in enumerate(frames):
+        t0 = time.perf_counter()
+        det = Dn.yolox_postprocess(raw, img_h=wl["img_h"], img_w=wl["img_w"])
+        body = det[det[:, 0] == 0]
+        b_int = body[:, 2:6].astype(np.int32)
+        t1 = time.perf_counter()
+        crops = Dn.crop_preprocess(frame, b_int)
+        t2 = time.perf_counter()
+        pooled = crops.reshape(len(b_int), 3, 256 // C4_POOL, C4_POOL, 128 // C4_POOL, C4_POOL).mean(axis=(3, 5))
+        f = pooled.reshape(len(b_int), -1).astype(np.float32) @ proj
+        f = (f / np.maximum(np.linalg.norm(f, axis=1, keepdims=True), 1e-12)).astype(np.float16).astype(np.float32)
+        t3 = time.perf_counter()
+        trk.update_arrays(b_int, body[:, 1].astype(np.float32), f)
+        t4 = time.perf_counter()
+        if k > 0:
+            times.append(t4 - t0)
+            parts.append((t1 - t0, t2 - t1, t3 - t2, t4 - t3))
+        n_live = len(trk.snapshot()["tracked"]["ids"])
+    return times, np.mean(np.array(parts), axis=0) if parts else np.zeros(4), n_live
+
+
+def c4_config(wl):
+    c = config_of(wl, 1)
+    c.update({"tracks": wl["persons"], "dets": "<= 50 bodies / frame (max_per_class)", "anchors": 6300, "classes": 4,
+              "crop": "3x256x128 float32 per body", "encoder": "stub (16x16 average pool + fixed 384x2048 projection, L2 "
+              "normalise, fp16) -- FastReID inference itself is out of scope (north_star: stays on TensorRT)"})
+    return c
+
+
+def run_c4_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    wl = WORKLOADS["c4"]
+    _all_host_threads()
+    K, W = args.steps, args.warmup
+    frames = c4_frames(wl, 1 + W + K, seed=1234)
+    t0 = time.perf_counter()
+    t_all, parts, n_live = c4_cpu_times(wl, frames)
+    t = t_all[W:]
+    ms = 1e3 * float(np.mean(t))
+    value = n_live / (ms / 1e3)
+    sample = (f"{len(t)} timed frames (+{W} warm-up) of the full chain on the host: decode+NMS "
+              f"{1e3 * parts[0]:.2f} ms, crop+normalise {1e3 * parts[1]:.2f} ms, stub encoder {1e3 * parts[2]:.2f} ms, "
+              f"tracker update {1e3 * parts[3]:.2f} ms per frame")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": c4_config(wl), "live_tracks_end": n_live, "frames_per_s": 1e3 / ms,
+        "run_wall_s": time.perf_counter() - t0,
+        "cpu_baseline": {"value": value, "unit": "tracks/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tracks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_c4(args):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    import botsort_b200 as bs
+    from botsort_b200._lib import BT_DEVICE, BT_F16
+    from botsort_b200.sharding import aggregate_throughput, max_over_ranks
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS["c4"]
+    D, H, Wd = wl["feat_dim"], wl["img_h"], wl["img_w"]
+    K, W = args.steps, max(args.warmup, 3)
+    ctx = bs.Context(max_tracks=256, max_dets=256, feat_dim=D, device=local)
+    ycfg = bs.BtYoloxConfig()
+    ctx.lib.bt_default_yolox_config(C.byref(ycfg))
+    mb = int(ycfg.max_per_class)
+    cu_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    n_frames = 1 + W + K
+    frames = c4_frames(wl, n_frames, seed=1234 + rank)
+    fh = [torch.from_numpy(f).pin_memory() for f, _ in frames]
+    rh = [torch.from_numpy(r).pin_memory() for _, r in frames]
+    fd = [x.to(dev) for x in fh]
+    rd = [x.to(dev) for x in rh]
+    proj = torch.from_numpy(c4_projection(D)).to(dev)
+    crops = torch.zeros((mb, 3, 256, 128), dtype=torch.float32, device=dev)
+    det_out = torch.zeros((256, 6), dtype=torch.float64, device=dev)
+    det_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    stage_f = torch.empty((H, Wd, 3), dtype=torch.uint8, device=dev)
+    stage_r = torch.empty_like(rd[0])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def chain(d_raw, d_frame):
+        """One frame, everything enqueued on the ctx stream, nothing visits the host between the stages."""
+        pb, ps, pf = ctx.input_buffers(0)
+        ctx.detect_stage(d_raw.data_ptr(), d_frame.data_ptr(), H, Wd, crops.data_ptr(), ycfg)
+        with torch.cuda.stream(cu_stream):                   # the stub encoder (library ops; stands in for TensorRT)
+            f32 = F.avg_pool2d(crops, C4_POOL).reshape(mb, -1) @ proj
+            f32 = f32 / f32.norm(dim=1, keepdim=True).clamp_min(1e-12)
+            torch.as_tensor(_RawCuda(pf, (mb, D), "<f2"), device=dev).copy_(f32.half())
+        ctx.update_streams_raw([0], [pb], [ps], [pf], [mb], BT_DEVICE, BT_F16)
+
+    def run_value_pass():
+        ctx.tracker_reset()
+        for i in range(1 + W):
+            chain(rd[i], fd[i])
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        l0 = ctx.launch_count
+        for k in range(K):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ev[k][0].record(cu_stream)
+            chain(rd[1 + W + k], fd[1 + W + k])
+            ev[k][1].record(cu_stream)
+        launches = ctx.launch_count - l0
+        barrier()
+        return [a.elapsed_time(b) for a, b in ev], launches
+
+    def run_e2e_pass():
+        ctx.tracker_reset()
+        for i in range(1 + W):
+            chain(rd[i], fd[i])
+        barrier()
+        t0 = time.perf_counter()
+        nbytes = 0
+        for k in range(K):
+            with torch.cuda.stream(cu_stream):
+                stage_f.copy_(fh[1 + W + k], non_blocking=True)
+                stage_r.copy_(rh[1 + W + k], non_blocking=True)
+            chain(stage_r, stage_f)
+            res = ctx.get_tracks(0)
+            nbytes = res["tlbr"].nbytes + res["ids"].nbytes
+        ctx.sync()
+        ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        return ms, nbytes
+
+    def time_kernel(fn):
+        """K stand-alone launches of one detector-side kernel on the ctx stream.  Before each one the L2 is flushed ON
+        THE SAME STREAM (2 x 256 MiB memset) and the launch is enqueued behind it without a host synchronisation, so
+        the event pair brackets the kernel alone and not the host's enqueue latency."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for k in range(K):
+            with torch.cuda.stream(cu_stream):
+                flush.zero_()
+                flush.zero_()
+            ev[k][0].record(cu_stream)
+            fn(k)
+            ev[k][1].record(cu_stream)
+            torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) for a, b in ev)
+        return float(np.mean(t)), t[len(t) // 2]
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    run_value_pass()
+    dev_ms, launches = run_value_pass()
+    n_live = int(len(ctx.get_tracks(0)["ids"]))
+    n_body = int((det_out[:, 0] == 0).sum().item()) if False else None
+    run_e2e_pass()
+    e2e_ms, d2h = run_e2e_pass()
+    # ---- per-kernel durations (stand-alone device-resident launches of the same frames) ----
+    boxes_dev = torch.zeros((mb, 4), dtype=torch.int32, device=dev)
+
+    def yolox_only(k):
+        ctx._check(ctx.lib.bt_yolox_postprocess(ctx.h, C.c_void_p(rd[1 + W + k].data_ptr()), C.byref(ycfg),
+                                                C.c_void_p(det_out.data_ptr()), 256, C.c_void_p(det_cnt.data_ptr()), BT_DEVICE))
+    yolox_ms, yolox_med = time_kernel(yolox_only)
+    torch.cuda.synchronize()
+    det = det_out.cpu().numpy()[: int(det_cnt.cpu()[0])]
+    body = det[det[:, 0] == 0][:, 2:6].astype(np.int32)
+    nb = len(body)
+    boxes_dev[:nb] = torch.from_numpy(body).to(dev)
+
+    def crop_only(k):
+        ctx._check(ctx.lib.bt_reid_crop_gather(ctx.h, C.c_void_p(fd[1 + W + k].data_ptr()), H, Wd, C.c_void_p(boxes_dev.data_ptr()),
+                                               nb, 256, 128, C.c_void_p(crops.data_ptr()), BT_DEVICE))
+    crop_ms, crop_med = time_kernel(crop_only)
+    t_end = time.perf_counter() + 0.6
+    while rank == 0 and time.perf_counter() < t_end:
+        for i in range(1 + W, 1 + W + K):
+            chain(rd[i], fd[i])
+    ctx.sync()
+    clocks = sampler.stop() if rank == 0 else None
+    total_dev_ms, total_e2e_ms = max_over_ranks([sum(dev_ms), e2e_ms], device="cuda")
+    value = aggregate_throughput(n_live, world, K, total_dev_ms)
+    e2e_value = aggregate_throughput(n_live, world, K, total_e2e_ms)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        crop_bytes = float(nb) * 3 * 256 * 128 * 4
+        yolo_bytes = float(rd[0].numel() * 4)
+        crop_traffic, crop_src = ncu_traffic("reid_crop_kernel", (nb, 256, 128))
+        yolo_traffic, yolo_src = ncu_traffic("yolox_post_kernel", (6300, 4))
+        roof = {"kernel": "reid_crop_kernel (crop + INTER_LINEAR resize + BGR->RGB + normalise, written once)", "bound": "hbm",
+                "achieved": crop_bytes / (crop_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                "algorithmic_bytes": crop_bytes, "bytes_per_det": 3 * 256 * 128 * 4, "dets": nb, "avg_launch_ms": crop_ms,
+                "median_launch_ms": crop_med, "traffic": crop_traffic, "traffic_source": crop_src,
+                "how": "CUDA events on the ctx stream around K stand-alone device-resident launches, each enqueued behind an "
+                       "L2 flush on the same stream (no host latency inside the bracket)"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof_y = {"kernel": "yolox_post (decode + per-class NMS + _postprocess)", "bound": "hbm",
+                  "achieved": yolo_bytes / (yolox_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                  "algorithmic_bytes": yolo_bytes, "avg_launch_ms": yolox_ms, "median_launch_ms": yolox_med,
+                  "traffic": yolo_traffic, "traffic_source": yolo_src,
+                  "note": "226.8 KB per frame: a latency chain (decode -> sort -> greedy NMS), not a bandwidth problem; "
+                          "the duration is what matters"}
+        roof_y["frac"] = roof_y["achieved"] / roof_y["peak"]
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            _all_host_threads()
+            t_cpu, parts, live_cpu = c4_cpu_times(wl, frames[: 2 + max(2, args.cpu_frames)])
+            v = live_cpu / float(np.mean(t_cpu))
+            cpu = {"value": v, "unit": "tracks/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": (f"{len(t_cpu)} full frames of the same chain on the host: decode+NMS {1e3 * parts[0]:.2f} ms, "
+                              f"crop+normalise {1e3 * parts[1]:.2f} ms, stub encoder {1e3 * parts[2]:.2f} ms, tracker "
+                              f"{1e3 * parts[3]:.2f} ms per frame"),
+                   "ratios": {"e2e_over_cpu": e2e_value / v, "value_over_cpu": value / v}}
+        ds = sorted(dev_ms)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "tracks/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 decode/NMS, u8 fixed-point resize, fp16 features, f64 Kalman/IoU/LAP", "data": "synthetic",
+            "config": c4_config(wl), "live_tracks_end": n_live, "bodies_per_frame": nb,
+            "frames_per_s": 1e3 * K * world / total_dev_ms,
+            "step_ms": {"min": ds[0], "median": ds[len(ds) // 2], "max": ds[-1]},
+            "e2e": {"value": e2e_value, "unit": "tracks/s", "ms_per_step": total_e2e_ms / K,
+                    "h2d_bytes_per_step": int(fh[0].numel() + rh[0].numel() * 4), "d2h_bytes_per_step": int(d2h),
+                    "how": "pinned host frame + raw head copied in on the ctx stream, the device chain, bt_get_tracks back; "
+                           "wall clock over the K steps"},
+            "gpu_launches": int(launches),
+            "gpu_launches_note": "this library's kernels only (the stub encoder's torch ops are not counted)",
+            "roofline": roof, "rooflines": [roof, roof_y], "cpu_baseline": cpu, "clocks": clocks}))
+    del crops, proj
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()                                 # blocks the allocator tied to the ctx's stream
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _CUDART = None
 
 
@@ -660,7 +945,9 @@ def main():
     ap.add_argument("--no-c5-full-scatter", dest="c5_full_scatter", action="store_false",
                     help="skip timing the NVLink scatter of the feature rows (config 5, mode 2)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "c4":
+        (run_c4_reference if args.impl == "reference" else run_c4)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

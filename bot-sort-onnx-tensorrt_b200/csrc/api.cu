@@ -177,9 +177,25 @@ int32_t bt_create_streams(int32_t device, int32_t n_streams, int32_t max_tracks,
     bt_fail(c, BT_ERR_CUDA, "cudaStreamCreate failed");
     return fail(BT_ERR_CUDA);
   }
-  if (cudaMalloc(&c->d_desc, 16384) != cudaSuccess) {
+  if (cudaMalloc(&c->d_desc, kBtCropLutOffset + 3 * 256 * sizeof(float)) != cudaSuccess) {
     bt_fail(c, BT_ERR_CUDA, "cudaMalloc failed");
     return fail(BT_ERR_CUDA);
+  }
+  {
+    // FastReID._preprocess (demo:1101-1142): (pixel / 255 - mean) / std in float64, then float32 -- one value per
+    // (RGB plane, 8-bit pixel value), tabulated once (IEEE float64 division: the host's results are the device's)
+    static const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    float lut[3][256];
+    for (int ch = 0; ch < 3; ++ch)
+      for (int v = 0; v < 256; ++v) {
+        volatile double q = (double)v / 255.0;
+        volatile double d = q - (double)mean[ch];
+        lut[ch][v] = (float)(d / (double)stdv[ch]);
+      }
+    if (cudaMemcpy(c->d_desc + kBtCropLutOffset, lut, sizeof(lut), cudaMemcpyHostToDevice) != cudaSuccess) {
+      bt_fail(c, BT_ERR_CUDA, "cudaMemcpy failed");
+      return fail(BT_ERR_CUDA);
+    }
   }
   if ((s = bt_arena_reserve(c, 1 << 20)) != BT_OK) return fail(s);
   if ((s = bt_lap_ws_create(c)) != BT_OK) return fail(s);

@@ -14,6 +14,7 @@
 
 struct bt_tracker;  // track_step.cu
 
+constexpr size_t kBtCropLutOffset = 16384;
 struct bt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -26,7 +27,8 @@ struct bt_ctx {
   int pdl = 1;   // programmatic dependent launch between the frame step's kernels (BT_NO_PDL=1 turns it off)
   std::string err;
   int64_t launches = 0;
-  char* d_desc = nullptr;   // device scratch for the launch descriptors of the stand-alone entry points (16 KB)
+  char* d_desc = nullptr;   // device scratch for the launch descriptors of the stand-alone entry points (16 KB), then the
+                            // crop normalisation table float[3][256] at kBtCropLutOffset (written once at create)
   // bump arena for the stand-alone entry points (device) and a pinned mirror for small results
   char* arena = nullptr;
   size_t arena_cap = 0, arena_off = 0;

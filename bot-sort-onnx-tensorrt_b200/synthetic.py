@@ -132,3 +132,86 @@ def steady_state_pair(n: int, m: int, feat_dim: int, seed: int = 0, with_feature
         for k in ("boxes", "scores", "feats", "gt"):
             f2[k] = f2[k][:m]
     return f1, f2
+
+
+# ------------------------------------------------------------------------------------------------
+# detector-side synthetic inputs (BASELINE config 4): a camera frame and the raw YOLOX head for it
+# ------------------------------------------------------------------------------------------------
+def yolox_anchor_grid(in_h: int, in_w: int):
+    """(grid_x, grid_y, stride) of every anchor, strides 8 / 16 / 32 in that order (YOLOX head layout)."""
+    gx, gy, st = [], [], []
+    for s in (8, 16, 32):
+        hh, ww = in_h // s, in_w // s
+        yy, xx = np.meshgrid(np.arange(hh), np.arange(ww), indexing="ij")
+        gx.append(xx.reshape(-1)); gy.append(yy.reshape(-1)); st.append(np.full(hh * ww, s))
+    return np.concatenate(gx), np.concatenate(gy), np.concatenate(st)
+
+
+class DetectorScene:
+    """`k` pedestrians random-walking over a (h, w) camera frame.  next_frame() returns the BGR uint8 frame (every
+    identity carries its own fixed texture, so a crop-based ReID stub sees the same person in every frame) and the
+    raw head [anchors, 5 + C] float32: background logits, threshold-level clutter, and for every person a cluster of
+    `dups` neighbouring anchors that all decode to (almost) the same box -- the work NMS exists for."""
+
+    def __init__(self, k: int = 40, h: int = 480, w: int = 640, num_classes: int = 4, dups: int = 6, clutter: int = 300,
+                 seed: int = 0):
+        self.rng = np.random.default_rng(seed)
+        self.k, self.h, self.w, self.C, self.dups, self.clutter = k, h, w, num_classes, dups, clutter
+        r = self.rng
+        cols = int(np.ceil(np.sqrt(k * w / h)))
+        rows = (k + cols - 1) // cols
+        self.bw = r.uniform(28, 0.8 * w / cols, k)
+        self.bh = r.uniform(60, 0.9 * h / rows, k)
+        self.cx = ((np.arange(k) % cols) + 0.5) * w / cols + r.uniform(-4, 4, k)
+        self.cy = ((np.arange(k) // cols) + 0.5) * h / rows + r.uniform(-4, 4, k)
+        self.tex = []
+        for i in range(k):                                   # blocky low-frequency texture: survives the encoder stub's pooling
+            tr = np.random.default_rng(seed * 1000 + 17 + i)
+            th, tw = int(self.bh[i]) + 8, int(self.bw[i]) + 8
+            coarse = tr.integers(0, 256, (16, 8, 3)).astype(np.float64)
+            yy = np.minimum(np.arange(th) * 16 // th, 15); xx = np.minimum(np.arange(tw) * 8 // tw, 7)
+            t = coarse[yy][:, xx] + tr.normal(0, 6, (th, tw, 3))
+            self.tex.append(np.clip(t, 0, 255).astype(np.uint8))
+        self.gx, self.gy, self.st = yolox_anchor_grid(h, w)
+        self.background = r.integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+    def boxes(self):
+        x1 = np.clip(self.cx - self.bw / 2, 0, self.w - 2); y1 = np.clip(self.cy - self.bh / 2, 0, self.h - 2)
+        x2 = np.clip(self.cx + self.bw / 2, x1 + 1, self.w - 1); y2 = np.clip(self.cy + self.bh / 2, y1 + 1, self.h - 1)
+        return np.stack([x1, y1, x2, y2], axis=1)
+
+    def next_frame(self):
+        r = self.rng
+        self.cx += r.uniform(-2, 2, self.k); self.cy += r.uniform(-2, 2, self.k)
+        b = self.boxes()
+        frame = self.background.copy()
+        for i, (x1, y1, x2, y2) in enumerate(b.astype(int)):
+            frame[y1:y2, x1:x2] = self.tex[i][: y2 - y1, : x2 - x1]
+        n, C = len(self.gx), self.C
+        raw = np.empty((n, 5 + C), np.float32)
+        raw[:, 0:2] = r.uniform(0, 1, (n, 2))
+        raw[:, 2:4] = r.normal(0.5, 0.5, (n, 2))
+        raw[:, 4] = r.normal(-6, 1, n)
+        raw[:, 5:] = r.normal(-3, 1, (n, C))
+        idx = r.choice(n, size=min(self.clutter, n), replace=False)
+        raw[idx, 4] = r.normal(-0.5, 0.7, len(idx))
+        raw[idx, 5:] = r.normal(0.0, 1.0, (len(idx), C))
+        logit = lambda p: np.log(p / (1 - p))
+        for i, (x1, y1, x2, y2) in enumerate(b):
+            cx, cy, w_, h_ = (x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1
+            s = 8 if max(w_, h_) < 64 else (16 if max(w_, h_) < 160 else 32)
+            base = 0 if s == 8 else ((self.h // 8) * (self.w // 8) if s == 16 else (self.h // 8) * (self.w // 8) + (self.h // 16) * (self.w // 16))
+            ww, hh = self.w // s, self.h // s
+            gxi, gyi = min(int(cx // s), ww - 1), min(int(cy // s), hh - 1)
+            for d in range(self.dups):                       # the cell itself, then its neighbours
+                ox, oy = ((0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (-1, -1), (1, -1), (-1, 1))[d % 9]
+                ax, ay = min(max(gxi + ox, 0), ww - 1), min(max(gyi + oy, 0), hh - 1)
+                if d and (ax, ay) == (gxi, gyi):
+                    continue
+                a = base + ay * ww + ax
+                jit = 0.0 if d == 0 else r.uniform(-1.5, 1.5)
+                p = np.sqrt(0.96 * (1.0 if d == 0 else r.uniform(0.5, 0.9)))
+                raw[a, 0] = (cx + jit) / s - self.gx[a]; raw[a, 1] = (cy + jit) / s - self.gy[a]
+                raw[a, 2] = np.log(w_ / s); raw[a, 3] = np.log(h_ / s)
+                raw[a, 4] = logit(p); raw[a, 5:] = -6.0; raw[a, 5] = logit(p)
+        return frame, raw
