@@ -428,13 +428,22 @@ class Context:
                                 None if info is None else C.pointer(info))
 
     def _raw_arrays(self, stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms):
+        # the argument vectors of a steady pipeline repeat (double-buffered addresses, fixed m): keep the last few
+        key = (tuple(stream_ids), tuple(boxes_ptrs), tuple(scores_ptrs), tuple(feats_ptrs), tuple(ms))
+        cache = self.__dict__.setdefault("_raw_cache", {})
+        hit = cache.get(key)
+        if hit is not None:
+            return hit
         n = len(stream_ids)
         ids = (C.c_int32 * n)(*stream_ids)
         bp = (C.c_void_p * n)(*boxes_ptrs)
         sp = (C.c_void_p * n)(*scores_ptrs)
         fp = (C.c_void_p * n)(*[p or None for p in feats_ptrs])
         mp = (C.c_int32 * n)(*ms)
-        return n, ids, bp, sp, fp, mp
+        if len(cache) >= 64:
+            cache.clear()
+        cache[key] = out = (n, ids, bp, sp, fp, mp)
+        return out
 
     def update_streams_raw(self, stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms, loc, dtype=BT_F32, infos=None):
         n, ids, bp, sp, fp, mp = self._raw_arrays(stream_ids, boxes_ptrs, scores_ptrs, feats_ptrs, ms)

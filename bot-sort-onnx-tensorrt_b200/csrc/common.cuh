@@ -295,7 +295,8 @@ int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const
 int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc,
                       cudaStream_t stream, int fixed);
 // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
-int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed);
+int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed,
+                      int with_ema);
 // births of one stream: Kalman initiate + feature adoption from the frame's detections
 int32_t btk_frame_births(bt_ctx* ctx, const bt_store& st, int32_t sid, int32_t parity, const int32_t* d_slot,
                          const int32_t* d_det, int32_t n_births, const bt_frame_cfg& fc, int32_t with_feat);

@@ -251,6 +251,82 @@ __device__ __forceinline__ void ema_row(const bt_store& st, const bt_frame_cfg& 
   }
 }
 
+// The same row update by HALF a CTA (128 threads, 16 floats of the row per thread): two rows per CTA keep twice
+// as many rows in flight per SM at the same register budget (the update is a chain of two DRAM round trips and two
+// reductions per row -- rows in flight, not bandwidth, bound it).  `half` selects named barrier 1 / 2.
+__device__ __forceinline__ float half_sum128(float v, float* red, int half) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = (threadIdx.x & 127) >> 5, lane = threadIdx.x & 31;
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+  if (lane == 0) red[half * 4 + warp] = v;
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+  return red[half * 4] + red[half * 4 + 1] + red[half * 4 + 2] + red[half * 4 + 3];
+}
+template <bool kF16>
+__device__ __forceinline__ void ema_row_half(const bt_store& st, const bt_frame_cfg& fc, size_t gs, size_t in_row,
+                                             float* red, int half) {
+  const int D = st.D;
+  constexpr int kHold = 4;
+  const int tid = threadIdx.x & 127;
+  __half* bank = st.feat16 + gs * D;
+  const __half* raw16 = st.det16 + in_row * D;
+  const float* raw32 = kF16 ? nullptr : st.det32 + in_row * D;
+  float* smooth = (fc.keep_smooth && st.smooth32) ? st.smooth32 + gs * D : nullptr;
+  float* curr = (!kF16 && st.curr32) ? st.curr32 + gs * D : nullptr;
+  float4 xv[kHold], ov[kHold];
+  float ss = 0.f;
+  const bool blend = smooth != nullptr;
+#pragma unroll
+  for (int t = 0; t < kHold; ++t) {
+    const int i = (tid + t * 128) * 4;
+    xv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ov[t] = xv[t];
+    if (i < D) {
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(raw16 + i));
+      if (blend) ov[t] = *reinterpret_cast<const float4*>(smooth + i);
+      *reinterpret_cast<uint2*>(bank + i) = q;     // the track adopts the raw fp16 row
+      if (kF16) {
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+        const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+        xv[t] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      } else {
+        xv[t] = __ldg(reinterpret_cast<const float4*>(raw32 + i));
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kHold; ++t) ss += xv[t].x * xv[t].x + xv[t].y * xv[t].y + xv[t].z * xv[t].z + xv[t].w * xv[t].w;
+  const float norm = sqrtf(half_sum128(ss, red, half));
+  if (tid == 0) st.norm[gs] = norm;
+  if (!smooth && !curr) return;
+  float ss2 = 0.f;
+#pragma unroll
+  for (int t = 0; t < kHold; ++t) {
+    if (norm > 0.f) { xv[t].x /= norm; xv[t].y /= norm; xv[t].z /= norm; xv[t].w /= norm; }
+    if (blend) {      // the blended row replaces the old one in place (registers)
+      ov[t].x = __fadd_rn(__fmul_rn(fc.alpha, ov[t].x), __fmul_rn(fc.one_minus_alpha, xv[t].x));
+      ov[t].y = __fadd_rn(__fmul_rn(fc.alpha, ov[t].y), __fmul_rn(fc.one_minus_alpha, xv[t].y));
+      ov[t].z = __fadd_rn(__fmul_rn(fc.alpha, ov[t].z), __fmul_rn(fc.one_minus_alpha, xv[t].z));
+      ov[t].w = __fadd_rn(__fmul_rn(fc.alpha, ov[t].w), __fmul_rn(fc.one_minus_alpha, xv[t].w));
+      ss2 += ov[t].x * ov[t].x + ov[t].y * ov[t].y + ov[t].z * ov[t].z + ov[t].w * ov[t].w;
+    }
+  }
+  float n2 = 1.f;
+  if (blend) n2 = sqrtf(half_sum128(ss2, red, half));   // half-uniform condition
+#pragma unroll
+  for (int t = 0; t < kHold; ++t) {
+    const int i = (tid + t * 128) * 4;
+    if (i >= D) continue;
+    if (curr) *reinterpret_cast<float4*>(curr + i) = xv[t];
+    if (smooth) {
+      float4 o = ov[t];
+      if (n2 > 0.f) { o.x /= n2; o.y /= n2; o.z /= n2; o.w /= n2; }
+      *reinterpret_cast<float4*>(smooth + i) = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 frame_post_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_res_layout L) {
   const bt_batch& b = *bp;
@@ -345,15 +421,40 @@ __device__ __forceinline__ double iou_of(const Box& a, const Box& b) {
 // (demo:1665-1680) only looks at tracked x lost pairs; both lists are subsets of the live slots, so the
 // host filters this (tiny) superset by list membership without a second round trip.
 // grid (j tile of 64, i tile of 256, batch entry), only tiles that can hold a pair j > i.
+//
+// The same launch also carries the matched tracks' feature update (EMA role, blocks past the duplicate tiles, two
+// rows per CTA): it only needs the assignment vectors, which are final before the Kalman update kernel starts, so
+// these CTAs do not wait for it -- they run beside the update and beside the duplicate test without a second
+// stream, a fork / join event pair or a launch of their own.
 __global__ void __launch_bounds__(256)
-frame_dup_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, bt_res_layout L) {
+frame_dup_ema_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, bt_res_layout L, int dup_jt,
+                     int dup_tiles) {
   const bt_batch& b = *bp;
   constexpr int JT = 64;
+  const int k = blockIdx.y;
+  if ((int)blockIdx.x >= dup_tiles) {
+    __shared__ float red[8];
+    const int half = threadIdx.x >> 7;
+    const int row = 2 * ((int)blockIdx.x - dup_tiles) + half;
+    if (row >= b.n_rows[k]) return;   // half-uniform (named barriers below)
+    const int32_t* x = reinterpret_cast<const int32_t*>(st.res + (size_t)k * L.stride) + L.o_x;
+    const int z1 = x[row], z2 = x[st.cap + row], z3 = x[2 * (size_t)st.cap + row];   // one round trip
+    const int z = z1 >= 0 ? z1 : (z2 >= 0 ? z2 : z3);
+    if (z < 0) return;
+    const size_t gs = (size_t)b.sid[k] * st.cap + row;
+    const size_t in_row = (size_t)b.parity[k] * st.S * st.md + (size_t)b.sid[k] * st.md + z;
+    const bool held = (st.D & 3) == 0 && st.D <= 128 * 4 * 4;
+    if (held) {
+      if (fc.f16_inputs) ema_row_half<true>(st, fc, gs, in_row, red, half);
+      else ema_row_half<false>(st, fc, gs, in_row, red, half);
+    }
+    return;
+  }
   bt_grid_dependency_wait();   // programmatic dependent of the Kalman update that writes the boxes
-  const int k = blockIdx.z;
+  const int bx_j = (int)blockIdx.x % dup_jt, bx_i = (int)blockIdx.x / dup_jt;
   const int n = b.n_rows[k];
-  if ((int)blockIdx.y * 256 >= n || (int)blockIdx.x * JT >= n) return;
-  if ((int)(blockIdx.x + 1) * JT <= (int)blockIdx.y * 256) return;
+  if (bx_i * 256 >= n || bx_j * JT >= n) return;
+  if ((bx_j + 1) * JT <= bx_i * 256) return;
   const size_t gs0 = (size_t)b.sid[k] * st.cap;
   const double* tlbr = st.tlbr + gs0 * 4;
   const float* tlbr_f32 = st.tlbr_f32 + gs0 * 4;
@@ -364,8 +465,8 @@ frame_dup_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, 
   int32_t* pairs = st.pairs + (size_t)k * 2 * st.pair_cap;
   __shared__ float4 sb[JT];
   __shared__ uint8_t sk[JT];
-  const int i = blockIdx.y * 256 + threadIdx.x;
-  const int j0 = blockIdx.x * JT;
+  const int i = bx_i * 256 + threadIdx.x;
+  const int j0 = bx_j * JT;
   const bool live_i = i < n && kind[i] != 0;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live_i) a = *reinterpret_cast<const float4*>(tlbr_f32 + (size_t)i * 4);
@@ -485,11 +586,21 @@ int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const 
   return BT_OK;
 }
 
-int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed) {
+int32_t btk_frame_dup(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed,
+                      int with_ema) {
   const int n = fixed ? st.cap : bt_batch_max(b.n_rows, b.count);
-  if (n <= 1) return BT_OK;
+  const bool held = (st.D & 3) == 0 && st.D <= 128 * 4 * 4;
+  if (with_ema && !held) {      // generic feature sizes: the one-row-per-CTA kernel, in stream order
+    BT_TRY(btk_frame_ema(ctx, st, b, db, fc, ctx->stream, fixed));
+    with_ema = 0;
+  }
+  const int dup_jt = n > 1 ? (n + 63) / 64 : 0, dup_it = n > 1 ? (n + 255) / 256 : 0;
+  const int dup_tiles = dup_jt * dup_it;
+  const int ema_ctas = (with_ema && n > 0) ? (n + 1) / 2 : 0;
+  if (dup_tiles + ema_ctas <= 0) return BT_OK;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch(ctx, true, frame_dup_kernel, dim3((n + 63) / 64, (n + 255) / 256, b.count), dim3(256), 0, st, db, fc, L));
+  BT_CUDA(bt_launch(ctx, true, frame_dup_ema_kernel, dim3(dup_tiles + ema_ctas, b.count), dim3(256), 0, st, db, fc, L,
+                    dup_jt > 0 ? dup_jt : 1, dup_tiles));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

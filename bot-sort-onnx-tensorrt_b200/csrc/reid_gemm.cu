@@ -680,7 +680,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                          cnt, (list == 1) ? spill_b : spill_a);
         if (added >= 0) { if (list == 1) { ++cnt_b; last_b = added; } else { ++cnt_a; last_a = added; } }
       };
-      long long t_l0 = 0, t_l1 = 0;
+      long long t_l0 = 0, t_l1 = 0, t_pa = 0, t_ex = 0;
       if (kDense) {
 #pragma unroll 1
         for (int ch = 0; ch < kChunks; ++ch) {
@@ -736,6 +736,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         }
         if (all_open) gatebits = (1u << kChunks) - 1u;
+        if (p.debug & 16) t_pa = clock64();
         // exact pass: float64 IoU distance of the remembered candidates, all lanes at once; slots 0 and 1
         // are evaluated together (two independent dependency chains), slots 2.. only if some row has them
         {
@@ -750,6 +751,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               if (j < npre) my_preiou[j * 32 + lane] = iou_dist_f64(rbox, s_col64 + (my_prekey[j * 32 + lane] & 0xffu) * 4);
           }
         }
+        if (p.debug & 16) t_ex = clock64();
         if ((p.debug & 2) || rkind == BT_ROW_NONE) gatebits = 0;
         // phase B: only chunks in which some row of the warp has an open gate are looked at again.
         // One rolled loop (one copy of the code: it runs once or twice per warp and would otherwise be
@@ -833,8 +835,8 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if ((p.debug & 16) && lane == 0 && (blockIdx.x % 37) == 0)
-        printf("EPI cta %d warp %d: go %lld bar1 +%lld staged +%lld bar2 +%lld rowloads +%lld rows +%lld box pass done +%lld acc +%lld ld0 +%lld ld1 +%lld sim pass +%lld tail +%lld (lane 0: box edges %d, open pairs %d)\n", blockIdx.x,
-               warp, t_go - t_start, t_s1 - t_go, t_s2 - t_go, t_s3 - t_go, t_rl - t_go, t_rows - t_go, t_shadow - t_go, t_acc - t_go, t_l0 - t_acc, t_l1 - t_l0, t_chunks - t_acc, clock64() - t_chunks, npre, dbg_open);
+        printf("EPI cta %d warp %d: go %lld bar1 +%lld staged +%lld bar2 +%lld rowloads +%lld rows +%lld box pass done +%lld acc +%lld ld0 +%lld ld1 +%lld phaseA +%lld exact +%lld sim pass +%lld tail +%lld (lane 0: box edges %d, open pairs %d)\n", blockIdx.x,
+               warp, t_go - t_start, t_s1 - t_go, t_s2 - t_go, t_s3 - t_go, t_rl - t_go, t_rows - t_go, t_shadow - t_go, t_acc - t_go, t_l0 - t_acc, t_l1 - t_l0, t_pa - t_acc, t_ex - t_acc, t_chunks - t_acc, clock64() - t_chunks, npre, dbg_open);
       if ((p.debug & 1024) && lane == 0) {
         unsigned long long g_end;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));

@@ -779,24 +779,14 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
       // demo:570-610) while the host is still waiting for / digesting the assignments.
       SEG_BEGIN(BT_SEG_UPDATE);
-      if (any_reid && (mx_m > 0 || fixed)) {
-        // the feature EMA only needs the assignment vectors: side stream, next to update + duplicate test
-        // (profiling keeps it on the main stream so that its time shows up in the segment)
-        cudaStream_t es = t->prof ? st : ctx->side_stream;
-        if (!t->prof) {
-          BT_CUDA(cudaEventRecord(t->ev_fork, st));
-          BT_CUDA(cudaStreamWaitEvent(es, t->ev_fork, 0));
-        }
-        BT_TRY(btk_frame_ema(ctx, dst, B, &dd->B, fc, es, fixed));
-        if (!t->prof) { BT_CUDA(cudaEventRecord(t->ev_join, es)); ema_pending = true; }
-      }
-      fmark("ema(fork/join)");
       BT_TRY(btk_frame_post(ctx, dst, B, &dd->B, fc, fixed));
       SEG_END(BT_SEG_UPDATE);
       fmark("post");
       // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
       SEG_BEGIN(BT_SEG_DUP);
-      BT_TRY(btk_frame_dup(ctx, dst, B, &dd->B, fc, fixed));
+      // ... and, in the same launch, the matched tracks' feature update (it only needs the assignment vectors: its
+      // CTAs run beside the Kalman update and the duplicate test)
+      BT_TRY(btk_frame_dup(ctx, dst, B, &dd->B, fc, fixed, (any_reid && (mx_m > 0 || fixed)) ? 1 : 0));
       SEG_END(BT_SEG_DUP);
       fmark("dup");
       // part B: pair count + first pairs, boxes of all slots
