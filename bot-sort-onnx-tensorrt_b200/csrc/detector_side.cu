@@ -566,8 +566,8 @@ static int32_t launch_crop(bt_ctx* ctx, const uint8_t* frame, int32_t h, int32_t
   BT_CHECK(out_w <= 2048, BT_ERR_CAPACITY, "crop width %d exceeds 2048", out_w);
   dim3 grid((out_h + kCropRows - 1) / kCropRows, n);
   const size_t smem = (size_t)(out_w + kCropRows) * sizeof(int4) + (size_t)kCropStagePixels * 4;
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(reid_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+  static std::once_flag once[64];          // function attributes are per device
+  std::call_once(once[ctx->device & 63], [] { cudaFuncSetAttribute(reid_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
   reid_crop_kernel<<<grid, 256, smem, ctx->stream>>>(frame, h, w, boxes, out_h, out_w, out, n_dev,
                                                      reinterpret_cast<const float*>(ctx->d_desc + kBtCropLutOffset));
   BT_LAUNCHED(ctx);

@@ -1208,9 +1208,9 @@ static int32_t launch_lap(bt_ctx* ctx, const bt_cand& cand, const bt_lap_batch& 
     BT_CHECK(B.n[k] <= ctx->lap->rows && B.m[k] <= ctx->lap->cols, BT_ERR_CAPACITY,
              "linear assignment %d x %d exceeds ctx capacity %d x %d", B.n[k], B.m[k], ctx->lap->rows, ctx->lap->cols);
   if (B.count <= 0) return BT_OK;
-  static std::once_flag attr_once;
+  static std::once_flag attr_once[64];     // function attributes are per device: one flag per device ordinal
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [&] {
+  std::call_once(attr_once[ctx->device & 63], [&] {
     attr_err = cudaFuncSetAttribute(lap_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem));
   });
   BT_CUDA(attr_err);

@@ -1033,9 +1033,9 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams
   BT_TRY(make_tmap(ctx, &ta, ap.a16, ap.a_rows_alloc, ap.d, BM));
   BT_TRY(make_tmap(ctx, &tb, ap.b16, ap.b_rows_alloc, ap.d, BN));
   auto kern = assoc_tc_kernel<BN, kDense>;
-  static std::once_flag attr_once;     // per instantiation; safe with several host threads (one ctx each)
+  static std::once_flag attr_once[64];  // per instantiation and device ordinal; safe with several host threads
   cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [&] {
+  std::call_once(attr_once[ctx->device & 63], [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kDyn);
   });
   BT_CUDA(attr_err);

@@ -422,10 +422,19 @@ class STrackView(STrack):
             self._owner._fill_lazy(self._list)
         return self._lazy[key]
 
-    mean = property(lambda self: self._fetch("mean"))
-    covariance = property(lambda self: self._fetch("cov"))
-    body_curr_feature = property(lambda self: self._fetch("curr"))
-    body_smooth_feature = property(lambda self: self._fetch("smooth"))
+    def _read_only(name):
+        def setter(self, value):
+            raise AttributeError(
+                f"STrackView.{name} is a read-only view of the device track store: the BoTSORT that owns the track "
+                f"updates it on the GPU every frame.  Copy the numbers into a plain STrack (or call the KalmanFilter / "
+                f"matching functions on arrays) to edit them on the host.")
+        return setter
+
+    mean = property(lambda self: self._fetch("mean"), _read_only("mean"))
+    covariance = property(lambda self: self._fetch("cov"), _read_only("covariance"))
+    body_curr_feature = property(lambda self: self._fetch("curr"), _read_only("body_curr_feature"))
+    body_smooth_feature = property(lambda self: self._fetch("smooth"), _read_only("body_smooth_feature"))
+    del _read_only
 
 
 # --------------------------------------------------------------------------------------------
@@ -625,17 +634,24 @@ class BoTSORT:
         self._cfg = cfg
         self.ctx.tracker_reset(cfg)
         self._views: Dict[int, STrackView] = {}
+        self._face_curr: Dict[int, np.ndarray] = {}      # track id -> face_curr_feature (host: the face model is the user's)
         self.last_info: dict = {}
 
     # -- frame API on arrays ------------------------------------------------------------------
-    def update_arrays(self, boxes, scores, feats=None, bodies: Optional[Sequence[Box]] = None) -> List[STrack]:
-        """One BoTSORT.update on detector/encoder outputs (class-0 boxes, int tlbr)."""
+    def update_arrays(self, boxes, scores, feats=None, bodies: Optional[Sequence[Box]] = None,
+                      face_sim=None) -> List[STrack]:
+        """One BoTSORT.update on detector/encoder outputs (class-0 boxes, int tlbr).  face_sim: None or the
+        float32 [n_pool, m] face similarity matrix of demo:1465-1486 (rows = `strack_pool()` order)."""
         self.frame_id += 1
         if not self._cfg.with_reid:
             feats = None
-        self.last_info = self.ctx.update_arrays(boxes, scores, feats)
+        self.last_info = self.ctx.update_arrays(boxes, scores, feats, face_sim=face_sim)
         self._refresh_views(bodies)
         return self.tracked_stracks
+
+    def strack_pool(self) -> List[STrack]:
+        """The reference's pool of this frame (demo:1415-1423): activated tracked tracks, then lost tracks."""
+        return [t for t in self.tracked_stracks if t.is_activated] + list(self.lost_stracks)
 
     def _refresh_views(self, bodies):
         lists = []
@@ -657,6 +673,7 @@ class BoTSORT:
                 v._tlbr = tr["tlbr"][i].copy()
                 v._lazy = {}
                 v._list, v._pos = which, i
+                v._det_index = int(tr["det_index"][i])
                 if bodies is not None and v.frame_id == self.frame_id and 0 <= tr["det_index"][i] < len(bodies):
                     v.body = bodies[int(tr["det_index"][i])]
                 out.append(v)
@@ -699,7 +716,50 @@ class BoTSORT:
             feats = np.asarray(out[1], dtype=np.float32).reshape(m, d)
         elif self._cfg.with_reid:
             feats = np.zeros((0, self.ctx.feat_dim), np.float32)
-        return self.update_arrays(boxes, scores, feats, bodies=bodies)
+        face_sim, face_feats = None, None
+        if self.face_encoder is not None and self._cfg.with_reid and m > 0:
+            face_sim, face_feats = self._face_term(image, bodies)
+        out = self.update_arrays(boxes, scores, feats, bodies=bodies, face_sim=face_sim)
+        if face_feats is not None:
+            self._adopt_face_features(face_feats)
+        return out
+
+    # -- face similarity term (demo:1437-1441, demo:1465-1486, demo:1541-1546) ---------------------------------
+    def _face_term(self, image, bodies):
+        """Face crops (or the reference's all-zero stand-in) -> user face encoder against the pool's current face
+        features -> [n_pool, m] similarity matrix.  The encoder returns (similarities[N, M], features[N, F]); the
+        reference reads them swapped for this model (demo:1478-1480), which is kept: a face encoder written for
+        the reference returns (features, similarities)."""
+        enc = self.face_encoder
+        fs = int(getattr(enc, "feature_size", 256) or 256)
+        shape = getattr(enc, "_input_shapes", [[1, 3, 128, 128]])[0][1:]
+        blank = np.zeros([d if isinstance(d, int) else 1 for d in shape], dtype=np.float32).transpose(1, 2, 0)
+        crops = [image[b.head.face.y1:b.head.face.y2, b.head.face.x1:b.head.face.x2, :]
+                 if (b.head is not None and b.head.face is not None) else blank for b in bodies]
+        pool = self.strack_pool()
+        none = np.zeros(fs, dtype=np.float32)
+        targets = [self._face_curr.get(t.track_id, none) for t in pool] if pool else np.zeros([0, fs], dtype=np.float32)
+        res = enc(base_images=crops, target_features=targets)
+        sims = np.asarray(res[1], dtype=np.float32).reshape(len(bodies), len(pool)).transpose(1, 0).copy()   # [M, N]
+        feats = np.asarray(res[0], dtype=np.float32).reshape(len(bodies), -1)
+        sims[np.isclose(sims, 0.9999999, atol=1e-08, rtol=1e-08)] = 0.0                                       # demo:1482-1483
+        return (sims if len(pool) else None), feats
+
+    def _adopt_face_features(self, face_feats):
+        """STrack.update_face_features (demo:504-514) for the tracks that took a detection this frame: the
+        detection's STrack normalised its face row in place when it was built, so that is what the track keeps."""
+        live = set()
+        for lst in (self.tracked_stracks, self.lost_stracks):
+            for t in lst:
+                live.add(t.track_id)
+        for t in self.tracked_stracks:
+            j = getattr(t, "_det_index", -1)
+            if t.frame_id == self.frame_id and 0 <= j < len(face_feats):
+                f = face_feats[j].copy()
+                f /= np.linalg.norm(f)
+                self._face_curr[t.track_id] = f
+        for tid in [k for k in self._face_curr if k not in live]:
+            del self._face_curr[tid]
 
     def close(self):
         if self._own_ctx:

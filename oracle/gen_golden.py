@@ -111,9 +111,45 @@ def gen_primitives():
     print("primitives ok", pre.shape)
 
 
+def gen_host_glue():
+    """KalmanFilter.gating_distance (demo:338-380) and STrack.multi_gmc (demo:538-554): dead code in the reference's
+    frame loop but part of its API -- pinned here so the host mirror cannot drift."""
+    import types
+    ref = load_reference()
+    rng = np.random.default_rng(47)
+    kf = ref.KalmanFilter()
+    out = {"versions": versions()}
+    z0 = np.stack([rng.uniform(50, 1500, 6), rng.uniform(50, 900, 6), rng.uniform(20, 150, 6), rng.uniform(40, 250, 6)], axis=1)
+    means, covs = [], []
+    for z in z0:
+        m, c = kf.initiate(z)
+        for _ in range(3):
+            m, c = kf.predict(m, c)
+        means.append(np.asarray(m, dtype=np.float64)); covs.append(np.asarray(c, dtype=np.float64))
+    out["gd_mean"], out["gd_cov"] = np.asarray(means), np.asarray(covs)
+    meas = np.stack([m[:4] + rng.normal(0, 6, (9, 4)) for m in means])            # [6, 9, 4]
+    out["gd_meas"] = meas
+    for metric in ("maha", "gaussian"):
+        for only_pos in (False, True):
+            out[f"gd_{metric}_{int(only_pos)}"] = np.asarray(
+                [kf.gating_distance(means[i], covs[i], meas[i].copy(), only_position=only_pos, metric=metric) for i in range(6)])
+    # multi_gmc on bare objects (the method only touches .mean / .covariance)
+    ang = 0.03
+    H = np.array([[np.cos(ang), -np.sin(ang), 4.5], [np.sin(ang), np.cos(ang), -2.25]])
+    tracks = [types.SimpleNamespace(mean=means[i].copy(), covariance=covs[i].copy()) for i in range(6)]
+    ref.STrack.multi_gmc(tracks, H)
+    out["gmc_H"] = H
+    out["gmc_mean"] = np.asarray([t.mean for t in tracks]); out["gmc_cov"] = np.asarray([t.covariance for t in tracks])
+    np.savez_compressed(os.path.join(OUT, "host_glue.npz"), **out)
+    print("host glue ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "host_glue":
+        return gen_host_glue()
     gen_primitives()
+    gen_host_glue()
     for name, (cfg, frames) in TRACKER_CASES.items():
         gen_tracker(name, cfg, frames)
 

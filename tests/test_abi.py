@@ -34,13 +34,12 @@ def test_defaults_match_reference_constants():
     lib = bs.load_library()
     cfg = bs.BtConfig()
     lib.bt_default_config(ctypes.byref(cfg))
-    assert np.float32(cfg.track_high_thresh) == np.float32(0.40)
-    assert np.float32(cfg.track_low_thresh) == np.float32(0.1)
-    assert np.float32(cfg.new_track_thresh) == np.float32(0.9)
+    # the thresholds are Python floats in the reference and doubles in bt_config: exact equality, no float32 detour
+    assert (cfg.track_high_thresh, cfg.track_low_thresh, cfg.new_track_thresh) == (0.40, 0.1, 0.9)
     assert (cfg.match_thresh, cfg.second_thresh, cfg.unconfirmed_thresh) == (0.8, 0.5, 0.7)
-    assert cfg.proximity_thresh == 0.5 and np.float32(cfg.appearance_thresh) == np.float32(0.25)
+    assert (cfg.proximity_thresh, cfg.appearance_thresh) == (0.5, 0.25)
     assert cfg.duplicate_iou_dist == 0.15 and cfg.track_buffer == 300 and cfg.frame_rate == 30
-    assert np.float32(cfg.ema_alpha) == np.float32(0.9) and cfg.with_reid == 1
+    assert cfg.ema_alpha == 0.9 and cfg.with_reid == 1
     y = bs.BtYoloxConfig()
     lib.bt_default_yolox_config(ctypes.byref(y))
     assert (y.in_h, y.in_w, y.num_classes, y.max_per_class) == (480, 640, 4, 50)

@@ -153,3 +153,67 @@ def test_botsort_update_with_stub_models(api):
         assert abs(np.linalg.norm(t0.body_smooth_feature) - 1) <= 1e-5
     finally:
         trk.close()
+
+
+class _FaceEnc:
+    """Face encoder stub with the reference's contract (demo:1207-1209 returns (similarities, base_features); the
+    tracker reads them swapped, demo:1478-1480, so a model built for the reference returns (features, similarities))."""
+    feature_size = 64
+    _input_shapes = [[1, 3, 128, 128]]
+
+    def __init__(self):
+        self.feats = None
+        self.calls = []
+
+    def __call__(self, *, base_images, target_features):
+        f = self.feats
+        t = np.asarray(target_features, dtype=np.float32).reshape(-1, self.feature_size)
+        sims = f @ t.T if len(t) else np.zeros((len(f), 0), np.float32)     # [N dets, M pool]
+        self.calls.append((len(base_images), len(t)))
+        return f.copy(), sims.astype(np.float32)
+
+
+def test_botsort_update_feeds_the_face_similarity_term(api):
+    """BoTSORT.update with a face encoder -> face crops / zero images -> encoder against the pool's
+    face_curr_feature -> face_sim[n_pool, m] into the frame step (demo:1465-1486, demo:1541-1546).  The oracle gets
+    the matrix from an independent mirror of the same bookkeeping."""
+    det, enc, fenc = _Det(api), _Enc(), _FaceEnc()
+    trk = api.BoTSORT(det, enc, fenc, frame_rate=30, max_tracks=256, max_dets=256)
+    oracle = O.OracleBoTSORT()
+    scene = SyntheticScene(SceneConfig(n_ids=40, feat_dim=2048, seed=9, low_frac=0.1, drop_frac=0.15, pitch_x=40.0, pitch_y=70.0,
+                                       feat_noise=0.03))
+    rng = np.random.default_rng(3)
+    ident_face = rng.standard_normal((400, 64)).astype(np.float32)
+    image = np.zeros((32, 32, 3), np.uint8)
+    face_curr = {}
+    try:
+        for k in range(12):
+            fr = scene.next_frame()
+            det.boxes, det.scores, enc.feats = fr["boxes"], fr["scores"], fr["feats"]
+            m = len(fr["boxes"])
+            # a (noisy, unnormalised) face feature per detection; the body's identity decides it
+            ff = (ident_face[fr["gt"]] + 0.05 * rng.standard_normal((m, 64))).astype(np.float32) if "gt" in fr \
+                else rng.standard_normal((m, 64)).astype(np.float32)
+            fenc.feats = ff
+            # --- oracle side: pool order, similarity against the mirror's current face features ---
+            pool = [t for t in oracle.tracked if t.is_activated] + list(oracle.lost)
+            if pool and m:
+                tf = np.stack([face_curr[t.track_id] for t in pool])
+                sim = (ff @ tf.T).astype(np.float32).T.copy()
+                sim[np.isclose(sim, 0.9999999, atol=1e-08, rtol=1e-08)] = 0.0
+            else:
+                sim = None
+            out = trk.update(image)
+            oracle.update_arrays(fr["boxes"], fr["scores"], fr["feats"], face_sims=sim)
+            snap = oracle.snapshot()
+            for i, tid in enumerate(snap["tracked"]["ids"]):
+                if snap["tracked"]["frame_id"][i] == k + 1 and snap["tracked"]["det_index"][i] >= 0:
+                    f = ff[snap["tracked"]["det_index"][i]].copy()
+                    face_curr[int(tid)] = f / np.linalg.norm(f)
+            assert [t.track_id for t in out] == list(snap["tracked"]["ids"]), f"frame {k + 1}"
+            assert [t.track_id for t in trk.lost_stracks] == list(snap["lost"]["ids"])
+            if m:
+                assert fenc.calls[-1] == (m, len(pool))
+        assert len(out) >= 30
+    finally:
+        trk.close()

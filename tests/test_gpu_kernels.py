@@ -209,6 +209,32 @@ def test_linear_assignment_random(ctx, n, m, density):
         np.testing.assert_array_equal(y, ry)
 
 
+@pytest.mark.parametrize("n,m", [(1000, 1000), (2000, 2000), (2000, 700)])
+def test_linear_assignment_dense_large(ctx, n, m):
+    """One giant component (every entry below the threshold competes): the solver's global-memory path, against
+    the C port of lap 0.4.0's Jonker-Volgenant."""
+    rng = np.random.default_rng(7 * n + m)
+    cost = rng.uniform(0.0, 1.0, (n, m))
+    big = bs_ctx_for(ctx, max(n, m))
+    try:
+        x, y = big.lapjv(cost, 0.8)
+        rx, ry = O.lapjv_extended(cost, 0.8, "jv")
+        np.testing.assert_array_equal(x, rx)
+        np.testing.assert_array_equal(y, ry)
+        assert int((x >= 0).sum()) == min(n, m)
+    finally:
+        if big is not ctx:
+            big.close()
+
+
+def bs_ctx_for(ctx, size):
+    """The shared fixture ctx if it is large enough, else a dedicated one."""
+    if ctx.max_tracks >= size and ctx.max_dets >= size:
+        return ctx
+    import botsort_b200 as bs
+    return bs.Context(max_tracks=size, max_dets=size, feat_dim=64)
+
+
 def test_linear_assignment_edge_cases(ctx):
     # nothing below the threshold
     x, y = ctx.lapjv(np.ones((5, 3)), 0.8)
