@@ -240,16 +240,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+// The MMA warp stays CONVERGED: every lane executes the main loop and one elected lane (always the same one: the
+// lowest) issues.  Under a divergent `if (lane == 0)` ptxas wraps every UTCHMMA / UTCBAR in an ELECT / R2UR.BROADCAST
+// / BRA.U.ANY loop (it cannot prove the operands uniform): ~60 cycles of issue-thread time per MMA, more than the
+// tensor pipe needs for the MMA itself once the loop's barrier wait and commit are added -- the main loop was
+// bound by its own issue thread (profiles/README.md, round 2).
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                                 uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -432,31 +441,38 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int ya = p.F->a_row0[k] + m0, yb = p.F->b_row0[k] + n0;
         for (int kb = (t == first_tile) ? pro_kb : 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          tma_load_2d(sa, &tmap_a, kb * BK, ya, &full_bar[stage]);
-          tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, yb, &full_bar[stage]);
+          if (p.debug & 4096) {                 // experiment: no operand traffic after the prologue (stale tiles)
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            tma_load_2d(sa, &tmap_a, kb * BK, ya, &full_bar[stage]);
+            tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, yb, &full_bar[stage]);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loop, one elected lane issues (see tcgen05_mma_f16) =====
+    {
       // instruction descriptor: D fp32 (1<<4), A/B fp16 K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(smem));
+      const uint64_t bdesc0 = make_kmajor_sw128_desc(smem_u32(smem) + L::kABytes);
+      uint32_t g = 0;                 // running k-block count: stage g % kStages, barrier parity (g / kStages) & 1
+      int acc = 0;
+      uint32_t acc_phase = 0;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t stage = g % kStages;
+          mbar_wait(&full_bar[stage], (g / kStages) & 1u);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + L::kABytes);
+          const uint64_t adesc = adesc0 + (uint64_t)(stage * (uint32_t)(L::kStageBytes >> 4));
+          const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (uint32_t)(L::kStageBytes >> 4));
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
             // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr>>4) field
@@ -464,7 +480,6 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                             (uint32_t)((kb | kk) != 0));
           }
           tcgen05_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -859,7 +874,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
-  if (p.debug && threadIdx.x == 0 && (blockIdx.x % 37) == 0) {
+  if ((p.debug & 1) && threadIdx.x == 0 && (blockIdx.x % 37) == 0) {
     unsigned long long g_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
     printf("cta %d: globaltimer start %llu end %llu (ns), lifetime %llu ns = %lld cycles\n", blockIdx.x, g_start, g_end,
