@@ -340,16 +340,17 @@ struct TcSmem {
   static constexpr int kBarOff = kPreKeyOff + 8 * 4 * 32 * 4;         // barriers (8B aligned)
   static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
   static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
-  static constexpr int kTotal = kTmemPtrOff + 16;
+  static constexpr int kFrameOff = kTmemPtrOff + 16;                   // bt_assoc_frame: the launch description, copied once
+  static constexpr int kTotal = kFrameOff + (int)sizeof(bt_assoc_frame);
   static constexpr int kDyn = kTotal + 1024;  // slack for manual 1024 B alignment
 };
 
 // tile t of the batch -> problem k and its tile coordinates
-__device__ __forceinline__ void tile_of(const EpiParams& p, int t, int bn, int& k, int& m0, int& n0) {
+__device__ __forceinline__ void tile_of(const bt_assoc_frame* F, int t, int bn, int& k, int& m0, int& n0) {
   k = 0;
-  while (k + 1 < p.F->count && t >= p.F->tile_start[k + 1]) ++k;
-  const int local = t - p.F->tile_start[k];
-  const int tiles_n = (p.F->m[k] + bn - 1) / bn;
+  while (k + 1 < F->count && t >= F->tile_start[k + 1]) ++k;
+  const int local = t - F->tile_start[k];
+  const int tiles_n = (F->m[k] + bn - 1) / bn;
   m0 = (local / tiles_n) * BM;
   n0 = (local % tiles_n) * bn;
 }
@@ -382,8 +383,23 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   unsigned long long g_start = 0;
   if (p.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
   const int num_kb = d / BK;
-  const int num_tiles = p.F->tile_start[p.F->count];
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  // The launch description lives in device memory (same kernel arguments every frame): warp 0 copies it to
+  // shared memory with ONE batch of independent loads -- walking it in place cost the producer four dependent
+  // global round trips (count -> tile_start -> m -> operand rows) before the first TMA request.
+  bt_assoc_frame* sF = reinterpret_cast<bt_assoc_frame*>(smem + L::kFrameOff);
+  if (warp == 0) {
+    constexpr int kWords = (int)(sizeof(bt_assoc_frame) / 8);
+    static_assert(sizeof(bt_assoc_frame) % 8 == 0, "frame description is copied in 8-byte words");
+    const uint2* src = reinterpret_cast<const uint2*>(p.F);
+    uint2 v[(kWords + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (kWords + 31) / 32; ++i) v[i] = (lane + 32 * i < kWords) ? src[lane + 32 * i] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < (kWords + 31) / 32; ++i)
+      if (lane + 32 * i < kWords) reinterpret_cast<uint2*>(sF)[lane + 32 * i] = v[i];
+    __syncwarp();
+  }
 
   // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as SMs free
   // up (it blocks in its own griddepcontrol.wait until this grid has completed and flushed).
@@ -399,17 +415,17 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // stream even starts when the host says so (operands_early): the main loop then runs under that
     // kernel; only the epilogue (boxes, kinds, candidate lists) waits for it.
     if (!p.operands_early) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (first_tile < num_tiles && !(p.debug & 64)) {
+    if (first_tile < sF->tile_start[sF->count] && !(p.debug & 64)) {
       // the pipeline's first kStages loads do not wait for anybody: request them before the TMEM
       // allocation and the CTA-wide sync so that their latency overlaps the rest of the ramp
       int k, m0, n0;
-      tile_of(p, first_tile, BN, k, m0, n0);
+      tile_of(sF, first_tile, BN, k, m0, n0);
       pro_kb = num_kb < kStages ? num_kb : kStages;
       for (int kb = 0; kb < pro_kb; ++kb) {
         mbar_expect_tx(&full_bar[kb], L::kStageBytes);
         uint8_t* sa = smem + kb * L::kStageBytes;
-        tma_load_2d(sa, &tmap_a, kb * BK, p.F->a_row0[k] + m0, &full_bar[kb]);
-        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, p.F->b_row0[k] + n0, &full_bar[kb]);
+        tma_load_2d(sa, &tmap_a, kb * BK, sF->a_row0[k] + m0, &full_bar[kb]);
+        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, sF->b_row0[k] + n0, &full_bar[kb]);
       }
     }
   }
@@ -429,6 +445,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const int num_tiles = sF->tile_start[sF->count];
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -437,8 +454,8 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = pro_kb == kStages ? 1u : 0u;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         int k, m0, n0;
-        tile_of(p, t, BN, k, m0, n0);
-        const int ya = p.F->a_row0[k] + m0, yb = p.F->b_row0[k] + n0;
+        tile_of(sF, t, BN, k, m0, n0);
+        const int ya = sF->a_row0[k] + m0, yb = sF->b_row0[k] + n0;
         for (int kb = (t == first_tile) ? pro_kb : 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (p.debug & 4096) {                 // experiment: no operand traffic after the prologue (stale tiles)
@@ -499,10 +516,10 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     if (p.debug & 1024) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_go));
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       int k, m0, n0;
-      tile_of(p, t, BN, k, m0, n0);
-      const int pn = p.F->n[k], pm = p.F->m[k];
-      const int sid = p.F->cand_sid[k];
-      const size_t R0 = (size_t)p.F->row0[k], C0 = (size_t)p.F->col0[k];
+      tile_of(sF, t, BN, k, m0, n0);
+      const int pn = sF->n[k], pm = sF->m[k];
+      const int sid = sF->cand_sid[k];
+      const size_t R0 = (size_t)sF->row0[k], C0 = (size_t)sF->col0[k];
       const int row = m0 + quarter * 32 + lane;
       int rkind = BT_ROW_NONE;
       double rbox[4] = {0.0, 0.0, 0.0, 0.0};
@@ -524,7 +541,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         float cn = 1.0f;
         if (row < pn) {
           const double2* s = reinterpret_cast<const double2*>(p.row_tlbr + (R0 + row) * 4);
-          rkind = reinterpret_cast<const uint8_t*>(p.row_kind_base + p.F->kind_off[k])[row];
+          rkind = reinterpret_cast<const uint8_t*>(p.row_kind_base + sF->kind_off[k])[row];
           rlo = s[0]; rhi = s[1];
           if (p.row_tlbr_f32) r32 = *reinterpret_cast<const float4*>(p.row_tlbr_f32 + (R0 + row) * 4);
           if (p.row_norm) rnorm = p.row_norm[R0 + row];
@@ -606,7 +623,7 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       //  3. exact float64 IoU distance against the stage threshold.
       // (With real face similarities the gate is not a function of the body similarity alone: everything
       // is left to the similarity pass.)
-      const bool all_open = p.F->face_sim[k] != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
+      const bool all_open = sF->face_sim[k] != nullptr || (p.debug & 32);   // no box pass: every pair goes through open_pair
       if (!kDense && !all_open && rkind != BT_ROW_NONE) {
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch) {
