@@ -196,16 +196,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+    host_cores = None
     if local_world > 1 and hasattr(os, "sched_setaffinity"):
-        # one rank per GPU on one host: give every rank its own slice of the host cores so that the ranks'
-        # enqueue / bookkeeping threads (they are on the frame's critical path) do not migrate onto each other
-        cores = sorted(os.sched_getaffinity(0))
-        per = max(1, len(cores) // local_world)
-        mine = cores[local * per:(local + 1) * per] or cores
+        # one rank per GPU on one host: every rank gets its own slice of the host cores NEXT TO ITS GPU (the
+        # enqueue / bookkeeping thread is on the frame's critical path, and the pinned staging buffers are
+        # first-touched on the node the GPU's DMA reads from)
+        from botsort_b200.sharding import gpu_local_cpus, split_cores_numa_local
+        topo = [gpu_local_cpus(r) for r in range(local_world)]
+        host_cores = split_cores_numa_local(topo, sorted(os.sched_getaffinity(0)), local)
         try:
-            os.sched_setaffinity(0, mine)
+            os.sched_setaffinity(0, host_cores)
         except OSError:
-            pass
+            host_cores = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -443,6 +445,8 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "host_placement": ({"cores": [host_cores[0], host_cores[-1]], "n_cores": len(host_cores),
+                                "gpu_local_cpulist_known": bool(topo[local])} if host_cores else None),
         }
     ctx.close()
     c5 = None

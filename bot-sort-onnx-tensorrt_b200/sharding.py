@@ -35,6 +35,50 @@ def aggregate_throughput(units_per_rank: int, world: int, steps: int, max_total_
     return units_per_rank * world * steps / (max_total_ms / 1e3)
 
 
+# ---- host placement of the ranks (one process per GPU on one node) -------------------------------------------
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (sysfs cpulist) -> [0, 1, 2, 3, 8, 10, 11]."""
+    out: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def split_cores_numa_local(local_cpus: Sequence[Sequence[int]], allowed: Sequence[int], local_rank: int) -> List[int]:
+    """Host cores for rank `local_rank`: `local_cpus[r]` = the cores next to rank r's GPU (its PCIe root's NUMA
+    node; empty when unknown).  Ranks whose GPUs hang off the same node share that node's cores in equal
+    contiguous slices; a rank with no topology information falls back to an equal slice of `allowed`.  The
+    rank's pinned staging buffers are then first-touched on the node its GPU's DMA reads from: without this,
+    8 ranks' 8 MB frame copies cross the socket interconnect and the end-to-end step time grows with the
+    number of ranks although no rank talks to another."""
+    allowed = sorted(allowed)
+    world = len(local_cpus)
+    mine = sorted(set(local_cpus[local_rank]) & set(allowed))
+    if not mine:
+        per = max(1, len(allowed) // max(1, world))
+        return allowed[local_rank * per:(local_rank + 1) * per] or allowed
+    peers = [r for r in range(world) if sorted(set(local_cpus[r]) & set(allowed)) == mine]
+    per = max(1, len(mine) // len(peers))
+    i = peers.index(local_rank)
+    return mine[i * per:(i + 1) * per] or mine
+
+
+def gpu_local_cpus(device_index: int) -> List[int]:
+    """Cores of the NUMA node GPU `device_index` is attached to (sysfs `local_cpulist` of its PCI function),
+    [] when the topology is not exposed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            return parse_cpulist(f.read())
+    except Exception:  # noqa: BLE001 -- no sysfs / old torch: the caller falls back to an even split
+        return []
+
+
 # ---- per-stream scatter / gather (BASELINE config 5) -------------------------------------------------------
 # One frame of one video stream travels as a fixed-size int32 slot (so that a rank's streams are one contiguous
 # message and `dist.scatter` needs no size negotiation):

@@ -111,3 +111,21 @@ def test_two_rank_gloo_scatter_gather(n_streams):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def test_numa_local_core_split():
+    """Ranks share the cores of the NUMA node their GPU hangs off; unknown topology -> even split (bench.py)."""
+    from botsort_b200.sharding import parse_cpulist, split_cores_numa_local
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    node0, node1 = list(range(0, 16)) + list(range(32, 48)), list(range(16, 32)) + list(range(48, 64))
+    topo = [node0] * 4 + [node1] * 4
+    allowed = list(range(64))
+    got = [split_cores_numa_local(topo, allowed, r) for r in range(8)]
+    assert all(len(g) == 8 for g in got)
+    assert all(set(got[r]) <= set(node0) for r in range(4)) and all(set(got[r]) <= set(node1) for r in range(4, 8))
+    assert len(set().union(*map(set, got))) == 64                      # disjoint, everything used
+    # no sysfs: the old even split
+    got = [split_cores_numa_local([[]] * 4, list(range(32)), r) for r in range(4)]
+    assert got == [list(range(8 * r, 8 * r + 8)) for r in range(4)]
+    # affinity mask narrower than the node
+    assert split_cores_numa_local([node0, node0], list(range(4)), 1) == [2, 3]
