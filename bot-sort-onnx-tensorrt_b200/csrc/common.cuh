@@ -285,6 +285,8 @@ struct bt_frame_cfg {
 // be replayed as a CUDA graph; `b` is the host copy, used for the launch geometry only.  fixed != 0: geometry
 // from the ctx capacities instead (what a captured graph needs; surplus blocks exit at once).
 // fp32 ingest: det32 rows -> det16 (raw, round to nearest) + L2 norms
+// control block: pinned host -> device by a kernel (no copy-engine command on the frame's critical path)
+int32_t btk_ctrl_upload(bt_ctx* ctx, const void* h_src, void* d_dst, size_t bytes);
 int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, int fixed);
 // detection prep (boxes -> tlbr / xywh / score class / packed corners) + batched Kalman predict of every
 // stream's pool + (optional) detection feature norms: one launch

@@ -28,6 +28,16 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
   return s;
 }
 
+// ---- control block upload ----------------------------------------------------------------------------
+// The frame's packed control block (launch description + pool lists, ~22 KB at 2000 tracks) is read by the GPU
+// straight from the pinned host buffer: a cudaMemcpyAsync of this size is staged through the command stream by
+// the driver and costs the enqueueing thread ~17 us at the very front of the frame's critical path, a launch ~4.
+__global__ void __launch_bounds__(256)
+ctrl_upload_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n16) dst[i] = src[i];
+}
+
 // ---- fp32 ingest: cast + norm ------------------------------------------------------------------
 // One CTA per detection row.  det16 = round-to-nearest fp16 of the RAW row (the reference feeds the raw
 // encoder output to the first association's similarity, demo:1453-1460; rows are normalised only
@@ -539,6 +549,16 @@ bt_res_layout bt_res_layout_for(int cap, int md, int prefetch_pairs) {
   L.o_tlbr_bytes = sizeof(int32_t) * o_endB_i;
   L.strideB = (L.o_tlbr_bytes + sizeof(double) * 4 * cap + 255) & ~size_t(255);
   return L;
+}
+
+int32_t btk_ctrl_upload(bt_ctx* ctx, const void* h_src, void* d_dst, size_t bytes) {
+  const int n16 = (int)((bytes + 15) / 16);
+  if (n16 <= 0) return BT_OK;
+  // a plain launch: the kernels behind it are full dependents (no programmatic overlap with the upload)
+  BT_CUDA(bt_launch(ctx, false, ctrl_upload_kernel, dim3((n16 + 255) / 256), dim3(256), 0,
+                    reinterpret_cast<const uint4*>(h_src), reinterpret_cast<uint4*>(d_dst), n16));
+  BT_LAUNCHED(ctx);
+  return BT_OK;
 }
 
 int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, int fixed) {

@@ -89,6 +89,14 @@ struct StreamState {
   uint64_t tlbr_gen = 0;
   bool boxes_valid = false;         // host_boxes (this frame's detections) has not been overwritten since the step
   bool tlbr_cache_valid = false;
+  // The NEXT frame's pool lists (control segment without the face positions), built from this frame's merged lists
+  // while the GPU finishes the frame (the host would otherwise idle in the final sync); dropped when the finish
+  // phase changes the lists (duplicates) or a pooled track still carries its float32 birth state.
+  bool pre_valid = false;
+  int pre_n_pool = 0, pre_n_rows = 0;
+  std::vector<int32_t> pre_idx, pre_state;
+  std::vector<uint8_t> pre_kind;
+  std::vector<int> pre_unconfirmed;
 };
 
 }  // namespace
@@ -150,6 +158,8 @@ struct bt_tracker {
   int in_seq = 0;
   bool host_debug = false;
   bool no_refine = false;           // BT_NO_REFINE=1: tests show what the exact re-costing buys
+  bool no_prebuild = false;         // BT_NO_PREBUILD=1: pool lists built at the start of the step (A/B)
+  bool ctrl_by_copy = false;        // BT_CTRL_COPY=1: control block by cudaMemcpyAsync instead of the upload kernel (A/B)
   bt_assoc_params last_assoc;       // for bt_profile_replay_assoc
   bt_assoc_frame last_AF;
   int last_assoc_precision = 0;
@@ -222,6 +232,7 @@ void reset_stream(bt_tracker* t, StreamState& s, const bt_config* cfg) {
   s.meta.assign(t->cap, SlotMeta());
   s.tracked.clear();
   s.lost.clear();
+  s.pre_valid = false;
   s.free_slots.clear();
   s.high_water = 0;
   s.id_count = 0;  // BaseTrack.clear_count(), demo:1264 (per tracker here)
@@ -314,6 +325,8 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   for (auto& e : t->in_events) BT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   t->host_debug = getenv("BT_HOST_DEBUG") != nullptr;
   t->no_refine = getenv("BT_NO_REFINE") != nullptr;
+  t->ctrl_by_copy = getenv("BT_CTRL_COPY") != nullptr;
+  t->no_prebuild = getenv("BT_NO_PREBUILD") != nullptr;
   // measured at C3 (profiles/README.md): replaying the captured frame costs one ~23 us cudaGraphLaunch before the GPU
   // starts, the plain enqueue ~70 us of driver calls of which only the first ~25 us delay the GPU -- the plain
   // enqueue wins on this driver, and clearly so when a copy stream is busy next to it (pipelined ingest).  The graph
@@ -592,9 +605,12 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     std::vector<int>& unconfirmed = s.v_unconfirmed; unconfirmed.clear();
     // pool = activated tracked tracks (list order) then lost tracks (joint_stracks, demo:1423: ids are unique per
     // slot, no overlap): written straight into the control segment, which the list bookkeeping reads back later
-    int n_act = 0;
-    for (int slot : s.tracked) n_act += meta[slot].activated ? 1 : 0;
-    s.n_pool = n_act + (int)s.lost.size();
+    if (s.pre_valid) s.n_pool = s.pre_n_pool;
+    else {
+      int n_act = 0;
+      for (int slot : s.tracked) n_act += meta[slot].activated ? 1 : 0;
+      s.n_pool = n_act + (int)s.lost.size();
+    }
     s.n_rows = s.high_water;
     const bool face = in.face_sim != nullptr && s.n_pool > 0;
     any_face = any_face || face;
@@ -603,25 +619,37 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     int32_t* h_state = h_idx + s.n_pool;
     uint8_t* h_kind = reinterpret_cast<uint8_t*>(h_state + s.n_pool);
     int32_t* h_pos = reinterpret_cast<int32_t*>(h_kind + (((size_t)s.n_rows + 3) & ~size_t(3)));
-    memset(h_kind, BT_ROW_NONE, ((size_t)s.n_rows + 3) & ~size_t(3));
-    if (face) for (int r = 0; r < s.n_rows; ++r) h_pos[r] = -1;
     bool all_f32 = s.n_pool > 0;
-    int np = 0;
-    auto add_pool = [&](int slot) {
-      SlotMeta& tm = meta[slot];
-      h_idx[np] = slot;
-      h_state[np] = tm.state;
-      h_kind[slot] = (tm.state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
-      if (face) h_pos[slot] = np;
-      all_f32 = all_f32 && tm.f32_state;
-      tm.f32_state = 0;     // predicted below: float64 from now on
-      ++np;
-    };
-    for (int slot : s.tracked) {
-      if (!meta[slot].activated) { unconfirmed.push_back(slot); h_kind[slot] = BT_ROW_UNCONFIRMED; }
-      else add_pool(slot);
+    if (s.pre_valid && !face && s.pre_n_rows == s.n_rows && s.pre_n_pool == s.n_pool) {
+      // built at the end of the previous step (no pooled track has float32 state there: all_f32 is false)
+      if (s.n_pool > 0) {
+        memcpy(h_idx, s.pre_idx.data(), sizeof(int32_t) * (size_t)s.n_pool);
+        memcpy(h_state, s.pre_state.data(), sizeof(int32_t) * (size_t)s.n_pool);
+      }
+      memcpy(h_kind, s.pre_kind.data(), ((size_t)s.n_rows + 3) & ~size_t(3));
+      unconfirmed.swap(s.pre_unconfirmed);
+      all_f32 = false;
+    } else {
+      memset(h_kind, BT_ROW_NONE, ((size_t)s.n_rows + 3) & ~size_t(3));
+      if (face) for (int r = 0; r < s.n_rows; ++r) h_pos[r] = -1;
+      int np = 0;
+      auto add_pool = [&](int slot) {
+        SlotMeta& tm = meta[slot];
+        h_idx[np] = slot;
+        h_state[np] = tm.state;
+        h_kind[slot] = (tm.state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
+        if (face) h_pos[slot] = np;
+        all_f32 = all_f32 && tm.f32_state;
+        tm.f32_state = 0;     // predicted below: float64 from now on
+        ++np;
+      };
+      for (int slot : s.tracked) {
+        if (!meta[slot].activated) { unconfirmed.push_back(slot); h_kind[slot] = BT_ROW_UNCONFIRMED; }
+        else add_pool(slot);
+      }
+      for (int slot : s.lost) add_pool(slot);
     }
-    for (int slot : s.lost) add_pool(slot);
+    s.pre_valid = false;
     s.pool = h_idx;
     s.n_unc = (int)unconfirmed.size();
     B.sid[k] = sid;
@@ -742,7 +770,8 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   // side stream joined back
   auto enqueue = [&](const int fixed) -> int32_t {
     const size_t ctrl_bytes_now = fixed ? kDescBytes + t->ctrl_stride * (size_t)count : ctrl_off;
-    BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_bytes_now, cudaMemcpyHostToDevice, st));
+    if (t->ctrl_by_copy) BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_bytes_now, cudaMemcpyHostToDevice, st));
+    else BT_TRY(btk_ctrl_upload(ctx, t->h_ctrl, dst.ctrl, ctrl_bytes_now));
     fmark("ctrl_h2d");
     SEG_BEGIN(BT_SEG_PREP);
     if (any_f32) BT_TRY(btk_frame_cast(ctx, dst, B, &dd->B, fixed));
@@ -931,6 +960,31 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   }
   fmark("L:merge");
   HOST_MARK(BT_SEG_HOST_LISTS);
+  // ---- the next frame's pool lists, while the GPU finishes this frame (Kalman update / EMA / duplicate test) ----
+  for (int k = 0; k < count && !t->no_prebuild; ++k) {
+    StreamState& s = t->streams[sids[k]];
+    const SlotMeta* meta = s.meta.data();
+    const int n_rows = s.high_water;
+    s.pre_kind.assign(((size_t)n_rows + 3) & ~size_t(3), (uint8_t)BT_ROW_NONE);
+    s.pre_idx.clear(); s.pre_state.clear(); s.pre_unconfirmed.clear();
+    bool any_f32 = false;
+    auto add_pool = [&](int slot) {
+      const SlotMeta& tm = meta[slot];
+      s.pre_idx.push_back(slot);
+      s.pre_state.push_back(tm.state);
+      s.pre_kind[slot] = (tm.state == BT_STATE_TRACKED) ? BT_ROW_POOL_TRACKED : BT_ROW_POOL_OTHER;
+      any_f32 = any_f32 || tm.f32_state;
+    };
+    for (int slot : s.v_new_tracked) {
+      if (!meta[slot].activated) { s.pre_unconfirmed.push_back(slot); s.pre_kind[slot] = BT_ROW_UNCONFIRMED; }
+      else add_pool(slot);
+    }
+    for (int slot : s.v_new_lost) add_pool(slot);
+    s.pre_n_pool = (int)s.pre_idx.size();
+    s.pre_n_rows = n_rows;
+    s.pre_valid = !any_f32;
+  }
+  fmark("prebuild");
   BT_CUDA(cudaStreamSynchronize(st));    // the frame's device work is complete, part B is on the host
   if (ema_pending) BT_CUDA(cudaEventSynchronize(t->ev_join));   // the side stream's EMA (usually done already)
   HOST_MARK(BT_SEG_HOST_WAIT2);
@@ -1040,6 +1094,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       for (int q = 0; q < n_bpairs; ++q)     // (birth index, lost position)
         resolve(pos_t[s.v_birth_slot[t->h_bpairs[2 * q]]], t->h_bpairs[2 * q + 1]);
     }
+    if (pairs_overflow || n_pairs > 0 || n_bpairs > 0) s.pre_valid = false;   // the lists may change below
     s.tracked.clear();
     s.lost.clear();
     for (int i = 0; i < nt; ++i)
