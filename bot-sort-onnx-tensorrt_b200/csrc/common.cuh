@@ -293,7 +293,8 @@ int32_t btk_frame_cast(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const
 int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed);
 // Kalman update of every slot matched by one of the three stages; feature EMA of the same slots (independent of
 // it: launched on `stream`, the ctx's side stream)
-int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed);
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed,
+                       int dependent);
 int32_t btk_frame_ema(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc,
                       cudaStream_t stream, int fixed);
 // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box

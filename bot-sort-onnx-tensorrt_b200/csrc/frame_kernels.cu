@@ -340,6 +340,9 @@ __device__ __forceinline__ void ema_row_half(const bt_store& st, const bt_frame_
 __global__ void __launch_bounds__(kThreads)
 frame_post_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_res_layout L) {
   const bt_batch& b = *bp;
+  // (possibly) a programmatic dependent of the LAP kernel: the assignment vectors are final once the wait returns.
+  // Only then may the launch behind this one start: its feature-update CTAs read the assignments without waiting.
+  bt_grid_dependency_wait();
   bt_grid_launch_dependents();   // the duplicate test is queued behind this kernel and waits for its boxes
   const int k = blockIdx.y;
   const int sid = b.sid[k];
@@ -586,12 +589,13 @@ int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const
   return BT_OK;
 }
 
-int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed) {
+int32_t btk_frame_post(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const bt_batch* db, const bt_frame_cfg& fc, int fixed,
+                       int dependent) {
   const int mx_rows = fixed ? st.cap : bt_batch_max(b.n_rows, b.count);
   if (mx_rows <= 0) return BT_OK;
   const int upd_blocks = (mx_rows * 8 + kThreads - 1) / kThreads;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch(ctx, false, frame_post_kernel, dim3(upd_blocks, b.count), dim3(kThreads), 0, st, db, L));
+  BT_CUDA(bt_launch(ctx, dependent != 0, frame_post_kernel, dim3(upd_blocks, b.count), dim3(kThreads), 0, st, db, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

@@ -158,6 +158,7 @@ struct bt_tracker {
   int in_seq = 0;
   bool host_debug = false;
   bool no_refine = false;           // BT_NO_REFINE=1: tests show what the exact re-costing buys
+  bool copy_inline = false;         // BT_COPY_INLINE=1: assignment read-back on the main stream (A/B)
   bool no_prebuild = false;         // BT_NO_PREBUILD=1: pool lists built at the start of the step (A/B)
   bool ctrl_by_copy = false;        // BT_CTRL_COPY=1: control block by cudaMemcpyAsync instead of the upload kernel (A/B)
   bt_assoc_params last_assoc;       // for bt_profile_replay_assoc
@@ -327,6 +328,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   t->no_refine = getenv("BT_NO_REFINE") != nullptr;
   t->ctrl_by_copy = getenv("BT_CTRL_COPY") != nullptr;
   t->no_prebuild = getenv("BT_NO_PREBUILD") != nullptr;
+  t->copy_inline = getenv("BT_COPY_INLINE") != nullptr;
   // measured at C3 (profiles/README.md): replaying the captured frame costs one ~23 us cudaGraphLaunch before the GPU
   // starts, the plain enqueue ~70 us of driver calls of which only the first ~25 us delay the GPU -- the plain
   // enqueue wins on this driver, and clearly so when a copy stream is busy next to it (pipelined ingest).  The graph
@@ -795,11 +797,19 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     // part A of the result regions: the assignment vectors (+ echoed scores / boxes of device inputs)
     const size_t widthA = sizeof(int32_t) * (any_dev_inputs ? L.o_endA : L.o_sc);
     if (mx_rows > 0 || (any_dev_inputs && mx_m > 0) || fixed) {
-      if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_res, dst.res, widthA, cudaMemcpyDeviceToHost, st));
-      else BT_CUDA(cudaMemcpy2DAsync(t->h_res, L.stride, dst.res, L.stride, widthA, count, cudaMemcpyDeviceToHost, st));
+      // plain enqueue: the read-back runs on the side stream, so that the Kalman update behind the LAP kernel does not
+      // queue behind a copy-engine round trip (it becomes a programmatic dependent of the LAP kernel instead)
+      const bool aside = !fixed && !t->copy_inline;
+      cudaStream_t cs = aside ? ctx->side_stream : st;
+      if (aside) {
+        BT_CUDA(cudaEventRecord(t->ev_fork, st));
+        BT_CUDA(cudaStreamWaitEvent(cs, t->ev_fork, 0));
+      }
+      if (count == 1) BT_CUDA(cudaMemcpyAsync(t->h_res, dst.res, widthA, cudaMemcpyDeviceToHost, cs));
+      else BT_CUDA(cudaMemcpy2DAsync(t->h_res, L.stride, dst.res, L.stride, widthA, count, cudaMemcpyDeviceToHost, cs));
       // under capture: an event RECORD NODE the host can wait on (a plain record would only order captured work)
       if (fixed) BT_CUDA(cudaEventRecordWithFlags(t->ev_x, st, cudaEventRecordExternal));
-      else BT_CUDA(cudaEventRecord(t->ev_x, st));
+      else BT_CUDA(cudaEventRecord(t->ev_x, cs));
       part_a_sent = true;
       fmark("copyA+ev");
     }
@@ -808,7 +818,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
       // vectors, so they run on the device straight away (STrack.update / re_activate arithmetic,
       // demo:570-610) while the host is still waiting for / digesting the assignments.
       SEG_BEGIN(BT_SEG_UPDATE);
-      BT_TRY(btk_frame_post(ctx, dst, B, &dd->B, fc, fixed));
+      BT_TRY(btk_frame_post(ctx, dst, B, &dd->B, fc, fixed, (!fixed && !t->copy_inline && part_a_sent) ? 1 : 0));
       SEG_END(BT_SEG_UPDATE);
       fmark("post");
       // duplicate candidates among all live slots (superset of tracked x lost) + every slot's box
