@@ -279,6 +279,7 @@ struct bt_frame_cfg {
   int32_t keep_smooth;
   int32_t prefetch_pairs;      // duplicate pairs kept in the result block
   int32_t with_reid;           // feature rows are part of the frame
+  int32_t l2_prefetch;         // the tensor-core association kernel follows: prefetch its operands into L2 beside the prep work
 };
 // The per-frame kernels read the batch description (`db`: bt_batch in DEVICE memory, uploaded with the frame's
 // control block) themselves, so their kernel arguments never change from frame to frame and the whole frame can

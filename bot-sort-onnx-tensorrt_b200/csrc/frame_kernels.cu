@@ -82,7 +82,7 @@ frame_cast_kernel(bt_store st, const bt_batch* __restrict__ bp) {
 // doubles), packed integer corners for the association kernel's overlap screen.
 __global__ void __launch_bounds__(kThreads)
 frame_prep_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc, int pred_blocks,
-                  int det_blocks, bt_res_layout L) {
+                  int det_blocks, int norm_blocks, int pf_blocks, bt_res_layout L) {
   const bt_batch& b = *bp;
   bt_grid_launch_dependents();   // the association kernel behind this one loads its operands meanwhile
   __shared__ float red[kThreads / 32];
@@ -132,9 +132,24 @@ frame_prep_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc,
     return;
   }
   bx -= det_blocks;
+  const int D = st.D;
+  if (bx >= norm_blocks) {
+    // ---- L2 prefetch of the association kernel's operands (the bank rows in use, this frame's detection rows):
+    //      the association kernel behind this launch streams them through a 4-stage TMA ring, which cannot cover
+    //      DRAM latency on first touch; these blocks pull the 16 MB at full memory-level parallelism meanwhile ----
+    bx -= norm_blocks;
+    if (bx >= pf_blocks || ((size_t)D * sizeof(__half)) % 128 != 0) return;
+    const size_t lines_a = (size_t)b.n_rows[k] * D * sizeof(__half) / 128, lines_b = (size_t)m * D * sizeof(__half) / 128;
+    const char* a0 = reinterpret_cast<const char*>(st.feat16 + (size_t)sid * st.cap * D);
+    const char* b0 = reinterpret_cast<const char*>(st.det16 + in0 * D);
+    for (size_t i = (size_t)bx * kThreads + threadIdx.x; i < lines_a + lines_b; i += (size_t)pf_blocks * kThreads) {
+      const char* ptr = i < lines_a ? a0 + i * 128 : b0 + (i - lines_a) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+    return;
+  }
   // ---- detection feature norms (fp16 ingest; only for streams with unconfirmed rows) ----
   if (!b.want_norm[k] || bx >= m) return;
-  const int D = st.D;
   const __half* src = st.det16 + (in0 + bx) * D;
   float ss = 0.f;
   if ((D & 7) == 0) {
@@ -581,10 +596,13 @@ int32_t btk_frame_prep(bt_ctx* ctx, const bt_store& st, const bt_batch& b, const
   else
     for (int k = 0; k < b.count; ++k)
       if (b.want_norm[k] && b.m[k] > norm_blocks) norm_blocks = b.m[k];
-  const int gx = pred_blocks + det_blocks + norm_blocks;
+  // operand prefetch blocks: only when the tensor-core association kernel follows (fp16 operands, rows x dets worth it)
+  const int pf_blocks = (fc.with_reid && fc.l2_prefetch && mx_m > 0 && mx_pool > 0) ? 256 : 0;
+  const int gx = pred_blocks + det_blocks + norm_blocks + pf_blocks;
   if (gx <= 0) return BT_OK;
   const bt_res_layout L = bt_res_layout_for(st.cap, st.md, fc.prefetch_pairs);
-  BT_CUDA(bt_launch(ctx, false, frame_prep_kernel, dim3(gx, b.count), dim3(kThreads), 0, st, db, fc, pred_blocks, det_blocks, L));
+  BT_CUDA(bt_launch(ctx, false, frame_prep_kernel, dim3(gx, b.count), dim3(kThreads), 0, st, db, fc, pred_blocks, det_blocks,
+                    norm_blocks, pf_blocks, L));
   BT_LAUNCHED(ctx);
   return BT_OK;
 }

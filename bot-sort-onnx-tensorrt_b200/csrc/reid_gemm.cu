@@ -785,10 +785,14 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         if (p.debug & 16) t_ex = clock64();
         if ((p.debug & 2) || rkind == BT_ROW_NONE) gatebits = 0;
-        // phase B: only chunks in which some row of the warp has an open gate are looked at again.
-        // One rolled loop (one copy of the code: it runs once or twice per warp and would otherwise be
-        // fetched cold every time); the tail chunk is loaded 32 wide and masked.
+        // phase B: only chunks in which some row of the warp has an open gate are looked at again (one rolled
+        // loop; the tail chunk is loaded 32 wide and masked).  The chunk loop only COLLECTS the open pairs --
+        // (local column, accumulator), two per lane in registers -- and the float64 fusion runs afterwards, once
+        // for all lanes: rows of a warp have their open pairs in different chunks, and evaluating them chunk by
+        // chunk ran the expensive part once per chunk with one or two lanes active.
         uint32_t need = __reduce_or_sync(0xffffffffu, gatebits);
+        int e0c = -1, e1c = -1;
+        float e0v = 0.f, e1v = 0.f;
         while (need) {                          // warp-uniform
           const int ch = __ffs(need) - 1;
           need &= need - 1;
@@ -821,10 +825,21 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 2; ++i) s2[i] = (c & 2) ? s4[i + 2] : s4[i];
               const float accv = __uint_as_float((c & 1) ? s2[1] : s2[0]);
-              open_pair(half * kHalfCols + ch * 32 + c, accv);
+              const int lc = half * kHalfCols + ch * 32 + c;
+              if (e0c < 0) { e0c = lc; e0v = accv; }
+              else if (e1c < 0) { e1c = lc; e1v = accv; }
+              else open_pair(lc, accv);          // a third open pair of one row in this half tile: on the spot
               ++dbg_open;
             }
           }
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+          const int lc = e ? e1c : e0c;
+          const float v = e ? e1v : e0v;
+          if (!__any_sync(0xffffffffu, lc >= 0)) break;
+          if (lc >= 0) open_pair(lc, v);
           __syncwarp();
         }
       }

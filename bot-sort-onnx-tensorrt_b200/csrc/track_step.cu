@@ -158,6 +158,7 @@ struct bt_tracker {
   int in_seq = 0;
   bool host_debug = false;
   bool no_refine = false;           // BT_NO_REFINE=1: tests show what the exact re-costing buys
+  bool no_l2_prefetch = false;      // BT_NO_L2_PREFETCH=1 (A/B)
   bool copy_inline = false;         // BT_COPY_INLINE=1: assignment read-back on the main stream (A/B)
   bool no_prebuild = false;         // BT_NO_PREBUILD=1: pool lists built at the start of the step (A/B)
   bool ctrl_by_copy = false;        // BT_CTRL_COPY=1: control block by cudaMemcpyAsync instead of the upload kernel (A/B)
@@ -329,6 +330,7 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   t->ctrl_by_copy = getenv("BT_CTRL_COPY") != nullptr;
   t->no_prebuild = getenv("BT_NO_PREBUILD") != nullptr;
   t->copy_inline = getenv("BT_COPY_INLINE") != nullptr;
+  t->no_l2_prefetch = getenv("BT_NO_L2_PREFETCH") != nullptr;
   // measured at C3 (profiles/README.md): replaying the captured frame costs one ~23 us cudaGraphLaunch before the GPU
   // starts, the plain enqueue ~70 us of driver calls of which only the first ~25 us delay the GPU -- the plain
   // enqueue wins on this driver, and clearly so when a copy stream is busy next to it (pipelined ingest).  The graph
@@ -685,6 +687,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   fc.keep_smooth = dst.smooth32 != nullptr;
   fc.prefetch_pairs = kPairPrefetch;
   fc.with_reid = any_reid ? 1 : 0;
+  fc.l2_prefetch = (any_reid && tensor_path && !t->no_l2_prefetch) ? 1 : 0;
 
   const int mx_rows = bt_batch_max(B.n_rows, count), mx_m = bt_batch_max(B.m, count);
   const int assoc_bn = (any_reid && tensor_path) ? btk_assoc_pick_bn(ctx, B.n_rows, B.m, count) : 256;
