@@ -587,12 +587,14 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
   const size_t rbase = (size_t)list * cand.rows_cap;
   for (int r0 = tid; r0 < n; r0 += kP1 * GT) {
     int degs[kP1], rcs[kP1], inds[kP1], rbl[kP1];
+    unsigned long long masks[kP1];      // the row's non-empty segments: fetched with the first level (no dependency)
 #pragma unroll
     for (int q = 0; q < kP1; ++q) {
       const int r = r0 + q * GT;
-      degs[q] = 0; rcs[q] = 0; rbl[q] = -1;
+      degs[q] = 0; rcs[q] = 0; rbl[q] = -1; masks[q] = 0ull;
       if (r < n) {
         degs[q] = cand.rowdeg[rbase + r]; rcs[q] = cand.rowcol[rbase + r];
+        if (a.clear_cnt) masks[q] = cand.segmask[rbase + r];
         if (row_block) rbl[q] = row_block[r];
       }
     }
@@ -616,8 +618,8 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
           x[r] = col1;
           if (a.need_y) y[col1] = r;               // (a scattered store per row: only when somebody reads y)
         }
-        if (a.clear_cnt) {                         // atomic emitter: leave the segment counters zeroed
-          unsigned long long mm = cand.segmask[rbase + r];
+        if (a.clear_cnt) {                         // leave the segment counters zeroed
+          unsigned long long mm = masks[q];
           while (mm) { const int g = __ffsll((long long)mm) - 1; mm &= mm - 1; segcnt_all[(size_t)r * cand.nseg + g] = 0; }
         }
         if (a.clear) cand.segmask[rbase + r] = 0ull;
@@ -998,6 +1000,23 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
     lap_stage(B, rf, sm);
     __syncthreads();
   }
+  // a stage's arguments (a few hundred bytes written by one thread); need_y is patched once the totals are known
+  auto setup_stage = [&](const int stage) {
+    StageArgs& sa = sm.sa;
+    const int list = P.nstages == 1 ? P.list0 : stage;
+    sa.cand = cand; sa.W = W; sa.kb = kb; sa.list = list; sa.n = n; sa.m = m; sa.clear = P.clear_lists; sa.debug = P.debug;
+    sa.clear_cnt = P.clear_lists && P.clear_cnt;
+    sa.need_y = 1;
+    sa.thresh = P.thresh[stage];
+    sa.x = B.x[kb] + (size_t)stage * B.x_stride[kb];
+    sa.y = B.y[kb] + (size_t)stage * B.y_stride;
+    // stage 2 (demo:1568-1571): rows unmatched in stage 1; stage 3 (demo:1588-1604): columns unmatched in stage 1
+    sa.row_block = (P.nstages == 3 && stage == 1) ? B.x[kb] : nullptr;
+    sa.col_block = (P.nstages == 3 && stage == 2) ? B.y[kb] : nullptr;
+    sa.tq = nullptr;
+    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.nP = 0; sm.big = 0;
+  };
+  if (tid == 0) setup_stage(0);      // the first stage's arguments are ready before the candidate lists are
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
   LAP_T(1);
@@ -1007,21 +1026,11 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
   for (int stage = 0; stage < P.nstages; ++stage) {
     const int list = P.nstages == 1 ? P.list0 : stage;
     if ((list == 0 ? tot0 : (list == 1 ? tot1 : tot2)) == 0) continue;   // nothing was emitted for this stage (CTA-uniform)
-    StageArgs& sa = sm.sa;
     if (tid == 0) {
-    sa.cand = cand; sa.W = W; sa.kb = kb; sa.list = list; sa.n = n; sa.m = m; sa.clear = P.clear_lists; sa.debug = P.debug;
-    sa.clear_cnt = P.clear_lists && P.clear_cnt;
-    // y (column -> row) of a stage is read by the caller of the stand-alone solver and, for the frame's first
-    // stage, by stage 3 (columns stage 1 took are blocked) -- when stage 3 has any candidates at all
-    sa.need_y = (P.nstages == 1) || (stage == 0 && tot2 != 0);
-    sa.thresh = P.thresh[stage];
-    sa.x = B.x[kb] + (size_t)stage * B.x_stride[kb];
-    sa.y = B.y[kb] + (size_t)stage * B.y_stride;
-    // stage 2 (demo:1568-1571): rows unmatched in stage 1; stage 3 (demo:1588-1604): columns unmatched in stage 1
-    sa.row_block = (P.nstages == 3 && stage == 1) ? B.x[kb] : nullptr;
-    sa.col_block = (P.nstages == 3 && stage == 2) ? B.y[kb] : nullptr;
-    sa.tq = nullptr;
-    sm.nC = 0; sm.nE = 0; sm.nR = 0; sm.nP = 0; sm.big = 0;
+      if (stage != 0) setup_stage(stage);
+      // y (column -> row) of a stage is read by the caller of the stand-alone solver and, for the frame's first
+      // stage, by stage 3 (columns stage 1 took are blocked) -- when stage 3 has any candidates at all
+      sm.sa.need_y = (P.nstages == 1) || (stage == 0 && tot2 != 0);
     }
     __syncthreads();
     lap_stage(B, rf, sm);

@@ -7,7 +7,7 @@ mkdir -p $O
 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu > $O/${TAG}_bench_c3_1gpu_8gpu_box.json 2> $O/${TAG}_1gpu.err
 for n in 2 4 8; do
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
-      bench.py --gpus $n --steps 20 --warmup 3 --no-cpu --c5-full-scatter > $O/${TAG}_bench_c3_${n}gpu.json 2> $O/${TAG}_${n}gpu.err
+      bench.py --gpus $n --steps 20 --warmup 3 --no-cpu > $O/${TAG}_bench_c3_${n}gpu.json 2> $O/${TAG}_${n}gpu.err
 done
 python - <<PY
 import json
