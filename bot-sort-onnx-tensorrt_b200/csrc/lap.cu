@@ -549,10 +549,140 @@ struct SmallSmem {
   int32_t pathrow[kSmallCols], seen[kSmallCols], insc[kSmallCols], yl[kSmallCols], clabel[kSmallCols], touched[kSmallCols];
   int32_t s_warp[32];
   int32_t s_carry;
+  double red_d[kLapThreads / 32];      // CTA-wide component solver: per-warp minima
+  int32_t red_c[kLapThreads / 32], red_f[kLapThreads / 32];
   int nC, nE, nR, nP, changed, big;
 };
 
 static_assert(sizeof(SmallSmem) <= 227 * 1024, "the LAP's on-chip state must fit the SM's shared memory");
+
+// Per-column solver state of the CTA-wide component solver: shared memory when the stream's detections fit
+// (kSmallCols), the global scratch otherwise.  ymir mirrors y (column -> row) for the columns of the component.
+struct ColState {
+  double* v; double* dist;
+  int32_t* pathrow; int32_t* seen; int32_t* insc; int32_t* ymir;
+};
+
+// The WHOLE CTA solves one large connected component exactly (a crowded scene, a dense cost matrix = one giant
+// component): the same shortest-augmenting-path algorithm, tie-breaking and floating-point operation order as
+// solve_component, with the relaxation of a row's edges and the minimum scan spread over all threads -- one warp
+// walked a dense 512 x 512 component in 131 ms (profiles/r02_lap_dense.json).  The scan covers all m columns of the
+// stream (stamps tell which are touched): no touched list, no compaction.
+__device__ void solve_component_cta(const SolveArrays& ws, int comp, double thresh, int m,
+                                    const int32_t* col_block, const int32_t* cnt,
+                                    const int32_t* ecol, const double* ecost,
+                                    int32_t* x, int32_t* y, const ColState& cs, SmallSmem& sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int GT = kLapThreads, NW = kLapThreads / 32;
+  const int r0 = ws.rowcnt[comp], nr = ws.rowcnt[comp + 1] - r0;
+  int32_t* rows = ws.sorted_rows + r0;
+  int32_t* treerows = ws.treerows + r0;
+  // deterministic processing order: ascending row index (rank sort through the tree-row scratch)
+  for (int a = tid; a < nr; a += GT) {
+    const int mine = rows[a];
+    int rank = 0;
+    for (int k = 0; k < nr; ++k) rank += (rows[k] < mine);
+    treerows[rank] = mine;
+  }
+  __syncthreads();
+  for (int a = tid; a < nr; a += GT) rows[a] = treerows[a];
+  __syncthreads();
+
+  for (int ri = 0; ri < nr; ++ri) {
+    const int i0 = rows[ri];
+    const int sid = i0 + 1;  // unique search stamp
+    int nTR = 0;
+    int i = i0;
+    double ui = ws.u[i0];
+    double minVal = 0.0;
+    double bestDummy = -ui;
+    int bestDummyRow = i0;
+    int sink = -1;       // >= 0: real column; -2: dummy of bestDummyRow
+    while (true) {
+      // ---- relax the edges of row i (a column occurs once per row: no write conflicts) ----
+      const int deg = cnt[i];
+      const size_t eb = ebase(ws, i);
+      for (int k = tid; k < deg; k += GT) {
+        const int c = ecol[eb + k];
+        if (edge_ok(col_block, c) && cs.insc[c] != sid) {
+          const double r = minVal + (ecost[eb + k] - thresh) - ui - cs.v[c];
+          if (cs.seen[c] != sid) { cs.seen[c] = sid; cs.dist[c] = r; cs.pathrow[c] = i; }
+          else if (r < cs.dist[c]) { cs.dist[c] = r; cs.pathrow[c] = i; }
+        }
+      }
+      __syncthreads();
+      // ---- closest touched column outside the scanned set ----
+      MinPair best{DBL_MAX, kInf, 0};
+      for (int c = tid; c < m; c += GT) {
+        if (cs.seen[c] != sid || cs.insc[c] == sid) continue;
+        MinPair cur{cs.dist[c], c, (cs.ymir[c] < 0) ? 1 : 0};
+        if (better(cur, best)) best = cur;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        MinPair oth{__shfl_xor_sync(0xffffffffu, best.d, o), __shfl_xor_sync(0xffffffffu, best.c, o),
+                    __shfl_xor_sync(0xffffffffu, best.freecol, o)};
+        if (better(oth, best)) best = oth;
+      }
+      if (lane == 0) { sm.red_d[warp] = best.d; sm.red_c[warp] = best.c; sm.red_f[warp] = best.freecol; }
+      __syncthreads();
+      best = MinPair{sm.red_d[0], sm.red_c[0], sm.red_f[0]};
+#pragma unroll
+      for (int w = 1; w < NW; ++w) {
+        MinPair oth{sm.red_d[w], sm.red_c[w], sm.red_f[w]};
+        if (better(oth, best)) best = oth;
+      }
+      if (best.c == kInf || bestDummy <= best.d) {
+        minVal = bestDummy;
+        sink = -2;
+        break;
+      }
+      minVal = best.d;
+      const int j = best.c;
+      if (tid == 0) cs.insc[j] = sid;
+      if (best.freecol) { sink = j; break; }
+      i = cs.ymir[j];
+      if (tid == 0) treerows[nTR] = i;
+      ++nTR;
+      ui = ws.u[i];
+      const double cand_d = minVal - ui;
+      if (cand_d < bestDummy) { bestDummy = cand_d; bestDummyRow = i; }
+      __syncthreads();                    // insc[j] is set before the next relaxation reads it; the minima slots are free again
+    }
+    // ---- dual updates (Crouse 2016, eq. step 4) ----
+    __syncthreads();
+    for (int k = tid; k < nTR; k += GT) {
+      const int r = treerows[k];
+      ws.u[r] += minVal - cs.dist[x[r]];
+    }
+    for (int c = tid; c < m; c += GT)
+      if (cs.insc[c] == sid) cs.v[c] -= minVal - cs.dist[c];
+    __syncthreads();
+    if (tid == 0) {
+      ws.u[i0] += minVal;
+      // ---- augment ----
+      int j;
+      bool go = true;
+      if (sink == -2) {
+        if (bestDummyRow == i0) go = false;
+        j = go ? x[bestDummyRow] : -1;
+        if (go) x[bestDummyRow] = -1;
+      } else {
+        j = sink;
+      }
+      while (go) {
+        const int pi = cs.pathrow[j];
+        y[j] = pi;
+        cs.ymir[j] = pi;
+        const int t = x[pi];
+        x[pi] = j;
+        j = t;
+        if (pi == i0) break;
+      }
+    }
+    __syncthreads();
+  }
+}
 
 // One association stage of one video stream.  A real (noinline) function on purpose: the kernel calls it once on
 // a two-row dummy problem BEFORE griddepcontrol.wait -- every phase of this latency-bound kernel runs exactly once
@@ -945,8 +1075,26 @@ __device__ __noinline__ void lap_stage(const bt_lap_batch& B, const bt_refine& r
     __syncthreads();
     const SolveArrays GA{W.rowcnt, W.colcnt, W.sorted_rows, W.touched, W.treerows, W.u, W.v, W.dist,
                          W.pathrow, W.seen, W.insc, nullptr, (size_t)cand.stride};
+    // large components: the whole CTA, one after the other (per-column state in shared memory when it fits) ...
+    constexpr int kCtaRows = 48;
+    bool any_cta = false;
+    for (int comp = 0; comp < ncomp; ++comp) any_cta = any_cta || (W.rowcnt[comp + 1] - W.rowcnt[comp] > kCtaRows);
+    if (any_cta) {                                  // CTA-uniform
+      ColState cs{W.v, W.dist, W.pathrow, W.seen, W.insc, y};
+      if (m <= kSmallCols) {
+        cs = ColState{sm.v, sm.dist, sm.pathrow, sm.seen, sm.insc, sm.yl};
+        for (int c = tid; c < m; c += GT) { sm.v[c] = 0.0; sm.seen[c] = 0; sm.insc[c] = 0; sm.yl[c] = -1; }
+      }
+      __syncthreads();
+      for (int comp = 0; comp < ncomp; ++comp)
+        if (W.rowcnt[comp + 1] - W.rowcnt[comp] > kCtaRows)
+          solve_component_cta(GA, comp, thresh, m, col_block, cnt, ecol, ecost, x, y, cs, sm);
+      __syncthreads();
+    }
+    // ... the others one warp each
     for (int comp = warp; comp < ncomp; comp += NW)
-      solve_component(GA, comp, thresh, col_block, cnt, ecol, ecost, x, y, lane);
+      if (W.rowcnt[comp + 1] - W.rowcnt[comp] <= kCtaRows)
+        solve_component(GA, comp, thresh, col_block, cnt, ecol, ecost, x, y, lane);
     dbg_ncomp = ncomp;
   }
   (void)kb;
