@@ -301,6 +301,27 @@ def run_ours(args):
         barrier()
         return [a.elapsed_time(b_) for a, b_ in ev], launches
 
+    def run_long_pass(n_steps=200):
+        """Per-step statistics over many steady-state steps (min / median / p99): the timed frames are
+        played forward and backward (a ping-pong keeps every track's motion continuous, so the scene stays in
+        steady state for as long as we like); no L2 flush, the K distinct 8 MB frames are larger than L2."""
+        ctx.tracker_reset(cfg)
+        for i in range(0, 1 + W):
+            b, s_, f, m = place_inputs(i)
+            ctx.update_streams_raw(sids, b, s_, f, m, BT_DEVICE, bt_feat)
+        order = list(range(1 + W, 1 + W + K)) + list(range(W + K - 1, W + 1, -1))
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        barrier()
+        for k in range(n_steps):
+            b, s_, f, m = place_inputs(order[k % len(order)])
+            torch.cuda.synchronize()
+            ev[k][0].record(cu_stream)
+            ctx.update_streams_raw(sids, b, s_, f, m, BT_DEVICE, bt_feat)
+            ev[k][1].record(cu_stream)
+        barrier()
+        live = sum(int(len(ctx.get_tracks(0, stream=k)["ids"])) for k in range(S))
+        return sorted(a.elapsed_time(b_) for a, b_ in ev), live
+
     def run_e2e_pass(pipelined):
         """Pinned host inputs: every step's host->device copy and the read-back of its tracks are inside the
         timed region.  pipelined: bt_submit_streams(frame k+1) is issued before bt_step_streams(frame k), so
@@ -339,6 +360,7 @@ def run_ours(args):
     dev_ms, launches = run_value_pass()                      # `value`
     # the other admissible protocol: no flush, every step reads a detection frame it has never touched
     dev_ms_warm, _ = run_value_pass(l2_flush=False)
+    long_ms, long_live = run_long_pass(200) if K >= 2 else ([0.0], 0)
     run_value_pass(profile=True)                             # same steps again with per-kernel CUDA events
     prof = ctx.profile_read()
     ctx.profile_enable(False)
@@ -440,6 +462,11 @@ def run_ours(args):
                 "value": aggregate_throughput(n * S, world, K, total_warm_ms), "unit": "tracks/s",
                 "ms_per_step": total_warm_ms / K,
                 "note": "same K steps without the L2 flush"},
+            "steady_200": {"steps": len(long_ms), "min_ms": long_ms[0], "median_ms": long_ms[len(long_ms) // 2],
+                           "p99_ms": long_ms[min(len(long_ms) - 1, int(0.99 * len(long_ms)))], "mean_ms": sum(long_ms) / len(long_ms),
+                           "live_tracks_end": long_live,
+                           "note": "rank 0: 200 consecutive steady-state steps (the timed frames played forward and backward), "
+                                   "per-step CUDA events, no L2 flush (distinct frames larger than L2)"},
             "gpu_launches": int(launches),
             "segments_ms": segs,
             "roofline": roof,
