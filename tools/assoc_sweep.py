@@ -1,6 +1,6 @@
-"""Profiling sweep of the fused association kernel on the GPU box: for each cluster shape run the
-C3 tracker for a few frames with segment timing on and print the assoc kernel's average time.
-Also checks that every variant returns the same track ids (correctness guard)."""
+"""Tile-width sweep of the fused association kernel on the GPU box: for BN = 224 / 256 run the C3 tracker for a
+few frames, replay the last frame's association launch 50 times back to back (bench.py's roofline measurement)
+and check that every variant returns the same track ids.  python tools/assoc_sweep.py [n]"""
 import os
 import sys
 
@@ -11,30 +11,17 @@ sys.path.insert(0, ROOT)
 import botsort_b200 as bs  # noqa: E402
 from botsort_b200.synthetic import SceneConfig, SyntheticScene  # noqa: E402
 
-n = int(os.environ.get("SWEEP_N", "2000"))
-frames_n = 14
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 scene = SyntheticScene(SceneConfig(n_ids=n, feat_dim=2048, seed=1))
-frames = [scene.next_frame() for _ in range(frames_n)]
+frames = [scene.next_frame() for _ in range(8)]
 ctx = bs.Context(max_tracks=n + 256, max_dets=n + 256, feat_dim=2048)
 ref_ids = None
-for variant in sys.argv[1:] or ["1x1", "1x2", "2x1", "2x2", "4x2", "2x4", "4x1", "1x4"]:
-    os.environ["BT_ASSOC_CLUSTER"] = variant
-    try:
-        ctx.tracker_reset()
-        for f in frames[:4]:
-            ctx.update_arrays(f["boxes"], f["scores"], f["feats"])
-        ctx.profile_enable(True)
-        for f in frames[4:]:
-            ctx.update_arrays(f["boxes"], f["scores"], f["feats"])
-        prof = ctx.profile_read()
-        ctx.profile_enable(False)
-        ids = ctx.get_tracks(0)["ids"]
-        if ref_ids is None:
-            ref_ids = ids
-        ok = np.array_equal(ids, ref_ids)
-        ms, cnt = prof["assoc"]
-        tf = 2.0 * n * n * 2048 / (ms / cnt * 1e-3) / 1e12
-        print(f"{variant}: assoc {1e3 * ms / cnt:8.2f} us  {tf:7.1f} TFLOP/s  ids_match={ok}  "
-              + " ".join(f"{k}={1e3 * v[0] / max(1, v[1]):.1f}us" for k, v in prof.items()), flush=True)
-    except Exception as e:  # noqa: BLE001
-        print(f"{variant}: FAILED {e}", flush=True)
+for bn in ("224", "256"):
+    os.environ["BT_ASSOC_BN"] = bn
+    ctx.tracker_reset()
+    for f in frames:
+        ctx.update_arrays(f["boxes"], f["scores"], f["feats"].astype(np.float16))
+    ids = ctx.get_tracks(0)["ids"]
+    ref_ids = ids if ref_ids is None else ref_ids
+    us = 1e3 * min(ctx.profile_replay_assoc(50) for _ in range(3))
+    print(f"BN={bn}: {us:7.2f} us per launch  {2.0 * n * n * 2048 / (us * 1e-6) / 1e12:7.1f} TFLOP/s  ids_match={np.array_equal(ids, ref_ids)}", flush=True)
