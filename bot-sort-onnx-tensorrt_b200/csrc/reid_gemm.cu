@@ -12,10 +12,13 @@
 //
 // B200 design: A = per-slot fp16 feature bank [n, d] (K-major), B = per-frame fp16 detection
 // features [m, d] (K-major).  One persistent CTA per SM walks 128 x BN output tiles:
-//   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring)
-//   warp 1   : tcgen05.mma issuer (one elected lane), fp32 accumulators in TMEM, 2 stages
-//   warps 2-5: epilogue -- tcgen05.ld the accumulator, apply the fusion rules above and emit
-//              only the *candidate edges* (cost < stage threshold) into per-row lists.
+//   warp 0   : TMA producer (cp.async.bulk.tensor, 128B swizzle, 4-stage mbarrier ring); first copies the
+//              launch description to shared memory with one batch of loads
+//   warp 1   : tcgen05.mma issue -- the warp stays converged, elect.sync predicates the MMA / commit
+//              (see tcgen05_mma_f16), fp32 accumulators in TMEM, 2 stages
+//   warps 2-9: epilogue -- integer box pass in the shadow of the main loop, then tcgen05.ld the accumulator,
+//              apply the fusion rules above and emit only the *candidate edges* (cost < stage threshold,
+//              flagged when their cost carries the tensor-core error) into per-row lists.
 // The N x M matrices never go to HBM on the tracker path (they are written only for the
 // stand-alone entry points / parity dumps): a 2000 x 2000 frame reads 2*8.2 MB of fp16
 // features and writes a few thousand edges.  Almost every pair is rejected by an fp32 test
@@ -58,7 +61,8 @@ struct EpiParams {
   // BT_ASSOC_DEBUG bits (profiling / bisection aids of the tensor-core kernel, device printf):
   //   1 sampled CTA timestamps   2 similarity pass off   4 every CTA's timestamps   16 epilogue phase times
   //   32 no box pass (every pair evaluated by the similarity pass)   64 no early TMA prologue
-  //   1024 globaltimer go/end of every epilogue warp
+  //   1024 globaltimer go/end of every epilogue warp   4096 no operand traffic after the prologue (the producer
+  //   marks stages full without a TMA: stale tiles, WRONG results -- measures what the loads cost the main loop)
   int debug;
   float sim_gate;  // smallest similarity for which the appearance gate is open
   float gate_band; // |sim - sim_gate| <= gate_band: the gate decision is within the tensor-core error (AMBIG)
