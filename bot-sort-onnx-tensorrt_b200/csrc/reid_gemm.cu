@@ -58,6 +58,9 @@ struct EpiParams {
   double* out_dists;
   int dense_stage;
   int operands_early;
+  // single-problem launches outside graph capture: the first tile's coordinates as kernel arguments, so that the
+  // producer's first TMA requests do not wait for the launch description's round trip (0 tiles_n = no hint)
+  int hint_tiles_n, hint_num_tiles, hint_a_row0, hint_b_row0;
   // BT_ASSOC_DEBUG bits (profiling / bisection aids of the tensor-core kernel, device printf):
   //   1 sampled CTA timestamps   2 similarity pass off   4 every CTA's timestamps   16 epilogue phase times
   //   32 no box pass (every pair evaluated by the similarity pass)   64 no early TMA prologue
@@ -392,23 +395,22 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   // shared memory with ONE batch of independent loads -- walking it in place cost the producer four dependent
   // global round trips (count -> tile_start -> m -> operand rows) before the first TMA request.
   bt_assoc_frame* sF = reinterpret_cast<bt_assoc_frame*>(smem + L::kFrameOff);
-  if (warp == 0) {
-    constexpr int kWords = (int)(sizeof(bt_assoc_frame) / 8);
-    static_assert(sizeof(bt_assoc_frame) % 8 == 0, "frame description is copied in 8-byte words");
-    const uint2* src = reinterpret_cast<const uint2*>(p.F);
-    uint2 v[(kWords + 31) / 32];
-#pragma unroll
-    for (int i = 0; i < (kWords + 31) / 32; ++i) v[i] = (lane + 32 * i < kWords) ? src[lane + 32 * i] : make_uint2(0u, 0u);
-#pragma unroll
-    for (int i = 0; i < (kWords + 31) / 32; ++i)
-      if (lane + 32 * i < kWords) reinterpret_cast<uint2*>(sF)[lane + 32 * i] = v[i];
-    __syncwarp();
-  }
-
   // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as SMs free
   // up (it blocks in its own griddepcontrol.wait until this grid has completed and flushed).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   int pro_kb = 0;   // k-blocks of the first tile already requested by the prologue below
+  // the pipeline's first kStages loads do not wait for anybody: they are requested before the TMEM allocation and
+  // the CTA-wide sync so that their latency overlaps the rest of the ramp
+  auto prologue_loads = [&](const int ya, const int yb) {
+    pro_kb = num_kb < kStages ? num_kb : kStages;
+    for (int kb = 0; kb < pro_kb; ++kb) {
+      mbar_expect_tx(&full_bar[kb], L::kStageBytes);
+      uint8_t* sa = smem + kb * L::kStageBytes;
+      tma_load_2d(sa, &tmap_a, kb * BK, ya, &full_bar[kb]);
+      tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, yb, &full_bar[kb]);
+    }
+  };
+  const bool hinted = p.hint_tiles_n > 0 && !(p.debug & 64);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
@@ -419,18 +421,25 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // stream even starts when the host says so (operands_early): the main loop then runs under that
     // kernel; only the epilogue (boxes, kinds, candidate lists) waits for it.
     if (!p.operands_early) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (first_tile < sF->tile_start[sF->count] && !(p.debug & 64)) {
-      // the pipeline's first kStages loads do not wait for anybody: request them before the TMEM
-      // allocation and the CTA-wide sync so that their latency overlaps the rest of the ramp
+    if (hinted && first_tile < p.hint_num_tiles)        // tile coordinates from the kernel arguments: no global round trip
+      prologue_loads(p.hint_a_row0 + (first_tile / p.hint_tiles_n) * BM, p.hint_b_row0 + (first_tile % p.hint_tiles_n) * BN);
+  }
+  if (warp == 0) {
+    __syncwarp();
+    constexpr int kWords = (int)(sizeof(bt_assoc_frame) / 8);
+    static_assert(sizeof(bt_assoc_frame) % 8 == 0, "frame description is copied in 8-byte words");
+    const uint2* src = reinterpret_cast<const uint2*>(p.F);
+    uint2 v[(kWords + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (kWords + 31) / 32; ++i) v[i] = (lane + 32 * i < kWords) ? src[lane + 32 * i] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int i = 0; i < (kWords + 31) / 32; ++i)
+      if (lane + 32 * i < kWords) reinterpret_cast<uint2*>(sF)[lane + 32 * i] = v[i];
+    __syncwarp();
+    if (lane == 0 && !hinted && first_tile < sF->tile_start[sF->count] && !(p.debug & 64)) {
       int k, m0, n0;
       tile_of(sF, first_tile, BN, k, m0, n0);
-      pro_kb = num_kb < kStages ? num_kb : kStages;
-      for (int kb = 0; kb < pro_kb; ++kb) {
-        mbar_expect_tx(&full_bar[kb], L::kStageBytes);
-        uint8_t* sa = smem + kb * L::kStageBytes;
-        tma_load_2d(sa, &tmap_a, kb * BK, sF->a_row0[k] + m0, &full_bar[kb]);
-        tma_load_2d(sa + L::kABytes, &tmap_b, kb * BK, sF->b_row0[k] + n0, &full_bar[kb]);
-      }
+      prologue_loads(sF->a_row0[k] + m0, sF->b_row0[k] + n0);
     }
   }
   if (warp == 1) {
@@ -1174,6 +1183,12 @@ int32_t btk_assoc_launch(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precisi
     BT_CHECK(dense || ap.cand.seg * 2 == bn, BT_ERR_STATE,
              "candidate segment size %d does not match the tile width %d", ap.cand.seg, bn);
     const int tiles = fixed ? ap.count * ((max_rows + BM - 1) / BM) * ((max_cols + bn - 1) / bn) : hf.tile_start[ap.count];
+    if (!fixed && ap.count == 1 && hf.n[0] > 0 && hf.m[0] > 0) {     // (a captured graph keeps its arguments: no hint)
+      ep.hint_tiles_n = (hf.m[0] + bn - 1) / bn;
+      ep.hint_num_tiles = hf.tile_start[1];
+      ep.hint_a_row0 = hf.a_row0[0];
+      ep.hint_b_row0 = hf.b_row0[0];
+    }
     if (bn == 224) return dense ? launch_tc<224, true>(ctx, ap, ep, tiles) : launch_tc<224, false>(ctx, ap, ep, tiles);
     return dense ? launch_tc<256, true>(ctx, ap, ep, tiles) : launch_tc<256, false>(ctx, ap, ep, tiles);
   }

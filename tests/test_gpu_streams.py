@@ -289,3 +289,30 @@ def test_near_tied_appearance_costs_are_recosted_exactly(dtype, monkeypatch):
             assert run(ctx) > 0
         finally:
             ctx.close()
+
+
+@pytest.mark.gpu
+def test_frame_graph_replay_matches_plain_launches(monkeypatch):
+    """BT_GRAPH=1 (the frame's enqueue replayed as a captured CUDA graph with capacity-sized geometry)
+    tracks exactly like the plain launches: ids, states and boxes over a sequence with births and lost tracks."""
+    from botsort_b200.synthetic import SceneConfig, SyntheticScene
+    scene = SyntheticScene(SceneConfig(n_ids=150, feat_dim=512, seed=31, drop_frac=0.1, newcomer_every=3))
+    frames = [scene.next_frame() for _ in range(12)]
+    out = []
+    for graph in (False, True):
+        if graph:
+            monkeypatch.setenv("BT_GRAPH", "1")
+        else:
+            monkeypatch.delenv("BT_GRAPH", raising=False)
+        ctx = bs.Context(max_tracks=512, max_dets=512, feat_dim=512)
+        ctx.tracker_reset()
+        seq = []
+        for f in frames:
+            ctx.update_arrays(f["boxes"], f["scores"], f["feats"].astype(np.float16))
+            tr = ctx.get_tracks(0)
+            seq.append((tr["ids"].copy(), tr["state"].copy(), tr["tlbr"].copy()))
+        out.append(seq)
+        ctx.close()
+    for (i0, s0, b0), (i1, s1, b1) in zip(*out):
+        assert np.array_equal(i0, i1) and np.array_equal(s0, s1)
+        np.testing.assert_array_equal(b0, b1)
