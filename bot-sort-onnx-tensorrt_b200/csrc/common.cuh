@@ -429,6 +429,7 @@ int32_t btk_assoc_launch(bt_ctx* ctx, const bt_assoc_params& p, int32_t precisio
                          const bt_assoc_frame* df, int fixed, int max_rows, int max_cols);
 // tile width that minimises (waves x MMA time per tile) for a batch of n[k] x m[k] problems on this GPU
 int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m, int32_t count);
+void btk_assoc_stamps_report(void);   // BT_ASSOC_DEBUG bit 32768
 int32_t bt_gemm_ws_create(bt_ctx* ctx);
 void bt_gemm_ws_destroy(bt_ctx* ctx);
 

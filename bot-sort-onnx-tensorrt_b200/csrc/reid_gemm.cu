@@ -66,6 +66,7 @@ struct EpiParams {
   //   32 no box pass (every pair evaluated by the similarity pass)   64 no early TMA prologue
   //   1024 globaltimer go/end of every epilogue warp   4096 no operand traffic after the prologue (the producer
   //   marks stages full without a TMA: stale tiles, WRONG results -- measures what the loads cost the main loop)
+  //   32768 per-SM globaltimer stamps at CTA entry / exit, summarised by bt_profile_replay_assoc
   int debug;
   float sim_gate;  // smallest similarity for which the appearance gate is open
   float gate_band; // |sim - sim_gate| <= gate_band: the gate decision is within the tensor-core error (AMBIG)
@@ -323,6 +324,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ------------------------------------------------------------------------------------------------
+// BT_ASSOC_DEBUG bit 32768: every CTA appends (globaltimer at entry, at exit) to its SM's list -- one CTA per SM at a
+// time, so no races; bt_profile_replay_assoc prints per-SM lifetimes and hand-over gaps between consecutive launches.
+constexpr int kStampSMs = 160, kStampDepth = 64;
+__device__ unsigned long long g_assoc_stamps[kStampSMs][kStampDepth][2];
+__device__ int g_assoc_stamp_cnt[kStampSMs];
 constexpr int BM = 128;
 constexpr int BK = 64;       // 64 fp16 = one 128 B swizzle row
 constexpr int UMMA_K = 16;
@@ -389,6 +395,11 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const long long t_start = clock64();
   unsigned long long g_start = 0;
   if (p.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+  int stamp_sm = -1, stamp_i = 0;
+  if ((p.debug & 32768) && threadIdx.x == 0) {
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(stamp_sm));
+    if (stamp_sm < kStampSMs) { stamp_i = g_assoc_stamp_cnt[stamp_sm]++ % kStampDepth; g_assoc_stamps[stamp_sm][stamp_i][0] = g_start; } else stamp_sm = -1;
+  }
   const int num_kb = d / BK;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
   // The launch description lives in device memory (same kernel arguments every frame): warp 0 copies it to
@@ -919,6 +930,11 @@ assoc_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  if ((p.debug & 32768) && threadIdx.x == 0 && stamp_sm >= 0) {
+    unsigned long long g_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+    g_assoc_stamps[stamp_sm][stamp_i][1] = g_end;
+  }
   if ((p.debug & 1) && threadIdx.x == 0 && (blockIdx.x % 37) == 0) {
     unsigned long long g_end;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
@@ -1215,4 +1231,29 @@ int32_t btk_assoc(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precision) {
   bt_assoc_frame* df = reinterpret_cast<bt_assoc_frame*>(ctx->d_desc);
   BT_CUDA(cudaMemcpyAsync(df, &hf, sizeof(hf), cudaMemcpyHostToDevice, ctx->stream));
   return btk_assoc_launch(ctx, ap, precision, hf, df, 0, 0, 0);
+}
+
+// profiling aid (BT_ASSOC_DEBUG bit 32768): per-SM CTA lifetimes and hand-over gaps of the launches recorded since the last call
+void btk_assoc_stamps_report(void) {
+  static unsigned long long h[kStampSMs][kStampDepth][2];
+  static int cnt[kStampSMs];
+  if (cudaMemcpyFromSymbol(h, g_assoc_stamps, sizeof(h)) != cudaSuccess) return;
+  if (cudaMemcpyFromSymbol(cnt, g_assoc_stamp_cnt, sizeof(cnt)) != cudaSuccess) return;
+  double life = 0.0, gap = 0.0, gap_max = 0.0;
+  long n_life = 0, n_gap = 0;
+  for (int sm = 0; sm < kStampSMs; ++sm) {
+    const int n = cnt[sm] < kStampDepth ? cnt[sm] : kStampDepth;
+    if (cnt[sm] > kStampDepth) continue;          // wrapped: order lost
+    for (int i = 0; i < n; ++i) {
+      if (h[sm][i][1] > h[sm][i][0]) { life += (double)(h[sm][i][1] - h[sm][i][0]); ++n_life; }
+      if (i + 1 < n && h[sm][i + 1][0] > h[sm][i][1]) {
+        const double g = (double)(h[sm][i + 1][0] - h[sm][i][1]);
+        gap += g; ++n_gap; if (g > gap_max) gap_max = g;
+      }
+    }
+  }
+  fprintf(stderr, "assoc stamps: %ld CTA lives, mean %.2f us; %ld per-SM hand-overs (exit of a launch's CTA -> entry of the next launch's CTA on that SM), mean %.2f us, max %.2f us\n",
+          n_life, n_life ? life / n_life / 1e3 : 0.0, n_gap, n_gap ? gap / n_gap / 1e3 : 0.0, gap_max / 1e3);
+  memset(cnt, 0, sizeof(cnt));
+  cudaMemcpyToSymbol(g_assoc_stamp_cnt, cnt, sizeof(cnt));
 }

@@ -1301,6 +1301,7 @@ int32_t bt_profile_replay_assoc(bt_ctx* ctx, int32_t iters, double* total_ms) {
   }
   BT_TRY(clear_lists());
   BT_CUDA(cudaStreamSynchronize(st));
+  if (getenv("BT_ASSOC_DEBUG") && (atoi(getenv("BT_ASSOC_DEBUG")) & 32768)) btk_assoc_stamps_report();
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *total_ms = sum;
