@@ -1125,14 +1125,21 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams
 
 int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m, int32_t count) {
   const char* e = getenv("BT_ASSOC_BN");
-  if (e) return atoi(e) == 224 ? 224 : 256;
+  if (e) { const int v = atoi(e); return (v == 224 || v == 128 || v == 64) ? v : 256; }
+  // A tile's main loop costs the tensor pipe max(BN, 116) / 2 cycles per MMA (tools/mma_issue_probe.cu: N <= 112 sits on
+  // the 58-cycle issue floor), so the launch costs waves x that.  Narrow tiles only pay for small problems -- a
+  // 128 x 256 tile spends 8 us of MMA issue on a 64 x 64 frame -- and only there do they fit the candidate lists'
+  // 64 segments per row (segment = half a tile).
+  int mx_m = 0;
+  for (int k = 0; k < count; ++k) mx_m = m[k] > mx_m ? m[k] : mx_m;
   long best_cost = -1;
   int best = 256;
-  for (int bn : {256, 224}) {
+  for (int bn : {256, 224, 128, 64}) {
+    if (bn < 224 && (mx_m + bn / 2 - 1) / (bn / 2) > BT_CAND_MAXSEG) continue;
     long tiles = 0;
     for (int k = 0; k < count; ++k) tiles += (long)((n[k] + BM - 1) / BM) * ((m[k] + bn - 1) / bn);
     const long waves = (tiles + ctx->num_sms - 1) / ctx->num_sms;
-    const long cost = waves * bn;      // a tile's main loop costs the tensor pipe time proportional to its width
+    const long cost = waves * (bn > 116 ? bn : 116);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -1206,6 +1213,9 @@ int32_t btk_assoc_launch(bt_ctx* ctx, const bt_assoc_params& ap, int32_t precisi
       ep.hint_b_row0 = hf.b_row0[0];
     }
     if (bn == 224) return dense ? launch_tc<224, true>(ctx, ap, ep, tiles) : launch_tc<224, false>(ctx, ap, ep, tiles);
+    if (bn == 128 && !dense) return launch_tc<128, false>(ctx, ap, ep, tiles);
+    if (bn == 64 && !dense) return launch_tc<64, false>(ctx, ap, ep, tiles);
+    BT_CHECK(bn == 256, BT_ERR_INVALID, "unsupported association tile width %d", bn);
     return dense ? launch_tc<256, true>(ctx, ap, ep, tiles) : launch_tc<256, false>(ctx, ap, ep, tiles);
   }
   ep.gate_band = 0.f;

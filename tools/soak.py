@@ -15,7 +15,7 @@ from test_gpu_tracker import _compare_frame
 n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 BIG = bool(os.environ.get("SOAK_BIG"))     # SOAK_BIG=1: 300-2200 identities, 2048-d features, a few frames each
-D = 2048 if BIG else 256
+D = int(os.environ.get("SOAK_D", "2048" if BIG else "256"))     # SOAK_D=512: small scenes through the tensor-core path (narrow tiles)
 ctx = bs.Context(max_tracks=2304 if BIG else 1024, max_dets=2304 if BIG else 1024, feat_dim=D,
                  flags=1 if os.environ.get("SOAK_SIMT") else 0)   # SOAK_SIMT=1: fp32 CUDA-core similarity (BT_FLAG_SIMT_SIM)
 bad = []
