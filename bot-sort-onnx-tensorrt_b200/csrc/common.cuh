@@ -229,6 +229,7 @@ struct bt_store {
   // per batch entry
   char* ctrl;          // packed control block
   char* res;           // result regions part A (read back right after the LAP): x1,x2,x3 [cap each] | scores[md] | boxes[4 md]
+  char* res_host;      // the pinned host copy of part A when the kernels publish it themselves (direct results), else null
   char* resB;          // result regions part B (read back at the end): pair count (2 ints) | pairs[2*prefetch] | tlbr[4*cap] f64
   int32_t* y;          // [BT_MAX_BATCH][3][md]
   int32_t* pairs;      // [BT_MAX_BATCH][2*pair_cap] duplicate candidates beyond the prefetch
@@ -468,6 +469,10 @@ struct bt_lap_batch {
   int32_t* y[BT_MAX_BATCH];         // y1,y2,y3 [y_stride each]
   int32_t y_stride;
   int32_t* zero_word[BT_MAX_BATCH]; // device word to clear (the frame's duplicate-pair counter)
+  // direct results: the LAP kernel copies the stream's assignment vectors into pinned host memory (same layout as x)
+  // and then sets the stream's flag word there -- the host polls it instead of waiting for a D2H copy + event
+  int32_t* hx[BT_MAX_BATCH];
+  uint32_t* hflag[BT_MAX_BATCH];
 };
 // atomic_emitter != 0: the lists were filled by the CUDA-core kernel (atomic appends: its segment counters must be
 // left zeroed for the next frame)

@@ -125,6 +125,11 @@ frame_prep_kernel(bt_store st, const bt_batch* __restrict__ bp, bt_frame_cfg fc,
       int32_t* res = reinterpret_cast<int32_t*>(st.res + (size_t)k * L.stride);
       reinterpret_cast<float*>(res + L.o_sc)[j] = s;
       *reinterpret_cast<int4*>(res + L.o_bx + (size_t)j * 4) = bb;
+      if (st.res_host) {      // direct results: straight into the pinned host copy (visible before the LAP kernel's flag)
+        int32_t* hres = reinterpret_cast<int32_t*>(st.res_host + (size_t)k * L.stride);
+        reinterpret_cast<float*>(hres + L.o_sc)[j] = s;
+        *reinterpret_cast<int4*>(hres + L.o_bx + (size_t)j * 4) = bb;
+      }
     }
     const double sd = (double)s;     // float(score), demo:1022
     st.col_kind[gd0 + j] = (sd > fc.high) ? BT_COL_HIGH : ((sd >= fc.low) ? BT_COL_LOW : BT_COL_NONE);

@@ -1190,6 +1190,17 @@ lap_stream_kernel(bt_cand cand_base, bt_lap_ws ws_base, const bt_lap_batch* __re
              sid, stage, n, m, sm.nC, sm.nE, sm.nR, tq[2] - tq[1], tq[6] - tq[1], tq[7] - tq[1], tq[0] - tq[1], tq[5] - tq[2], tq[3] - tq[2], tq[4] - tq[3]);
     LAP_T(1);
   }
+  // ---- direct results: the assignment vectors go to the host by plain stores over PCIe, then the flag ----
+  if (B.hx[kb]) {
+    for (int s = 0; s < P.nstages; ++s) {
+      const int32_t* x = B.x[kb] + (size_t)s * B.x_stride[kb];
+      int32_t* hx = B.hx[kb] + (size_t)s * B.x_stride[kb];
+      for (int r = tid; r < n; r += GT) hx[r] = x[r];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile uint32_t*>(B.hflag[kb]) = 1u;
+  }
 }
 
 // dense float64 cost -> candidate list (ordered by column): one warp per row
