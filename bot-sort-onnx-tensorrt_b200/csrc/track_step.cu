@@ -140,6 +140,8 @@ struct bt_tracker {
   char* h_ctrl = nullptr;
   char* h_res = nullptr;            // part A regions
   uint32_t* h_flags = nullptr;      // direct results: one word per batch entry, set by the LAP kernel (pinned)
+  // device-side aliases of the pinned buffers kernels touch directly (cudaHostGetDevicePointer; identical under UVA)
+  char* h_ctrl_dev = nullptr; char* h_res_dev = nullptr; uint32_t* h_flags_dev = nullptr;
   bool direct_results = false;      // BT_DIRECT_RESULT=1: the LAP kernel publishes the assignments into pinned host memory (A/B: slower)
   char* h_resB = nullptr;           // part B regions
   int32_t* h_in_boxes = nullptr;    // [2][S*md][4] pinned copies of the submitted boxes / scores of host inputs: the
@@ -315,6 +317,9 @@ int32_t bt_tracker_create(bt_ctx* ctx) {
   BT_CUDA(cudaMallocHost(&t->h_resB, t->L.strideB * S));
   BT_CUDA(cudaMallocHost(&t->h_flags, sizeof(uint32_t) * BT_MAX_BATCH));
   memset(t->h_flags, 0, sizeof(uint32_t) * BT_MAX_BATCH);
+  BT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&t->h_ctrl_dev), t->h_ctrl, 0));
+  BT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&t->h_res_dev), t->h_res, 0));
+  BT_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&t->h_flags_dev), t->h_flags, 0));
   BT_CUDA(cudaMallocHost(&t->h_in_boxes, sizeof(int32_t) * 2 * ND * 4));
   BT_CUDA(cudaMallocHost(&t->h_in_scores, sizeof(float) * 2 * ND));
   BT_CUDA(cudaMallocHost(&t->h_birth, sizeof(int32_t) * (size_t)S * (2 * md + cap)));
@@ -701,7 +706,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   // the LAP kernel and the host.  Measured on the C3 step: 0.103 ms against 0.098 ms with the side-stream copy (the
   // SM-issued PCIe stores + system fence at the end of the single LAP CTA cost more than the copy engine's round trip).
   const bool direct = t->direct_results && !t->use_graph && mx_rows > 0;
-  dst.res_host = direct ? t->h_res : nullptr;
+  dst.res_host = direct ? t->h_res_dev : nullptr;
   if (direct) for (int k = 0; k < count; ++k) t->h_flags[k] = 0u;
   const int assoc_bn = (any_reid && tensor_path) ? btk_assoc_pick_bn(ctx, B.n_rows, B.m, count) : 256;
   const int assoc_precision = (any_reid && tensor_path) ? 0 : 1;
@@ -739,8 +744,8 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
     LB.x[k] = dresA + L.o_x; LB.x_stride[k] = t->cap;
     LB.y[k] = dst.y + (size_t)k * 3 * t->md;
     LB.zero_word[k] = reinterpret_cast<int32_t*>(dst.resB + (size_t)k * L.strideB) + L.o_hdr;
-    LB.hx[k] = direct ? reinterpret_cast<int32_t*>(t->h_res + (size_t)k * L.stride) + L.o_x : nullptr;
-    LB.hflag[k] = direct ? t->h_flags + k : nullptr;
+    LB.hx[k] = direct ? reinterpret_cast<int32_t*>(t->h_res_dev + (size_t)k * L.stride) + L.o_x : nullptr;
+    LB.hflag[k] = direct ? t->h_flags_dev + k : nullptr;
   }
   p.d = any_reid ? D : 0;
   p.a_rows_alloc = t->S * t->cap; p.b_rows_alloc = (int32_t)(2 * ND);
@@ -791,7 +796,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
   auto enqueue = [&](const int fixed) -> int32_t {
     const size_t ctrl_bytes_now = fixed ? kDescBytes + t->ctrl_stride * (size_t)count : ctrl_off;
     if (t->ctrl_by_copy) BT_CUDA(cudaMemcpyAsync(dst.ctrl, t->h_ctrl, ctrl_bytes_now, cudaMemcpyHostToDevice, st));
-    else BT_TRY(btk_ctrl_upload(ctx, t->h_ctrl, dst.ctrl, ctrl_bytes_now));
+    else BT_TRY(btk_ctrl_upload(ctx, t->h_ctrl_dev, dst.ctrl, ctrl_bytes_now));
     fmark("ctrl_h2d");
     SEG_BEGIN(BT_SEG_PREP);
     if (any_f32) BT_TRY(btk_frame_cast(ctx, dst, B, &dd->B, fixed));
