@@ -291,19 +291,24 @@ def test_near_tied_appearance_costs_are_recosted_exactly(dtype, monkeypatch):
             ctx.close()
 
 
+_SWITCHES = ["BT_GRAPH", "BT_DIRECT_RESULT", "BT_CTRL_COPY", "BT_NO_PREBUILD", "BT_COPY_INLINE", "BT_NO_L2_PREFETCH", "BT_NO_PDL"]
+
+
 @pytest.mark.gpu
-def test_frame_graph_replay_matches_plain_launches(monkeypatch):
-    """BT_GRAPH=1 (the frame's enqueue replayed as a captured CUDA graph with capacity-sized geometry)
-    tracks exactly like the plain launches: ids, states and boxes over a sequence with births and lost tracks."""
-    from botsort_b200.synthetic import SceneConfig, SyntheticScene
+@pytest.mark.parametrize("switch", _SWITCHES)
+def test_runtime_switches_do_not_change_the_tracking(monkeypatch, switch):
+    """Every A/B switch of the frame step (captured frame graph, LAP kernel publishing the
+    assignments itself, control block by memcpy, pool lists built at the start of the step, read-back on the main
+    stream, no operand prefetch, no programmatic dependent launch) tracks exactly like the default path: ids,
+    states and boxes over a sequence with births, lost and re-found tracks."""
     scene = SyntheticScene(SceneConfig(n_ids=150, feat_dim=512, seed=31, drop_frac=0.1, newcomer_every=3))
     frames = [scene.next_frame() for _ in range(12)]
     out = []
-    for graph in (False, True):
-        if graph:
-            monkeypatch.setenv("BT_GRAPH", "1")
-        else:
-            monkeypatch.delenv("BT_GRAPH", raising=False)
+    for on in (False, True):
+        for name in _SWITCHES:
+            monkeypatch.delenv(name, raising=False)
+        if on:
+            monkeypatch.setenv(switch, "1")
         ctx = bs.Context(max_tracks=512, max_dets=512, feat_dim=512)
         ctx.tracker_reset()
         seq = []
