@@ -1124,14 +1124,18 @@ static int32_t launch_tc(bt_ctx* ctx, const bt_assoc_params& ap, const EpiParams
 }
 
 int32_t btk_assoc_pick_bn(const bt_ctx* ctx, const int32_t* n, const int32_t* m, int32_t count) {
+  int mx_m = 0;
+  for (int k = 0; k < count; ++k) mx_m = m[k] > mx_m ? m[k] : mx_m;
   const char* e = getenv("BT_ASSOC_BN");
-  if (e) { const int v = atoi(e); return (v == 224 || v == 128 || v == 64) ? v : 256; }
+  if (e) {     // profiling override; a narrow tile that would not fit the 64 segments per row is ignored
+    const int v = atoi(e);
+    if ((v == 224 || v == 128 || v == 64) && (mx_m + v / 2 - 1) / (v / 2) <= BT_CAND_MAXSEG) return v;
+    return 256;
+  }
   // A tile's main loop costs the tensor pipe max(BN, 116) / 2 cycles per MMA (tools/mma_issue_probe.cu: N <= 112 sits on
   // the 58-cycle issue floor), so the launch costs waves x that.  Narrow tiles only pay for small problems -- a
   // 128 x 256 tile spends 8 us of MMA issue on a 64 x 64 frame -- and only there do they fit the candidate lists'
   // 64 segments per row (segment = half a tile).
-  int mx_m = 0;
-  for (int k = 0; k < count; ++k) mx_m = m[k] > mx_m ? m[k] : mx_m;
   long best_cost = -1;
   int best = 256;
   for (int bn : {256, 224, 128, 64}) {
