@@ -641,7 +641,7 @@ static int32_t step_batch(bt_ctx* ctx, int32_t count, const int32_t* sids, bt_fr
         memcpy(h_idx, s.pre_idx.data(), sizeof(int32_t) * (size_t)s.n_pool);
         memcpy(h_state, s.pre_state.data(), sizeof(int32_t) * (size_t)s.n_pool);
       }
-      memcpy(h_kind, s.pre_kind.data(), ((size_t)s.n_rows + 3) & ~size_t(3));
+      if (s.n_rows > 0) memcpy(h_kind, s.pre_kind.data(), ((size_t)s.n_rows + 3) & ~size_t(3));
       unconfirmed.swap(s.pre_unconfirmed);
       all_f32 = false;
     } else {
